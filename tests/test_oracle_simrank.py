@@ -1,0 +1,128 @@
+"""Pin the SimRank CPU oracle.  CPU only.
+ * exact SimRank vs the repo's only golden vector (IsoMap_LE/data/0_333_5038_simrank_navie_top10)
+ * TopSim_Enumerate restatement == SAMPLE x exact truncated SimRank (deterministic)
+ * SingleRandomWalk / TopSim_singleSample restatements converge to the same expectation
+ * java.util.Random clone vs published known answers
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from oracle import simrank_oracle as S
+from conftest import DATA
+
+
+@pytest.fixture(scope="module")
+def g333():
+    return S.load_multigraph(os.path.join(DATA, "0_333_5038.txt"), 333, separator=" ")
+
+
+def test_java_random_known_answers():
+    out = np.zeros(2, dtype=np.int32)
+    S.lib().jr_fill32.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
+    S.lib().jr_fill32(42, 2, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+    assert out.tolist() == [-1170105035, 234785527]          # new Random(42).nextInt() x2
+    S.lib().jr_fill32(0, 1, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+    assert int(out[0]) == -1155484576                        # new Random(0).nextInt()
+    # bounded draws: range, power-of-two shortcut == high bits, uniformity
+    r = S.java_random_ints(7, 10, 20000)
+    assert r.min() == 0 and r.max() == 9
+    cnt = np.bincount(r, minlength=10)
+    assert ((cnt - 2000) ** 2 / 2000).sum() < 27.9           # chi2 df=9, alpha=1e-3
+    r16 = S.java_random_ints(7, 16, 100)
+    S.lib().jr_fill32(7, 2, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+    assert int(r16[0]) == ((int(out[0]) & 0xFFFFFFFF) >> 1) * 16 >> 31
+
+
+def test_multigraph_loader(g333):
+    assert g333["V"] == 333 and g333["row_ptr"][-1] == 2 * 5038      # both directions per line
+    # file lists each undirected edge in both directions -> every neighbour appears twice
+    a, b = int(g333["row_ptr"][0]), int(g333["row_ptr"][1])
+    nb, cnt = np.unique(g333["col"][a:b], return_counts=True)
+    assert (cnt == 2).all()
+
+
+def test_exact_simrank_matches_golden(g333):
+    """C=0.8, 30 sweeps reproduces every id:score of the shipped golden to 5e-8 (file is %.8f)."""
+    sim = S.simrank_exact_matrix(g333, 0.8, 30)
+    gold = S.read_sim_file(os.path.join(DATA, "0_333_5038_simrank_navie_top10.txt.sim.txt"), separator=" ")
+    assert len(gold) == 333
+    worst = 0.0
+    for v, row in gold:
+        for i, x in row:
+            worst = max(worst, abs(sim[v, i] - x))
+        # the golden row is the top-10 of the exact row; the printer that wrote the golden
+        # dropped zero scores (9 rows are shorter than 10), so shorter rows must be padded by zeros
+        ids, vals = S.fixedmaxpq_topk(sim[v], 10)
+        assert np.allclose(vals[:len(row)], [x for _, x in row], atol=5e-8)
+        assert (vals[len(row):] < S.MIN).all()
+    assert worst <= 5e-8
+
+
+def test_naive_loop_equals_matrix_form(g333):
+    a = S.simrank_exact_naive(g333, 0.6, 3)       # the committed defaults C=0.6 STEP=3
+    b = S.simrank_exact_matrix(g333, 0.6, 3)
+    assert np.abs(a - b).max() < 1e-12
+
+
+@pytest.fixture(scope="module")
+def karate_multi():
+    s, d = S.read_edge_file(os.path.join(DATA, "karate.edgelist"), " ")
+    return S.build_multigraph(s, d, 35)            # slot 0 isolated, duplicate pair (9,33) kept
+
+
+@pytest.mark.parametrize("v,step", [(1, 2), (12, 2), (34, 2), (0, 2), (5, 3)])
+def test_enumerate_is_sample_times_truncated_exact(karate_multi, v, step):
+    sample = 1000
+    exact = S.simrank_exact_matrix(karate_multi, 0.6, step)
+    row, made, _ = S.topsim_row(karate_multi, v, sample, step, 0.6, mode=1, max_paths=1 << 21)
+    assert np.abs(row / sample - exact[v]).max() < 1e-9
+
+
+def test_single_random_walk_converges(g333):
+    step = 3
+    exact = S.simrank_exact_matrix(g333, 0.6, step)
+    v, sample = 5, 200000
+    row, steps, _ = S.single_random_walk_row(g333, v, sample, step, 0.6, seed_state=S.java_seed(1))
+    assert steps == sample * 2 * step
+    top = np.argsort(-exact[v])[:20]
+    assert np.abs(row[top] - exact[v][top]).max() < 4e-3
+    assert np.sqrt(np.mean((row[top] - exact[v][top]) ** 2)) < 1.5e-3
+    assert abs(row.sum() - exact[v].sum()) < 2e-2 * exact[v].sum()
+
+
+def test_topsim_single_sample_converges(g333):
+    step = 3
+    exact = S.simrank_exact_matrix(g333, 0.6, step)
+    v, sample = 5, 200000
+    row, made, _ = S.topsim_row(g333, v, sample, step, 0.6, mode=0, seed_state=S.java_seed(2))
+    top = np.argsort(-exact[v])[:20]
+    assert np.abs(row[top] / sample - exact[v][top]).max() < 4e-3
+
+
+def test_fixedmaxpq_semantics():
+    # replace only if strictly greater: the earlier id keeps its place on ties at the boundary
+    ids, vals = S.fixedmaxpq_topk(np.array([0.5, 0.1, 0.5, 0.1, 0.1]), 3)
+    assert sorted(ids.tolist()) == [0, 1, 2] and vals.tolist() == [0.5, 0.5, 0.1]
+    ids, vals = S.fixedmaxpq_topk(np.zeros(50), 20)
+    assert sorted(ids.tolist()) == list(range(20))
+    ids, vals = S.fixedmaxpq_topk(np.array([0.3, 0.9]), 20)
+    assert ids.tolist() == [1, 0]
+    # FixedMaxPQ.main : capacity 2, offers luo, liu, zhang -> descending zhang, luo (numbers stand in)
+    ids, vals = S.fixedmaxpq_topk(np.array([2.0, 1.0, 3.0]), 2)
+    assert ids.tolist() == [2, 0]
+
+
+def test_print_and_eval_roundtrip(tmp_path, g333):
+    sim = S.simrank_exact_matrix(g333, 0.6, 3)
+    p = str(tmp_path / "out.txt")
+    S.print_by_order(sim, p, 20, 6)
+    raw = open(p + ".sim.txt", "rb").read()
+    assert raw.count(b"\r\n") == 333
+    rows = S.read_sim_file(p + ".sim.txt")
+    assert rows[0][0] == 0 and len(rows[0][1]) == 20
+    mean, pres = S.precision_rows(rows, rows)
+    assert mean == 1.0
+    assert S.java_fmt(0.0000005, 6) == "0.000001" and S.java_fmt(0.125, 2) == "0.13"
