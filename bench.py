@@ -1,0 +1,453 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the walk engine (driver contract in the task statement).
+
+Default (N=1): BASELINE.json configs[2] — node2vec on synthetic R-MAT scale-22 (reference generator
+probabilities .45/.15/.15/.25, 16*2^22 edge tuples), p=0.25 q=4, walk_length=80.  One "step" is one
+walk iteration: one walk from every non-isolated vertex (= one pass of simulate_walks' inner loop,
+node2vec.py:53-57); num_walks=10 is `--steps 10`.
+
+  value  walk-steps/s, corpus produced into a resident HBM buffer from resident start nodes
+  e2e    same metric through the host-buffer C-ABI call (gw_node2vec_walks): pinned host start
+         nodes -> H2D -> kernel -> D2H of the whole corpus, all inside the timed region
+  roofline  algorithmic bytes (68 + 32*S(d_prev) per step, measured on the corpus
+         actually produced) / CUDA-event kernel time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the oracle's python port of the reference walker, 1 core, bounded sample
+
+`--workload simrank` measures TopSim queries/s on a Barabasi-Albert graph (configs[4] shape).
+`--impl reference` times the CPU port on all host cores (rank 0 only).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="node2vec", choices=["node2vec", "simrank"])
+    ap.add_argument("--scale", type=int, default=22)
+    ap.add_argument("--edge-factor", type=int, default=16)
+    ap.add_argument("--p", type=float, default=0.25)
+    ap.add_argument("--q", type=float, default=4.0)
+    ap.add_argument("--walk-length", type=int, default=80)
+    ap.add_argument("--ba-nodes", type=int, default=10_000_000)
+    ap.add_argument("--ba-m", type=int, default=8)
+    ap.add_argument("--queries-per-step", type=int, default=8192)
+    ap.add_argument("--sample", type=int, default=10000)
+    ap.add_argument("--sr-step", type=int, default=5)
+    ap.add_argument("--topk", type=int, default=20)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def finish(self):
+        self._stop.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arms (oracle port).  These are the ONLY places bench.py touches oracle/.
+# ---------------------------------------------------------------------------------------------
+def _rmat_edges_numpy(scale, n_tuples, a, b, c, seed):
+    rs = np.random.RandomState(seed)
+    frm = np.zeros(n_tuples, dtype=np.int64)
+    to = np.zeros(n_tuples, dtype=np.int64)
+    for _ in range(scale):
+        x = rs.rand(n_tuples)
+        fb = ((x >= a) & (x < a + b)) | (x >= a + b + c)
+        tb = x >= a + b
+        frm = (frm << 1) | fb
+        to = (to << 1) | tb
+    keep = frm != to
+    return frm[keep], to[keep]
+
+
+def _cpu_node2vec_worker(args):
+    """One process: python port of simulate_walks on its shard of start nodes."""
+    g, p, q, L, starts, seed, budget = args
+    from oracle import n2v_oracle as O
+    an = O.alias_nodes_flat(g)
+    ae = O.alias_edges_flat(g, p, q)
+    rng = np.random.RandomState(seed)
+    t0 = time.perf_counter()
+    steps = 0
+    i = 0
+    while time.perf_counter() - t0 < budget:
+        s = int(starts[i % len(starts)])
+        i += 1
+        u = rng.rand(2 * (L - 1))
+        w, _ = O.walk_replay(g, an, ae, L, s, u, 0)
+        steps += len(w) - 1
+    return steps, time.perf_counter() - t0
+
+
+def cpu_node2vec(p, q, L, seconds, procs):
+    """Reference-structured walker (materialised alias tables, per-step python loop, two uniform
+    draws per step) on a down-scaled R-MAT of the benchmark shape: the reference cannot preprocess
+    sum(deg^2) at scale-22, and its steps/s does not depend on graph size."""
+    from oracle import n2v_oracle as O
+    scale = 10
+    s, d = _rmat_edges_numpy(scale, 16 << scale, 0.45, 0.15, 0.15, 1)
+    g = O.build_simple_graph(s, d, np.ones(len(s)), directed=False)
+    starts = np.nonzero(np.diff(g["row_ptr"]) > 0)[0]
+    if procs == 1:
+        res = [_cpu_node2vec_worker((g, p, q, L, starts, 1, seconds))]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_cpu_node2vec_worker, [(g, p, q, L, starts[i::procs], i + 1, seconds) for i in range(procs)])
+    steps = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    sample = ("python port of node2vec_walk/alias_draw (oracle/n2v_oracle.py) on R-MAT scale-%d, p=%g q=%g L=%d, "
+              "%d walk-steps in %.1fs on %d process(es); alias preprocessing untimed" % (scale, p, q, L, steps, wall, procs))
+    return steps / wall, sample
+
+
+def cpu_simrank(sample, step, k, seconds, procs, n=100_000, m=8):
+    """C restatement of SingleRandomWalk.walk + FixedMaxPQ top-k on a down-scaled BA graph."""
+    from oracle import simrank_oracle as S
+    rs = np.random.RandomState(1)
+    # small BA by the same rule as the library's host generator, numpy/py only (bounded size)
+    rep, src, dst = [], [], []
+    for i in range(m):
+        for j in range(i + 1, m):
+            src.append(i); dst.append(j); rep += [i, j]
+    for v in range(m, n):
+        tg = set()
+        while len(tg) < m:
+            tg.add(rep[rs.randint(len(rep))])
+        for t in tg:
+            src.append(v); dst.append(t); rep += [v, t]
+    g = S.build_multigraph(np.array(src), np.array(dst), n)
+
+    def worker(seed, out):
+        st = S.java_seed(seed)
+        rq = np.random.RandomState(seed)
+        t0 = time.perf_counter()
+        nqd = 0
+        while time.perf_counter() - t0 < seconds:
+            v = int(rq.randint(n))
+            row, _, st = S.single_random_walk_row(g, v, sample, step, 0.6, st)
+            S.fixedmaxpq_topk(row, k)
+            nqd += 1
+        out.append((nqd, time.perf_counter() - t0))
+    outs = []
+    ths = [threading.Thread(target=worker, args=(i + 1, outs)) for i in range(procs)]   # ctypes releases the GIL
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    nqd = sum(o[0] for o in outs)
+    wall = max(o[1] for o in outs)
+    desc = ("C restatement of SingleRandomWalk.walk + FixedMaxPQ (oracle/simrank_oracle.c, not a JVM) on BA n=%d m=%d, "
+            "SAMPLE=%d STEP=%d k=%d, %d queries in %.1fs on %d thread(s)" % (n, m, sample, step, k, nqd, wall, procs))
+    return nqd / wall, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    t_all = time.perf_counter()
+    vals = []
+    for _ in range(max(1, min(args.steps, 2))):
+        if args.workload == "node2vec":
+            v, sample = cpu_node2vec(args.p, args.q, args.walk_length, args.cpu_seconds, cores)
+        else:
+            v, sample = cpu_simrank(args.sample, args.sr_step, args.topk, args.cpu_seconds, cores)
+        vals.append(v)
+    v = float(np.mean(vals))
+    metric, unit = metric_unit(args)
+    line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": config_of(args),
+            "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t_all}
+    print(json.dumps(line), flush=True)
+
+
+def metric_unit(args):
+    if args.workload == "node2vec":
+        return "node2vec walk-steps/sec", "walk-steps/s"
+    return "TopSim SimRank queries/sec", "queries/s"
+
+
+def config_of(args):
+    if args.workload == "node2vec":
+        return {"workload": "node2vec on synthetic R-MAT scale-%d (%d*2^%d tuples, a,b,c,d=.45/.15/.15/.25), p=%g q=%g, "
+                            "walk_length=%d, one step = one walk per non-isolated vertex" %
+                            (args.scale, args.edge_factor, args.scale, args.p, args.q, args.walk_length),
+                "cache": "inputs larger than L2 (col_idx %.0f MB, corpus %.0f MB per step)" %
+                         (4.0 * 2 * args.edge_factor * (1 << args.scale) / 1e6,
+                          4.0 * args.walk_length * (1 << args.scale) / 1e6),
+                "sharding": "graph replicated per GPU, disjoint walk ids per rank, no data-path collective"}
+    return {"workload": "TopSim SimRank top-%d on synthetic Barabasi-Albert n=%d m=%d, c=0.6 STEP=%d SAMPLE=%d, "
+                        "one step = %d queries" % (args.topk, args.ba_nodes, args.ba_m, args.sr_step, args.sample,
+                                                   args.queries_per_step),
+            "cache": "inputs larger than L2 (col_idx %.0f MB)" % (4.0 * 2 * args.ba_m * args.ba_nodes / 1e6),
+            "sharding": "graph replicated per GPU, disjoint query slices per rank, no data-path collective"}
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from graph_embedding_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    _lib.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream().cuda_stream
+    peak, peak_src = measured_peak()
+    launches0 = _lib.kernel_launches()
+    metric, unit = metric_unit(args)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    extra = {}
+    if args.workload == "node2vec":
+        L = args.walk_length
+        t0 = time.perf_counter()
+        g = _lib.GraphHandle.rmat(args.scale, args.edge_factor << args.scale, seed=1)
+        starts_np = g.nonisolated()
+        extra["graph_build_s"] = round(time.perf_counter() - t0, 3)
+        nw = len(starts_np)
+        extra["graph"] = {"nodes": g.n, "non_isolated": nw, "directed_entries": g.nnz, "max_degree": g.max_degree}
+        rs = np.random.RandomState(1234 + rank)
+        d_out = torch.empty((nw, L), dtype=torch.int32, device=dev)
+        perms = []
+        for s in range(args.warmup + args.steps):
+            perms.append(torch.from_numpy(rs.permutation(starts_np)).to(dev))    # random.shuffle(nodes), :51
+        units_per_step = None
+        second_order = not (args.p == 1.0 and args.q == 1.0)
+
+        def step(i):
+            g.walks_dev(args.p, args.q, L, perms[i].data_ptr(), nw, d_out.data_ptr(), seed=42,
+                        walk_id_base=(rank * 1000 + i) * nw, stream=stream)
+
+        for i in range(args.warmup):
+            step(i)
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        launches_t0 = _lib.kernel_launches()
+        ev[0].record()
+        for i in range(args.steps):
+            step(args.warmup + i)
+            ev[i + 1].record()
+        barrier()
+        clocks = sampler.finish()
+        gpu_launches = _lib.kernel_launches() - launches_t0
+        ms_total = ev[0].elapsed_time(ev[-1])
+        per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+        steps_exec, sum_s = g.byte_model_dev(d_out.data_ptr(), nw, L, second_order, stream=stream)
+        units_per_step = steps_exec
+        alg_bytes = 68.0 * steps_exec + 32.0 * sum_s
+        kernel_ms = float(np.mean(per_launch_ms))
+        roof = {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "traffic": None, "kernel": "k_walk_free<false,false>", "peak_source": peak_src,
+                "bytes_per_unit": alg_bytes / steps_exec, "mean_search_sectors": sum_s / steps_exec,
+                "units_per_launch": steps_exec, "launch_ms": kernel_ms}
+        roof["frac"] = roof["achieved"] / peak
+
+        # ---- e2e: host buffers through the blocking C-ABI entry point ----
+        e2e = None
+        if not args.no_e2e:
+            import ctypes
+            h_starts = torch.from_numpy(rs.permutation(starts_np)).pin_memory()
+            h_out = torch.empty((nw, L), dtype=torch.int32).pin_memory()
+            L_ = _lib.load()
+
+            def e2e_step(i):
+                _lib.check(L_.gw_node2vec_walks(g.h, args.p, args.q, L, ctypes.cast(h_starts.data_ptr(), _lib.c_i64p),
+                                                nw, 43, (rank * 1000 + i) * nw,
+                                                ctypes.cast(h_out.data_ptr(), _lib.c_i32p), None))
+            e2e_step(0)
+            barrier()
+            n_e2e = max(1, min(args.steps, 3))
+            t0 = time.perf_counter()
+            for i in range(n_e2e):
+                e2e_step(1 + i)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e = {"value": world * n_e2e * steps_exec / float(tt.item()), "unit": unit,
+                   "h2d_bytes_per_step": nw * 8, "d2h_bytes_per_step": nw * L * 4, "steps": n_e2e,
+                   "api": "gw_node2vec_walks (host start nodes in, host corpus out)"}
+    else:
+        t0 = time.perf_counter()
+        g = _lib.GraphHandle.barabasi_albert(args.ba_nodes, args.ba_m, seed=1)
+        extra["graph_build_s"] = round(time.perf_counter() - t0, 3)
+        extra["graph"] = {"nodes": g.n, "directed_entries": g.nnz, "max_degree": g.max_degree}
+        nq = args.queries_per_step
+        rs = np.random.RandomState(2)
+        total_q = nq * (args.warmup + args.steps) * world
+        allq = rs.choice(g.n, size=min(total_q, g.n), replace=False).astype(np.int64)
+        myq = allq[rank::world]
+        d_q = torch.from_numpy(myq).to(dev)
+        d_ids = torch.empty((nq, args.topk), dtype=torch.int32, device=dev)
+        d_sc = torch.empty((nq, args.topk), dtype=torch.float64, device=dev)
+
+        def step(i):
+            g.simrank_topk_dev(d_q.data_ptr() + 8 * nq * i, nq, 0.6, args.sr_step, args.sample, args.topk,
+                               d_ids.data_ptr(), d_sc.data_ptr(), seed=7, query_id_base=(rank * 100000 + i) * nq,
+                               stream=stream)
+        for i in range(args.warmup):
+            step(i)
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        launches_t0 = _lib.kernel_launches()
+        ev[0].record()
+        for i in range(args.steps):
+            step(args.warmup + i)
+            ev[i + 1].record()
+        barrier()
+        clocks = sampler.finish()
+        gpu_launches = _lib.kernel_launches() - launches_t0
+        ms_total = ev[0].elapsed_time(ev[-1])
+        per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+        units_per_step = nq
+        walk_steps = g.simrank_last_steps()
+        kernel_ms = float(np.mean(per_launch_ms))
+        alg_bytes = walk_steps * 64.0 + nq * args.topk * 12.0
+        roof = {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "traffic": None, "kernel": "k_simrank_mc<%d>" % args.sr_step, "peak_source": peak_src,
+                "bytes_per_unit": alg_bytes / nq, "units_per_launch": nq, "launch_ms": kernel_ms,
+                "walk_steps_per_s": walk_steps / (kernel_ms * 1e-3)}
+        roof["frac"] = roof["achieved"] / peak
+        e2e = None
+        if not args.no_e2e:
+            hq = myq[:nq].copy()
+            g.simrank_topk(hq, 0.6, args.sr_step, args.sample, args.topk, seed=8)
+            barrier()
+            n_e2e = max(1, min(args.steps, 3))
+            t0 = time.perf_counter()
+            for i in range(n_e2e):
+                g.simrank_topk(hq, 0.6, args.sr_step, args.sample, args.topk, seed=9 + i)
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e = {"value": world * n_e2e * nq / float(tt.item()), "unit": unit, "h2d_bytes_per_step": nq * 8,
+                   "d2h_bytes_per_step": nq * args.topk * 12, "steps": n_e2e,
+                   "api": "gw_simrank_topk (host queries in, host top-k out)"}
+
+    # max over ranks of the device-timed region
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * args.steps * units_per_step / (ms_total * 1e-3)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if args.workload == "node2vec":
+            v, sample = cpu_node2vec(args.p, args.q, args.walk_length, args.cpu_seconds, 1)
+        else:
+            v, sample = cpu_simrank(args.sample, args.sr_step, args.topk, args.cpu_seconds, 1)
+        cpu = {"value": v, "unit": unit, "cores": 1, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": config_of(args), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": int(gpu_launches), "clocks": clocks, "per_launch_ms": [round(x, 3) for x in per_launch_ms]}
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

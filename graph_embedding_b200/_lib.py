@@ -1,0 +1,319 @@
+"""ctypes binding of libgraphwalk.so (include/graphwalk.h).  No torch types cross this boundary.
+
+The library is built in-tree by ``graph_embedding_b200/build.py`` (nvcc, sm_100a).  There is no
+CPU fallback: if the shared object is missing and cannot be built, or no CUDA device is present,
+compute calls raise ``GraphWalkError``.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgraphwalk.so")
+
+GW_OK, GW_E_INVALID, GW_E_CUDA, GW_E_IO, GW_E_TOO_LARGE, GW_E_STATE, GW_E_KEY = 0, -1, -2, -3, -4, -5, -6
+GW_MODE_SIMPLE, GW_MODE_MULTI = 0, 1
+GW_F_DIRECTED, GW_F_WEIGHTED, GW_F_MULTI = 1, 2, 4
+GW_SIMRANK_MC, GW_SIMRANK_HYBRID = 0, 1
+
+
+class GraphWalkError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libgraphwalk error %d: %s" % (code, msg))
+        self.code = code
+
+
+c_i64p = ctypes.POINTER(ctypes.c_int64)
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+c_f64p = ctypes.POINTER(ctypes.c_double)
+c_vp = ctypes.c_void_p
+
+# name -> (restype, argtypes); every symbol graphwalk.h declares
+SIGNATURES = {
+    "gw_version": (ctypes.c_int, []),
+    "gw_last_error": (ctypes.c_char_p, []),
+    "gw_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "gw_set_device": (ctypes.c_int, [ctypes.c_int]),
+    "gw_kernel_launches": (ctypes.c_int64, []),
+    "gw_graph_from_edges": (ctypes.c_int, [c_i64p, c_i64p, c_f64p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int64, ctypes.POINTER(c_vp)]),
+    "gw_graph_load_edgelist": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_int, ctypes.c_int64, ctypes.POINTER(c_vp)]),
+    "gw_graph_rmat": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_double,
+                                     ctypes.c_double, ctypes.c_uint64, ctypes.POINTER(c_vp)]),
+    "gw_graph_barabasi_albert": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(c_vp)]),
+    "gw_graph_free": (ctypes.c_int, [c_vp]),
+    "gw_graph_info": (ctypes.c_int, [c_vp, c_i64p, c_i64p, c_i32p, c_i32p, c_i32p]),
+    "gw_graph_csr": (ctypes.c_int, [c_vp, c_i64p, c_i32p, c_f64p, c_i64p, c_i64p]),
+    "gw_graph_device_views": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp)]),
+    "gw_graph_nonisolated": (ctypes.c_int, [c_vp, c_i64p, c_i64p]),
+    "gw_alias_setup": (ctypes.c_int, [c_f64p, ctypes.c_int64, c_i32p, c_f64p]),
+    "gw_alias_nodes": (ctypes.c_int, [c_vp, c_i32p, c_f64p]),
+    "gw_alias_edges_size": (ctypes.c_int, [c_vp, c_i64p]),
+    "gw_alias_edges": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_int64, c_i64p, c_i32p, c_f64p]),
+    "gw_node2vec_walks": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_int32, c_i64p,
+                                         ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint64, c_i32p, c_i32p]),
+    "gw_node2vec_walks_dev": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_int32, c_vp,
+                                             ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint64, c_vp, c_vp, c_vp]),
+    "gw_node2vec_walks_replay": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i64p, ctypes.c_int64, c_f64p,
+                                                ctypes.c_int64, c_i64p, c_i32p, c_i32p]),
+    "gw_walks_byte_model_dev": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int, c_i64p,
+                                               c_i64p, c_vp]),
+    "gw_simrank_topk": (ctypes.c_int, [c_vp, c_i64p, ctypes.c_int64, ctypes.c_double, ctypes.c_int32,
+                                       ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64,
+                                       ctypes.c_uint64, c_i32p, c_f64p]),
+    "gw_simrank_topk_dev": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, ctypes.c_double, ctypes.c_int32,
+                                           ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64,
+                                           ctypes.c_uint64, c_vp, c_vp, c_vp]),
+    "gw_simrank_rows": (ctypes.c_int, [c_vp, c_i64p, ctypes.c_int64, ctypes.c_double, ctypes.c_int32,
+                                       ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64, c_f64p]),
+    "gw_simrank_last_steps": (ctypes.c_int, [c_vp, c_i64p]),
+    "gw_simrank_exact": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_int32, c_i64p, ctypes.c_int64, c_f64p]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads (building first if needed) libgraphwalk.so and types every entry point."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    L = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)          # AttributeError here = header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != GW_OK:
+        raise_for(rc)
+
+
+def raise_for(rc):
+    msg = load().gw_last_error().decode("utf-8", "replace")
+    if rc == GW_E_KEY:
+        raise KeyError(msg)             # the reference raises KeyError on unknown nodes / edges
+    if rc == GW_E_IO:
+        raise IOError(msg)
+    if rc == GW_E_INVALID:
+        raise ValueError(msg)
+    if rc == GW_E_TOO_LARGE:
+        raise MemoryError(msg)
+    raise GraphWalkError(rc, msg)
+
+
+def ptr(a, ctype):
+    if a is None:
+        return None
+    return a.ctypes.data_as(ctypes.POINTER(ctype))
+
+
+def as_c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class GraphHandle:
+    """Owns one gw_graph*; frees it on garbage collection."""
+
+    def __init__(self, raw):
+        self._h = c_vp(raw)
+        L = load()
+        n, nnz = ctypes.c_int64(), ctypes.c_int64()
+        flags, maxd, dev = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        check(L.gw_graph_info(self._h, ctypes.byref(n), ctypes.byref(nnz), ctypes.byref(flags), ctypes.byref(maxd),
+                              ctypes.byref(dev)))
+        self.n, self.nnz, self.flags, self.max_degree, self.device = n.value, nnz.value, flags.value, maxd.value, dev.value
+
+    @property
+    def h(self):
+        if self._h is None:
+            raise GraphWalkError(GW_E_STATE, "graph already freed")
+        return self._h
+
+    def close(self):
+        if self._h is not None:
+            load().gw_graph_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- constructors ----
+    @staticmethod
+    def from_edges(src, dst, w=None, directed=False, mode=GW_MODE_SIMPLE, n_slots=-1):
+        L = load()
+        src, dst = as_c(src, np.int64), as_c(dst, np.int64)
+        if len(src) != len(dst):
+            raise ValueError("src/dst length mismatch")
+        wv = None if w is None else as_c(w, np.float64)
+        out = c_vp()
+        check(L.gw_graph_from_edges(ptr(src, ctypes.c_int64), ptr(dst, ctypes.c_int64), ptr(wv, ctypes.c_double),
+                                    len(src), int(bool(directed)), int(mode), int(n_slots), ctypes.byref(out)))
+        return GraphHandle(out.value)
+
+    @staticmethod
+    def from_file(path, delimiter=None, weighted=False, directed=False, mode=GW_MODE_SIMPLE, n_slots=-1):
+        L = load()
+        out = c_vp()
+        d = None if delimiter is None else delimiter.encode()
+        check(L.gw_graph_load_edgelist(os.fsencode(path), d, int(bool(weighted)), int(bool(directed)), int(mode),
+                                       int(n_slots), ctypes.byref(out)))
+        return GraphHandle(out.value)
+
+    @staticmethod
+    def rmat(scale, n_tuples, a=0.45, b=0.15, c=0.15, seed=1):
+        out = c_vp()
+        check(load().gw_graph_rmat(int(scale), int(n_tuples), a, b, c, int(seed), ctypes.byref(out)))
+        return GraphHandle(out.value)
+
+    @staticmethod
+    def barabasi_albert(n, m, seed=1):
+        out = c_vp()
+        check(load().gw_graph_barabasi_albert(int(n), int(m), int(seed), ctypes.byref(out)))
+        return GraphHandle(out.value)
+
+    # ---- export ----
+    def csr(self, weights=False, node_ids=True, first_seen=True):
+        rp = np.empty(self.n + 1, dtype=np.int64)
+        col = np.empty(self.nnz, dtype=np.int32)
+        w = np.empty(self.nnz, dtype=np.float64) if weights else None
+        ids = np.empty(self.n, dtype=np.int64) if node_ids else None
+        fs = np.empty(self.n, dtype=np.int64) if first_seen else None
+        check(load().gw_graph_csr(self.h, ptr(rp, ctypes.c_int64), ptr(col, ctypes.c_int32), ptr(w, ctypes.c_double),
+                                  ptr(ids, ctypes.c_int64), ptr(fs, ctypes.c_int64)))
+        return dict(row_ptr=rp, col_idx=col, weights=w, node_ids=ids, first_seen=fs)
+
+    def nonisolated(self):
+        cnt = ctypes.c_int64()
+        out = np.empty(self.n, dtype=np.int64)
+        check(load().gw_graph_nonisolated(self.h, ptr(out, ctypes.c_int64), ctypes.byref(cnt)))
+        return out[:cnt.value].copy()
+
+    # ---- alias tables ----
+    def alias_nodes(self):
+        J = np.empty(self.nnz, dtype=np.int32)
+        q = np.empty(self.nnz, dtype=np.float64)
+        check(load().gw_alias_nodes(self.h, ptr(J, ctypes.c_int32), ptr(q, ctypes.c_double)))
+        return J, q
+
+    def alias_edges_size(self):
+        t = ctypes.c_int64()
+        check(load().gw_alias_edges_size(self.h, ctypes.byref(t)))
+        return t.value
+
+    def alias_edges(self, p, q, budget_bytes=0, fetch=True):
+        L = load()
+        if not fetch:
+            check(L.gw_alias_edges(self.h, float(p), float(q), int(budget_bytes), None, None, None))
+            return None
+        total = self.alias_edges_size()
+        off = np.empty(self.nnz + 1, dtype=np.int64)
+        J = np.empty(total, dtype=np.int32)
+        qq = np.empty(total, dtype=np.float64)
+        check(L.gw_alias_edges(self.h, float(p), float(q), int(budget_bytes), ptr(off, ctypes.c_int64),
+                               ptr(J, ctypes.c_int32), ptr(qq, ctypes.c_double)))
+        return off, J, qq
+
+    # ---- walks ----
+    def walks(self, p, q, walk_length, starts, seed=0, walk_id_base=0, lens=True):
+        starts = as_c(starts, np.int64)
+        out = np.empty((len(starts), walk_length), dtype=np.int32)
+        ln = np.empty(len(starts), dtype=np.int32) if lens else None
+        check(load().gw_node2vec_walks(self.h, float(p), float(q), int(walk_length), ptr(starts, ctypes.c_int64),
+                                       len(starts), int(seed), int(walk_id_base), ptr(out, ctypes.c_int32),
+                                       ptr(ln, ctypes.c_int32)))
+        return (out, ln) if lens else out
+
+    def walks_dev(self, p, q, walk_length, d_starts, n_starts, d_out, d_lens=0, seed=0, walk_id_base=0, stream=0):
+        check(load().gw_node2vec_walks_dev(self.h, float(p), float(q), int(walk_length), c_vp(d_starts),
+                                           int(n_starts), int(seed), int(walk_id_base), c_vp(d_out),
+                                           c_vp(d_lens) if d_lens else None, c_vp(stream) if stream else None))
+
+    def walks_replay(self, walk_length, starts, uniforms, draw_offset=None):
+        starts = as_c(starts, np.int64)
+        uniforms = as_c(uniforms, np.float64)
+        do = None if draw_offset is None else as_c(draw_offset, np.int64)
+        out = np.empty((len(starts), walk_length), dtype=np.int32)
+        ln = np.empty(len(starts), dtype=np.int32)
+        check(load().gw_node2vec_walks_replay(self.h, int(walk_length), ptr(starts, ctypes.c_int64), len(starts),
+                                              ptr(uniforms, ctypes.c_double), len(uniforms),
+                                              ptr(do, ctypes.c_int64), ptr(out, ctypes.c_int32),
+                                              ptr(ln, ctypes.c_int32)))
+        return out, ln
+
+    def byte_model_dev(self, d_walks, n_walks, walk_length, second_order, stream=0):
+        steps, sec = ctypes.c_int64(), ctypes.c_int64()
+        check(load().gw_walks_byte_model_dev(self.h, c_vp(d_walks), int(n_walks), int(walk_length),
+                                             int(bool(second_order)), ctypes.byref(steps), ctypes.byref(sec),
+                                             c_vp(stream) if stream else None))
+        return steps.value, sec.value
+
+    # ---- SimRank ----
+    def simrank_topk(self, queries, c, step, sample, k, mode=GW_SIMRANK_MC, seed=0, query_id_base=0):
+        queries = as_c(queries, np.int64)
+        ids = np.empty((len(queries), k), dtype=np.int32)
+        sc = np.empty((len(queries), k), dtype=np.float64)
+        check(load().gw_simrank_topk(self.h, ptr(queries, ctypes.c_int64), len(queries), float(c), int(step),
+                                     int(sample), int(k), int(mode), int(seed), int(query_id_base),
+                                     ptr(ids, ctypes.c_int32), ptr(sc, ctypes.c_double)))
+        return ids, sc
+
+    def simrank_topk_dev(self, d_queries, nq, c, step, sample, k, d_ids, d_scores, mode=GW_SIMRANK_MC, seed=0,
+                         query_id_base=0, stream=0):
+        check(load().gw_simrank_topk_dev(self.h, c_vp(d_queries), int(nq), float(c), int(step), int(sample), int(k),
+                                         int(mode), int(seed), int(query_id_base), c_vp(d_ids), c_vp(d_scores),
+                                         c_vp(stream) if stream else None))
+
+    def simrank_rows(self, queries, c, step, sample, mode=GW_SIMRANK_MC, seed=0, query_id_base=0):
+        queries = as_c(queries, np.int64)
+        out = np.empty((len(queries), self.n), dtype=np.float64)
+        check(load().gw_simrank_rows(self.h, ptr(queries, ctypes.c_int64), len(queries), float(c), int(step),
+                                     int(sample), int(mode), int(seed), int(query_id_base),
+                                     ptr(out, ctypes.c_double)))
+        return out
+
+    def simrank_last_steps(self):
+        s = ctypes.c_int64()
+        check(load().gw_simrank_last_steps(self.h, ctypes.byref(s)))
+        return s.value
+
+    def simrank_exact(self, c, iters, rows=None):
+        rows = np.arange(self.n, dtype=np.int64) if rows is None else as_c(rows, np.int64)
+        out = np.empty((len(rows), self.n), dtype=np.float64)
+        check(load().gw_simrank_exact(self.h, float(c), int(iters), ptr(rows, ctypes.c_int64), len(rows),
+                                      ptr(out, ctypes.c_double)))
+        return out
+
+
+def alias_setup(probs):
+    probs = as_c(probs, np.float64)
+    J = np.zeros(len(probs), dtype=np.int32)
+    q = np.zeros(len(probs), dtype=np.float64)
+    check(load().gw_alias_setup(ptr(probs, ctypes.c_double), len(probs), ptr(J, ctypes.c_int32),
+                                ptr(q, ctypes.c_double)))
+    return J, q
+
+
+def device_count():
+    c = ctypes.c_int()
+    rc = load().gw_device_count(ctypes.byref(c))
+    return c.value if rc == GW_OK else 0
+
+
+def set_device(i):
+    check(load().gw_set_device(int(i)))
+
+
+def kernel_launches():
+    return int(load().gw_kernel_launches())

@@ -1,0 +1,139 @@
+// common.cuh — shared declarations of libgraphwalk (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/graphwalk.h"
+
+namespace gw {
+
+// ---- error plumbing -------------------------------------------------------------------------
+std::string &last_error();
+int fail(int code, const char *fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+#define GW_CUDA(expr)                                                                      \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return gw::fail(GW_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                            __FILE__, __LINE__);                                           \
+    } while (0)
+
+#define GW_TRY(expr)                 \
+    do {                             \
+        int _r = (expr);             \
+        if (_r != GW_OK) return _r;  \
+    } while (0)
+
+// counts a kernel launch and checks the launch error
+#define GW_LAUNCHED()                                                                         \
+    do {                                                                                      \
+        gw::g_launches.fetch_add(1, std::memory_order_relaxed);                               \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess)                                                                \
+            return gw::fail(GW_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                            __FILE__, __LINE__);                                              \
+    } while (0)
+
+template <typename T>
+struct DevBuf {  // RAII device allocation
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void **)&p, count * sizeof(T));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    T *take() {
+        T *r = p;
+        p = nullptr;
+        n = 0;
+        return r;
+    }
+};
+
+int device_info(int *sm_count, size_t *free_bytes);
+
+}  // namespace gw
+
+// ---- the graph handle -------------------------------------------------------------------------
+// HBM layout:
+//   meta[n]  uint2 {offset, degree}: ONE 8-byte load gives both ends of a row; the whole array
+//            is 33.5 MB at R-MAT scale-22 and stays L2 resident (126 MB L2).
+//   col[nnz] int32 neighbour lists; SIMPLE mode rows ascending, MULTI mode rows in file order.
+//   w[nnz]   fp64 weights, only for weighted graphs.
+struct gw_graph {
+    int device = 0;
+    int64_t n = 0;
+    int64_t nnz = 0;
+    int32_t flags = 0;
+    int32_t max_degree = 0;
+    uint2 *d_meta = nullptr;
+    int32_t *d_col = nullptr;
+    double *d_w = nullptr;
+    int64_t *d_row_ptr = nullptr;  // int64[n+1], API export + table offsets
+    std::vector<int64_t> node_ids;    // empty = identity
+    std::vector<int64_t> first_seen;  // empty = identity
+    // alias_nodes (lazy)
+    int32_t *d_anJ = nullptr;
+    double *d_anq = nullptr;
+    // alias_edges (lazy) + the p,q they were built for
+    int64_t *d_aeoff = nullptr;
+    int32_t *d_aeJ = nullptr;
+    double *d_aeq = nullptr;
+    int64_t ae_total = 0;
+    double ae_p = 0, ae_q = 0;
+    // SimRank bookkeeping
+    int64_t simrank_last_steps = 0;
+    void *d_simrank_scratch = nullptr;
+    size_t simrank_scratch_bytes = 0;
+};
+
+// ---- Philox4x32-10 (Salmon et al., SC'11), counter-based ------------------------------------------
+namespace gw {
+struct Philox {
+    static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    __host__ __device__ static inline uint4 gen(uint4 ctr, uint2 key) {
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+#ifdef __CUDA_ARCH__
+            uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+            uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+#else
+            uint64_t p0 = (uint64_t)M0 * ctr.x, p1 = (uint64_t)M1 * ctr.z;
+            uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+            uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+            ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+            key.x += W0;
+            key.y += W1;
+        }
+        return ctr;
+    }
+};
+// uniform index in [0,d) from 32 random bits (bias <= d / 2^32)
+__host__ __device__ static inline uint32_t scale_u32(uint32_t r, uint32_t d) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(r, d);
+#else
+    return (uint32_t)(((uint64_t)r * d) >> 32);
+#endif
+}
+}  // namespace gw

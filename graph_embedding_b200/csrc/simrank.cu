@@ -1,0 +1,560 @@
+// simrank.cu — DeepSim/TopSim Monte-Carlo SimRank: fused walk-and-meet kernel + per-query top-k.
+//
+// Replaces DeepSim/TopSimAll/src/simrank/SingleRandomWalk.java:39-106 (compute / walk /
+// computePathSim / isFirstMeet), utils/Print.java:31-41 + lxctools/FixedMaxPQ.java (top-k) and
+// simrank/SimRank.java:36-77 (exact iteration).
+//
+// One persistent CTA per in-flight query.  Each thread owns whole samples: it walks 2*STEP
+// uniform steps from the query vertex with the path in registers, tests first meeting
+// (path[j] != path[2i-j] for j < i) and adds C^i * deg(path[i]) / deg(path[2i]) / SAMPLE to the
+// query's accumulator, which is a two-tier open-addressing hash table: tier 1 in shared memory
+// (hot, many-hit targets), tier 2 in a per-CTA global scratch that stays in L2 (the long tail of
+// single-hit targets).  Scores are accumulated as 32.32 fixed point with native 32-bit atomics
+// (low word add + carry into the high word), so a query's result is bit-identical for any
+// launch geometry, thread interleaving or GPU count.  Top-k = one histogram pass over tier 1
+// (lower bound on the k-th score), one candidate-collection pass over the touched slots, rank
+// by counting among the candidates; a k-round arg-max fallback covers mass ties.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace gw {
+
+constexpr int SR_BLOCK = 512;
+constexpr int SR_HS = 8192;          // tier-1 slots (shared memory)
+constexpr int SR_T1_PROBES = 8;      // bounded probing in tier 1, then fall through to tier 2
+constexpr int SR_BINS = 1024;
+constexpr int SR_CAND = 512;
+constexpr uint32_t SR_EMPTY = 0xFFFFFFFFu;
+constexpr double SR_FIX = 4294967296.0;   // 2^32
+
+struct SimrankParams {
+    const uint2 *meta;
+    const int32_t *col;
+    const int64_t *queries;
+    int64_t nq;
+    int64_t n;
+    int32_t sample;
+    int32_t k;
+    double coef[16];                 // C^i (i = 1..STEP)
+    uint2 key;
+    uint64_t query_id_base;
+    // per-CTA global scratch
+    uint32_t *gkeys, *glo, *ghi, *olist;
+    uint32_t gs_mask;                // tier-2 slots - 1 (power of two)
+    uint32_t olist_cap;
+    // outputs
+    int32_t *out_ids;
+    double *out_scores;
+    double *out_dense;               // optional dense rows [nq * n]
+    unsigned long long *steps;
+    int *err;
+};
+
+struct SrShared {
+    uint32_t keys[SR_HS];
+    uint32_t lo[SR_HS];
+    uint32_t hi[SR_HS];
+    uint32_t hist[SR_BINS];
+    unsigned long long cand_score[SR_CAND];
+    uint32_t cand_id[SR_CAND];
+    uint32_t ocount;                 // touched slots (both tiers)
+    uint32_t ccount;                 // candidates
+    uint32_t thr_bin;
+    unsigned long long red_score[SR_BLOCK / 32];
+    uint32_t red_id[SR_BLOCK / 32];
+    unsigned long long sel_score;
+    uint32_t sel_id;
+};
+
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+__device__ __forceinline__ uint32_t score_bin(unsigned long long s) {   // monotone, 16 bins per octave
+    if (s == 0) return 0;
+    int p = 63 - __clzll((long long)s);
+    uint32_t sub = p >= 4 ? (uint32_t)((s >> (p - 4)) & 15) : (uint32_t)((s << (4 - p)) & 15);
+    return (uint32_t)p * 16 + sub;
+}
+
+// (score desc, id asc) strict order: is a better than b ?
+__device__ __forceinline__ bool better(unsigned long long sa, uint32_t ia, unsigned long long sb, uint32_t ib) {
+    return sa > sb || (sa == sb && ia < ib);
+}
+
+__device__ __forceinline__ void fixed_add(uint32_t *lo, uint32_t *hi, unsigned long long v) {
+    uint32_t vl = (uint32_t)v;
+    uint32_t old = atomicAdd(lo, vl);
+    uint32_t carry = (uint32_t)(old + vl < old);
+    uint32_t vh = (uint32_t)(v >> 32) + carry;
+    if (vh) atomicAdd(hi, vh);
+}
+
+__device__ __forceinline__ void acc_add(SrShared &S, const SimrankParams &P, uint32_t *gkeys, uint32_t *glo,
+                                        uint32_t *ghi, uint32_t *olist, uint32_t key, unsigned long long v) {
+    uint32_t h = hash32(key);
+    // tier 1
+#pragma unroll 1
+    for (int pr = 0; pr < SR_T1_PROBES; pr++) {
+        uint32_t slot = (h + pr) & (SR_HS - 1);
+        uint32_t k0 = ((volatile uint32_t *)S.keys)[slot];
+        if (k0 == SR_EMPTY) {
+            k0 = atomicCAS(&S.keys[slot], SR_EMPTY, key);
+            if (k0 == SR_EMPTY) {
+                uint32_t o = atomicAdd(&S.ocount, 1u);
+                if (o < P.olist_cap) olist[o] = slot; else atomicExch(P.err, 1);
+                k0 = key;
+            }
+        }
+        if (k0 == key) { fixed_add(&S.lo[slot], &S.hi[slot], v); return; }
+    }
+    // tier 2
+    uint32_t g = (h >> 3) * 0x9E3779B1u;
+#pragma unroll 1
+    for (uint32_t pr = 0; pr <= P.gs_mask; pr++) {
+        uint32_t slot = (g + pr) & P.gs_mask;
+        uint32_t k0 = __ldcg(gkeys + slot);   // L2: tier-2 words are updated by atomics, never trust L1
+        if (k0 == SR_EMPTY) {
+            k0 = atomicCAS(&gkeys[slot], SR_EMPTY, key);
+            if (k0 == SR_EMPTY) {
+                uint32_t o = atomicAdd(&S.ocount, 1u);
+                if (o < P.olist_cap) olist[o] = slot | 0x80000000u; else atomicExch(P.err, 1);
+                k0 = key;
+            }
+        }
+        if (k0 == key) { fixed_add(&glo[slot], &ghi[slot], v); return; }
+    }
+    atomicExch(P.err, 2);
+}
+
+__device__ __forceinline__ void read_entry(const SrShared &S, const uint32_t *gkeys, const uint32_t *glo,
+                                           const uint32_t *ghi, uint32_t o, uint32_t &id, unsigned long long &sc) {
+    if (o & 0x80000000u) {
+        uint32_t s = o & 0x7FFFFFFFu;
+        id = __ldcg(gkeys + s);
+        sc = ((unsigned long long)__ldcg(ghi + s) << 32) | __ldcg(glo + s);
+    } else {
+        id = S.keys[o];
+        sc = ((unsigned long long)S.hi[o] << 32) | S.lo[o];
+    }
+}
+
+template <int STEP>
+__global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_mc(SimrankParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SrShared &S = *reinterpret_cast<SrShared *>(smem_raw);
+    constexpr int LEN = 2 * STEP;
+    const int tid = threadIdx.x;
+    const size_t gs = (size_t)P.gs_mask + 1;
+    uint32_t *gkeys = P.gkeys + blockIdx.x * gs;
+    uint32_t *glo = P.glo + blockIdx.x * gs;
+    uint32_t *ghi = P.ghi + blockIdx.x * gs;
+    uint32_t *olist = P.olist + (size_t)blockIdx.x * P.olist_cap;
+
+    for (int i = tid; i < SR_HS; i += SR_BLOCK) { S.keys[i] = SR_EMPTY; S.lo[i] = 0; S.hi[i] = 0; }
+    if (tid == 0) { S.ocount = 0; S.ccount = 0; }
+    __syncthreads();
+    unsigned long long my_steps = 0;
+
+    for (int64_t qi = blockIdx.x; qi < P.nq; qi += gridDim.x) {
+        const int32_t v = (int32_t)P.queries[qi];
+        const uint64_t qid = P.query_id_base + (uint64_t)qi;
+        const double inv_sample = 1.0;   // division by SAMPLE is applied per contribution below
+        (void)inv_sample;
+
+        // ---------------- phase A: walk + first-meet accumulation ----------------
+        for (int32_t s = tid; s < P.sample; s += SR_BLOCK) {
+            int32_t path[LEN + 1];
+            uint32_t dg[LEN + 1];
+            path[0] = v;
+            int32_t cur = v;
+            int len = 0;
+            uint4 r;
+#pragma unroll
+            for (int t = 0; t < LEN; t++) {
+                if ((t & 3) == 0)
+                    r = Philox::gen(make_uint4((uint32_t)qid, (uint32_t)(qid >> 32), (uint32_t)s, (uint32_t)(t >> 2)), P.key);
+                uint32_t rw = (t & 3) == 0 ? r.x : (t & 3) == 1 ? r.y : (t & 3) == 2 ? r.z : r.w;
+                path[t + 1] = -1;
+                dg[t] = 0;
+                if (len == t) {                               // still alive
+                    uint2 m = __ldg(P.meta + cur);
+                    dg[t] = m.y;
+                    if (m.y != 0) {                           // Graph.randNeighbor (Graph.java:69-73)
+                        cur = __ldg(P.col + m.x + scale_u32(rw, m.y));
+                        path[t + 1] = cur;
+                        len = t + 1;
+                    }
+                }
+            }
+            dg[LEN] = (len == LEN) ? __ldg(P.meta + cur).y : 0;
+            my_steps += (unsigned long long)len;
+            // computePathSim (SingleRandomWalk.java:81-92)
+#pragma unroll
+            for (int i = 1; i <= STEP; i++) {
+                if (2 * i <= len) {
+                    int32_t target = path[2 * i];
+                    bool ok = target != v;
+#pragma unroll
+                    for (int j = 0; j < i; j++) ok &= (path[j] != path[2 * i - j]);   // isFirstMeet :100-106
+                    if (ok) {
+                        double x = P.coef[i] * (double)dg[i] / (double)dg[2 * i] / (double)P.sample;
+                        unsigned long long fx = __double2ull_rn(x * SR_FIX);
+                        acc_add(S, P, gkeys, glo, ghi, olist, (uint32_t)target, fx);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t M = min(S.ocount, P.olist_cap);
+
+        if (P.out_dense) {
+            // ---------------- dense row (getResult()) ----------------
+            double *row = P.out_dense + (size_t)qi * (size_t)P.n;
+            for (uint32_t e = tid; e < M; e += SR_BLOCK) {
+                uint32_t id; unsigned long long sc;
+                read_entry(S, gkeys, glo, ghi, olist[e], id, sc);
+                row[id] = (double)sc * (1.0 / SR_FIX);
+            }
+        }
+        if (P.out_ids) {
+            // ---------------- phase B: top-k ----------------
+            const uint32_t K = (uint32_t)P.k;
+            for (int i = tid; i < SR_BINS; i += SR_BLOCK) S.hist[i] = 0;
+            __syncthreads();
+            // histogram over tier-1 entries only: their k-th largest score is a lower bound of
+            // the final k-th largest
+            uint32_t n_t1 = 0;
+            for (uint32_t e = tid; e < M; e += SR_BLOCK) {
+                uint32_t o = olist[e];
+                if (!(o & 0x80000000u)) {
+                    unsigned long long sc = ((unsigned long long)S.hi[o] << 32) | S.lo[o];
+                    atomicAdd(&S.hist[score_bin(sc)], 1u);
+                    n_t1++;
+                }
+            }
+            __syncthreads();
+            if (tid < 32) {   // suffix scan: largest bin b with count(bins >= b) >= K, else 0
+                uint32_t base = (31 - tid) * 32;   // lane 0 owns the top 32 bins
+                uint32_t cnt = 0;
+                for (int j = 0; j < 32; j++) cnt += S.hist[base + j];
+                uint32_t incl = cnt;
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (tid >= o) incl += t;
+                }
+                uint32_t before = incl - cnt;      // entries in bins above this lane's range
+                uint32_t found = 0xFFFFFFFFu;
+                if (before < K && incl >= K) {
+                    uint32_t c = before;
+                    for (int j = 31; j >= 0; j--) { c += S.hist[base + j]; if (c >= K) { found = base + j; break; } }
+                }
+                uint32_t any = __ballot_sync(0xffffffffu, found != 0xFFFFFFFFu);
+                uint32_t thr = 0;
+                if (any) thr = __shfl_sync(0xffffffffu, found, __ffs(any) - 1);
+                if (tid == 0) { S.thr_bin = thr; S.ccount = 0; }
+            }
+            __syncthreads();
+            const uint32_t thr = S.thr_bin;
+            for (uint32_t e = tid; e < M; e += SR_BLOCK) {
+                uint32_t id; unsigned long long sc;
+                read_entry(S, gkeys, glo, ghi, olist[e], id, sc);
+                if (sc != 0 && score_bin(sc) >= thr) {
+                    uint32_t c = atomicAdd(&S.ccount, 1u);
+                    if (c < SR_CAND) { S.cand_score[c] = sc; S.cand_id[c] = id; }
+                }
+            }
+            __syncthreads();
+            const uint32_t C = S.ccount;
+            int32_t *oid = P.out_ids + (size_t)qi * K;
+            double *osc = P.out_scores + (size_t)qi * K;
+            if (C <= SR_CAND) {
+                // rank by counting among the candidates
+                for (uint32_t a = tid; a < C; a += SR_BLOCK) {
+                    unsigned long long sa = S.cand_score[a];
+                    uint32_t ia = S.cand_id[a];
+                    uint32_t rank = 0;
+                    for (uint32_t b = 0; b < C; b++) rank += better(S.cand_score[b], S.cand_id[b], sa, ia) ? 1u : 0u;
+                    if (rank < K) { oid[rank] = (int32_t)ia; osc[rank] = (double)sa * (1.0 / SR_FIX); }
+                }
+                for (uint32_t r = C + tid; r < K; r += SR_BLOCK) { oid[r] = -1; osc[r] = 0.0; }
+            } else {
+                // fallback (mass ties at the threshold): K rounds of block arg-max over all entries
+                unsigned long long last_s = ~0ull;
+                uint32_t last_i = 0;
+                bool first = true;
+                for (uint32_t r = 0; r < K; r++) {
+                    unsigned long long bs = 0; uint32_t bi = SR_EMPTY;
+                    for (uint32_t e = tid; e < M; e += SR_BLOCK) {
+                        uint32_t id; unsigned long long sc;
+                        read_entry(S, gkeys, glo, ghi, olist[e], id, sc);
+                        if (sc == 0) continue;
+                        if (!first && !better(last_s, last_i, sc, id)) continue;   // already emitted
+                        if (bi == SR_EMPTY || better(sc, id, bs, bi)) { bs = sc; bi = id; }
+                    }
+                    for (int o = 16; o; o >>= 1) {
+                        unsigned long long s2 = __shfl_xor_sync(0xffffffffu, bs, o);
+                        uint32_t i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+                        if (i2 != SR_EMPTY && (bi == SR_EMPTY || better(s2, i2, bs, bi))) { bs = s2; bi = i2; }
+                    }
+                    if ((tid & 31) == 0) { S.red_score[tid >> 5] = bs; S.red_id[tid >> 5] = bi; }
+                    __syncthreads();
+                    if (tid == 0) {
+                        unsigned long long fs = 0; uint32_t fi = SR_EMPTY;
+                        for (int w = 0; w < SR_BLOCK / 32; w++) {
+                            uint32_t i2 = S.red_id[w];
+                            if (i2 != SR_EMPTY && (fi == SR_EMPTY || better(S.red_score[w], i2, fs, fi))) { fs = S.red_score[w]; fi = i2; }
+                        }
+                        S.sel_score = fs; S.sel_id = fi;
+                        if (fi != SR_EMPTY) { oid[r] = (int32_t)fi; osc[r] = (double)fs * (1.0 / SR_FIX); }
+                        else { oid[r] = -1; osc[r] = 0.0; }
+                    }
+                    __syncthreads();
+                    last_s = S.sel_score; last_i = S.sel_id; first = false;
+                    if (last_i == SR_EMPTY) {   // exhausted: pad the rest
+                        for (uint32_t r2 = r + 1 + tid; r2 < K; r2 += SR_BLOCK) { oid[r2] = -1; osc[r2] = 0.0; }
+                        break;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---------------- phase C: clear only the touched slots ----------------
+        for (uint32_t e = tid; e < M; e += SR_BLOCK) {
+            uint32_t o = olist[e];
+            if (o & 0x80000000u) { uint32_t s = o & 0x7FFFFFFFu; gkeys[s] = SR_EMPTY; glo[s] = 0; ghi[s] = 0; }
+            else { S.keys[o] = SR_EMPTY; S.lo[o] = 0; S.hi[o] = 0; }
+        }
+        if (tid == 0) { S.ocount = 0; S.ccount = 0; }
+        __syncthreads();
+    }
+    for (int o = 16; o; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
+    if ((tid & 31) == 0 && my_steps) atomicAdd(P.steps, my_steps);
+}
+
+// ---------------- exact SimRank (SimRank.java:36-77) as dense sweeps ----------------
+// T[i][:] = mean over a in N(i) of S[a][:]   (rows of degree 0 -> 0)
+__global__ void k_row_average(const uint2 *__restrict__ meta, const int32_t *__restrict__ col, int64_t n,
+                              const double *__restrict__ Sm, double *__restrict__ T, double scale,
+                              int pin_diag) {
+    int64_t i = blockIdx.y;
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint2 m = meta[i];
+    double acc = 0.0;
+    for (uint32_t a = 0; a < m.y; a++) acc += Sm[(int64_t)col[m.x + a] * n + j];
+    double r = m.y ? scale * acc / (double)m.y : 0.0;
+    if (pin_diag && i == j) r = 1.0;
+    T[i * n + j] = r;
+}
+__global__ void k_transpose(const double *__restrict__ A, double *__restrict__ B, int64_t n) {
+    __shared__ double tile[32][33];
+    int64_t x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y)
+        if (x < n && y0 + r < n) tile[r][threadIdx.x] = A[(y0 + r) * n + x];
+    __syncthreads();
+    int64_t tx = blockIdx.y * 32 + threadIdx.x, ty0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y)
+        if (tx < n && ty0 + r < n) B[(ty0 + r) * n + tx] = tile[threadIdx.x][r];
+}
+__global__ void k_identity(double *__restrict__ A, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) A[i * n + i] = 1.0;
+}
+__global__ void k_gather_rows_zero_diag(const double *__restrict__ A, int64_t n, const int64_t *__restrict__ rows,
+                                        int64_t nrows, double *__restrict__ out) {
+    int64_t r = blockIdx.y;
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n || r >= nrows) return;
+    int64_t i = rows[r];
+    out[r * n + j] = (i == j) ? 0.0 : A[i * n + j];
+}
+
+}  // namespace gw
+
+using namespace gw;
+
+template <int STEP>
+static int launch_mc(const SimrankParams &P, int grid, cudaStream_t st) {
+    size_t smem = sizeof(SrShared);
+    GW_CUDA(cudaFuncSetAttribute(k_simrank_mc<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_simrank_mc<STEP><<<grid, SR_BLOCK, smem, st>>>(P);
+    GW_LAUNCHED();
+    return GW_OK;
+}
+
+static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double c, int32_t step, int32_t sample,
+                       int32_t k, int32_t mode, uint64_t seed, uint64_t query_id_base, int32_t *d_out_ids,
+                       double *d_out_scores, double *d_out_dense, cudaStream_t st, bool sync_steps) {
+    if (!g) return fail(GW_E_INVALID, "graph is NULL");
+    if (g->flags & GW_F_DIRECTED) return fail(GW_E_INVALID, "SimRank path is defined on undirected graphs (structures/Graph.java)");
+    if (step < 1 || step > 10) return fail(GW_E_INVALID, "step must be in 1..10");
+    if (sample < 1) return fail(GW_E_INVALID, "sample must be positive");
+    if (!(c > 0) || !(c < 1)) return fail(GW_E_INVALID, "decay c must be in (0,1)");
+    if (d_out_ids && (k < 1 || k > SR_CAND / 2)) return fail(GW_E_INVALID, "k must be in 1..%d", SR_CAND / 2);
+    if (mode != GW_SIMRANK_MC) return fail(GW_E_INVALID, "estimator mode %d is not built yet (GW_SIMRANK_MC only)", mode);
+    if (nq == 0) return GW_OK;
+    GW_CUDA(cudaSetDevice(g->device));
+    int sms = 0;
+    GW_TRY(device_info(&sms, nullptr));
+    int grid = (int)std::min<int64_t>(nq, (int64_t)sms * 2);
+    // tier-2 table: >= 2x the distinct targets one query can produce
+    int64_t distinct = std::min<int64_t>((int64_t)sample * step, g->n);
+    uint32_t gs = 1024;
+    while ((int64_t)gs < 2 * distinct) gs <<= 1;
+    uint32_t ocap = (uint32_t)distinct + 1;
+    size_t need = (size_t)grid * ((size_t)gs * 3 + ocap) * sizeof(uint32_t) + 64;
+    if (g->simrank_scratch_bytes < need) {
+        cudaFree(g->d_simrank_scratch);
+        g->d_simrank_scratch = nullptr;
+        g->simrank_scratch_bytes = 0;
+        GW_CUDA(cudaMalloc(&g->d_simrank_scratch, need));
+        g->simrank_scratch_bytes = need;
+    }
+    unsigned char *base = (unsigned char *)g->d_simrank_scratch;
+    SimrankParams P;
+    P.steps = (unsigned long long *)base;
+    P.err = (int *)(base + 16);
+    P.gkeys = (uint32_t *)(base + 64);
+    P.glo = P.gkeys + (size_t)grid * gs;
+    P.ghi = P.glo + (size_t)grid * gs;
+    P.olist = P.ghi + (size_t)grid * gs;
+    GW_CUDA(cudaMemsetAsync(base, 0, 64, st));
+    GW_CUDA(cudaMemsetAsync(P.gkeys, 0xFF, (size_t)grid * gs * sizeof(uint32_t), st));
+    GW_CUDA(cudaMemsetAsync(P.glo, 0, (size_t)grid * gs * 2 * sizeof(uint32_t), st));
+    P.meta = g->d_meta; P.col = g->d_col; P.queries = d_queries; P.nq = nq; P.n = g->n;
+    P.sample = sample; P.k = k;
+    for (int i = 0; i < 16; i++) P.coef[i] = 0;
+    for (int i = 1; i <= step; i++) P.coef[i] = pow(c, i);    // cache[i] = Math.pow(C, i) (SingleRandomWalk.java:34-36)
+    P.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    P.query_id_base = query_id_base;
+    P.gs_mask = gs - 1; P.olist_cap = ocap;
+    P.out_ids = d_out_ids; P.out_scores = d_out_scores; P.out_dense = d_out_dense;
+    switch (step) {
+        case 1: GW_TRY(launch_mc<1>(P, grid, st)); break;
+        case 2: GW_TRY(launch_mc<2>(P, grid, st)); break;
+        case 3: GW_TRY(launch_mc<3>(P, grid, st)); break;
+        case 4: GW_TRY(launch_mc<4>(P, grid, st)); break;
+        case 5: GW_TRY(launch_mc<5>(P, grid, st)); break;
+        case 6: GW_TRY(launch_mc<6>(P, grid, st)); break;
+        case 7: GW_TRY(launch_mc<7>(P, grid, st)); break;
+        case 8: GW_TRY(launch_mc<8>(P, grid, st)); break;
+        case 9: GW_TRY(launch_mc<9>(P, grid, st)); break;
+        default: GW_TRY(launch_mc<10>(P, grid, st)); break;
+    }
+    if (sync_steps) {
+        unsigned long long hs = 0;
+        int herr = 0;
+        GW_CUDA(cudaMemcpyAsync(&hs, P.steps, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        GW_CUDA(cudaMemcpyAsync(&herr, P.err, sizeof(herr), cudaMemcpyDeviceToHost, st));
+        GW_CUDA(cudaStreamSynchronize(st));
+        g->simrank_last_steps = (int64_t)hs;
+        if (herr) return fail(GW_E_STATE, "SimRank accumulator overflow (code %d)", herr);
+    }
+    return GW_OK;
+}
+
+static int check_queries_host(const gw_graph *g, const int64_t *q, int64_t nq) {
+    for (int64_t i = 0; i < nq; i++)
+        if (q[i] < 0 || q[i] >= g->n) return fail(GW_E_KEY, "query vertex %lld is outside [0, %lld)", (long long)q[i], (long long)g->n);
+    return GW_OK;
+}
+
+extern "C" {
+
+int gw_simrank_topk_dev(gw_graph *g, const int64_t *d_queries, int64_t nq, double c, int32_t step, int32_t sample,
+                        int32_t k, int32_t mode, uint64_t seed, uint64_t query_id_base, int32_t *d_out_ids,
+                        double *d_out_scores, void *stream) {
+    if (nq < 0 || (nq > 0 && (!d_queries || !d_out_ids || !d_out_scores))) return fail(GW_E_INVALID, "bad arguments");
+    return simrank_run(g, d_queries, nq, c, step, sample, k, mode, seed, query_id_base, d_out_ids, d_out_scores, nullptr,
+                       (cudaStream_t)stream, false);
+}
+
+int gw_simrank_topk(gw_graph *g, const int64_t *queries, int64_t nq, double c, int32_t step, int32_t sample, int32_t k,
+                    int32_t mode, uint64_t seed, uint64_t query_id_base, int32_t *out_ids, double *out_scores) {
+    if (!g) return fail(GW_E_INVALID, "graph is NULL");
+    if (nq < 0 || (nq > 0 && (!queries || !out_ids || !out_scores))) return fail(GW_E_INVALID, "bad arguments");
+    if (k < 1) return fail(GW_E_INVALID, "k must be positive");
+    GW_TRY(check_queries_host(g, queries, nq));
+    if (nq == 0) return GW_OK;
+    GW_CUDA(cudaSetDevice(g->device));
+    DevBuf<int64_t> dq;
+    DevBuf<int32_t> di;
+    DevBuf<double> dsc;
+    GW_CUDA(dq.alloc((size_t)nq)); GW_CUDA(di.alloc((size_t)nq * k)); GW_CUDA(dsc.alloc((size_t)nq * k));
+    GW_CUDA(cudaMemcpy(dq.p, queries, sizeof(int64_t) * (size_t)nq, cudaMemcpyHostToDevice));
+    GW_TRY(simrank_run(g, dq.p, nq, c, step, sample, k, mode, seed, query_id_base, di.p, dsc.p, nullptr, nullptr, true));
+    GW_CUDA(cudaMemcpy(out_ids, di.p, sizeof(int32_t) * (size_t)nq * k, cudaMemcpyDeviceToHost));
+    GW_CUDA(cudaMemcpy(out_scores, dsc.p, sizeof(double) * (size_t)nq * k, cudaMemcpyDeviceToHost));
+    return GW_OK;
+}
+
+int gw_simrank_rows(gw_graph *g, const int64_t *queries, int64_t nq, double c, int32_t step, int32_t sample,
+                    int32_t mode, uint64_t seed, uint64_t query_id_base, double *out_dense) {
+    if (!g) return fail(GW_E_INVALID, "graph is NULL");
+    if (nq < 0 || (nq > 0 && (!queries || !out_dense))) return fail(GW_E_INVALID, "bad arguments");
+    GW_TRY(check_queries_host(g, queries, nq));
+    if (nq == 0) return GW_OK;
+    GW_CUDA(cudaSetDevice(g->device));
+    DevBuf<int64_t> dq;
+    DevBuf<double> dd;
+    GW_CUDA(dq.alloc((size_t)nq)); GW_CUDA(dd.alloc((size_t)nq * (size_t)g->n));
+    GW_CUDA(cudaMemcpy(dq.p, queries, sizeof(int64_t) * (size_t)nq, cudaMemcpyHostToDevice));
+    GW_CUDA(cudaMemset(dd.p, 0, sizeof(double) * (size_t)nq * (size_t)g->n));
+    GW_TRY(simrank_run(g, dq.p, nq, c, step, sample, 0, mode, seed, query_id_base, nullptr, nullptr, dd.p, nullptr, true));
+    GW_CUDA(cudaMemcpy(out_dense, dd.p, sizeof(double) * (size_t)nq * (size_t)g->n, cudaMemcpyDeviceToHost));
+    return GW_OK;
+}
+
+int gw_simrank_last_steps(const gw_graph *g, int64_t *steps) {
+    if (!g || !steps) return fail(GW_E_INVALID, "bad arguments");
+    if (g->d_simrank_scratch) {   // refresh from the device counter (covers the _dev entry point)
+        unsigned long long hs = 0;
+        GW_CUDA(cudaSetDevice(g->device));
+        GW_CUDA(cudaDeviceSynchronize());
+        GW_CUDA(cudaMemcpy(&hs, g->d_simrank_scratch, sizeof(hs), cudaMemcpyDeviceToHost));
+        *steps = (int64_t)hs;
+        return GW_OK;
+    }
+    *steps = g->simrank_last_steps;
+    return GW_OK;
+}
+
+int gw_simrank_exact(gw_graph *g, double c, int32_t iters, const int64_t *rows, int64_t nrows, double *out_dense) {
+    if (!g) return fail(GW_E_INVALID, "graph is NULL");
+    if (g->flags & GW_F_DIRECTED) return fail(GW_E_INVALID, "SimRank path is defined on undirected graphs");
+    if (iters < 0 || nrows < 0 || (nrows > 0 && (!rows || !out_dense))) return fail(GW_E_INVALID, "bad arguments");
+    GW_TRY(check_queries_host(g, rows, nrows));
+    if (nrows == 0) return GW_OK;
+    GW_CUDA(cudaSetDevice(g->device));
+    const int64_t n = g->n;
+    size_t freeb = 0;
+    GW_TRY(device_info(nullptr, &freeb));
+    size_t mat = sizeof(double) * (size_t)n * (size_t)n;
+    if (mat * 2 + sizeof(double) * (size_t)nrows * n > freeb / 10 * 9)
+        return fail(GW_E_TOO_LARGE, "exact SimRank needs two dense %lld x %lld fp64 matrices", (long long)n, (long long)n);
+    DevBuf<double> A, B, out;
+    DevBuf<int64_t> dr;
+    GW_CUDA(A.alloc((size_t)n * n)); GW_CUDA(B.alloc((size_t)n * n));
+    GW_CUDA(out.alloc((size_t)nrows * n)); GW_CUDA(dr.alloc((size_t)nrows));
+    GW_CUDA(cudaMemcpy(dr.p, rows, sizeof(int64_t) * (size_t)nrows, cudaMemcpyHostToDevice));
+    GW_CUDA(cudaMemset(A.p, 0, mat));
+    k_identity<<<(unsigned)((n + 255) / 256), 256>>>(A.p, n); GW_LAUNCHED();
+    dim3 ga((unsigned)((n + 255) / 256), (unsigned)n), gt((unsigned)((n + 31) / 32), (unsigned)((n + 31) / 32));
+    for (int it = 0; it < iters; it++) {
+        // S <- c * P S P^T with the diagonal pinned to 1:   T = P S ; S' = c * P T^T
+        k_row_average<<<ga, 256>>>(g->d_meta, g->d_col, n, A.p, B.p, 1.0, 0); GW_LAUNCHED();
+        k_transpose<<<gt, dim3(32, 8)>>>(B.p, A.p, n); GW_LAUNCHED();
+        k_row_average<<<ga, 256>>>(g->d_meta, g->d_col, n, A.p, B.p, c, 1); GW_LAUNCHED();
+        std::swap(A.p, B.p);
+    }
+    dim3 gg((unsigned)((n + 255) / 256), (unsigned)nrows);
+    k_gather_rows_zero_diag<<<gg, 256>>>(A.p, n, dr.p, nrows, out.p); GW_LAUNCHED();
+    GW_CUDA(cudaMemcpy(out_dense, out.p, sizeof(double) * (size_t)nrows * n, cudaMemcpyDeviceToHost));
+    return GW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,347 @@
+// walk.cu — node2vec second-order biased walks on the device.
+//
+// Replaces node2vec/src/node2vec.py:13-39 node2vec_walk, :41-59 simulate_walks and :150-160
+// alias_draw.  Two walkers:
+//
+//  * replay  — consumes the reference's own uniform stream and materialised alias tables and
+//              reproduces its walks bit for bit (fp64 floor(U1*K), fp64 U2 < q[kk]).
+//  * free    — the production walker.  alias_edges (sum deg^2 entries) cannot exist at scale, so
+//              the second-order law of get_alias_edge (:61-81) is sampled ON THE FLY by
+//              rejection: propose x from the static first-order law of N(cur) (uniform for
+//              unweighted graphs, alias_nodes otherwise), accept with w(x)/ub where
+//              w = 1/p (x == prev), 1 (x adjacent to prev), 1/q (otherwise).  For undirected
+//              unweighted graphs the return edge's excess mass (1/p - ub) is folded into one
+//              extra proposal slot, and proposals whose acceptance variate is below
+//              min(1, 1/q) are accepted without touching N(prev) at all.  Adjacency of x and
+//              prev is a binary search in the sorted row of prev (whose {offset,degree} stay in
+//              registers) — or of x when the graph is directed.  RNG = Philox4x32-10 keyed by
+//              (seed, global walk id), counter (step, attempt block): the corpus is independent
+//              of launch geometry, batch split and GPU count.
+//
+// HBM traffic per accepted step: one 8-byte meta load (L2 resident), one 32-byte
+// sector of col[] per proposal, S(d_prev) sectors per membership search, 4 bytes stored.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace gw {
+
+// ---------------------------------------------------------------------------------------------
+// replay walker
+// ---------------------------------------------------------------------------------------------
+__global__ void k_walk_replay(const uint2 *__restrict__ meta, const int32_t *__restrict__ col,
+                              const int32_t *__restrict__ anJ, const double *__restrict__ anq,
+                              const int64_t *__restrict__ aeoff, const int32_t *__restrict__ aeJ,
+                              const double *__restrict__ aeq, int32_t L, const int64_t *__restrict__ starts,
+                              int64_t n_walks, const double *__restrict__ uni, int64_t n_uni,
+                              const int64_t *__restrict__ draw_off, int32_t *__restrict__ out,
+                              int32_t *__restrict__ lens, int *__restrict__ err) {
+    int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (w >= n_walks) return;
+    int64_t pos = draw_off ? draw_off[w] : (int64_t)2 * (L - 1) * w;
+    int32_t *o = out + w * L;
+    int32_t cur = (int32_t)starts[w];
+    o[0] = cur;
+    int64_t e_prev = -1;
+    int32_t len = 1;
+    for (; len < L; len++) {
+        uint2 m = meta[cur];
+        int32_t K = (int32_t)m.y;
+        if (K == 0) break;                                      // node2vec.py:36-37
+        if (pos + 2 > n_uni) { atomicExch(err, 1); break; }
+        double u1 = uni[pos], u2 = uni[pos + 1];
+        pos += 2;
+        const int32_t *J;
+        const double *q;
+        if (len == 1) { J = anJ + m.x; q = anq + m.x; }         // :28-29
+        else { J = aeJ + aeoff[e_prev]; q = aeq + aeoff[e_prev]; }   // :32-34
+        int32_t kk = (int32_t)floor(__dmul_rn(u1, (double)K));  // :156
+        int32_t k = (u2 < q[kk]) ? kk : J[kk];                  // :157-160
+        e_prev = (int64_t)m.x + k;
+        cur = col[e_prev];
+        o[len] = cur;
+    }
+    if (lens) lens[w] = len;
+    for (int32_t i = len; i < L; i++) o[i] = -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// free-running walker
+// ---------------------------------------------------------------------------------------------
+struct WalkParams {
+    const uint2 *meta;
+    const int32_t *col;
+    const double *w;        // weighted only
+    const int32_t *anJ;     // weighted only
+    const double *anq;      // weighted only
+    const int64_t *starts;
+    int64_t n_walks;
+    int32_t L;
+    float inv_p, inv_q;     // 1/p, 1/q
+    float ub;               // envelope height for non-folded slots
+    float lb;               // weight every non-return candidate is guaranteed to reach
+    float ret_w;            // acceptance height of prev when drawn from a regular slot
+    uint32_t fold16;        // width of the folded return slot in 16.16 slot units, 0 = no folding
+    int32_t first_order;    // p == q == 1
+    uint2 key;
+    uint64_t walk_id_base;
+    int32_t *out;
+    int32_t *lens;
+};
+
+__device__ __forceinline__ float u32_to_unit(uint32_t r) {   // [0,1) with 24 bits
+    return (float)(r >> 8) * (1.0f / 16777216.0f);
+}
+
+// lower_bound of x in the sorted row [row, row+d); true when present
+__device__ __forceinline__ bool row_contains(const int32_t *__restrict__ row, uint32_t d, int32_t x) {
+    uint32_t lo = 0, hi = d;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        int32_t v = __ldg(row + mid);
+        if (v < x) lo = mid + 1; else hi = mid;
+    }
+    return lo < d && __ldg(row + lo) == x;
+}
+
+template <bool WEIGHTED, bool DIRECTED>
+__global__ void __launch_bounds__(256) k_walk_free(WalkParams P) {
+    int64_t wi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (wi >= P.n_walks) return;
+    const uint64_t wid = P.walk_id_base + (uint64_t)wi;
+    int32_t *o = P.out + wi * P.L;
+    int32_t cur = (int32_t)P.starts[wi];
+    int32_t prev = -1;
+    uint2 mprev = make_uint2(0, 0);
+    o[0] = cur;
+    int32_t len = 1;
+    for (; len < P.L; len++) {
+        const uint2 m = __ldg(P.meta + cur);
+        const uint32_t d = m.y;
+        if (d == 0) break;
+        int32_t nxt = -1;
+        uint32_t attempt = 0;
+        if (!WEIGHTED) {
+            // every Philox call yields two (slot, variate) proposals
+            for (;;) {
+                uint4 r = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)len, attempt), P.key);
+                attempt++;
+                uint32_t rs[2] = {r.x, r.z}, ry[2] = {r.y, r.w};
+#pragma unroll
+                for (int t = 0; t < 2; t++) {
+                    if (nxt >= 0) break;
+                    if (prev < 0 || P.first_order) {       // first step / p=q=1: plain uniform draw
+                        nxt = __ldg(P.col + m.x + scale_u32(rs[t], d));
+                        break;
+                    }
+                    // slots [0,d) regular, [d, d+fold) = folded return mass; 16.16 fixed point
+                    uint64_t s16 = __umul64hi((uint64_t)rs[t] << 32, ((uint64_t)d << 16) + P.fold16);
+                    uint32_t k = (uint32_t)(s16 >> 16);
+                    if (k >= d) { nxt = prev; break; }
+                    int32_t x = __ldg(P.col + m.x + k);
+                    float y = u32_to_unit(ry[t]) * P.ub;
+                    if (x == prev) { if (y < P.ret_w) nxt = x; continue; }
+                    if (y < P.lb) { nxt = x; continue; }   // accepted whatever the adjacency is
+                    bool adj;
+                    if (DIRECTED) {   // G.has_edge(x, prev): prev in N_out(x)   (node2vec.py:73)
+                        uint2 mx = __ldg(P.meta + x);
+                        adj = row_contains(P.col + mx.x, mx.y, prev);
+                    } else {          // undirected: same as x in N(prev); prev's row bounds are in registers
+                        adj = row_contains(P.col + mprev.x, mprev.y, x);
+                    }
+                    if (y < (adj ? 1.0f : P.inv_q)) nxt = x;
+                }
+                if (nxt >= 0) break;
+            }
+        } else {
+            // one proposal per Philox call: alias_draw on alias_nodes[cur] (static first-order
+            // weights, node2vec.py:150-160), then the p/q acceptance test
+            for (;;) {
+                uint4 r = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)len, attempt), P.key);
+                attempt++;
+                uint32_t kk = scale_u32(r.x, d);
+                double qk = __ldg(P.anq + m.x + kk);
+                uint32_t k = ((double)u32_to_unit(r.y) < qk) ? kk : (uint32_t)__ldg(P.anJ + m.x + kk);
+                int32_t x = __ldg(P.col + m.x + k);
+                if (prev < 0 || P.first_order) { nxt = x; break; }
+                float y = u32_to_unit(r.z) * P.ub;
+                if (x == prev) { if (y < P.ret_w) { nxt = x; break; } continue; }
+                if (y < P.lb) { nxt = x; break; }
+                bool adj;
+                if (DIRECTED) {
+                    uint2 mx = __ldg(P.meta + x);
+                    adj = row_contains(P.col + mx.x, mx.y, prev);
+                } else {
+                    adj = row_contains(P.col + mprev.x, mprev.y, x);
+                }
+                if (y < (adj ? 1.0f : P.inv_q)) { nxt = x; break; }
+            }
+        }
+        o[len] = nxt;
+        prev = cur;
+        mprev = m;
+        cur = nxt;
+    }
+    if (P.lens) P.lens[wi] = len;
+    for (int32_t i = len; i < P.L; i++) o[i] = -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// byte model of SURVEY.md §8(d): steps and sum of S(d_prev) = max(1, ceil(log2(d+1)) - 2)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_byte_model(const uint2 *__restrict__ meta, const int32_t *__restrict__ walks, int64_t n_walks,
+                             int32_t L, int second_order, unsigned long long *__restrict__ acc) {
+    int64_t wi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    unsigned long long steps = 0, sec = 0;
+    if (wi < n_walks) {
+        const int32_t *o = walks + wi * L;
+        for (int32_t i = 1; i < L; i++) {
+            if (o[i] < 0) break;
+            steps++;
+            if (second_order && i >= 2) {
+                uint32_t d = meta[o[i - 2]].y;
+                int lg = 32 - __clz(d);                  // ceil(log2(d+1)) for d >= 1
+                sec += (unsigned long long)max(1, lg - 2);
+            }
+        }
+    }
+    for (int ofs = 16; ofs; ofs >>= 1) {
+        steps += __shfl_xor_sync(0xffffffffu, steps, ofs);
+        sec += __shfl_xor_sync(0xffffffffu, sec, ofs);
+    }
+    if ((threadIdx.x & 31) == 0 && steps) { atomicAdd(acc, steps); atomicAdd(acc + 1, sec); }
+}
+
+}  // namespace gw
+
+using namespace gw;
+
+static int check_starts_host(const gw_graph *g, const int64_t *starts, int64_t n) {
+    for (int64_t i = 0; i < n; i++)
+        if (starts[i] < 0 || starts[i] >= g->n)
+            return fail(GW_E_KEY, "start node index %lld is not a vertex of the graph", (long long)starts[i]);
+    return GW_OK;
+}
+
+extern "C" {
+
+int gw_node2vec_walks_dev(gw_graph *g, double p, double q, int32_t walk_length, const int64_t *d_starts,
+                          int64_t n_starts, uint64_t seed, uint64_t walk_id_base, int32_t *d_out_walks,
+                          int32_t *d_out_lens, void *stream) {
+    if (!g) return fail(GW_E_INVALID, "graph is NULL");
+    if (!(p > 0) || !(q > 0)) return fail(GW_E_INVALID, "p and q must be positive");
+    if (walk_length < 1 || n_starts < 0) return fail(GW_E_INVALID, "bad walk_length / n_starts");
+    if (g->flags & GW_F_MULTI) return fail(GW_E_STATE, "node2vec walks need a SIMPLE-mode (sorted) graph");
+    if (n_starts == 0) return GW_OK;
+    GW_CUDA(cudaSetDevice(g->device));
+    const bool weighted = (g->flags & GW_F_WEIGHTED) != 0, directed = (g->flags & GW_F_DIRECTED) != 0;
+    if (weighted && !g->d_anJ) GW_TRY(gw_alias_nodes(g, nullptr, nullptr));
+    WalkParams P;
+    P.meta = g->d_meta; P.col = g->d_col; P.w = g->d_w; P.anJ = g->d_anJ; P.anq = g->d_anq;
+    P.starts = d_starts; P.n_walks = n_starts; P.L = walk_length;
+    P.inv_p = (float)(1.0 / p); P.inv_q = (float)(1.0 / q);
+    P.first_order = (p == 1.0 && q == 1.0);
+    float ub_nr = std::max(1.0f, P.inv_q);          // bound over non-return candidates
+    if (!weighted && !directed && P.inv_p > ub_nr) {   // fold the return edge's excess into one slot
+        P.ub = ub_nr; P.ret_w = ub_nr;
+        P.fold16 = (uint32_t)std::min(4.0e9, std::floor((double)(P.inv_p - ub_nr) / ub_nr * 65536.0 + 0.5));
+    } else {
+        P.ub = std::max(ub_nr, P.inv_p); P.ret_w = P.inv_p; P.fold16 = 0;
+    }
+    P.lb = std::min(1.0f, P.inv_q);
+    P.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    P.walk_id_base = walk_id_base;
+    P.out = d_out_walks; P.lens = d_out_lens;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned grid = (unsigned)((n_starts + 255) / 256);
+    if (weighted && directed) k_walk_free<true, true><<<grid, 256, 0, st>>>(P);
+    else if (weighted) k_walk_free<true, false><<<grid, 256, 0, st>>>(P);
+    else if (directed) k_walk_free<false, true><<<grid, 256, 0, st>>>(P);
+    else k_walk_free<false, false><<<grid, 256, 0, st>>>(P);
+    GW_LAUNCHED();
+    return GW_OK;
+}
+
+int gw_node2vec_walks(gw_graph *g, double p, double q, int32_t walk_length, const int64_t *starts, int64_t n_starts,
+                      uint64_t seed, uint64_t walk_id_base, int32_t *out_walks, int32_t *out_lens) {
+    if (!g) return fail(GW_E_INVALID, "graph is NULL");
+    if (n_starts < 0 || (n_starts > 0 && (!starts || !out_walks))) return fail(GW_E_INVALID, "bad arguments");
+    if (walk_length < 1) return fail(GW_E_INVALID, "bad walk_length");
+    GW_TRY(check_starts_host(g, starts, n_starts));
+    if (n_starts == 0) return GW_OK;
+    GW_CUDA(cudaSetDevice(g->device));
+    DevBuf<int64_t> ds;
+    DevBuf<int32_t> dw, dl;
+    GW_CUDA(ds.alloc((size_t)n_starts));
+    GW_CUDA(dw.alloc((size_t)n_starts * walk_length));
+    if (out_lens) GW_CUDA(dl.alloc((size_t)n_starts));
+    GW_CUDA(cudaMemcpy(ds.p, starts, sizeof(int64_t) * (size_t)n_starts, cudaMemcpyHostToDevice));
+    GW_TRY(gw_node2vec_walks_dev(g, p, q, walk_length, ds.p, n_starts, seed, walk_id_base, dw.p, dl.p, nullptr));
+    GW_CUDA(cudaMemcpy(out_walks, dw.p, sizeof(int32_t) * (size_t)n_starts * walk_length, cudaMemcpyDeviceToHost));
+    if (out_lens) GW_CUDA(cudaMemcpy(out_lens, dl.p, sizeof(int32_t) * (size_t)n_starts, cudaMemcpyDeviceToHost));
+    return GW_OK;
+}
+
+int gw_node2vec_walks_replay(gw_graph *g, int32_t walk_length, const int64_t *starts, int64_t n_starts,
+                             const double *uniforms, int64_t n_uniforms, const int64_t *draw_offset,
+                             int32_t *out_walks, int32_t *out_lens) {
+    if (!g) return fail(GW_E_INVALID, "graph is NULL");
+    if (n_starts < 0 || (n_starts > 0 && (!starts || !out_walks)) || n_uniforms < 0 || (n_uniforms > 0 && !uniforms))
+        return fail(GW_E_INVALID, "bad arguments");
+    if (walk_length < 1) return fail(GW_E_INVALID, "bad walk_length");
+    if (!g->d_anJ || !g->d_aeoff)
+        return fail(GW_E_STATE, "replay needs gw_alias_nodes and gw_alias_edges (preprocess_transition_probs) first");
+    GW_TRY(check_starts_host(g, starts, n_starts));
+    if (n_starts == 0) return GW_OK;
+    GW_CUDA(cudaSetDevice(g->device));
+    DevBuf<int64_t> ds, doff;
+    DevBuf<double> du;
+    DevBuf<int32_t> dw, dl;
+    DevBuf<int> derr;
+    GW_CUDA(ds.alloc((size_t)n_starts));
+    GW_CUDA(du.alloc((size_t)std::max<int64_t>(n_uniforms, 1)));
+    GW_CUDA(dw.alloc((size_t)n_starts * walk_length));
+    GW_CUDA(dl.alloc((size_t)n_starts));
+    GW_CUDA(derr.alloc(1));
+    GW_CUDA(cudaMemset(derr.p, 0, sizeof(int)));
+    GW_CUDA(cudaMemcpy(ds.p, starts, sizeof(int64_t) * (size_t)n_starts, cudaMemcpyHostToDevice));
+    if (n_uniforms) GW_CUDA(cudaMemcpy(du.p, uniforms, sizeof(double) * (size_t)n_uniforms, cudaMemcpyHostToDevice));
+    if (draw_offset) {
+        GW_CUDA(doff.alloc((size_t)n_starts + 1));
+        GW_CUDA(cudaMemcpy(doff.p, draw_offset, sizeof(int64_t) * (size_t)(n_starts + 1), cudaMemcpyHostToDevice));
+    }
+    k_walk_replay<<<(unsigned)((n_starts + 127) / 128), 128>>>(g->d_meta, g->d_col, g->d_anJ, g->d_anq, g->d_aeoff,
+                                                               g->d_aeJ, g->d_aeq, walk_length, ds.p, n_starts, du.p,
+                                                               n_uniforms, doff.p, dw.p, dl.p, derr.p);
+    GW_LAUNCHED();
+    int herr = 0;
+    GW_CUDA(cudaMemcpy(&herr, derr.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (herr) return fail(GW_E_INVALID, "uniform stream exhausted: %lld draws do not cover the walks", (long long)n_uniforms);
+    GW_CUDA(cudaMemcpy(out_walks, dw.p, sizeof(int32_t) * (size_t)n_starts * walk_length, cudaMemcpyDeviceToHost));
+    if (out_lens) GW_CUDA(cudaMemcpy(out_lens, dl.p, sizeof(int32_t) * (size_t)n_starts, cudaMemcpyDeviceToHost));
+    return GW_OK;
+}
+
+int gw_walks_byte_model_dev(const gw_graph *g, const int32_t *d_walks, int64_t n_walks, int32_t walk_length,
+                            int second_order, int64_t *steps, int64_t *sum_search_sectors, void *stream) {
+    if (!g || !d_walks || !steps || !sum_search_sectors) return fail(GW_E_INVALID, "bad arguments");
+    GW_CUDA(cudaSetDevice(g->device));
+    DevBuf<unsigned long long> acc;
+    GW_CUDA(acc.alloc(2));
+    cudaStream_t st = (cudaStream_t)stream;
+    GW_CUDA(cudaMemsetAsync(acc.p, 0, 2 * sizeof(unsigned long long), st));
+    if (n_walks > 0) {
+        k_byte_model<<<(unsigned)((n_walks + 255) / 256), 256, 0, st>>>(g->d_meta, d_walks, n_walks, walk_length,
+                                                                        second_order, acc.p);
+        GW_LAUNCHED();
+    }
+    unsigned long long h[2];
+    GW_CUDA(cudaMemcpyAsync(h, acc.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    GW_CUDA(cudaStreamSynchronize(st));
+    *steps = (int64_t)h[0];
+    *sum_search_sectors = (int64_t)h[1];
+    return GW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,300 @@
+"""Python host mirror of the reference's Java TopSim surface (DeepSim/TopSimAll/src), backed by
+libgraphwalk.  Class and method names follow the Java so the reference's drivers
+(benchmark/Test_u_u_SingleRandomWalk_Sample.java:21-68) translate line by line:
+
+    g   = Graph(path, V)                              # structures/Graph.java:28
+    srw = SingleRandomWalk(g, sample, step)           # simrank/SingleRandomWalk.java:28
+    srw.compute(); sim = srw.getResult()              # :39-45 (dense V x V, small graphs)
+    ids, scores = srw.topk(k)                         # per-query top-k straight from the device
+    Print.printByOrder(sim, outPath, TOPK, k)         # utils/Print.java:25-53
+    Eval.precision(gold, outPath + ".sim.txt", prePath, k)   # utils/Eval.java:81-131
+
+The Java binding of the same C ABI (Panama FFM) is in graph_embedding_b200/java/.
+"""
+import gzip
+from decimal import Decimal, ROUND_HALF_UP
+
+import numpy as np
+
+from . import _lib
+
+
+class MyConfiguration:
+    """conf/MyConfiguration.java:16-22 (static mutable, as in the reference)."""
+    SEPARATOR = ","
+    SEPARATOR_KV = ":"
+    TOPK = 20
+    MIN = 0.000000001
+    C = 0.6
+    testTopK = [20]
+
+
+class Graph:
+    """structures/Graph.java: undirected unweighted multigraph, V vertex slots, both directions
+    appended per line, duplicates and file order kept."""
+
+    def __init__(self, graphPath, V, separator=None):
+        sep = MyConfiguration.SEPARATOR if separator is None else separator
+        if str(graphPath).endswith(".gz"):
+            src, dst = [], []
+            with gzip.open(graphPath, "rt") as f:
+                for line in f:
+                    line = line.rstrip("\r\n")
+                    if line:
+                        ids = line.split(sep)
+                        src.append(int(ids[0])); dst.append(int(ids[1]))
+            self.handle = _lib.GraphHandle.from_edges(src, dst, None, directed=False, mode=_lib.GW_MODE_MULTI,
+                                                      n_slots=V)
+        else:
+            self.handle = _lib.GraphHandle.from_file(graphPath, delimiter=sep, weighted=False, directed=False,
+                                                     mode=_lib.GW_MODE_MULTI, n_slots=V)
+        self.vCount = self.handle.n
+        self.eCount = self.handle.nnz // 2
+        self._csr = None
+
+    @classmethod
+    def from_handle(cls, handle):
+        g = cls.__new__(cls)
+        g.handle = handle
+        g.vCount = handle.n
+        g.eCount = handle.nnz // 2
+        g._csr = None
+        return g
+
+    def _c(self):
+        if self._csr is None:
+            self._csr = self.handle.csr(weights=False, node_ids=False, first_seen=False)
+        return self._csr
+
+    def degree(self, v):
+        c = self._c()
+        return int(c["row_ptr"][v + 1] - c["row_ptr"][v])
+
+    def neighbors(self, v):
+        c = self._c()
+        return c["col_idx"][c["row_ptr"][v]:c["row_ptr"][v + 1]].tolist()
+
+    def getVCount(self):
+        return self.vCount
+
+    def getECount(self):
+        return self.eCount
+
+
+class SingleRandomWalk:
+    """simrank/SingleRandomWalk.java: pure Monte-Carlo single-walk estimator (scores / SAMPLE)."""
+    MODE = _lib.GW_SIMRANK_MC
+    SAMPLE = 10000
+
+    def __init__(self, g, sample, step, seed=None):
+        self.topk_k = MyConfiguration.TOPK
+        self.STEP = step
+        self.SAMPLE = sample
+        self.g = g
+        self.COUNT = g.getVCount()
+        self.sim = None
+        self.seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
+
+    def compute(self, queries=None):
+        """compute() (:39-45): every vertex 0..COUNT-1 is a query; dense result like double[][]."""
+        q = np.arange(self.COUNT, dtype=np.int64) if queries is None else np.asarray(queries, dtype=np.int64)
+        self._queries = q
+        self.sim = self.g.handle.simrank_rows(q, MyConfiguration.C, self.STEP, self.SAMPLE, self.MODE, self.seed)
+        return self
+
+    def getResult(self):
+        return self.sim
+
+    def topk(self, k=None, queries=None):
+        """Fused walk-and-meet + per-query top-k on the device (no V x V matrix)."""
+        k = self.topk_k if k is None else k
+        q = np.arange(self.COUNT, dtype=np.int64) if queries is None else np.asarray(queries, dtype=np.int64)
+        return self.g.handle.simrank_topk(q, MyConfiguration.C, self.STEP, self.SAMPLE, k, self.MODE, self.seed)
+
+
+class TopSim_singleSample(SingleRandomWalk):
+    """simrank/TopSim_singleSample.java: hybrid enumerate-while-weight>=degree else sample
+    (scores x SAMPLE, unnormalised, as the reference :189)."""
+    MODE = _lib.GW_SIMRANK_HYBRID
+
+
+class SimRank:
+    """simrank/SimRank.java: naive exact SimRank, STEP Jacobi sweeps (STEP = 3 as committed)."""
+
+    def __init__(self, g, step=3):
+        self.g = g
+        self.STEP = step
+        self.COUNT = g.getVCount()
+        self.sim = None
+
+    def compute(self):
+        self.sim = self.g.handle.simrank_exact(MyConfiguration.C, self.STEP)
+        return self
+
+    def getResult(self):
+        return self.sim
+
+
+# ---------------- lxctools/FixedMaxPQ.java + Pair.java ----------------
+class FixedMaxPQ:
+    """Size-k min-heap with java.util.PriorityQueue's exact sift rules; replaces the minimum only
+    when the offer is strictly greater (FixedMaxPQ.java:30-39); sortedElement() is a stable
+    descending sort of the heap array (:72-76)."""
+
+    def __init__(self, capacity):
+        self.capacity = capacity
+        self.q = []
+
+    def _up(self, k, x):
+        q = self.q
+        while k > 0:
+            parent = (k - 1) >> 1
+            if x[1] >= q[parent][1]:
+                break
+            q[k] = q[parent]
+            k = parent
+        q[k] = x
+
+    def _down(self, k, x):
+        q = self.q
+        size = len(q)
+        half = size >> 1
+        while k < half:
+            child = 2 * k + 1
+            right = child + 1
+            if right < size and q[child][1] > q[right][1]:
+                child = right
+            if x[1] <= q[child][1]:
+                break
+            q[k] = q[child]
+            k = child
+        q[k] = x
+
+    def offer(self, key, value):
+        e = (key, value)
+        if len(self.q) < self.capacity:
+            self.q.append(e)
+            self._up(len(self.q) - 1, e)
+        elif self.capacity > 0 and self.q[0][1] < value:
+            last = self.q.pop()
+            if self.q:
+                self._down(0, last)
+            self.q.append(e)
+            self._up(len(self.q) - 1, e)
+
+    def sortedElement(self):
+        return sorted(self.q, key=lambda kv: -kv[1])          # python's sort is stable, like Collections.sort
+
+
+def java_format(x, digits):
+    """String.format("%.<digits>f"): java.util.Formatter rounds HALF_UP on the shortest decimal
+    representation of the double."""
+    return format(Decimal(repr(float(x))).quantize(Decimal(1).scaleb(-digits), rounding=ROUND_HALF_UP), "f")
+
+
+def _row_topk_exact(row, topk):
+    """FixedMaxPQ fed with every column of a dense row in ascending id (Print.java:31-37).  Zero
+    offers after the heap is full can never replace anything (scores are >= 0), so only the
+    first `topk` columns and the positive ones need to be offered."""
+    pq = FixedMaxPQ(topk)
+    n = len(row)
+    head = min(topk, n)
+    for i in range(head):
+        pq.offer(i, float(row[i]))
+    if n > head:
+        rest = np.nonzero(row[head:] > 0)[0] + head
+        for i in rest.tolist():
+            pq.offer(i, float(row[i]))
+    return pq.sortedElement()
+
+
+class Print:
+    @staticmethod
+    def _write(sim, outPath, topk, digits):
+        sep, kv = MyConfiguration.SEPARATOR, MyConfiguration.SEPARATOR_KV
+        with open(outPath, "w", newline="") as out, open(outPath + ".sim.txt", "w", newline="") as outsim:
+            for v in range(len(sim)):
+                out.write(str(v)); outsim.write(str(v))
+                for key, val in _row_topk_exact(np.asarray(sim[v]), topk):
+                    out.write(sep + str(key))
+                    outsim.write(sep + str(key) + kv + java_format(val, digits))
+                out.write("\r\n"); outsim.write("\r\n")
+
+    @staticmethod
+    def printByOrder(sim, outPath, topk, testTopK=None):
+        """utils/Print.java:25-53: `<v>,<id>,...` and `<v>,<id>:<%.6f>,...`, CRLF."""
+        Print._write(sim, outPath, topk, 6)
+
+    @staticmethod
+    def printByOrderAll(sim, outPath, topk, testTopK=None):
+        """utils/Print.java:55-84 (%.7f)."""
+        Print._write(sim, outPath, topk, 7)
+
+    @staticmethod
+    def printTopk(ids, scores, outPath, queries=None, digits=6):
+        """Same files from the device top-k (ids/scores [nq, k]; id -1 = no further positive
+        score): rows are padded with the lowest unused ids at score 0, which downstream readers
+        drop (Eval.java:99-108 filters < MIN, DeepSim/src/main.py:99 filters <= 1e-8)."""
+        sep, kv = MyConfiguration.SEPARATOR, MyConfiguration.SEPARATOR_KV
+        nq, k = ids.shape
+        with open(outPath, "w", newline="") as out, open(outPath + ".sim.txt", "w", newline="") as outsim:
+            for r in range(nq):
+                v = r if queries is None else int(queries[r])
+                out.write(str(v)); outsim.write(str(v))
+                used = set(int(x) for x in ids[r] if x >= 0)
+                pad = 0
+                for c in range(k):
+                    key, val = int(ids[r, c]), float(scores[r, c])
+                    if key < 0:
+                        while pad in used:
+                            pad += 1
+                        key, val = pad, 0.0
+                        used.add(pad)
+                    out.write(sep + str(key))
+                    outsim.write(sep + str(key) + kv + java_format(val, digits))
+                out.write("\r\n"); outsim.write("\r\n")
+
+
+class Eval:
+    @staticmethod
+    def precision(path1, path2, prePath, K):
+        """utils/Eval.java:81-131: mean over vertices of |gold ∩ out| / min(TOPK, |gold|) on ids
+        whose score >= MIN; writes `<v>,<precision>` lines; returns the mean as a string."""
+        sep, kv = MyConfiguration.SEPARATOR, MyConfiguration.SEPARATOR_KV
+        total, ssum, mn = 0, 0.0, float("inf")
+        with open(prePath, "w", newline="") as out, open(path1, newline="") as f1, open(path2, newline="") as f2:
+            for line1 in f1:
+                line2 = f2.readline()
+                t1 = line1.rstrip("\r\n").split(sep)
+                t2 = line2.rstrip("\r\n").split(sep)
+                if t1[0] != t2[0]:
+                    print("error !" + t1[0] + "\t" + t2[0])
+                    continue
+                s1 = {t.split(kv)[0] for t in t1[1:] if float(t.split(kv)[1]) >= MyConfiguration.MIN}
+                s2 = {t.split(kv)[0] for t in t2[1:] if float(t.split(kv)[1]) >= MyConfiguration.MIN}
+                realK = min(MyConfiguration.TOPK, len(s1))
+                pre = 1.0 if realK == 0 else 1.0 * len(s1 & s2) / realK
+                ssum += pre
+                out.write(t1[0] + sep + repr(pre) + "\r\n")
+                total += 1
+                mn = min(mn, pre)
+        print("total nodes:" + str(total) + "\tavg precision: " + str(ssum / total) + "\tmin pre: " + str(mn))
+        return str(ssum / total)
+
+
+def read_simrank(path):
+    """DeepSim/src/main.py:83-107: the consumer of `.sim.txt` (entries <= 1e-8 dropped)."""
+    simrank = []
+    with open(path) as f:
+        for line in f.readlines():
+            words = line.split(",")
+            sim = []
+            for i in range(1, len(words)):
+                if i == len(words) - 1:
+                    words[i] = words[i][:-1]
+                ts = words[i].split(":")
+                if float(ts[1]) <= 0.00000001:
+                    continue
+                sim.append((ts[0], ts[1]))
+            simrank.append(sim)
+    return simrank

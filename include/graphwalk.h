@@ -1,0 +1,167 @@
+/* graphwalk.h — C ABI of libgraphwalk.so, the B200 (sm_100a) random-walk engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of Junshuai-Song/Graph-Embedding:
+ *   node2vec second-order walk generation   (reference: node2vec/src/node2vec.py)
+ *   DeepSim/TopSim Monte-Carlo SimRank       (reference: DeepSim/TopSimAll/src/simrank/*.java)
+ * The reference has no FFI layer of its own; every entry point below names the
+ * reference function it replaces.  Host bindings: Python ctypes (graph_embedding_b200/_lib.py),
+ * Java Panama FFM / JNI (graph_embedding_b200/java/).
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 (GW_OK) or a negative GW_E_* code and
+ *     gw_last_error() returns a thread-local message for the last failure on this thread;
+ *   - handles are opaque; output buffers are caller-owned and sized by the caller (sizes come
+ *     from gw_graph_info / gw_alias_edges_size); the library never frees caller memory;
+ *   - functions without the _dev suffix take HOST pointers and block until the result is in
+ *     host memory (H2D copy, kernels, D2H copy inside the call);
+ *   - functions with the _dev suffix take DEVICE pointers on the graph's device plus a
+ *     cudaStream_t (passed as void*, NULL = legacy default stream) and only enqueue work;
+ *   - vertices are addressed by DENSE index 0..n-1 = rank of the original id in ascending
+ *     order (SIMPLE mode) or the original id itself (MULTI mode / generators);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     GW_E_CUDA.
+ */
+#ifndef GRAPHWALK_H
+#define GRAPHWALK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GW_OK 0
+#define GW_E_INVALID (-1)   /* bad argument */
+#define GW_E_CUDA (-2)      /* CUDA runtime error / no device */
+#define GW_E_IO (-3)        /* file could not be read / parsed */
+#define GW_E_TOO_LARGE (-4) /* result would exceed the library's / caller's budget */
+#define GW_E_STATE (-5)     /* call order violated (e.g. tables not built) */
+#define GW_E_KEY (-6)       /* unknown vertex / edge (the reference raises KeyError) */
+
+/* graph construction modes */
+#define GW_MODE_SIMPLE 0 /* networkx semantics of node2vec/src/main.py:76-89: ids ranked, duplicates
+                            collapse, sorted adjacency */
+#define GW_MODE_MULTI 1  /* structures/Graph.java:28-57: V slots, every line appends both directions,
+                            duplicates and file order kept */
+
+/* graph flags reported by gw_graph_info */
+#define GW_F_DIRECTED 1
+#define GW_F_WEIGHTED 2
+#define GW_F_MULTI 4
+
+/* SimRank estimator modes */
+#define GW_SIMRANK_MC 0     /* simrank/SingleRandomWalk.java:53-106 (scores / SAMPLE) */
+#define GW_SIMRANK_HYBRID 1 /* simrank/TopSim_singleSample.java:62-203 (scores x SAMPLE, as the reference) */
+
+typedef struct gw_graph gw_graph;
+
+/* ---- library / device ------------------------------------------------------------------- */
+int gw_version(void);
+const char *gw_last_error(void);
+int gw_device_count(int *count);
+/* Binds the calling thread (and graphs created afterwards) to a CUDA device. */
+int gw_set_device(int device);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t gw_kernel_launches(void);
+
+/* ---- graph loading  (node2vec/src/main.py:76-89 read_graph ; structures/Graph.java:28-57) ---- */
+/* Builds the device CSR from host edge arrays.  src/dst: original ids, w: NULL => weight 1
+ * (unweighted).  n_slots: MULTI mode = vertex count V of Graph(path, V); SIMPLE mode = -1 (rank
+ * the ids that occur) or n > max id to keep ids as dense indices (generators). */
+int gw_graph_from_edges(const int64_t *src, const int64_t *dst, const double *w, int64_t m,
+                        int directed, int mode, int64_t n_slots, gw_graph **out);
+/* Parses "u<delim>v[<delim>w]" lines like networkx.read_edgelist (SIMPLE; '#' comments, lines
+ * with < 2 fields skipped; delimiter NULL/"" = any whitespace) or like Graph(String,int)
+ * (MULTI; String.split(delim)), then calls gw_graph_from_edges.  '.gz' is not handled here. */
+int gw_graph_load_edgelist(const char *path, const char *delimiter, int weighted, int directed,
+                           int mode, int64_t n_slots, gw_graph **out);
+/* Synthetic inputs, generated on the device (benchmark shapes of BASELINE.json; the quadrant
+ * probabilities default to utils/graphTools/RMATGraphGenerator.java:179-182 = .45/.15/.15/.25).
+ * R-MAT: 2^scale ids, n_tuples edge tuples, symmetrised, self loops and duplicates dropped. */
+int gw_graph_rmat(int scale, int64_t n_tuples, double a, double b, double c, uint64_t seed,
+                  gw_graph **out);
+/* Barabasi-Albert: n vertices, each new vertex attaches to m distinct targets ~ degree;
+ * seed graph = m-clique.  Undirected, simple. */
+int gw_graph_barabasi_albert(int64_t n, int m, uint64_t seed, gw_graph **out);
+int gw_graph_free(gw_graph *g);
+
+int gw_graph_info(const gw_graph *g, int64_t *n_nodes, int64_t *n_entries, int32_t *flags,
+                  int32_t *max_degree, int32_t *device);
+/* Copies the CSR to host.  Any pointer may be NULL.  row_ptr[n+1], col_idx[nnz], weights[nnz],
+ * node_ids[n] (original ids, ascending), first_seen[n] (dense indices in list(G.nodes()) order,
+ * node2vec.py:47; identity for generated graphs). */
+int gw_graph_csr(const gw_graph *g, int64_t *row_ptr, int32_t *col_idx, double *weights,
+                 int64_t *node_ids, int64_t *first_seen);
+/* Device views (borrowed; valid until gw_graph_free): meta[n] = {uint32 offset, uint32 degree},
+ * col[nnz] int32. */
+int gw_graph_device_views(const gw_graph *g, const void **meta, const int32_t **col);
+/* Dense indices of vertices with degree > 0, ascending (the reference only knows nodes that
+ * occur in an edge).  out may be NULL to query the count. */
+int gw_graph_nonisolated(const gw_graph *g, int64_t *out, int64_t *count);
+
+/* ---- alias tables  (node2vec.py:116-147 alias_setup, :83-113 preprocess_transition_probs) ---- */
+/* One table: bit-exact alias_setup(probs) on the device (J as int32, q as fp64). */
+int gw_alias_setup(const double *probs, int64_t K, int32_t *J, double *q);
+/* alias_nodes for every vertex, flattened at CSR offsets (J[nnz], q[nnz]).  Builds and keeps
+ * the device copy; J/q may be NULL to only build. */
+int gw_alias_nodes(gw_graph *g, int32_t *J, double *q);
+/* Total entries of alias_edges = sum over directed CSR entries (u->v) of deg(v). */
+int gw_alias_edges_size(const gw_graph *g, int64_t *total);
+/* alias_edges for every directed CSR entry e=(u->v), table e at off[e]..off[e+1] (off[nnz+1]).
+ * Builds and keeps the device copy for replay; fails with GW_E_TOO_LARGE above budget_bytes
+ * (0 = 3/4 of free device memory).  off/J/q may be NULL to only build. */
+int gw_alias_edges(gw_graph *g, double p, double q, int64_t budget_bytes, int64_t *off,
+                   int32_t *J, double *qv);
+
+/* ---- node2vec walks  (node2vec.py:13-59 node2vec_walk / simulate_walks) ---- */
+/* Free-running walks, one per entry of starts[] (dense indices), Philox4x32-10 keyed by
+ * (seed, walk_id_base + i): the corpus does not depend on how starts are split over calls,
+ * ranks or GPUs.  out_walks[n_starts*walk_length] int32 dense indices, -1 padded after a dead
+ * end (node2vec.py:36-37); out_lens[n_starts] may be NULL. */
+int gw_node2vec_walks(gw_graph *g, double p, double q, int32_t walk_length, const int64_t *starts,
+                      int64_t n_starts, uint64_t seed, uint64_t walk_id_base, int32_t *out_walks,
+                      int32_t *out_lens);
+int gw_node2vec_walks_dev(gw_graph *g, double p, double q, int32_t walk_length,
+                          const int64_t *d_starts, int64_t n_starts, uint64_t seed,
+                          uint64_t walk_id_base, int32_t *d_out_walks, int32_t *d_out_lens,
+                          void *stream);
+/* Replay: consumes the reference's own np.random.rand() stream (two fp64 draws per executed
+ * step, node2vec.py:156-160) and start order; needs gw_alias_nodes + gw_alias_edges built with
+ * the same p,q.  draw_offset[n_starts+1] may be NULL when no walk can hit a dead end
+ * (then walk i starts at 2*(walk_length-1)*i). */
+int gw_node2vec_walks_replay(gw_graph *g, int32_t walk_length, const int64_t *starts,
+                             int64_t n_starts, const double *uniforms, int64_t n_uniforms,
+                             const int64_t *draw_offset, int32_t *out_walks, int32_t *out_lens);
+/* Byte model of SURVEY.md §8(d) evaluated on a device-resident corpus: number of executed
+ * steps and sum over steps of S(d_prev) (0 for first steps). */
+int gw_walks_byte_model_dev(const gw_graph *g, const int32_t *d_walks, int64_t n_walks,
+                            int32_t walk_length, int second_order, int64_t *steps,
+                            int64_t *sum_search_sectors, void *stream);
+
+/* ---- SimRank  (SingleRandomWalk.java, TopSim_singleSample.java, Print.java/FixedMaxPQ.java) ---- */
+/* Per query: SAMPLE reverse walks of length 2*step, first-meeting accumulation with decay c,
+ * then top-k (score descending, id ascending; the source itself excluded, zero scores padded
+ * with id -1).  out_ids[nq*k] int32, out_scores[nq*k] fp64.  Philox keyed by
+ * (seed, query_id_base + i). */
+int gw_simrank_topk(gw_graph *g, const int64_t *queries, int64_t nq, double c, int32_t step,
+                    int32_t sample, int32_t k, int32_t mode, uint64_t seed,
+                    uint64_t query_id_base, int32_t *out_ids, double *out_scores);
+int gw_simrank_topk_dev(gw_graph *g, const int64_t *d_queries, int64_t nq, double c, int32_t step,
+                        int32_t sample, int32_t k, int32_t mode, uint64_t seed,
+                        uint64_t query_id_base, int32_t *d_out_ids, double *d_out_scores,
+                        void *stream);
+/* Dense rows of the same estimator (getResult() of the reference): out[nq*n] fp64. */
+int gw_simrank_rows(gw_graph *g, const int64_t *queries, int64_t nq, double c, int32_t step,
+                    int32_t sample, int32_t mode, uint64_t seed, uint64_t query_id_base,
+                    double *out_dense);
+/* Total walk steps executed by the last gw_simrank_* call on this graph. */
+int gw_simrank_last_steps(const gw_graph *g, int64_t *steps);
+/* Exact SimRank (simrank/SimRank.java:36-77): iters Jacobi sweeps of S <- c P S P^T, diag = 1,
+ * diag zeroed at the end; returns the requested rows out[nrows*n].  O(n^2) device memory. */
+int gw_simrank_exact(gw_graph *g, double c, int32_t iters, const int64_t *rows, int64_t nrows,
+                     double *out_dense);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPHWALK_H */

@@ -1,0 +1,203 @@
+"""GPU parity tests of the node2vec path, through the C ABI (ctypes) and the drop-in module.
+Bit-exact: CSR, alias tables, replayed walks.  Statistical: free-running walks (chi-square
+against the exact law from the oracle, alpha = 1e-4 on the pooled statistic)."""
+import json
+import os
+
+import numpy as np
+import pytest
+from scipy import stats
+
+from conftest import GOLDEN, DATA
+from helpers import CASES, case, load_npz, data_path, chi2_transitions
+from oracle import n2v_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+from graph_embedding_b200 import _lib, node2vec as n2v  # noqa: E402
+
+
+def open_graph(meta):
+    return _lib.GraphHandle.from_file(data_path(meta), delimiter=meta["delimiter"], weighted=meta["weighted"],
+                                      directed=meta["directed"])
+
+
+@pytest.mark.parametrize("meta", CASES, ids=[c["name"] for c in CASES])
+def test_csr_bit_exact(meta):
+    z = load_npz(meta)
+    h = open_graph(meta)
+    c = h.csr(weights=True)
+    for k in ("node_ids", "first_seen", "row_ptr", "col_idx"):
+        assert np.array_equal(c[k], z[k]), k
+    assert c["weights"].tobytes() == z["weights"].tobytes()
+    assert h.n == meta["n_nodes"] and h.nnz == meta["nnz"]
+
+
+def test_alias_setup_kats():
+    for kat in json.load(open(os.path.join(GOLDEN, "alias_setup_kat.json"))):
+        J, q = n2v.alias_setup(kat["probs"])
+        assert [int(x) for x in J] == kat["J"]
+        assert [float(x).hex() for x in q] == kat["q_hex"]
+    rs = np.random.RandomState(3)
+    for K in (2, 7, 33, 257, 4000):
+        p = rs.rand(K); p /= p.sum()
+        J, q = n2v.alias_setup(p)
+        Jo, qo = O.alias_setup(list(p))
+        assert np.array_equal(J, Jo) and q.tobytes() == qo.tobytes()
+
+
+@pytest.mark.parametrize("meta", CASES, ids=[c["name"] for c in CASES])
+def test_alias_tables_bit_exact(meta):
+    z = load_npz(meta)
+    h = open_graph(meta)
+    J, q = h.alias_nodes()
+    assert np.array_equal(J, z["an_J"])
+    assert q.tobytes() == z["an_q"].tobytes()
+    assert h.alias_edges_size() == meta["n_alias_edge_entries"]
+    off, J, q = h.alias_edges(meta["p"], meta["q"])
+    assert np.array_equal(off, z["ae_off"])
+    assert np.array_equal(J, z["ae_J"])
+    assert q.tobytes() == z["ae_q"].tobytes()
+
+
+@pytest.mark.parametrize("meta", CASES, ids=[c["name"] for c in CASES])
+def test_replay_walks_bit_exact(meta):
+    z = load_npz(meta)
+    h = open_graph(meta)
+    G = n2v.Graph(n2v.EdgeListGraph(h), meta["directed"], meta["p"], meta["q"])
+    G.preprocess_transition_probs()
+    ids = z["node_ids"]
+    walks = G.simulate_walks_replay(meta["walk_length"], ids[z["starts"]], z["uniforms"])
+    assert len(walks) == meta["n_walks"]
+    for i, w in enumerate(walks):
+        assert w == ids[z["walks"][i, :z["lens"][i]]].tolist()
+    # dict-like table access of the reference (node2vec.py:110-111)
+    u = int(ids[0]); v = int(ids[z["col_idx"][0]])
+    J, q = G.alias_edges[(u, v)]
+    assert np.array_equal(J, z["ae_J"][z["ae_off"][0]:z["ae_off"][1]])
+    with pytest.raises(KeyError):
+        G.alias_edges[(u, 10 ** 9)]
+
+
+def test_alias_edges_too_large_is_reported():
+    h = open_graph(case("g333_p025_q4"))
+    with pytest.raises(MemoryError):
+        h.alias_edges(0.25, 4.0, budget_bytes=1000)
+
+
+@pytest.mark.parametrize("name,reps", [("karate_p025_q4", 3000), ("karate_p3_q07", 3000), ("karate_p1_q1", 1500),
+                                       ("wdir_p05_q2", 3000), ("wund_p2_q05", 3000), ("moreno_p025_q4", 40)])
+def test_free_running_chi_square(name, reps):
+    """>= 1e6 GPU steps per case; H0: transitions follow get_alias_edge's law (node2vec.py:61-81)."""
+    meta = case(name)
+    h = open_graph(meta)
+    g = O.load_graph(data_path(meta), meta["delimiter"], meta["weighted"], meta["directed"])
+    L = 40
+    starts = np.tile(np.arange(h.n, dtype=np.int64), reps)
+    walks, lens = h.walks(meta["p"], meta["q"], L, starts, seed=1234)
+    assert (walks[:, 0] == starts).all()
+    chi2, df = chi2_transitions(walks, lens, g, lambda c: O.first_step_law(g, c),
+                                lambda a, b: O.second_order_law(g, a, b, meta["p"], meta["q"]))
+    pval = stats.chi2.sf(chi2, df)
+    assert df > 50
+    assert pval > 1e-4, (chi2, df, pval)
+    # a deliberately wrong law must be rejected by the same statistic (power check)
+    chi2w, dfw = chi2_transitions(walks, lens, g, lambda c: O.first_step_law(g, c),
+                                  lambda a, b: O.second_order_law(g, a, b, meta["p"] * 1.3, meta["q"]))
+    if not (meta["p"] == 1.0 and meta["q"] == 1.0):
+        assert stats.chi2.sf(chi2w, dfw) < 1e-6
+
+
+def test_walks_independent_of_batch_split():
+    meta = case("karate_p025_q4")
+    h = open_graph(meta)
+    starts = np.tile(np.arange(h.n, dtype=np.int64), 20)
+    whole, _ = h.walks(0.25, 4.0, 30, starts, seed=7, walk_id_base=100)
+    a, _ = h.walks(0.25, 4.0, 30, starts[:123], seed=7, walk_id_base=100)
+    b, _ = h.walks(0.25, 4.0, 30, starts[123:], seed=7, walk_id_base=223)
+    assert np.array_equal(whole, np.concatenate([a, b]))
+    other, _ = h.walks(0.25, 4.0, 30, starts, seed=8, walk_id_base=100)
+    assert not np.array_equal(whole, other)
+
+
+def test_dead_ends_and_errors():
+    meta = case("wdir_p05_q2")
+    h = open_graph(meta)
+    c = h.csr()
+    deg = np.diff(c["row_ptr"])
+    sink = int(np.nonzero(deg == 0)[0][0])
+    w, l = h.walks(0.5, 2.0, 10, [sink], seed=1)
+    assert l[0] == 1 and w[0, 0] == sink and (w[0, 1:] == -1).all()
+    with pytest.raises(KeyError):
+        h.walks(0.5, 2.0, 10, [h.n + 5])
+    with pytest.raises(ValueError):
+        h.walks(0.0, 2.0, 10, [0])
+    w, l = h.walks(0.5, 2.0, 10, np.zeros(0, dtype=np.int64))
+    assert w.shape == (0, 10)
+    # empty graph and missing file
+    e = _lib.GraphHandle.from_edges([], [])
+    assert e.n == 0 and e.nnz == 0
+    with pytest.raises(IOError):
+        _lib.GraphHandle.from_file("/nonexistent/file.txt")
+
+
+def test_drop_in_module_and_cli(tmp_path):
+    """The reference's call sequence (node2vec/src/main.py:104-112) on the karate anchor config."""
+    import random
+    from graph_embedding_b200 import main as cli
+    out = str(tmp_path / "walks.txt")
+    args = cli.parse_args(["--input", os.path.join(DATA, "karate.edgelist"), "--delimiter", " ", "--output", out,
+                           "--p", "1", "--q", "1", "--walk-length", "80", "--num-walks", "10"])
+    random.seed(0); np.random.seed(0)
+    walks = cli.main(args)
+    assert len(walks) == 340 and all(len(w) == 80 for w in walks)
+    # iteration structure of simulate_walks: every iteration starts once from every node
+    for it in range(10):
+        assert sorted(w[0] for w in walks[it * 34:(it + 1) * 34]) == list(range(1, 35))
+    edges = set()
+    for line in open(os.path.join(DATA, "karate.edgelist")):
+        a, b = map(int, line.split()); edges.add((a, b)); edges.add((b, a))
+    assert all((a, b) in edges for w in walks for a, b in zip(w, w[1:]))
+    assert cli.read_list(out)[0] == [str(x) for x in walks[0]]
+    random.seed(0); np.random.seed(0)
+    assert cli.main(args) == walks             # the global-RNG seed interface reproduces the run
+    # networkx entry (what the reference passes)
+    nx = pytest.importorskip("networkx")
+    Gx = nx.read_edgelist(os.path.join(DATA, "karate.edgelist"), nodetype=int, create_using=nx.DiGraph())
+    for e in Gx.edges():
+        Gx[e[0]][e[1]]['weight'] = 1
+    Gx = Gx.to_undirected()
+    G = n2v.Graph(Gx, False, 0.25, 4.0)
+    G.preprocess_transition_probs()
+    z = load_npz(case("karate_p025_q4"))
+    J, q = G.alias_nodes[1]
+    assert np.array_equal(J, z["an_J"][:len(J)]) and q.tobytes() == z["an_q"][:len(q)].tobytes()
+    w = G.node2vec_walk(80, 12)
+    assert w[0] == 12 and len(w) == 80
+
+
+def test_rmat_graph_and_walk_validity():
+    h = _lib.GraphHandle.rmat(14, 16 << 14, seed=1)
+    c = h.csr()
+    rp, col = c["row_ptr"], c["col_idx"]
+    n = h.n
+    assert n == 1 << 14 and rp[-1] == h.nnz == len(col)
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    assert (rows != col).all()                                   # no self loops
+    key = rows.astype(np.int64) * n + col
+    assert (np.diff(key) > 0).all()                              # sorted rows, no duplicates
+    assert np.array_equal(np.sort(col.astype(np.int64) * n + rows), key)   # symmetric
+    assert h.max_degree == np.diff(rp).max()
+    starts = h.nonisolated()
+    assert np.array_equal(starts, np.nonzero(np.diff(rp) > 0)[0])
+    h2 = _lib.GraphHandle.rmat(14, 16 << 14, seed=1)
+    assert np.array_equal(h2.csr()["col_idx"], col)              # deterministic in the seed
+    walks, lens = h.walks(0.25, 4.0, 80, starts, seed=3)
+    assert (lens == 80).all()
+    a, b = walks[:, :-1].astype(np.int64), walks[:, 1:].astype(np.int64)
+    assert np.isin((a * n + b).ravel(), key).all()               # every step follows an edge
+    # size-independent property: stationary first-order walks visit vertices ~ degree
+    w1, _ = h.walks(1.0, 1.0, 40, np.tile(starts, 4), seed=5)
+    visits = np.bincount(w1[:, 20:].ravel(), minlength=n).astype(np.float64)
+    deg = np.diff(rp).astype(np.float64)
+    assert np.corrcoef(visits, deg)[0, 1] > 0.98
