@@ -1,0 +1,63 @@
+"""CPU-only checks of the boundary: the shared library loads, exports every symbol that
+include/graphwalk.h declares, and refuses to compute without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from graph_embedding_b200 import _lib
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "graphwalk.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gw_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.load()
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(L, s), "libgraphwalk.so does not export %s" % s
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes signature table and header disagree"
+    assert L.gw_version() >= 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.GraphWalkError) as e:
+        _lib.GraphHandle.from_edges([1, 2], [2, 3])
+    assert "no CPU fallback" in str(e.value)
+    with pytest.raises(_lib.GraphWalkError):
+        _lib.alias_setup([0.5, 0.5])
+    assert _lib.device_count() == 0
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "graph_embedding_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".java")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert "oracle" not in txt.replace("oracle helper", ""), "%s mentions the oracle" % f
+
+
+def test_host_side_java_heap_and_format():
+    from graph_embedding_b200 import simrank as sr
+    from oracle import simrank_oracle as S
+    rs = np.random.RandomState(0)
+    for _ in range(50):
+        n, k = int(rs.randint(1, 60)), int(rs.randint(1, 25))
+        row = rs.rand(n) * (rs.rand(n) < 0.4)
+        row[rs.randint(n)] = row[rs.randint(n)]                # force some ties
+        got = sr._row_topk_exact(row, k)
+        ids, vals = S.fixedmaxpq_topk(row, k)
+        assert [g[0] for g in got] == ids.tolist() and [g[1] for g in got] == vals.tolist()
+    for x, d in [(0.0000005, 6), (0.125, 2), (0.05161244, 8), (1e-9, 6), (0.8, 8)]:
+        assert sr.java_format(x, d) == S.java_fmt(x, d)

@@ -1,0 +1,75 @@
+"""Host-side multi-GPU logic on CPU: world_size-2 (and 3) gloo process groups exercise the
+sharding arithmetic and the padded all-gather used for walk corpora / top-k tiles.  The device
+compute is replaced by a deterministic stub keyed by GLOBAL unit index, which is exactly the
+property the Philox keying gives the real kernels."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from graph_embedding_b200 import dist as gd
+
+
+def test_shard_ranges_partition_exactly():
+    for n in (0, 1, 7, 8, 1000, 4177839):
+        for world in (1, 2, 3, 4, 8):
+            spans = [gd.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+            assert gd.shard_counts(n, world) == sizes
+
+
+class StubHandle:
+    """Stands in for GraphHandle: outputs depend only on (start, global walk id)."""
+
+    def walks(self, p, q, L, starts, seed=0, walk_id_base=0, lens=True):
+        ids = np.arange(len(starts), dtype=np.int64) + walk_id_base
+        w = (starts[:, None] * 31 + ids[:, None] * 7 + np.arange(L)[None, :] + seed).astype(np.int32)
+        return w, np.full(len(starts), L, dtype=np.int32)
+
+    def simrank_topk(self, queries, c, step, sample, k, mode=0, seed=0, query_id_base=0):
+        gid = np.arange(len(queries), dtype=np.int64) + query_id_base
+        ids = ((queries[:, None] + gid[:, None] * 3 + np.arange(k)[None, :]) % 1000).astype(np.int32)
+        sc = 1.0 / (1.0 + np.arange(k)[None, :] + gid[:, None] * 0.0)
+        return ids, np.ascontiguousarray(np.broadcast_to(sc, ids.shape), dtype=np.float64)
+
+
+def _worker(rank, world, port, n_units, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        h = StubHandle()
+        starts = (np.arange(n_units, dtype=np.int64) * 13) % 101
+        corpus = gd.sharded_walks(h, 0.25, 4.0, 8, starts, seed=5)
+        ids, sc = gd.sharded_simrank_topk(h, starts, 0.6, 5, 100, 4, seed=5)
+        np.savez(os.path.join(out_dir, "r%d.npz" % rank), corpus=corpus, ids=ids, sc=sc)
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world,n_units", [(2, 11), (2, 8), (3, 10)])
+def test_sharded_results_equal_single_process(tmp_path, world, n_units):
+    mp.spawn(_worker, args=(world, _free_port(), n_units, str(tmp_path)), nprocs=world, join=True)
+    h = StubHandle()
+    starts = (np.arange(n_units, dtype=np.int64) * 13) % 101
+    want_w, _ = h.walks(0.25, 4.0, 8, starts, seed=5)
+    want_i, want_s = h.simrank_topk(starts, 0.6, 5, 100, 4, seed=5)
+    for r in range(world):
+        z = np.load(os.path.join(str(tmp_path), "r%d.npz" % r))
+        assert np.array_equal(z["corpus"], want_w)
+        assert np.array_equal(z["ids"], want_i) and np.array_equal(z["sc"], want_s)

@@ -53,23 +53,31 @@ def test_exact_simrank_class_defaults(g333, o333):
 
 @pytest.mark.parametrize("step", [1, 3, 5])
 def test_mc_estimator_converges_to_truncated_exact(g333, o333, step):
-    sample = 100000
+    # the reference estimator's own rms error on the exact top-20 is ~1e-3 at SAMPLE = 1e5
+    # (BASELINE.md §2), i.e. the 1e-3 criterion sits AT the noise level there; at SAMPLE = 1e6 the
+    # noise is ~3e-4 and 1e-3 becomes a > 3 sigma bound on any bias of the kernel.
+    sample = 1000000
     exact = S.simrank_exact_matrix(o333, 0.6, step)
     q = np.array([0, 5, 17, 100, 200, 287, 332], dtype=np.int64)
     rows = g333.handle.simrank_rows(q, 0.6, step, sample, seed=11)
-    assert g333.handle.simrank_last_steps() == len(q) * sample * 2 * step - 0 * sample or True
+    assert g333.handle.simrank_last_steps() == len(q) * sample * 2 * step
     for r, v in enumerate(q):
         top = np.argsort(-exact[v])[:20]
         d = rows[r][top] - exact[v][top]
         assert np.sqrt(np.mean(d ** 2)) <= 1e-3, (v, d)
-        assert np.abs(d).max() <= 5e-3
+        assert np.abs(d).max() <= 3e-3
         assert rows[r][v] == 0.0
         # total mass is an unbiased estimate too
         assert abs(rows[r].sum() - exact[v].sum()) <= 0.02 * max(exact[v].sum(), 1e-9) + 1e-3
     # same estimator as the CPU restatement: agreement within the two runs' own noise
-    ref, _, _ = S.single_random_walk_row(o333, 5, sample, step, 0.6, seed_state=S.java_seed(3))
+    ref, _, _ = S.single_random_walk_row(o333, 5, 100000, step, 0.6, seed_state=S.java_seed(3))
     top = np.argsort(-exact[5])[:20]
     assert np.sqrt(np.mean((rows[1][top] - ref[top]) ** 2)) <= 2e-3
+    # and at the reference's SAMPLE the device estimator is as noisy as the CPU one, not more
+    r5 = g333.handle.simrank_rows([5], 0.6, step, 100000, seed=12)[0]
+    e_gpu = np.sqrt(np.mean((r5[top] - exact[5][top]) ** 2))
+    e_cpu = np.sqrt(np.mean((ref[top] - exact[5][top]) ** 2))
+    assert e_gpu <= 2.5 * e_cpu + 2e-4
 
 
 def test_topk_equals_topk_of_dense_rows_and_is_deterministic(g333):
@@ -98,10 +106,11 @@ def _isolated_steps(g, q, sample, L):
 
 
 def test_isolated_query_and_small_k(g333):
-    iso = [v for v in range(333) if g333.degree(v) == 0]
-    assert iso, "fixture has isolated slots"
-    ids, sc = g333.handle.simrank_topk(iso[:1], 0.6, 5, 1000, 20, seed=1)
-    assert (ids == -1).all() and (sc == 0).all()
+    gk = sr.Graph(os.path.join(DATA, "karate.edgelist"), 35, separator=" ")     # slot 0 never occurs
+    assert gk.degree(0) == 0
+    ids, sc = gk.handle.simrank_topk([0, 1], 0.6, 5, 1000, 20, seed=1)
+    assert (ids[0] == -1).all() and (sc[0] == 0).all() and sc[1, 0] > 0
+    assert gk.handle.simrank_last_steps() == 1000 * 10
     ids, sc = g333.handle.simrank_topk([0], 0.6, 5, 20000, 1, seed=1)
     rows = g333.handle.simrank_rows([0], 0.6, 5, 20000, seed=1)
     assert ids[0, 0] == int(np.argmax(rows[0])) and sc[0, 0] == rows[0].max()
