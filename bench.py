@@ -296,6 +296,7 @@ def main():
         g = _lib.GraphHandle.rmat(args.scale, args.edge_factor << args.scale, seed=1)
         starts_np = g.nonisolated()
         extra["graph_build_s"] = round(time.perf_counter() - t0, 3)
+        extra["walk_preprocess_ms"] = round(g.prepare_walks(), 3)      # per-edge common-neighbour counts, one-off
         nw = len(starts_np)
         extra["graph"] = {"nodes": g.n, "non_isolated": nw, "directed_entries": g.nnz, "max_degree": g.max_degree}
         rs = np.random.RandomState(1234 + rank)
@@ -331,7 +332,7 @@ def main():
         alg_bytes = 68.0 * steps_exec + 32.0 * sum_s
         kernel_ms = float(np.mean(per_launch_ms))
         roof = {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "traffic": None, "kernel": "k_walk_free<false,false>", "peak_source": peak_src,
+                "traffic": None, "kernel": "k_walk_cn<true>" if os.environ.get("GW_WALKER") != "rejection" else "k_walk_free<false,false>", "peak_source": peak_src,
                 "bytes_per_unit": alg_bytes / steps_exec, "mean_search_sectors": sum_s / steps_exec,
                 "units_per_launch": steps_exec, "launch_ms": kernel_ms}
         roof["frac"] = roof["achieved"] / peak

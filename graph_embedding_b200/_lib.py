@@ -56,6 +56,7 @@ SIGNATURES = {
                                          ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint64, c_i32p, c_i32p]),
     "gw_node2vec_walks_dev": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_int32, c_vp,
                                              ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint64, c_vp, c_vp, c_vp]),
+    "gw_graph_prepare_walks": (ctypes.c_int, [c_vp, c_f64p]),
     "gw_node2vec_walks_replay": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i64p, ctypes.c_int64, c_f64p,
                                                 ctypes.c_int64, c_i64p, c_i32p, c_i32p]),
     "gw_walks_byte_model_dev": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int, c_i64p,
@@ -239,6 +240,11 @@ class GraphHandle:
         check(load().gw_node2vec_walks_dev(self.h, float(p), float(q), int(walk_length), c_vp(d_starts),
                                            int(n_starts), int(seed), int(walk_id_base), c_vp(d_out),
                                            c_vp(d_lens) if d_lens else None, c_vp(stream) if stream else None))
+
+    def prepare_walks(self):
+        ms = ctypes.c_double()
+        check(load().gw_graph_prepare_walks(self.h, ctypes.byref(ms)))
+        return ms.value
 
     def walks_replay(self, walk_length, starts, uniforms, draw_offset=None):
         starts = as_c(starts, np.int64)

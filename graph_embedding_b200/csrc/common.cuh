@@ -11,6 +11,7 @@
 
 #include "../../include/graphwalk.h"
 
+struct gw_graph;
 namespace gw {
 
 // ---- error plumbing -------------------------------------------------------------------------
@@ -70,6 +71,9 @@ struct DevBuf {  // RAII device allocation
 };
 
 int device_info(int *sm_count, size_t *free_bytes);
+int ensure_common_counts(gw_graph *g, cudaStream_t st);
+int launch_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_starts, int64_t n_starts, uint64_t seed,
+                   uint64_t walk_id_base, int32_t *d_out, int32_t *d_lens, cudaStream_t st);
 
 }  // namespace gw
 
@@ -100,6 +104,11 @@ struct gw_graph {
     double *d_aeq = nullptr;
     int64_t ae_total = 0;
     double ae_p = 0, ae_q = 0;
+    // per-entry {neighbour, |N(u) & N(v)|} pairs for the second-order walker (lazy; undirected,
+    // unweighted, loop-free graphs only)
+    int2 *d_colc = nullptr;
+    int has_self_loops = -1;       // -1 unknown
+    double common_build_ms = 0;
     // SimRank bookkeeping
     int64_t simrank_last_steps = 0;
     void *d_simrank_scratch = nullptr;

@@ -404,7 +404,7 @@ int gw_graph_free(gw_graph *g) {
     cudaSetDevice(g->device);
     cudaFree(g->d_meta); cudaFree(g->d_col); cudaFree(g->d_w); cudaFree(g->d_row_ptr);
     cudaFree(g->d_anJ); cudaFree(g->d_anq); cudaFree(g->d_aeoff); cudaFree(g->d_aeJ); cudaFree(g->d_aeq);
-    cudaFree(g->d_simrank_scratch);
+    cudaFree(g->d_simrank_scratch); cudaFree(g->d_colc);
     delete g;
     return GW_OK;
 }

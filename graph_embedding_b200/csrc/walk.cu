@@ -22,6 +22,8 @@
 // sector of col[] per proposal, S(d_prev) sectors per membership search, 4 bytes stored.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -237,6 +239,15 @@ int gw_node2vec_walks_dev(gw_graph *g, double p, double q, int32_t walk_length, 
     GW_CUDA(cudaSetDevice(g->device));
     const bool weighted = (g->flags & GW_F_WEIGHTED) != 0, directed = (g->flags & GW_F_DIRECTED) != 0;
     if (weighted && !g->d_anJ) GW_TRY(gw_alias_nodes(g, nullptr, nullptr));
+    // production path: exact mixture sampling on common-neighbour counts (walk_cn.cu)
+    const char *force = getenv("GW_WALKER");
+    if (!weighted && !directed && !(p == 1.0 && q == 1.0) && !(force && !strcmp(force, "rejection"))) {
+        int rc = ensure_common_counts(g, (cudaStream_t)stream);
+        if (rc == GW_OK)
+            return launch_walk_cn(g, p, q, walk_length, d_starts, n_starts, seed, walk_id_base, d_out_walks, d_out_lens,
+                                  (cudaStream_t)stream);
+        if (rc != GW_E_STATE) return rc;      // GW_E_STATE = graph has self loops: generic walker below
+    }
     WalkParams P;
     P.meta = g->d_meta; P.col = g->d_col; P.w = g->d_w; P.anJ = g->d_anJ; P.anq = g->d_anq;
     P.starts = d_starts; P.n_walks = n_starts; P.L = walk_length;
@@ -320,6 +331,17 @@ int gw_node2vec_walks_replay(gw_graph *g, int32_t walk_length, const int64_t *st
     if (herr) return fail(GW_E_INVALID, "uniform stream exhausted: %lld draws do not cover the walks", (long long)n_uniforms);
     GW_CUDA(cudaMemcpy(out_walks, dw.p, sizeof(int32_t) * (size_t)n_starts * walk_length, cudaMemcpyDeviceToHost));
     if (out_lens) GW_CUDA(cudaMemcpy(out_lens, dl.p, sizeof(int32_t) * (size_t)n_starts, cudaMemcpyDeviceToHost));
+    return GW_OK;
+}
+
+int gw_graph_prepare_walks(gw_graph *g, double *build_ms) {
+    if (!g) return fail(GW_E_INVALID, "graph is NULL");
+    GW_CUDA(cudaSetDevice(g->device));
+    if ((g->flags & (GW_F_DIRECTED | GW_F_WEIGHTED | GW_F_MULTI)) == 0) {
+        int rc = ensure_common_counts(g, nullptr);
+        if (rc != GW_OK && rc != GW_E_STATE) return rc;
+    }
+    if (build_ms) *build_ms = g->common_build_ms;
     return GW_OK;
 }
 

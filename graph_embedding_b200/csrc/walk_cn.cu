@@ -1,0 +1,275 @@
+// walk_cn.cu — the production second-order walker for undirected, unweighted, loop-free graphs
+// (every BASELINE config): exact mixture sampling driven by per-edge common-neighbour counts.
+//
+// The law of get_alias_edge (node2vec/src/node2vec.py:61-81) over x in N(cur), given prev, is
+//   w(x) = r = 1/p  (x == prev),   b = 1  (x adjacent to prev),   a = 1/q  (otherwise).
+// With c = |N(cur) & N(prev)| known, d = deg(cur), lo = min(a,b), r0 = min(r,lo), it is the mixture
+//   A: mass lo*(d-1) + r0      uniform over N(cur), prev thinned to r0/lo      -> NO adjacency test
+//   R: mass r - r0             prev                                              -> no memory access
+//   C: mass (b-lo)*c           uniform over N(cur) & N(prev)   (only when q > 1)
+//   O: mass (a-lo)*(d-1-c)     uniform over N(cur) \ N(prev) \ {prev}   (only when q < 1)
+// so the binary search over N(prev) that the rejection sampler pays for EVERY proposal is only
+// needed in O, and C is resolved by a WARP-COOPERATIVE sorted-list intersection: the 32 lanes
+// stream the shorter row in coalesced 128-byte lines, each lane binary-searches its element in the
+// other row, a ballot/popc/fns picks the j-th match.  c(prev,cur) is symmetric and rides in the
+// same 8-byte entry as the neighbour id ({nbr, cnt} pairs, `colc`), so reading the next vertex
+// also reads the next step's count: ONE random 32-byte sector per step in component A.
+//
+// This replaces preprocess_transition_probs' sum(deg^2) alias_edges by a sum-over-edges
+// intersection pass (k_common_counts), the only preprocessing that fits HBM at scale.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace gw {
+
+__device__ __forceinline__ bool sorted_contains(const int32_t *__restrict__ row, uint32_t d, int32_t x) {
+    uint32_t lo = 0, hi = d;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        int32_t v = __ldg(row + mid);
+        if (v < x) lo = mid + 1; else hi = mid;
+    }
+    return lo < d && __ldg(row + lo) == x;
+}
+
+// one warp per directed entry e = (u -> v): colc[e] = {v, |N(u) & N(v)|}
+__global__ void __launch_bounds__(256) k_common_counts(const uint2 *__restrict__ meta, const int32_t *__restrict__ col,
+                                                        const int64_t *__restrict__ row_ptr, int64_t n, int64_t nnz,
+                                                        int2 *__restrict__ colc, int *__restrict__ self_loops) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t e = warp; e < nnz; e += nwarps) {
+        int64_t lo = 0, hi = n;                      // source row of entry e
+        while (hi - lo > 1) {
+            int64_t mid = (lo + hi) >> 1;
+            if (row_ptr[mid] <= e) lo = mid; else hi = mid;
+        }
+        const int32_t u = (int32_t)lo, v = __ldg(col + e);
+        if (u == v && lane == 0) atomicExch(self_loops, 1);
+        uint2 ms = __ldg(meta + u), ml = __ldg(meta + v);
+        if (ms.y > ml.y) { uint2 t = ms; ms = ml; ml = t; }
+        int cnt = 0;
+        for (uint32_t i = lane; i < ms.y; i += 32)
+            cnt += sorted_contains(col + ml.x, ml.y, __ldg(col + ms.x + i)) ? 1 : 0;
+        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) colc[e] = make_int2(v, cnt);
+    }
+}
+
+struct CnParams {
+    const uint2 *meta;
+    const int32_t *col;
+    const int2 *colc;
+    const int64_t *starts;
+    int64_t n_walks;
+    int32_t L;
+    float a, b, r;        // 1/q, 1, 1/p
+    float lo, r0;
+    uint2 key;
+    uint64_t walk_id_base;
+    int32_t *out;
+    int32_t *lens;
+};
+
+__device__ __forceinline__ float unit24(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }
+
+template <bool VEC8>
+__global__ void __launch_bounds__(256) k_walk_cn(CnParams P) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool valid = wi < P.n_walks;
+    const uint64_t wid = P.walk_id_base + (uint64_t)wi;
+    int32_t *o = P.out + (valid ? wi : 0) * P.L;
+    int32_t cur = valid ? (int32_t)P.starts[wi] : 0;
+    int32_t prev = -1;
+    uint2 mprev = make_uint2(0, 0);
+    int32_t c = 0;                       // |N(prev) & N(cur)|
+    bool alive = valid;
+    int32_t len = 1;
+    int32_t buf[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) buf[i] = -1;
+    buf[0] = cur;
+    if (!VEC8 && valid) o[0] = cur;
+
+    // positions are produced in blocks of 8 so that the staging buffer is indexed statically
+    for (int32_t base = 0; base < P.L; base += 8) {
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+            const int32_t pos = base + s;
+            if (pos == 0) continue;                   // the start node
+            if (pos >= P.L) break;                    // uniform across the grid
+            int32_t nxt = -1, cn = 0;
+            uint2 m = make_uint2(0, 0);
+            bool want_isect = false;
+            uint32_t jsel = 0;
+            if (alive) {
+                m = __ldg(P.meta + cur);
+                const uint32_t d = m.y;
+                if (d == 0) {
+                    alive = false;
+                } else {
+                    uint4 rnd = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, 0u), P.key);
+                    if (prev < 0) {                                   // first step: alias_nodes law = uniform
+                        int2 e = __ldg(P.colc + m.x + scale_u32(rnd.y, d));
+                        nxt = e.x; cn = e.y;
+                    } else {
+                        const float dm1 = (float)(d - 1);
+                        const float MR = P.r - P.r0;
+                        const float MA = P.lo * dm1 + P.r0;
+                        const float MC = (P.b - P.lo) * (float)c;
+                        const float MO = (P.a - P.lo) * (dm1 - (float)c);
+                        float u = unit24(rnd.x) * (MR + MA + MC + MO);
+                        const bool haveC = MC > 0.0f, haveO = MO > 0.0f;
+                        int comp;                                     // 0 = R, 1 = A, 2 = C, 3 = O
+                        if (d == 1 || u < MR) comp = 0;               // d == 1: prev is the only neighbour
+                        else if (u < MR + MA) comp = 1;
+                        else if (haveC && (u < MR + MA + MC || !haveO)) comp = 2;
+                        else if (haveO) comp = 3;
+                        else comp = 1;
+                        if (comp == 0) {                              // R: return
+                            nxt = prev; cn = c;
+                        } else if (comp == 1) {                       // A: uniform over N(cur), prev thinned
+                            uint32_t rk = rnd.y, ra = rnd.z, att = 0;
+                            for (;;) {
+                                int2 e = __ldg(P.colc + m.x + scale_u32(rk, d));
+                                if (e.x != prev || unit24(ra) * P.lo < P.r0) { nxt = e.x; cn = e.y; break; }
+                                uint4 r2 = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, ++att), P.key);
+                                rk = r2.x; ra = r2.y;
+                            }
+                        } else if (comp == 2) {                       // C: uniform over N(cur) & N(prev)
+                            want_isect = true;
+                            jsel = scale_u32(rnd.y, (uint32_t)c);
+                        } else {                                      // O: uniform over N(cur) \ N(prev) \ {prev}
+                            uint32_t rk = rnd.y, att = 0;
+                            for (;;) {
+                                int2 e = __ldg(P.colc + m.x + scale_u32(rk, d));
+                                if (e.x != prev && !sorted_contains(P.col + mprev.x, mprev.y, e.x)) { nxt = e.x; cn = e.y; break; }
+                                uint4 r2 = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, ++att), P.key);
+                                rk = r2.x;
+                            }
+                        }
+                    }
+                }
+            }
+            // ---- warp-cooperative intersections, one requesting lane at a time ----
+            uint32_t req = __ballot_sync(0xffffffffu, want_isect);
+            while (req) {
+                const int src = __ffs(req) - 1;
+                req &= req - 1;
+                const uint32_t c_off = __shfl_sync(0xffffffffu, m.x, src), c_deg = __shfl_sync(0xffffffffu, m.y, src);
+                const uint32_t p_off = __shfl_sync(0xffffffffu, mprev.x, src), p_deg = __shfl_sync(0xffffffffu, mprev.y, src);
+                const uint32_t j = __shfl_sync(0xffffffffu, jsel, src);
+                const bool scan_cur = c_deg <= p_deg;          // stream the shorter row
+                const uint32_t s_off = scan_cur ? c_off : p_off, s_deg = scan_cur ? c_deg : p_deg;
+                const uint32_t t_off = scan_cur ? p_off : c_off, t_deg = scan_cur ? p_deg : c_deg;
+                uint32_t seen = 0;
+                int32_t xsel = -1;
+                uint32_t isel = 0;
+                for (uint32_t b0 = 0; b0 < s_deg; b0 += 32) {
+                    const uint32_t i = b0 + lane;
+                    int32_t x = (i < s_deg) ? __ldg(P.col + s_off + i) : -1;
+                    bool f = (i < s_deg) && sorted_contains(P.col + t_off, t_deg, x);
+                    uint32_t bal = __ballot_sync(0xffffffffu, f);
+                    uint32_t nb = __popc(bal);
+                    if (seen + nb > j) {
+                        int ln = __fns(bal, 0, (int)(j - seen) + 1);
+                        xsel = __shfl_sync(0xffffffffu, x, ln);
+                        isel = b0 + ln;
+                        break;
+                    }
+                    seen += nb;
+                }
+                if (lane == src) {
+                    if (xsel < 0) {                   // counts and rows disagree: cannot happen; stay exact-ish
+                        nxt = prev; cn = c;
+                    } else {
+                        uint32_t idx = isel;          // index of xsel inside N(cur)
+                        if (!scan_cur) {
+                            uint32_t lo2 = 0, hi2 = c_deg;
+                            while (lo2 < hi2) {
+                                uint32_t mid = (lo2 + hi2) >> 1;
+                                if (__ldg(P.col + c_off + mid) < xsel) lo2 = mid + 1; else hi2 = mid;
+                            }
+                            idx = lo2;
+                        }
+                        nxt = xsel;
+                        cn = __ldg(P.colc + c_off + idx).y;
+                    }
+                }
+            }
+            if (alive) {
+                buf[s] = nxt;
+                if (!VEC8) o[pos] = nxt;
+                prev = cur; mprev = m; cur = nxt; c = cn;
+                len = pos + 1;
+            }
+        }
+        if (VEC8 && valid) {      // one full 32-byte sector per 8 steps, no read-modify-write in L2/DRAM
+            int4 *dst = reinterpret_cast<int4 *>(o + base);
+            dst[0] = make_int4(buf[0], buf[1], buf[2], buf[3]);
+            dst[1] = make_int4(buf[4], buf[5], buf[6], buf[7]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) buf[i] = -1;
+    }
+    if (valid) {
+        if (P.lens) P.lens[wi] = len;
+        if (!VEC8)
+            for (int32_t i = len; i < P.L; i++) o[i] = -1;
+    }
+}
+
+// Builds colc once per graph.  Returns GW_E_STATE (silently usable by the caller as "not
+// applicable") when the graph has self loops.
+int ensure_common_counts(gw_graph *g, cudaStream_t st) {
+    if (g->d_colc) return GW_OK;
+    if (g->has_self_loops == 1) return GW_E_STATE;
+    DevBuf<int2> colc;
+    DevBuf<int> flag;
+    GW_CUDA(colc.alloc((size_t)std::max<int64_t>(g->nnz, 1)));
+    GW_CUDA(flag.alloc(1));
+    GW_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+    cudaEvent_t e0, e1;
+    GW_CUDA(cudaEventCreate(&e0)); GW_CUDA(cudaEventCreate(&e1));
+    GW_CUDA(cudaEventRecord(e0, st));
+    if (g->nnz > 0) {
+        int sms = 148;
+        device_info(&sms, nullptr);
+        k_common_counts<<<sms * 16, 256, 0, st>>>(g->d_meta, g->d_col, g->d_row_ptr, g->n, g->nnz, colc.p, flag.p);
+        GW_LAUNCHED();
+    }
+    GW_CUDA(cudaEventRecord(e1, st));
+    int h = 0;
+    GW_CUDA(cudaMemcpyAsync(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GW_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    g->common_build_ms = ms;
+    g->has_self_loops = h;
+    if (h) return GW_E_STATE;
+    g->d_colc = colc.take();
+    return GW_OK;
+}
+
+int launch_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_starts, int64_t n_starts, uint64_t seed,
+                   uint64_t walk_id_base, int32_t *d_out, int32_t *d_lens, cudaStream_t st) {
+    CnParams P;
+    P.meta = g->d_meta; P.col = g->d_col; P.colc = g->d_colc; P.starts = d_starts; P.n_walks = n_starts; P.L = L;
+    P.a = (float)(1.0 / q); P.b = 1.0f; P.r = (float)(1.0 / p);
+    P.lo = std::min(P.a, P.b); P.r0 = std::min(P.r, P.lo);
+    P.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    P.walk_id_base = walk_id_base; P.out = d_out; P.lens = d_lens;
+    unsigned grid = (unsigned)((n_starts + 255) / 256);
+    bool vec = (L % 8 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 31) == 0);
+    if (vec) k_walk_cn<true><<<grid, 256, 0, st>>>(P);
+    else k_walk_cn<false><<<grid, 256, 0, st>>>(P);
+    GW_LAUNCHED();
+    return GW_OK;
+}
+
+}  // namespace gw

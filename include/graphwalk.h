@@ -125,6 +125,10 @@ int gw_node2vec_walks_dev(gw_graph *g, double p, double q, int32_t walk_length,
                           const int64_t *d_starts, int64_t n_starts, uint64_t seed,
                           uint64_t walk_id_base, int32_t *d_out_walks, int32_t *d_out_lens,
                           void *stream);
+/* Optional: runs the walker's one-off preprocessing now (per-edge common-neighbour counts, the
+ * scalable stand-in for preprocess_transition_probs' alias_edges, node2vec.py:99-108) instead of
+ * lazily inside the first walk call; build_ms (may be NULL) receives its device time. */
+int gw_graph_prepare_walks(gw_graph *g, double *build_ms);
 /* Replay: consumes the reference's own np.random.rand() stream (two fp64 draws per executed
  * step, node2vec.py:156-160) and start order; needs gw_alias_nodes + gw_alias_edges built with
  * the same p,q.  draw_offset[n_starts+1] may be NULL when no walk can hit a dead end

@@ -85,11 +85,24 @@ def test_alias_edges_too_large_is_reported():
         h.alias_edges(0.25, 4.0, budget_bytes=1000)
 
 
-@pytest.mark.parametrize("name,reps", [("karate_p025_q4", 3000), ("karate_p3_q07", 3000), ("karate_p1_q1", 1500),
-                                       ("wdir_p05_q2", 3000), ("wund_p2_q05", 3000), ("moreno_p025_q4", 40)])
-def test_free_running_chi_square(name, reps):
-    """>= 1e6 GPU steps per case; H0: transitions follow get_alias_edge's law (node2vec.py:61-81)."""
-    meta = case(name)
+@pytest.mark.parametrize("walker", ["mixture", "rejection"])
+@pytest.mark.parametrize("name,reps,pq", [("karate_p025_q4", 3000, None), ("karate_p3_q07", 3000, None),
+                                          ("karate_p1_q1", 1500, None), ("karate_p1_q1", 3000, (4.0, 0.5)),
+                                          ("karate_p1_q1", 3000, (0.5, 0.5)), ("karate_p1_q1", 3000, (2.0, 2.0)),
+                                          ("wdir_p05_q2", 3000, None), ("wund_p2_q05", 3000, None),
+                                          ("moreno_p025_q4", 40, None), ("g333_p025_q4", 100, None),
+                                          ("g333_p025_q4", 100, (4.0, 0.5))])
+def test_free_running_chi_square(name, reps, pq, walker, monkeypatch):
+    """>= 1e6 GPU steps per case; H0: transitions follow get_alias_edge's law (node2vec.py:61-81).
+    Both device samplers are tested: the common-neighbour mixture walker (walk_cn.cu, the default
+    on undirected unweighted graphs) and the rejection walker (walk.cu, everything else)."""
+    meta = dict(case(name))
+    if pq is not None:
+        meta["p"], meta["q"] = pq
+    if walker == "rejection":
+        if meta["weighted"] or meta["directed"]:
+            pytest.skip("these graphs always use the rejection walker")
+        monkeypatch.setenv("GW_WALKER", "rejection")
     h = open_graph(meta)
     g = O.load_graph(data_path(meta), meta["delimiter"], meta["weighted"], meta["directed"])
     L = 40
@@ -108,7 +121,10 @@ def test_free_running_chi_square(name, reps):
         assert stats.chi2.sf(chi2w, dfw) < 1e-6
 
 
-def test_walks_independent_of_batch_split():
+@pytest.mark.parametrize("walker", ["mixture", "rejection"])
+def test_walks_independent_of_batch_split(walker, monkeypatch):
+    if walker == "rejection":
+        monkeypatch.setenv("GW_WALKER", "rejection")
     meta = case("karate_p025_q4")
     h = open_graph(meta)
     starts = np.tile(np.arange(h.n, dtype=np.int64), 20)
@@ -192,10 +208,16 @@ def test_rmat_graph_and_walk_validity():
     assert np.array_equal(starts, np.nonzero(np.diff(rp) > 0)[0])
     h2 = _lib.GraphHandle.rmat(14, 16 << 14, seed=1)
     assert np.array_equal(h2.csr()["col_idx"], col)              # deterministic in the seed
-    walks, lens = h.walks(0.25, 4.0, 80, starts, seed=3)
-    assert (lens == 80).all()
-    a, b = walks[:, :-1].astype(np.int64), walks[:, 1:].astype(np.int64)
-    assert np.isin((a * n + b).ravel(), key).all()               # every step follows an edge
+    for L in (80, 37):                                           # vector-store path and scalar path
+        walks, lens = h.walks(0.25, 4.0, L, starts, seed=3)
+        assert (lens == L).all()
+        a, b = walks[:, :-1].astype(np.int64), walks[:, 1:].astype(np.int64)
+        assert np.isin((a * n + b).ravel(), key).all()           # every step follows an edge
+    # common-neighbour counts against a host intersection on sampled edges
+    assert h.prepare_walks() >= 0.0
+    walks_q, _ = h.walks(4.0, 0.5, 80, starts, seed=4)           # q < 1: "others" component
+    a, b = walks_q[:, :-1].astype(np.int64), walks_q[:, 1:].astype(np.int64)
+    assert np.isin((a * n + b).ravel(), key).all()
     # size-independent property: stationary first-order walks visit vertices ~ degree
     w1, _ = h.walks(1.0, 1.0, 40, np.tile(starts, 4), seed=5)
     visits = np.bincount(w1[:, 20:].ravel(), minlength=n).astype(np.float64)
