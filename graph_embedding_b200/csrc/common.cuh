@@ -137,6 +137,38 @@ struct Philox {
         return ctr;
     }
 };
+// ---- L2 residency control (sm_80+ cache-policy operands) -----------------------------------------
+// meta[] (8 B per vertex, 33.5 MB at scale-22) is re-read by every step and fits the 126 MB L2;
+// the adjacency arrays are touched once per random sector.  Loads of the former carry an
+// evict_last policy, loads of the latter evict_first, so the stream of one-shot sectors does not
+// wash the row descriptors out of L2.
+#ifdef __CUDACC__
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint2 ld_u2_policy(const uint2 *ptr, uint64_t pol) {
+    uint2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int2 ld_i2_policy(const int2 *ptr, uint64_t pol) {
+    int2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.s32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int32_t ld_i32_policy(const int32_t *ptr, uint64_t pol) {
+    int32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
+    return v;
+}
+#endif
 // uniform index in [0,d) from 32 random bits (bias <= d / 2^32)
 __host__ __device__ static inline uint32_t scale_u32(uint32_t r, uint32_t d) {
 #ifdef __CUDA_ARCH__

@@ -37,11 +37,12 @@ struct SimrankParams {
     int64_t n;
     int32_t sample;
     int32_t k;
-    double coef[16];                 // C^i (i = 1..STEP)
+    float coef[16];                  // C^i / SAMPLE (i = 1..STEP)
     uint2 key;
     uint64_t query_id_base;
     // per-CTA global scratch
-    uint32_t *gkeys, *glo, *ghi, *olist;
+    uint32_t *gkeys, *olist;
+    unsigned long long *gval;        // tier-2 scores, 32.32 fixed point, one native 64-bit RED per hit
     uint32_t gs_mask;                // tier-2 slots - 1 (power of two)
     uint32_t olist_cap;
     // outputs
@@ -93,49 +94,57 @@ __device__ __forceinline__ void fixed_add(uint32_t *lo, uint32_t *hi, unsigned l
     if (vh) atomicAdd(hi, vh);
 }
 
-__device__ __forceinline__ void acc_add(SrShared &S, const SimrankParams &P, uint32_t *gkeys, uint32_t *glo,
-                                        uint32_t *ghi, uint32_t *olist, uint32_t key, unsigned long long v) {
-    uint32_t h = hash32(key);
-    // tier 1
+// Warp-lock-step insert: all 32 lanes probe together (one slot per pending lane per round) and
+// leave together, so the five inserts of a sample never desynchronise the warp.  Tier 1 (shared
+// memory) is probed a bounded number of rounds; what does not fit goes to tier 2 (global, L2):
+// one CAS that either claims or matches the slot, then a fire-and-forget 64-bit RED.
+__device__ __forceinline__ void acc_add_warp(SrShared &S, const SimrankParams &P, uint32_t *gkeys,
+                                             unsigned long long *gval, uint32_t *olist, bool has, uint32_t key,
+                                             unsigned long long v) {
+    const uint32_t h = hash32(key);
+    bool pending = has;
+    uint32_t slot = h & (SR_HS - 1);
 #pragma unroll 1
     for (int pr = 0; pr < SR_T1_PROBES; pr++) {
-        uint32_t slot = (h + pr) & (SR_HS - 1);
-        uint32_t k0 = ((volatile uint32_t *)S.keys)[slot];
-        if (k0 == SR_EMPTY) {
-            k0 = atomicCAS(&S.keys[slot], SR_EMPTY, key);
+        if (!__any_sync(0xffffffffu, pending)) return;
+        if (pending) {
+            uint32_t k0 = ((volatile uint32_t *)S.keys)[slot];
             if (k0 == SR_EMPTY) {
-                uint32_t o = atomicAdd(&S.ocount, 1u);
-                if (o < P.olist_cap) olist[o] = slot; else atomicExch(P.err, 1);
-                k0 = key;
+                k0 = atomicCAS(&S.keys[slot], SR_EMPTY, key);
+                if (k0 == SR_EMPTY) {
+                    uint32_t o = atomicAdd(&S.ocount, 1u);
+                    if (o < P.olist_cap) olist[o] = slot; else atomicExch(P.err, 1);
+                    k0 = key;
+                }
             }
+            if (k0 == key) { fixed_add(&S.lo[slot], &S.hi[slot], v); pending = false; }
+            else slot = (slot + 1) & (SR_HS - 1);
         }
-        if (k0 == key) { fixed_add(&S.lo[slot], &S.hi[slot], v); return; }
     }
-    // tier 2
-    uint32_t g = (h >> 3) * 0x9E3779B1u;
+    uint32_t g = ((h >> 3) * 0x9E3779B1u) & P.gs_mask;
 #pragma unroll 1
     for (uint32_t pr = 0; pr <= P.gs_mask; pr++) {
-        uint32_t slot = (g + pr) & P.gs_mask;
-        uint32_t k0 = __ldcg(gkeys + slot);   // L2: tier-2 words are updated by atomics, never trust L1
-        if (k0 == SR_EMPTY) {
-            k0 = atomicCAS(&gkeys[slot], SR_EMPTY, key);
+        if (!__any_sync(0xffffffffu, pending)) return;
+        if (pending) {
+            uint32_t k0 = atomicCAS(&gkeys[g], SR_EMPTY, key);
             if (k0 == SR_EMPTY) {
                 uint32_t o = atomicAdd(&S.ocount, 1u);
-                if (o < P.olist_cap) olist[o] = slot | 0x80000000u; else atomicExch(P.err, 1);
+                if (o < P.olist_cap) olist[o] = g | 0x80000000u; else atomicExch(P.err, 1);
                 k0 = key;
             }
+            if (k0 == key) { atomicAdd(&gval[g], v); pending = false; }
+            else g = (g + 1) & P.gs_mask;
         }
-        if (k0 == key) { fixed_add(&glo[slot], &ghi[slot], v); return; }
     }
-    atomicExch(P.err, 2);
+    if (pending) atomicExch(P.err, 2);
 }
 
-__device__ __forceinline__ void read_entry(const SrShared &S, const uint32_t *gkeys, const uint32_t *glo,
-                                           const uint32_t *ghi, uint32_t o, uint32_t &id, unsigned long long &sc) {
-    if (o & 0x80000000u) {
+__device__ __forceinline__ void read_entry(const SrShared &S, const uint32_t *gkeys, const unsigned long long *gval,
+                                           uint32_t o, uint32_t &id, unsigned long long &sc) {
+    if (o & 0x80000000u) {       // tier-2 words are updated by atomics in L2: never trust L1
         uint32_t s = o & 0x7FFFFFFFu;
         id = __ldcg(gkeys + s);
-        sc = ((unsigned long long)__ldcg(ghi + s) << 32) | __ldcg(glo + s);
+        sc = __ldcg(gval + s);
     } else {
         id = S.keys[o];
         sc = ((unsigned long long)S.hi[o] << 32) | S.lo[o];
@@ -150,8 +159,7 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_mc(SimrankParams P) {
     const int tid = threadIdx.x;
     const size_t gs = (size_t)P.gs_mask + 1;
     uint32_t *gkeys = P.gkeys + blockIdx.x * gs;
-    uint32_t *glo = P.glo + blockIdx.x * gs;
-    uint32_t *ghi = P.ghi + blockIdx.x * gs;
+    unsigned long long *gval = P.gval + blockIdx.x * gs;
     uint32_t *olist = P.olist + (size_t)blockIdx.x * P.olist_cap;
 
     for (int i = tid; i < SR_HS; i += SR_BLOCK) { S.keys[i] = SR_EMPTY; S.lo[i] = 0; S.hi[i] = 0; }
@@ -162,16 +170,18 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_mc(SimrankParams P) {
     for (int64_t qi = blockIdx.x; qi < P.nq; qi += gridDim.x) {
         const int32_t v = (int32_t)P.queries[qi];
         const uint64_t qid = P.query_id_base + (uint64_t)qi;
-        const double inv_sample = 1.0;   // division by SAMPLE is applied per contribution below
-        (void)inv_sample;
 
         // ---------------- phase A: walk + first-meet accumulation ----------------
-        for (int32_t s = tid; s < P.sample; s += SR_BLOCK) {
+        // warp-uniform trip count: every lane runs every round, lanes past SAMPLE are masked
+        for (int32_t s0 = tid - (tid & 31); s0 < P.sample; s0 += SR_BLOCK) {
+            const int32_t s = s0 + (tid & 31);
+            const bool live = s < P.sample;
             int32_t path[LEN + 1];
             uint32_t dg[LEN + 1];
             path[0] = v;
             int32_t cur = v;
             int len = 0;
+            bool alive = live;
             uint4 r;
 #pragma unroll
             for (int t = 0; t < LEN; t++) {
@@ -180,32 +190,31 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_mc(SimrankParams P) {
                 uint32_t rw = (t & 3) == 0 ? r.x : (t & 3) == 1 ? r.y : (t & 3) == 2 ? r.z : r.w;
                 path[t + 1] = -1;
                 dg[t] = 0;
-                if (len == t) {                               // still alive
+                if (alive) {
                     uint2 m = __ldg(P.meta + cur);
                     dg[t] = m.y;
                     if (m.y != 0) {                           // Graph.randNeighbor (Graph.java:69-73)
                         cur = __ldg(P.col + m.x + scale_u32(rw, m.y));
                         path[t + 1] = cur;
-                        len = t + 1;
+                        len++;
+                    } else {
+                        alive = false;                        // dead end: path stays truncated (:66)
                     }
                 }
             }
-            dg[LEN] = (len == LEN) ? __ldg(P.meta + cur).y : 0;
+            dg[LEN] = alive ? __ldg(P.meta + cur).y : 0;
             my_steps += (unsigned long long)len;
             // computePathSim (SingleRandomWalk.java:81-92)
 #pragma unroll
             for (int i = 1; i <= STEP; i++) {
-                if (2 * i <= len) {
-                    int32_t target = path[2 * i];
-                    bool ok = target != v;
+                int32_t target = path[2 * i];
+                bool ok = (2 * i <= len) && target != v;
 #pragma unroll
-                    for (int j = 0; j < i; j++) ok &= (path[j] != path[2 * i - j]);   // isFirstMeet :100-106
-                    if (ok) {
-                        double x = P.coef[i] * (double)dg[i] / (double)dg[2 * i] / (double)P.sample;
-                        unsigned long long fx = __double2ull_rn(x * SR_FIX);
-                        acc_add(S, P, gkeys, glo, ghi, olist, (uint32_t)target, fx);
-                    }
-                }
+                for (int j = 0; j < i; j++) ok &= (path[j] != path[2 * i - j]);   // isFirstMeet :100-106
+                // C^i * deg(path[i]) / deg(path[2i]) / SAMPLE, as 32.32 fixed point
+                float x = __fdividef(P.coef[i] * (float)dg[i], (float)max(dg[2 * i], 1u));
+                unsigned long long fx = __float2ull_rn(x * 4294967296.0f);
+                acc_add_warp(S, P, gkeys, gval, olist, ok, (uint32_t)target, fx);
             }
         }
         __syncthreads();
@@ -216,7 +225,7 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_mc(SimrankParams P) {
             double *row = P.out_dense + (size_t)qi * (size_t)P.n;
             for (uint32_t e = tid; e < M; e += SR_BLOCK) {
                 uint32_t id; unsigned long long sc;
-                read_entry(S, gkeys, glo, ghi, olist[e], id, sc);
+                read_entry(S, gkeys, gval, olist[e], id, sc);
                 row[id] = (double)sc * (1.0 / SR_FIX);
             }
         }
@@ -261,7 +270,7 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_mc(SimrankParams P) {
             const uint32_t thr = S.thr_bin;
             for (uint32_t e = tid; e < M; e += SR_BLOCK) {
                 uint32_t id; unsigned long long sc;
-                read_entry(S, gkeys, glo, ghi, olist[e], id, sc);
+                read_entry(S, gkeys, gval, olist[e], id, sc);
                 if (sc != 0 && score_bin(sc) >= thr) {
                     uint32_t c = atomicAdd(&S.ccount, 1u);
                     if (c < SR_CAND) { S.cand_score[c] = sc; S.cand_id[c] = id; }
@@ -290,7 +299,7 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_mc(SimrankParams P) {
                     unsigned long long bs = 0; uint32_t bi = SR_EMPTY;
                     for (uint32_t e = tid; e < M; e += SR_BLOCK) {
                         uint32_t id; unsigned long long sc;
-                        read_entry(S, gkeys, glo, ghi, olist[e], id, sc);
+                        read_entry(S, gkeys, gval, olist[e], id, sc);
                         if (sc == 0) continue;
                         if (!first && !better(last_s, last_i, sc, id)) continue;   // already emitted
                         if (bi == SR_EMPTY || better(sc, id, bs, bi)) { bs = sc; bi = id; }
@@ -325,7 +334,7 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_mc(SimrankParams P) {
         // ---------------- phase C: clear only the touched slots ----------------
         for (uint32_t e = tid; e < M; e += SR_BLOCK) {
             uint32_t o = olist[e];
-            if (o & 0x80000000u) { uint32_t s = o & 0x7FFFFFFFu; gkeys[s] = SR_EMPTY; glo[s] = 0; ghi[s] = 0; }
+            if (o & 0x80000000u) { uint32_t s = o & 0x7FFFFFFFu; gkeys[s] = SR_EMPTY; gval[s] = 0ull; }
             else { S.keys[o] = SR_EMPTY; S.lo[o] = 0; S.hi[o] = 0; }
         }
         if (tid == 0) { S.ocount = 0; S.ccount = 0; }
@@ -406,7 +415,7 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     uint32_t gs = 1024;
     while ((int64_t)gs < 2 * distinct) gs <<= 1;
     uint32_t ocap = (uint32_t)distinct + 1;
-    size_t need = (size_t)grid * ((size_t)gs * 3 + ocap) * sizeof(uint32_t) + 64;
+    size_t need = (size_t)grid * ((size_t)gs * 3 + ocap) * sizeof(uint32_t) + 64 + 8;
     if (g->simrank_scratch_bytes < need) {
         cudaFree(g->d_simrank_scratch);
         g->d_simrank_scratch = nullptr;
@@ -418,17 +427,16 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     SimrankParams P;
     P.steps = (unsigned long long *)base;
     P.err = (int *)(base + 16);
-    P.gkeys = (uint32_t *)(base + 64);
-    P.glo = P.gkeys + (size_t)grid * gs;
-    P.ghi = P.glo + (size_t)grid * gs;
-    P.olist = P.ghi + (size_t)grid * gs;
+    P.gval = (unsigned long long *)(base + 64);                 // 8-byte aligned
+    P.gkeys = (uint32_t *)(P.gval + (size_t)grid * gs);
+    P.olist = P.gkeys + (size_t)grid * gs;
     GW_CUDA(cudaMemsetAsync(base, 0, 64, st));
+    GW_CUDA(cudaMemsetAsync(P.gval, 0, (size_t)grid * gs * sizeof(unsigned long long), st));
     GW_CUDA(cudaMemsetAsync(P.gkeys, 0xFF, (size_t)grid * gs * sizeof(uint32_t), st));
-    GW_CUDA(cudaMemsetAsync(P.glo, 0, (size_t)grid * gs * 2 * sizeof(uint32_t), st));
     P.meta = g->d_meta; P.col = g->d_col; P.queries = d_queries; P.nq = nq; P.n = g->n;
     P.sample = sample; P.k = k;
     for (int i = 0; i < 16; i++) P.coef[i] = 0;
-    for (int i = 1; i <= step; i++) P.coef[i] = pow(c, i);    // cache[i] = Math.pow(C, i) (SingleRandomWalk.java:34-36)
+    for (int i = 1; i <= step; i++) P.coef[i] = (float)(pow(c, i) / (double)sample);   // cache[i] = Math.pow(C, i) (:34-36), / SAMPLE (:89)
     P.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     P.query_id_base = query_id_base;
     P.gs_mask = gs - 1; P.olist_cap = ocap;

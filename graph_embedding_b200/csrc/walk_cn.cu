@@ -79,6 +79,7 @@ __device__ __forceinline__ float unit24(uint32_t r) { return (float)(r >> 8) * (
 template <bool VEC8>
 __global__ void __launch_bounds__(256) k_walk_cn(CnParams P) {
     const int lane = threadIdx.x & 31;
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
     const int64_t wi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const bool valid = wi < P.n_walks;
     const uint64_t wid = P.walk_id_base + (uint64_t)wi;
@@ -107,14 +108,14 @@ __global__ void __launch_bounds__(256) k_walk_cn(CnParams P) {
             bool want_isect = false;
             uint32_t jsel = 0;
             if (alive) {
-                m = __ldg(P.meta + cur);
+                m = ld_u2_policy(P.meta + cur, pol_keep);
                 const uint32_t d = m.y;
                 if (d == 0) {
                     alive = false;
                 } else {
                     uint4 rnd = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, 0u), P.key);
                     if (prev < 0) {                                   // first step: alias_nodes law = uniform
-                        int2 e = __ldg(P.colc + m.x + scale_u32(rnd.y, d));
+                        int2 e = ld_i2_policy(P.colc + m.x + scale_u32(rnd.y, d), pol_stream);
                         nxt = e.x; cn = e.y;
                     } else {
                         const float dm1 = (float)(d - 1);
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(256) k_walk_cn(CnParams P) {
                         } else if (comp == 1) {                       // A: uniform over N(cur), prev thinned
                             uint32_t rk = rnd.y, ra = rnd.z, att = 0;
                             for (;;) {
-                                int2 e = __ldg(P.colc + m.x + scale_u32(rk, d));
+                                int2 e = ld_i2_policy(P.colc + m.x + scale_u32(rk, d), pol_stream);
                                 if (e.x != prev || unit24(ra) * P.lo < P.r0) { nxt = e.x; cn = e.y; break; }
                                 uint4 r2 = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, ++att), P.key);
                                 rk = r2.x; ra = r2.y;
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(256) k_walk_cn(CnParams P) {
                         } else {                                      // O: uniform over N(cur) \ N(prev) \ {prev}
                             uint32_t rk = rnd.y, att = 0;
                             for (;;) {
-                                int2 e = __ldg(P.colc + m.x + scale_u32(rk, d));
+                                int2 e = ld_i2_policy(P.colc + m.x + scale_u32(rk, d), pol_stream);
                                 if (e.x != prev && !sorted_contains(P.col + mprev.x, mprev.y, e.x)) { nxt = e.x; cn = e.y; break; }
                                 uint4 r2 = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, ++att), P.key);
                                 rk = r2.x;

@@ -116,7 +116,7 @@ def test_free_running_chi_square(name, reps, pq, walker, monkeypatch):
     assert pval > 1e-4, (chi2, df, pval)
     # a deliberately wrong law must be rejected by the same statistic (power check)
     chi2w, dfw = chi2_transitions(walks, lens, g, lambda c: O.first_step_law(g, c),
-                                  lambda a, b: O.second_order_law(g, a, b, meta["p"] * 1.3, meta["q"]))
+                                  lambda a, b: O.second_order_law(g, a, b, meta["p"] * 1.5, meta["q"] / 1.5))
     if not (meta["p"] == 1.0 and meta["q"] == 1.0):
         assert stats.chi2.sf(chi2w, dfw) < 1e-6
 
