@@ -399,10 +399,11 @@ def main():
         per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
         units_per_step = nq
         walk_steps = g.simrank_last_steps()
+        extra["slow_path_queries_last_step"] = g.simrank_last_slow_queries()
         kernel_ms = float(np.mean(per_launch_ms))
         alg_bytes = walk_steps * 64.0 + nq * args.topk * 12.0
         roof = {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "traffic": None, "kernel": "k_simrank_mc<%d>" % args.sr_step, "peak_source": peak_src,
+                "traffic": None, "kernel": "k_simrank_log<%d>" % args.sr_step, "peak_source": peak_src,
                 "bytes_per_unit": alg_bytes / nq, "units_per_launch": nq, "launch_ms": kernel_ms,
                 "walk_steps_per_s": walk_steps / (kernel_ms * 1e-3)}
         roof["frac"] = roof["achieved"] / peak
@@ -414,7 +415,9 @@ def main():
             n_e2e = max(1, min(args.steps, 3))
             t0 = time.perf_counter()
             for i in range(n_e2e):
+                t1 = time.perf_counter()
                 g.simrank_topk(hq, 0.6, args.sr_step, args.sample, args.topk, seed=9 + i)
+                sys.stderr.write("e2e call %d: %.2f ms\n" % (i, (time.perf_counter() - t1) * 1e3))
             dt = time.perf_counter() - t0
             tt = torch.tensor([dt], device=dev)
             if world > 1:

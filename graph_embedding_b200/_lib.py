@@ -70,6 +70,7 @@ SIGNATURES = {
     "gw_simrank_rows": (ctypes.c_int, [c_vp, c_i64p, ctypes.c_int64, ctypes.c_double, ctypes.c_int32,
                                        ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64, c_f64p]),
     "gw_simrank_last_steps": (ctypes.c_int, [c_vp, c_i64p]),
+    "gw_simrank_last_slow_queries": (ctypes.c_int, [c_vp, c_i64p]),
     "gw_simrank_exact": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_int32, c_i64p, ctypes.c_int64, c_f64p]),
 }
 
@@ -292,6 +293,11 @@ class GraphHandle:
     def simrank_last_steps(self):
         s = ctypes.c_int64()
         check(load().gw_simrank_last_steps(self.h, ctypes.byref(s)))
+        return s.value
+
+    def simrank_last_slow_queries(self):
+        s = ctypes.c_int64()
+        check(load().gw_simrank_last_slow_queries(self.h, ctypes.byref(s)))
         return s.value
 
     def simrank_exact(self, c, iters, rows=None):

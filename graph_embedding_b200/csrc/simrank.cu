@@ -16,6 +16,8 @@
 // by counting among the candidates; a k-round arg-max fallback covers mass ties.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -51,6 +53,12 @@ struct SimrankParams {
     double *out_dense;               // optional dense rows [nq * n]
     unsigned long long *steps;
     int *err;
+    // log kernel: per-CTA append log; slow-path hand-over list
+    uint2 *log;
+    uint32_t log_cap;
+    int32_t *qlist_out;              // written by the log kernel
+    const int32_t *qlist;            // read by the hash kernel (NULL = all queries)
+    uint32_t *qcount;
 };
 
 struct SrShared {
@@ -151,6 +159,94 @@ __device__ __forceinline__ void read_entry(const SrShared &S, const uint32_t *gk
     }
 }
 
+// One sample: 2*STEP uniform steps from v with the whole path in registers, then the first-meet
+// contributions (SingleRandomWalk.java:53-92).  emit(ok, target, fx) is called STEP times by
+// every lane (lock-step), fx = C^i * deg(path[i]) / deg(path[2i]) / SAMPLE in 32.32 fixed point.
+template <int STEP, typename Emit>
+__device__ __forceinline__ int walk_sample(const SimrankParams &P, int32_t v, uint64_t qid, int32_t s, bool live,
+                                           Emit &&emit) {
+    constexpr int LEN = 2 * STEP;
+    int32_t path[LEN + 1];
+    uint32_t dg[LEN + 1];
+    path[0] = v;
+    int32_t cur = v;
+    int len = 0;
+    bool alive = live;
+    uint4 r;
+#pragma unroll
+    for (int t = 0; t < LEN; t++) {
+        if ((t & 3) == 0)
+            r = Philox::gen(make_uint4((uint32_t)qid, (uint32_t)(qid >> 32), (uint32_t)s, (uint32_t)(t >> 2)), P.key);
+        uint32_t rw = (t & 3) == 0 ? r.x : (t & 3) == 1 ? r.y : (t & 3) == 2 ? r.z : r.w;
+        path[t + 1] = -1;
+        dg[t] = 0;
+        if (alive) {
+            uint2 m = __ldg(P.meta + cur);
+            dg[t] = m.y;
+            if (m.y != 0) {                           // Graph.randNeighbor (Graph.java:69-73)
+                cur = __ldg(P.col + m.x + scale_u32(rw, m.y));
+                path[t + 1] = cur;
+                len++;
+            } else {
+                alive = false;                        // dead end: path stays truncated (:66)
+            }
+        }
+    }
+    dg[LEN] = alive ? __ldg(P.meta + cur).y : 0;
+    // computePathSim (SingleRandomWalk.java:81-92)
+#pragma unroll
+    for (int i = 1; i <= STEP; i++) {
+        int32_t target = path[2 * i];
+        bool ok = (2 * i <= len) && target != v;
+#pragma unroll
+        for (int j = 0; j < i; j++) ok &= (path[j] != path[2 * i - j]);   // isFirstMeet :100-106
+        float x = __fdividef(P.coef[i] * (float)dg[i], (float)max(dg[2 * i], 1u));
+        emit(ok, (uint32_t)target, x);
+    }
+    return len;
+}
+
+__device__ __forceinline__ unsigned long long to_fixed(float x) { return __float2ull_rn(x * 4294967296.0f); }
+
+// largest bin b with count(bins >= b) >= K (0 when fewer than K entries); warp 0 only
+__device__ __forceinline__ uint32_t threshold_bin(const uint32_t *hist, uint32_t K, int lane) {
+    uint32_t base = (31 - lane) * 32;      // lane 0 owns the top 32 bins
+    uint32_t cnt = 0;
+    for (int j = 0; j < 32; j++) cnt += hist[base + j];
+    uint32_t incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    uint32_t before = incl - cnt;          // entries in bins above this lane's range
+    uint32_t found = 0xFFFFFFFFu;
+    if (before < K && incl >= K) {
+        uint32_t c = before;
+        for (int j = 31; j >= 0; j--) { c += hist[base + j]; if (c >= K) { found = base + j; break; } }
+    }
+    uint32_t any = __ballot_sync(0xffffffffu, found != 0xFFFFFFFFu);
+    uint32_t thr = 0;
+    if (any) thr = __shfl_sync(0xffffffffu, found, __ffs(any) - 1);
+    return thr;
+}
+
+// rank-by-counting among the candidates in shared memory; writes the K best (score desc, id asc)
+template <typename Sh>
+__device__ __forceinline__ void emit_ranked(const Sh &S, uint32_t C, uint32_t K, int32_t *oid, double *osc, int tid) {
+    for (uint32_t a = tid; a < C; a += SR_BLOCK) {
+        unsigned long long sa = S.cand_score[a];
+        uint32_t ia = S.cand_id[a];
+        uint32_t rank = 0;
+        for (uint32_t b = 0; b < C; b++) rank += better(S.cand_score[b], S.cand_id[b], sa, ia) ? 1u : 0u;
+        if (rank < K) { oid[rank] = (int32_t)ia; osc[rank] = (double)sa * (1.0 / SR_FIX); }
+    }
+    for (uint32_t r = C + tid; r < K; r += SR_BLOCK) { oid[r] = -1; osc[r] = 0.0; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// hash kernel: two-tier hash accumulator (tier 2 in global memory).  Exact for every input;
+// used for dense rows and as the slow path of the log kernel below.
+// ---------------------------------------------------------------------------------------------
 template <int STEP>
 __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_mc(SimrankParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -167,7 +263,10 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_mc(SimrankParams P) {
     __syncthreads();
     unsigned long long my_steps = 0;
 
-    for (int64_t qi = blockIdx.x; qi < P.nq; qi += gridDim.x) {
+    // slow-path launch: the queries the log kernel could not finish exactly (P.qlist / P.qcount)
+    const int64_t n_work = P.qlist ? (int64_t)*P.qcount : P.nq;
+    for (int64_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        const int64_t qi = P.qlist ? (int64_t)P.qlist[wi] : wi;
         const int32_t v = (int32_t)P.queries[qi];
         const uint64_t qid = P.query_id_base + (uint64_t)qi;
 
@@ -175,47 +274,10 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_mc(SimrankParams P) {
         // warp-uniform trip count: every lane runs every round, lanes past SAMPLE are masked
         for (int32_t s0 = tid - (tid & 31); s0 < P.sample; s0 += SR_BLOCK) {
             const int32_t s = s0 + (tid & 31);
-            const bool live = s < P.sample;
-            int32_t path[LEN + 1];
-            uint32_t dg[LEN + 1];
-            path[0] = v;
-            int32_t cur = v;
-            int len = 0;
-            bool alive = live;
-            uint4 r;
-#pragma unroll
-            for (int t = 0; t < LEN; t++) {
-                if ((t & 3) == 0)
-                    r = Philox::gen(make_uint4((uint32_t)qid, (uint32_t)(qid >> 32), (uint32_t)s, (uint32_t)(t >> 2)), P.key);
-                uint32_t rw = (t & 3) == 0 ? r.x : (t & 3) == 1 ? r.y : (t & 3) == 2 ? r.z : r.w;
-                path[t + 1] = -1;
-                dg[t] = 0;
-                if (alive) {
-                    uint2 m = __ldg(P.meta + cur);
-                    dg[t] = m.y;
-                    if (m.y != 0) {                           // Graph.randNeighbor (Graph.java:69-73)
-                        cur = __ldg(P.col + m.x + scale_u32(rw, m.y));
-                        path[t + 1] = cur;
-                        len++;
-                    } else {
-                        alive = false;                        // dead end: path stays truncated (:66)
-                    }
-                }
-            }
-            dg[LEN] = alive ? __ldg(P.meta + cur).y : 0;
-            my_steps += (unsigned long long)len;
-            // computePathSim (SingleRandomWalk.java:81-92)
-#pragma unroll
-            for (int i = 1; i <= STEP; i++) {
-                int32_t target = path[2 * i];
-                bool ok = (2 * i <= len) && target != v;
-#pragma unroll
-                for (int j = 0; j < i; j++) ok &= (path[j] != path[2 * i - j]);   // isFirstMeet :100-106
-                // C^i * deg(path[i]) / deg(path[2i]) / SAMPLE, as 32.32 fixed point
-                float x = __fdividef(P.coef[i] * (float)dg[i], (float)max(dg[2 * i], 1u));
-                unsigned long long fx = __float2ull_rn(x * 4294967296.0f);
-                acc_add_warp(S, P, gkeys, gval, olist, ok, (uint32_t)target, fx);
-            }
+            my_steps += (unsigned long long)walk_sample<STEP>(P, v, qid, s, s < P.sample,
+                [&](bool ok, uint32_t target, float x) {
+                    acc_add_warp(S, P, gkeys, gval, olist, ok, target, to_fixed(x));
+                });
         }
         __syncthreads();
         const uint32_t M = min(S.ocount, P.olist_cap);
@@ -246,24 +308,8 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_mc(SimrankParams P) {
                 }
             }
             __syncthreads();
-            if (tid < 32) {   // suffix scan: largest bin b with count(bins >= b) >= K, else 0
-                uint32_t base = (31 - tid) * 32;   // lane 0 owns the top 32 bins
-                uint32_t cnt = 0;
-                for (int j = 0; j < 32; j++) cnt += S.hist[base + j];
-                uint32_t incl = cnt;
-                for (int o = 1; o < 32; o <<= 1) {
-                    uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (tid >= o) incl += t;
-                }
-                uint32_t before = incl - cnt;      // entries in bins above this lane's range
-                uint32_t found = 0xFFFFFFFFu;
-                if (before < K && incl >= K) {
-                    uint32_t c = before;
-                    for (int j = 31; j >= 0; j--) { c += S.hist[base + j]; if (c >= K) { found = base + j; break; } }
-                }
-                uint32_t any = __ballot_sync(0xffffffffu, found != 0xFFFFFFFFu);
-                uint32_t thr = 0;
-                if (any) thr = __shfl_sync(0xffffffffu, found, __ffs(any) - 1);
+            if (tid < 32) {
+                uint32_t thr = threshold_bin(S.hist, K, tid);
                 if (tid == 0) { S.thr_bin = thr; S.ccount = 0; }
             }
             __syncthreads();
@@ -281,15 +327,7 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_mc(SimrankParams P) {
             int32_t *oid = P.out_ids + (size_t)qi * K;
             double *osc = P.out_scores + (size_t)qi * K;
             if (C <= SR_CAND) {
-                // rank by counting among the candidates
-                for (uint32_t a = tid; a < C; a += SR_BLOCK) {
-                    unsigned long long sa = S.cand_score[a];
-                    uint32_t ia = S.cand_id[a];
-                    uint32_t rank = 0;
-                    for (uint32_t b = 0; b < C; b++) rank += better(S.cand_score[b], S.cand_id[b], sa, ia) ? 1u : 0u;
-                    if (rank < K) { oid[rank] = (int32_t)ia; osc[rank] = (double)sa * (1.0 / SR_FIX); }
-                }
-                for (uint32_t r = C + tid; r < K; r += SR_BLOCK) { oid[r] = -1; osc[r] = 0.0; }
+                emit_ranked(S, C, K, oid, osc, tid);
             } else {
                 // fallback (mass ties at the threshold): K rounds of block arg-max over all entries
                 unsigned long long last_s = ~0ull;
@@ -341,7 +379,188 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_mc(SimrankParams P) {
         __syncthreads();
     }
     for (int o = 16; o; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
-    if ((tid & 31) == 0 && my_steps) atomicAdd(P.steps, my_steps);
+    if ((tid & 31) == 0 && my_steps && !P.qlist) atomicAdd(P.steps, my_steps);   // handed-over queries were counted by the log kernel
+}
+
+// ---------------------------------------------------------------------------------------------
+// log kernel (production): no global atomics.  A contribution goes to the shared-memory table when
+// its key fits there; otherwise it is APPENDED to a per-CTA log (coalesced 8-byte stores) and its
+// value is added to a small shared-memory sketch cell (an upper bound of every logged key's total).
+// Top-k: threshold bin from the table (a lower bound of the k-th score), table candidates, then ONE
+// streaming pass over the log that keeps only entries whose sketch cell could reach the threshold
+// (almost none: logged keys are the single-hit tail) and sums those exactly in a tiny third table.
+// A query that cannot be finished exactly this way (threshold at the single-hit level, sketch
+// saturation, too many survivors) is flagged and re-run by the hash kernel; both kernels add the
+// same 32.32 fixed-point integers, so the result does not depend on which one produced it.
+// ---------------------------------------------------------------------------------------------
+constexpr int SR_SKETCH = 8192;
+constexpr int SR_T3 = 512;
+constexpr int SR_LCAND = 256;
+
+struct SrLogShared {
+    uint32_t keys[SR_HS];
+    uint32_t lo[SR_HS];                  // 0.32 fixed point; a carry out of it sends the query to the hash kernel
+    uint32_t sketch[SR_SKETCH];          // 2^-24 units, rounded up
+    uint32_t hist[SR_BINS];              // threshold histogram, then tier-3 keys (SR_T3 <= SR_BINS)
+    uint32_t t3lo[SR_T3], t3hi[SR_T3];
+    unsigned long long cand_score[SR_LCAND];
+    uint32_t cand_id[SR_LCAND];
+    uint32_t lcount;                     // log entries
+    uint32_t ccount;                     // candidates
+    uint32_t t3count;
+    uint32_t thr_bin;
+    uint32_t slow;                       // this query needs the hash kernel
+};
+
+template <int STEP>
+__global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_log(SimrankParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SrLogShared &S = *reinterpret_cast<SrLogShared *>(smem_raw);
+    const int tid = threadIdx.x, lane = threadIdx.x & 31;
+    uint2 *log = P.log + (size_t)blockIdx.x * P.log_cap;
+    uint32_t *t3keys = S.hist;
+
+    for (int i = tid; i < SR_HS; i += SR_BLOCK) { S.keys[i] = SR_EMPTY; S.lo[i] = 0; }
+    for (int i = tid; i < SR_SKETCH; i += SR_BLOCK) S.sketch[i] = 0;
+    if (tid == 0) { S.lcount = 0; S.ccount = 0; S.t3count = 0; S.slow = 0; }
+    __syncthreads();
+    unsigned long long my_steps = 0;
+
+    for (int64_t qi = blockIdx.x; qi < P.nq; qi += gridDim.x) {
+        const int32_t v = (int32_t)P.queries[qi];
+        const uint64_t qid = P.query_id_base + (uint64_t)qi;
+
+        // ---------------- phase A ----------------
+        for (int32_t s0 = tid - lane; s0 < P.sample; s0 += SR_BLOCK) {
+            const int32_t s = s0 + lane;
+            my_steps += (unsigned long long)walk_sample<STEP>(P, v, qid, s, s < P.sample,
+                [&](bool ok, uint32_t key, float x) {
+                    const unsigned long long fx = to_fixed(x);
+                    const uint32_t h = hash32(key);
+                    bool pending = ok;
+                    uint32_t slot = h & (SR_HS - 1);
+#pragma unroll 1
+                    for (int pr = 0; pr < SR_T1_PROBES; pr++) {
+                        if (!__any_sync(0xffffffffu, pending)) break;
+                        if (pending) {
+                            uint32_t k0 = ((volatile uint32_t *)S.keys)[slot];
+                            if (k0 == SR_EMPTY) {
+                                k0 = atomicCAS(&S.keys[slot], SR_EMPTY, key);
+                                if (k0 == SR_EMPTY) k0 = key;
+                            }
+                            if (k0 == key) {
+                                uint32_t vl = (uint32_t)fx, old = atomicAdd(&S.lo[slot], vl);
+                                if (old + vl < old || (fx >> 32)) S.slow = 1;       // score >= 1.0: exact path
+                                pending = false;
+                            }
+                            else slot = (slot + 1) & (SR_HS - 1);
+                        }
+                    }
+                    // overflow: append to the log, one shared-memory atomic per warp
+                    uint32_t mask = __ballot_sync(0xffffffffu, pending);
+                    if (mask) {
+                        uint32_t basep = 0;
+                        if (lane == __ffs(mask) - 1) basep = atomicAdd(&S.lcount, (uint32_t)__popc(mask));
+                        basep = __shfl_sync(0xffffffffu, basep, __ffs(mask) - 1);
+                        if (pending) {
+                            uint32_t pos = basep + __popc(mask & ((1u << lane) - 1));
+                            if (pos < P.log_cap) log[pos] = make_uint2(key, __float_as_uint(x));
+                            uint32_t add = (uint32_t)min((fx >> 8) + 1ull, 0xFFFFFFFFull);
+                            uint32_t old = atomicAdd(&S.sketch[(h >> 13) & (SR_SKETCH - 1)], add);
+                            if (old + add < old) S.slow = 1;          // sketch cell wrapped
+                        }
+                    }
+                });
+        }
+        __syncthreads();
+        const uint32_t Lc = min(S.lcount, P.log_cap);
+        if (S.lcount > P.log_cap && tid == 0) S.slow = 1;
+
+        // ---------------- phase B: top-k ----------------
+        const uint32_t K = (uint32_t)P.k;
+        for (int i = tid; i < SR_BINS; i += SR_BLOCK) S.hist[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < SR_HS; i += SR_BLOCK) {
+            if (S.keys[i] != SR_EMPTY) {
+                unsigned long long sc = S.lo[i];
+                if (sc) atomicAdd(&S.hist[score_bin(sc)], 1u);
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {
+            uint32_t thr = threshold_bin(S.hist, K, tid);
+            if (tid == 0) { S.thr_bin = thr; S.ccount = 0; S.t3count = 0; }
+        }
+        __syncthreads();
+        const uint32_t thr = S.thr_bin;
+        if (thr == 0 && Lc > 0 && tid == 0) S.slow = 1;   // no usable lower bound: every logged key could matter
+        for (int i = tid; i < SR_T3; i += SR_BLOCK) { t3keys[i] = SR_EMPTY; S.t3lo[i] = 0; S.t3hi[i] = 0; }
+        for (int i = tid; i < SR_HS; i += SR_BLOCK) {     // table candidates
+            uint32_t id = S.keys[i];
+            if (id != SR_EMPTY) {
+                unsigned long long sc = S.lo[i];
+                if (sc != 0 && score_bin(sc) >= thr) {
+                    uint32_t c = atomicAdd(&S.ccount, 1u);
+                    if (c < SR_LCAND) { S.cand_score[c] = sc; S.cand_id[c] = id; }
+                }
+            }
+        }
+        __syncthreads();
+        if (thr != 0) {
+            // one streaming pass over the log; survivors are summed exactly in tier 3
+            for (uint32_t e = tid; e < Lc; e += SR_BLOCK) {
+                uint2 en = log[e];
+                uint32_t cell = S.sketch[(hash32(en.x) >> 13) & (SR_SKETCH - 1)];
+                if (score_bin((unsigned long long)cell << 8) >= thr) {
+                    uint32_t slot = (hash32(en.x) >> 4) & (SR_T3 - 1);
+                    bool done = false;
+                    for (int pr = 0; pr < SR_T3 && !done; pr++) {
+                        uint32_t k0 = ((volatile uint32_t *)t3keys)[slot];
+                        if (k0 == SR_EMPTY) {
+                            k0 = atomicCAS(&t3keys[slot], SR_EMPTY, en.x);
+                            if (k0 == SR_EMPTY) {
+                                if (atomicAdd(&S.t3count, 1u) >= (uint32_t)(SR_T3 * 3 / 4)) S.slow = 1;
+                                k0 = en.x;
+                            }
+                        }
+                        if (k0 == en.x) { fixed_add(&S.t3lo[slot], &S.t3hi[slot], to_fixed(__uint_as_float(en.y))); done = true; }
+                        else slot = (slot + 1) & (SR_T3 - 1);
+                    }
+                    if (!done) S.slow = 1;
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < SR_T3; i += SR_BLOCK) {
+                uint32_t id = t3keys[i];
+                if (id != SR_EMPTY) {
+                    unsigned long long sc = ((unsigned long long)S.t3hi[i] << 32) | S.t3lo[i];
+                    if (sc != 0 && score_bin(sc) >= thr) {
+                        uint32_t c = atomicAdd(&S.ccount, 1u);
+                        if (c < SR_LCAND) { S.cand_score[c] = sc; S.cand_id[c] = id; }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t C = S.ccount;
+        int32_t *oid = P.out_ids + (size_t)qi * K;
+        double *osc = P.out_scores + (size_t)qi * K;
+        const bool slow = S.slow != 0 || C > SR_LCAND;
+        if (!slow) {
+            emit_ranked(S, C, K, oid, osc, tid);
+        } else if (tid == 0) {
+            uint32_t w = atomicAdd(P.qcount, 1u);     // hand the query to the hash kernel
+            P.qlist_out[w] = (int32_t)qi;
+        }
+        __syncthreads();
+        // ---------------- phase C: reset ----------------
+        for (int i = tid; i < SR_HS; i += SR_BLOCK) { S.keys[i] = SR_EMPTY; S.lo[i] = 0; }
+        for (int i = tid; i < SR_SKETCH; i += SR_BLOCK) S.sketch[i] = 0;
+        if (tid == 0) { S.lcount = 0; S.ccount = 0; S.t3count = 0; S.slow = 0; }
+        __syncthreads();
+    }
+    for (int o = 16; o; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
+    if (lane == 0 && my_steps) atomicAdd(P.steps, my_steps);
 }
 
 // ---------------- exact SimRank (SimRank.java:36-77) as dense sweeps ----------------
@@ -387,10 +606,19 @@ __global__ void k_gather_rows_zero_diag(const double *__restrict__ A, int64_t n,
 using namespace gw;
 
 template <int STEP>
-static int launch_mc(const SimrankParams &P, int grid, cudaStream_t st) {
+static int launch_kernels(const SimrankParams &P, int grid, bool use_log, cudaStream_t st) {
+    if (use_log) {
+        size_t smem = sizeof(SrLogShared);
+        GW_CUDA(cudaFuncSetAttribute(k_simrank_log<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_simrank_log<STEP><<<grid, SR_BLOCK, smem, st>>>(P);
+        GW_LAUNCHED();
+    }
+    // hash kernel: everything (dense rows / forced) or only the queries the log kernel handed over
+    SimrankParams Q = P;
+    if (use_log) Q.qlist = P.qlist_out;
     size_t smem = sizeof(SrShared);
     GW_CUDA(cudaFuncSetAttribute(k_simrank_mc<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_simrank_mc<STEP><<<grid, SR_BLOCK, smem, st>>>(P);
+    k_simrank_mc<STEP><<<grid, SR_BLOCK, smem, st>>>(Q);
     GW_LAUNCHED();
     return GW_OK;
 }
@@ -403,19 +631,30 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     if (step < 1 || step > 10) return fail(GW_E_INVALID, "step must be in 1..10");
     if (sample < 1) return fail(GW_E_INVALID, "sample must be positive");
     if (!(c > 0) || !(c < 1)) return fail(GW_E_INVALID, "decay c must be in (0,1)");
-    if (d_out_ids && (k < 1 || k > SR_CAND / 2)) return fail(GW_E_INVALID, "k must be in 1..%d", SR_CAND / 2);
+    if (d_out_ids && (k < 1 || k > SR_LCAND / 2)) return fail(GW_E_INVALID, "k must be in 1..%d", SR_LCAND / 2);
     if (mode != GW_SIMRANK_MC) return fail(GW_E_INVALID, "estimator mode %d is not built yet (GW_SIMRANK_MC only)", mode);
     if (nq == 0) return GW_OK;
+    if (nq >= ((int64_t)1 << 31)) return fail(GW_E_TOO_LARGE, "more than 2^31-1 queries in one call");
     GW_CUDA(cudaSetDevice(g->device));
     int sms = 0;
     GW_TRY(device_info(&sms, nullptr));
-    int grid = (int)std::min<int64_t>(nq, (int64_t)sms * 2);
-    // tier-2 table: >= 2x the distinct targets one query can produce
-    int64_t distinct = std::min<int64_t>((int64_t)sample * step, g->n);
+    const int grid = (int)std::min<int64_t>(nq, (int64_t)sms * 2);
+    const char *force = getenv("GW_SIMRANK");
+    const bool use_log = d_out_ids && !d_out_dense && !(force && !strcmp(force, "hash"));
+    // hash-kernel tier-2 table: >= 2x the distinct targets one query can produce
+    const int64_t distinct = std::min<int64_t>((int64_t)sample * step, g->n);
     uint32_t gs = 1024;
     while ((int64_t)gs < 2 * distinct) gs <<= 1;
-    uint32_t ocap = (uint32_t)distinct + 1;
-    size_t need = (size_t)grid * ((size_t)gs * 3 + ocap) * sizeof(uint32_t) + 64 + 8;
+    const uint32_t ocap = (uint32_t)distinct + 1;
+    const uint32_t log_cap = (uint32_t)std::min<int64_t>((int64_t)sample * step, (int64_t)0x7FFFFFFF);
+    // layout: [64 B header][gval u64 grid*gs][gkeys u32 grid*gs][olist u32 grid*ocap][log uint2 grid*log_cap][qlist i32 nq]
+    size_t off_gval = 64;
+    size_t off_gkeys = off_gval + (size_t)grid * gs * 8;
+    size_t off_olist = off_gkeys + (size_t)grid * gs * 4;
+    size_t off_log = (off_olist + (size_t)grid * ocap * 4 + 15) & ~(size_t)15;
+    size_t off_qlist = off_log + (size_t)grid * log_cap * 8;
+    size_t need = off_qlist + (size_t)nq * 4 + 16;
+    const bool fresh = g->simrank_scratch_bytes < need || g->simrank_layout != (uint64_t)gs * 1000003u + (uint64_t)grid;
     if (g->simrank_scratch_bytes < need) {
         cudaFree(g->d_simrank_scratch);
         g->d_simrank_scratch = nullptr;
@@ -427,12 +666,21 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     SimrankParams P;
     P.steps = (unsigned long long *)base;
     P.err = (int *)(base + 16);
-    P.gval = (unsigned long long *)(base + 64);                 // 8-byte aligned
-    P.gkeys = (uint32_t *)(P.gval + (size_t)grid * gs);
-    P.olist = P.gkeys + (size_t)grid * gs;
+    P.qcount = (uint32_t *)(base + 32);
+    P.gval = (unsigned long long *)(base + off_gval);
+    P.gkeys = (uint32_t *)(base + off_gkeys);
+    P.olist = (uint32_t *)(base + off_olist);
+    P.log = (uint2 *)(base + off_log);
+    P.qlist_out = (int32_t *)(base + off_qlist);
+    P.qlist = nullptr;
+    P.log_cap = log_cap;
     GW_CUDA(cudaMemsetAsync(base, 0, 64, st));
-    GW_CUDA(cudaMemsetAsync(P.gval, 0, (size_t)grid * gs * sizeof(unsigned long long), st));
-    GW_CUDA(cudaMemsetAsync(P.gkeys, 0xFF, (size_t)grid * gs * sizeof(uint32_t), st));
+    if (fresh || g->simrank_dirty) {   // the hash kernel leaves its tables clean; only (re)initialise when the layout changes
+        GW_CUDA(cudaMemsetAsync(P.gval, 0, (size_t)grid * gs * 8, st));
+        GW_CUDA(cudaMemsetAsync(P.gkeys, 0xFF, (size_t)grid * gs * 4, st));
+        g->simrank_layout = (uint64_t)gs * 1000003u + (uint64_t)grid;
+        g->simrank_dirty = 0;
+    }
     P.meta = g->d_meta; P.col = g->d_col; P.queries = d_queries; P.nq = nq; P.n = g->n;
     P.sample = sample; P.k = k;
     for (int i = 0; i < 16; i++) P.coef[i] = 0;
@@ -442,25 +690,28 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     P.gs_mask = gs - 1; P.olist_cap = ocap;
     P.out_ids = d_out_ids; P.out_scores = d_out_scores; P.out_dense = d_out_dense;
     switch (step) {
-        case 1: GW_TRY(launch_mc<1>(P, grid, st)); break;
-        case 2: GW_TRY(launch_mc<2>(P, grid, st)); break;
-        case 3: GW_TRY(launch_mc<3>(P, grid, st)); break;
-        case 4: GW_TRY(launch_mc<4>(P, grid, st)); break;
-        case 5: GW_TRY(launch_mc<5>(P, grid, st)); break;
-        case 6: GW_TRY(launch_mc<6>(P, grid, st)); break;
-        case 7: GW_TRY(launch_mc<7>(P, grid, st)); break;
-        case 8: GW_TRY(launch_mc<8>(P, grid, st)); break;
-        case 9: GW_TRY(launch_mc<9>(P, grid, st)); break;
-        default: GW_TRY(launch_mc<10>(P, grid, st)); break;
+        case 1: GW_TRY(launch_kernels<1>(P, grid, use_log, st)); break;
+        case 2: GW_TRY(launch_kernels<2>(P, grid, use_log, st)); break;
+        case 3: GW_TRY(launch_kernels<3>(P, grid, use_log, st)); break;
+        case 4: GW_TRY(launch_kernels<4>(P, grid, use_log, st)); break;
+        case 5: GW_TRY(launch_kernels<5>(P, grid, use_log, st)); break;
+        case 6: GW_TRY(launch_kernels<6>(P, grid, use_log, st)); break;
+        case 7: GW_TRY(launch_kernels<7>(P, grid, use_log, st)); break;
+        case 8: GW_TRY(launch_kernels<8>(P, grid, use_log, st)); break;
+        case 9: GW_TRY(launch_kernels<9>(P, grid, use_log, st)); break;
+        default: GW_TRY(launch_kernels<10>(P, grid, use_log, st)); break;
     }
     if (sync_steps) {
         unsigned long long hs = 0;
         int herr = 0;
+        uint32_t nslow = 0;
         GW_CUDA(cudaMemcpyAsync(&hs, P.steps, sizeof(hs), cudaMemcpyDeviceToHost, st));
         GW_CUDA(cudaMemcpyAsync(&herr, P.err, sizeof(herr), cudaMemcpyDeviceToHost, st));
+        GW_CUDA(cudaMemcpyAsync(&nslow, P.qcount, sizeof(nslow), cudaMemcpyDeviceToHost, st));
         GW_CUDA(cudaStreamSynchronize(st));
         g->simrank_last_steps = (int64_t)hs;
-        if (herr) return fail(GW_E_STATE, "SimRank accumulator overflow (code %d)", herr);
+        g->simrank_last_slow = (int64_t)nslow;
+        if (herr) { g->simrank_dirty = 1; return fail(GW_E_STATE, "SimRank accumulator overflow (code %d)", herr); }
     }
     return GW_OK;
 }
@@ -528,6 +779,19 @@ int gw_simrank_last_steps(const gw_graph *g, int64_t *steps) {
         return GW_OK;
     }
     *steps = g->simrank_last_steps;
+    return GW_OK;
+}
+
+int gw_simrank_last_slow_queries(const gw_graph *g, int64_t *count) {
+    if (!g || !count) return fail(GW_E_INVALID, "bad arguments");
+    *count = g->simrank_last_slow;
+    if (g->d_simrank_scratch) {
+        uint32_t h = 0;
+        GW_CUDA(cudaSetDevice(g->device));
+        GW_CUDA(cudaDeviceSynchronize());
+        GW_CUDA(cudaMemcpy(&h, (unsigned char *)g->d_simrank_scratch + 32, sizeof(h), cudaMemcpyDeviceToHost));
+        *count = (int64_t)h;
+    }
     return GW_OK;
 }
 

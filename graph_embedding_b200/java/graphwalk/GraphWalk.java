@@ -1,0 +1,138 @@
+package graphwalk;
+
+import java.lang.foreign.Arena;
+import java.lang.foreign.FunctionDescriptor;
+import java.lang.foreign.Linker;
+import java.lang.foreign.MemorySegment;
+import java.lang.foreign.SymbolLookup;
+import java.lang.foreign.ValueLayout;
+import java.lang.invoke.MethodHandle;
+
+/**
+ * Panama FFM (JDK 22+) binding of libgraphwalk.so — include/graphwalk.h.
+ *
+ * NOT COMPILED IN THIS REPOSITORY'S IMAGE: the build container has no JDK (SURVEY.md §8c), so
+ * this file is the binding a maintainer adds to DeepSim/TopSimAll/src; the same C ABI is
+ * exercised end to end from Python (graph_embedding_b200/_lib.py, tests/).  Every downcall
+ * mirrors one prototype of graphwalk.h; status != 0 raises with gw_last_error().
+ */
+public final class GraphWalk {
+    public static final int MODE_SIMPLE = 0, MODE_MULTI = 1;
+    public static final int SIMRANK_MC = 0, SIMRANK_HYBRID = 1;
+
+    private static final Linker LINKER = Linker.nativeLinker();
+    private static final SymbolLookup LIB =
+        SymbolLookup.libraryLookup(System.getProperty("graphwalk.lib", "libgraphwalk.so"), Arena.global());
+
+    private static MethodHandle h(String name, FunctionDescriptor fd) {
+        return LINKER.downcallHandle(LIB.find(name).orElseThrow(() -> new UnsatisfiedLinkError(name)), fd);
+    }
+
+    private static final ValueLayout.OfInt I = ValueLayout.JAVA_INT;
+    private static final ValueLayout.OfLong J = ValueLayout.JAVA_LONG;
+    private static final ValueLayout.OfDouble D = ValueLayout.JAVA_DOUBLE;
+    private static final ValueLayout P = ValueLayout.ADDRESS;
+
+    private static final MethodHandle LAST_ERROR = h("gw_last_error", FunctionDescriptor.of(P));
+    private static final MethodHandle SET_DEVICE = h("gw_set_device", FunctionDescriptor.of(I, I));
+    private static final MethodHandle LOAD = h("gw_graph_load_edgelist",
+        FunctionDescriptor.of(I, P, P, I, I, I, J, P));
+    private static final MethodHandle FREE = h("gw_graph_free", FunctionDescriptor.of(I, P));
+    private static final MethodHandle INFO = h("gw_graph_info", FunctionDescriptor.of(I, P, P, P, P, P, P));
+    private static final MethodHandle CSR = h("gw_graph_csr", FunctionDescriptor.of(I, P, P, P, P, P, P));
+    private static final MethodHandle TOPK = h("gw_simrank_topk",
+        FunctionDescriptor.of(I, P, P, J, D, I, I, I, I, J, J, P, P));
+    private static final MethodHandle ROWS = h("gw_simrank_rows",
+        FunctionDescriptor.of(I, P, P, J, D, I, I, I, J, J, P));
+    private static final MethodHandle EXACT = h("gw_simrank_exact",
+        FunctionDescriptor.of(I, P, D, I, P, J, P));
+
+    private GraphWalk() {}
+
+    static void check(int rc) {
+        if (rc == 0) return;
+        try {
+            MemorySegment msg = ((MemorySegment) LAST_ERROR.invokeExact()).reinterpret(1024);
+            throw new IllegalStateException("libgraphwalk error " + rc + ": " + msg.getString(0));
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable t) {
+            throw new IllegalStateException("libgraphwalk error " + rc, t);
+        }
+    }
+
+    public static void setDevice(int device) {
+        try { check((int) SET_DEVICE.invokeExact(device)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
+    }
+
+    /** gw_graph_load_edgelist(path, delimiter, weighted=0, directed=0, MULTI, V) -> handle */
+    public static MemorySegment loadMultigraph(String path, String separator, long vCount) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment out = a.allocate(P);
+            check((int) LOAD.invokeExact(a.allocateFrom(path), a.allocateFrom(separator), 0, 0, MODE_MULTI, vCount, out));
+            return out.get(P, 0);
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
+    }
+
+    public static void free(MemorySegment g) {
+        try { check((int) FREE.invokeExact(g)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
+    }
+
+    /** returns {n_nodes, n_entries} */
+    public static long[] info(MemorySegment g) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment n = a.allocate(J), nnz = a.allocate(J);
+            check((int) INFO.invokeExact(g, n, nnz, MemorySegment.NULL, MemorySegment.NULL, MemorySegment.NULL));
+            return new long[] {n.get(J, 0), nnz.get(J, 0)};
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
+    }
+
+    /** CSR copy: rowPtr[n+1], col[nnz] (file order inside each row, duplicates kept). */
+    public static void csr(MemorySegment g, long[] rowPtr, int[] col) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment rp = a.allocate(J, rowPtr.length), c = a.allocate(I, Math.max(col.length, 1));
+            check((int) CSR.invokeExact(g, rp, c, MemorySegment.NULL, MemorySegment.NULL, MemorySegment.NULL));
+            MemorySegment.copy(rp, J, 0, rowPtr, 0, rowPtr.length);
+            MemorySegment.copy(c, I, 0, col, 0, col.length);
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
+    }
+
+    /** gw_simrank_topk: ids[nq*k], scores[nq*k] (score descending, id ascending, -1 padding). */
+    public static void simrankTopk(MemorySegment g, long[] queries, double c, int step, int sample, int k, int mode,
+                                   long seed, int[] outIds, double[] outScores) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment q = a.allocateFrom(J, queries);
+            MemorySegment ids = a.allocate(I, (long) queries.length * k), sc = a.allocate(D, (long) queries.length * k);
+            check((int) TOPK.invokeExact(g, q, (long) queries.length, c, step, sample, k, mode, seed, 0L, ids, sc));
+            MemorySegment.copy(ids, I, 0, outIds, 0, outIds.length);
+            MemorySegment.copy(sc, D, 0, outScores, 0, outScores.length);
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
+    }
+
+    /** gw_simrank_rows: dense rows sim[query][*] (the reference's double[][] result). */
+    public static double[][] simrankRows(MemorySegment g, long[] queries, int vCount, double c, int step, int sample,
+                                         int mode, long seed) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment q = a.allocateFrom(J, queries);
+            MemorySegment out = a.allocate(D, (long) queries.length * vCount);
+            check((int) ROWS.invokeExact(g, q, (long) queries.length, c, step, sample, mode, seed, 0L, out));
+            double[][] sim = new double[queries.length][vCount];
+            for (int r = 0; r < queries.length; r++) MemorySegment.copy(out, D, (long) r * vCount * 8, sim[r], 0, vCount);
+            return sim;
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
+    }
+
+    /** gw_simrank_exact: all rows of the exact iteration (SimRank.java). */
+    public static double[][] simrankExact(MemorySegment g, int vCount, double c, int iters) {
+        try (Arena a = Arena.ofConfined()) {
+            long[] rows = new long[vCount];
+            for (int i = 0; i < vCount; i++) rows[i] = i;
+            MemorySegment r = a.allocateFrom(J, rows);
+            MemorySegment out = a.allocate(D, (long) vCount * vCount);
+            check((int) EXACT.invokeExact(g, c, iters, r, (long) vCount, out));
+            double[][] sim = new double[vCount][vCount];
+            for (int i = 0; i < vCount; i++) MemorySegment.copy(out, D, (long) i * vCount * 8, sim[i], 0, vCount);
+            return sim;
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
+    }
+}

@@ -160,6 +160,9 @@ int gw_simrank_rows(gw_graph *g, const int64_t *queries, int64_t nq, double c, i
                     double *out_dense);
 /* Total walk steps executed by the last gw_simrank_* call on this graph. */
 int gw_simrank_last_steps(const gw_graph *g, int64_t *steps);
+/* Queries of the last gw_simrank_topk* call that were finished by the exact hash-table kernel
+ * instead of the log-structured fast path (threshold at the single-hit level; results identical). */
+int gw_simrank_last_slow_queries(const gw_graph *g, int64_t *count);
 /* Exact SimRank (simrank/SimRank.java:36-77): iters Jacobi sweeps of S <- c P S P^T, diag = 1,
  * diag zeroed at the end; returns the requested rows out[nrows*n].  O(n^2) device memory. */
 int gw_simrank_exact(gw_graph *g, double c, int32_t iters, const int64_t *rows, int64_t nrows,

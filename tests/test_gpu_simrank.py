@@ -131,6 +131,22 @@ def test_tiny_sample_many_ties_uses_fallback(g333):
         assert ids[v, :len(order)].tolist() == order.tolist()
 
 
+def test_log_kernel_and_hash_kernel_agree_bit_for_bit(monkeypatch):
+    """The production (log-structured) kernel and the exact hash kernel add the same 32.32
+    fixed-point integers: identical ids and scores on a graph large enough to overflow tier 1."""
+    h = _lib.GraphHandle.barabasi_albert(200000, 8, seed=3)
+    q = np.random.RandomState(5).choice(h.n, 96, replace=False).astype(np.int64)
+    q[:4] = [0, 1, 2, 3]                                         # hubs: many single-hit ties
+    a_ids, a_sc = h.simrank_topk(q, 0.6, 5, 10000, 20, seed=21)
+    slow = h.simrank_last_slow_queries()
+    steps = h.simrank_last_steps()
+    monkeypatch.setenv("GW_SIMRANK", "hash")
+    b_ids, b_sc = h.simrank_topk(q, 0.6, 5, 10000, 20, seed=21)
+    assert np.array_equal(a_ids, b_ids) and a_sc.tobytes() == b_sc.tobytes()
+    assert steps == h.simrank_last_steps() == 96 * 10000 * 10
+    assert 0 < slow < 48                                         # hubs go through the hash kernel, the bulk does not
+
+
 def test_java_shaped_driver_and_wire_format(tmp_path, g333, o333):
     """benchmark/Test_u_u_SingleRandomWalk_Sample.java:41-59 line by line."""
     gold = sr.SimRank(g333, step=5).compute().getResult()
