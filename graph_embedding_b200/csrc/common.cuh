@@ -109,6 +109,12 @@ struct gw_graph {
     int2 *d_colc = nullptr;
     int has_self_loops = -1;       // -1 unknown
     double common_build_ms = 0;
+    // host-API workspace (grow-only): staging buffers and two streams for the chunked pipeline
+    void *ws_starts = nullptr; size_t ws_starts_bytes = 0;
+    void *ws_out[2] = {nullptr, nullptr}; size_t ws_out_bytes = 0;
+    void *ws_lens[2] = {nullptr, nullptr}; size_t ws_lens_bytes = 0;
+    cudaStream_t ws_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ws_event = nullptr;
     // SimRank bookkeeping
     int64_t simrank_last_steps = 0;
     void *d_simrank_scratch = nullptr;

@@ -274,6 +274,19 @@ int gw_node2vec_walks_dev(gw_graph *g, double p, double q, int32_t walk_length, 
     return GW_OK;
 }
 
+// Host-buffer entry point: chunked, double-buffered pipeline.  The corpus is 4*L bytes per walk
+// (1.3 GB per pass at R-MAT scale-22), so the call is PCIe-bound; chunk c+1 is walked on one
+// stream while chunk c is copied to the caller's buffer on the other.  Staging buffers and streams
+// live in the graph handle (grow-only), so repeated calls do not touch cudaMalloc.
+static int grow(void **p, size_t *have, size_t need) {
+    if (*have >= need) return GW_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *have = 0;
+    GW_CUDA(cudaMalloc(p, need));
+    *have = need;
+    return GW_OK;
+}
+
 int gw_node2vec_walks(gw_graph *g, double p, double q, int32_t walk_length, const int64_t *starts, int64_t n_starts,
                       uint64_t seed, uint64_t walk_id_base, int32_t *out_walks, int32_t *out_lens) {
     if (!g) return fail(GW_E_INVALID, "graph is NULL");
@@ -282,15 +295,42 @@ int gw_node2vec_walks(gw_graph *g, double p, double q, int32_t walk_length, cons
     GW_TRY(check_starts_host(g, starts, n_starts));
     if (n_starts == 0) return GW_OK;
     GW_CUDA(cudaSetDevice(g->device));
-    DevBuf<int64_t> ds;
-    DevBuf<int32_t> dw, dl;
-    GW_CUDA(ds.alloc((size_t)n_starts));
-    GW_CUDA(dw.alloc((size_t)n_starts * walk_length));
-    if (out_lens) GW_CUDA(dl.alloc((size_t)n_starts));
-    GW_CUDA(cudaMemcpy(ds.p, starts, sizeof(int64_t) * (size_t)n_starts, cudaMemcpyHostToDevice));
-    GW_TRY(gw_node2vec_walks_dev(g, p, q, walk_length, ds.p, n_starts, seed, walk_id_base, dw.p, dl.p, nullptr));
-    GW_CUDA(cudaMemcpy(out_walks, dw.p, sizeof(int32_t) * (size_t)n_starts * walk_length, cudaMemcpyDeviceToHost));
-    if (out_lens) GW_CUDA(cudaMemcpy(out_lens, dl.p, sizeof(int32_t) * (size_t)n_starts, cudaMemcpyDeviceToHost));
+    const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(n_starts, ((int64_t)48 << 20) / ((int64_t)walk_length * 4)));
+    for (int i = 0; i < 2; i++)
+        if (!g->ws_stream[i]) GW_CUDA(cudaStreamCreateWithFlags(&g->ws_stream[i], cudaStreamNonBlocking));
+    if (!g->ws_event) GW_CUDA(cudaEventCreateWithFlags(&g->ws_event, cudaEventDisableTiming));
+    GW_TRY(grow(&g->ws_starts, &g->ws_starts_bytes, sizeof(int64_t) * (size_t)n_starts));
+    {
+        size_t ob = g->ws_out_bytes, lb = g->ws_lens_bytes;
+        for (int i = 0; i < 2; i++) {
+            size_t o2 = ob, l2 = lb;
+            GW_TRY(grow(&g->ws_out[i], &o2, sizeof(int32_t) * (size_t)chunk * walk_length));
+            GW_TRY(grow(&g->ws_lens[i], &l2, sizeof(int32_t) * (size_t)chunk));
+            if (i == 1) { g->ws_out_bytes = o2; g->ws_lens_bytes = l2; }
+        }
+    }
+    // one-off preprocessing (common-neighbour counts) must not race with the two streams
+    if (!(g->flags & (GW_F_DIRECTED | GW_F_WEIGHTED)) && !(p == 1.0 && q == 1.0)) {
+        int rc = ensure_common_counts(g, g->ws_stream[0]);
+        if (rc != GW_OK && rc != GW_E_STATE) return rc;
+    }
+    if ((g->flags & GW_F_WEIGHTED) && !g->d_anJ) GW_TRY(gw_alias_nodes(g, nullptr, nullptr));
+    GW_CUDA(cudaMemcpyAsync(g->ws_starts, starts, sizeof(int64_t) * (size_t)n_starts, cudaMemcpyHostToDevice, g->ws_stream[0]));
+    GW_CUDA(cudaEventRecord(g->ws_event, g->ws_stream[0]));
+    GW_CUDA(cudaStreamWaitEvent(g->ws_stream[1], g->ws_event, 0));
+    int c = 0;
+    for (int64_t lo = 0; lo < n_starts; lo += chunk, c ^= 1) {
+        const int64_t cnt = std::min(chunk, n_starts - lo);
+        cudaStream_t st = g->ws_stream[c];
+        GW_TRY(gw_node2vec_walks_dev(g, p, q, walk_length, (const int64_t *)g->ws_starts + lo, cnt, seed, walk_id_base + (uint64_t)lo,
+                                     (int32_t *)g->ws_out[c], out_lens ? (int32_t *)g->ws_lens[c] : nullptr, st));
+        GW_CUDA(cudaMemcpyAsync(out_walks + lo * walk_length, g->ws_out[c], sizeof(int32_t) * (size_t)cnt * walk_length,
+                                cudaMemcpyDeviceToHost, st));
+        if (out_lens)
+            GW_CUDA(cudaMemcpyAsync(out_lens + lo, g->ws_lens[c], sizeof(int32_t) * (size_t)cnt, cudaMemcpyDeviceToHost, st));
+    }
+    GW_CUDA(cudaStreamSynchronize(g->ws_stream[0]));
+    GW_CUDA(cudaStreamSynchronize(g->ws_stream[1]));
     return GW_OK;
 }
 
