@@ -105,6 +105,15 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read+write per launch of the named kernel from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(kernel)
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -329,12 +338,36 @@ def main():
         per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
         steps_exec, sum_s = g.byte_model_dev(d_out.data_ptr(), nw, L, second_order, stream=stream)
         units_per_step = steps_exec
-        alg_bytes = 68.0 * steps_exec + 32.0 * sum_s
         kernel_ms = float(np.mean(per_launch_ms))
+        survey_bytes = 68.0 * steps_exec + 32.0 * sum_s          # 68 + 32*S(d_prev) per step
+        mixture = os.environ.get("GW_WALKER") != "rejection"
+        if mixture:
+            # the production walker needs fewer bytes than the binary-search model: count ITS algorithmic
+            # HBM bytes by re-running the last timed step's walks in counting mode
+            last = args.warmup + args.steps - 1
+            tr = g.walk_traffic_dev(args.p, args.q, L, perms[last].data_ptr(), nw, seed=42,
+                                    walk_id_base=(rank * 1000 + last) * nw, stream=stream)
+            assert tr["steps"] == steps_exec, (tr, steps_exec)
+            alg_bytes = float(tr["bytes"])
+            kname = "k_walk_cn<true,false>"
+        else:
+            alg_bytes, tr = survey_bytes, None
+            kname = "k_walk_free<false,false>"
         roof = {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "traffic": None, "kernel": "k_walk_cn<true>" if os.environ.get("GW_WALKER") != "rejection" else "k_walk_free<false,false>", "peak_source": peak_src,
-                "bytes_per_unit": alg_bytes / steps_exec, "mean_search_sectors": sum_s / steps_exec,
-                "units_per_launch": steps_exec, "launch_ms": kernel_ms}
+                "traffic": ncu_traffic(kname), "kernel": kname, "peak_source": peak_src,
+                "bytes_per_unit": alg_bytes / steps_exec, "units_per_launch": steps_exec, "launch_ms": kernel_ms,
+                "model": ("mixture walker: 36 B/step (one {nbr,cnt,offset,degree} sector + 4 B store; 4 B for a return step) "
+                          "+ both rows per intersection + 32*S(d_prev) per adjacency search" if mixture else
+                          "SURVEY 8(d): 68 + 32*S(d_prev) per step"),
+                "survey_model": {"bytes_per_unit": survey_bytes / steps_exec, "mean_search_sectors": sum_s / steps_exec,
+                                 "achieved": survey_bytes / (kernel_ms * 1e-3) / 1e9,
+                                 "frac": survey_bytes / (kernel_ms * 1e-3) / 1e9 / peak,
+                                 "roofline_steps_per_s": peak * 1e9 / (survey_bytes / steps_exec),
+                                 "note": "byte model of a binary-search walker; > 1 means the sampler needs fewer "
+                                         "bytes than that model, not that work is skipped"}}
+        if tr:
+            roof["intersections_per_step"] = tr["intersections"] / steps_exec
+            roof["extra_proposals_per_step"] = tr["extra_proposals"] / steps_exec
         roof["frac"] = roof["achieved"] / peak
 
         # ---- e2e: host buffers through the blocking C-ABI entry point ----
@@ -403,7 +436,7 @@ def main():
         kernel_ms = float(np.mean(per_launch_ms))
         alg_bytes = walk_steps * 64.0 + nq * args.topk * 12.0
         roof = {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "traffic": None, "kernel": "k_simrank_log<%d>" % args.sr_step, "peak_source": peak_src,
+                "traffic": ncu_traffic("k_simrank_log<%d>" % args.sr_step), "kernel": "k_simrank_log<%d>" % args.sr_step, "peak_source": peak_src,
                 "bytes_per_unit": alg_bytes / nq, "units_per_launch": nq, "launch_ms": kernel_ms,
                 "walk_steps_per_s": walk_steps / (kernel_ms * 1e-3)}
         roof["frac"] = roof["achieved"] / peak

@@ -59,6 +59,8 @@ SIGNATURES = {
     "gw_graph_prepare_walks": (ctypes.c_int, [c_vp, c_f64p]),
     "gw_node2vec_walks_replay": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i64p, ctypes.c_int64, c_f64p,
                                                 ctypes.c_int64, c_i64p, c_i32p, c_i32p]),
+    "gw_node2vec_walk_traffic_dev": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_int32, c_vp,
+                                                    ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint64, c_i64p, c_vp]),
     "gw_walks_byte_model_dev": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int, c_i64p,
                                                c_i64p, c_vp]),
     "gw_simrank_topk": (ctypes.c_int, [c_vp, c_i64p, ctypes.c_int64, ctypes.c_double, ctypes.c_int32,
@@ -258,6 +260,13 @@ class GraphHandle:
                                               ptr(do, ctypes.c_int64), ptr(out, ctypes.c_int32),
                                               ptr(ln, ctypes.c_int32)))
         return out, ln
+
+    def walk_traffic_dev(self, p, q, walk_length, d_starts, n_starts, seed=0, walk_id_base=0, stream=0):
+        out = np.zeros(4, dtype=np.int64)
+        check(load().gw_node2vec_walk_traffic_dev(self.h, float(p), float(q), int(walk_length), c_vp(d_starts),
+                                                  int(n_starts), int(seed), int(walk_id_base),
+                                                  ptr(out, ctypes.c_int64), c_vp(stream) if stream else None))
+        return dict(steps=int(out[0]), bytes=int(out[1]), intersections=int(out[2]), extra_proposals=int(out[3]))
 
     def byte_model_dev(self, d_walks, n_walks, walk_length, second_order, stream=0):
         steps, sec = ctypes.c_int64(), ctypes.c_int64()

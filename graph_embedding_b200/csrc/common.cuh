@@ -71,7 +71,9 @@ struct DevBuf {  // RAII device allocation
 };
 
 int device_info(int *sm_count, size_t *free_bytes);
-int ensure_common_counts(gw_graph *g, cudaStream_t st);
+int ensure_common_counts(gw_graph *g, cudaStream_t st, bool need_counts = true);
+int count_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_starts, int64_t n_starts, uint64_t seed,
+                  uint64_t walk_id_base, unsigned long long *d_stats, cudaStream_t st);
 int launch_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_starts, int64_t n_starts, uint64_t seed,
                    uint64_t walk_id_base, int32_t *d_out, int32_t *d_lens, cudaStream_t st);
 
@@ -106,7 +108,8 @@ struct gw_graph {
     double ae_p = 0, ae_q = 0;
     // per-entry {neighbour, |N(u) & N(v)|} pairs for the second-order walker (lazy; undirected,
     // unweighted, loop-free graphs only)
-    int2 *d_colc = nullptr;
+    int4 *d_nbr4 = nullptr;        // {neighbour, |N(u) & N(v)|, offset(v), degree(v)} per directed entry
+    int nbr4_has_counts = 0;
     int has_self_loops = -1;       // -1 unknown
     double common_build_ms = 0;
     // host-API workspace (grow-only): staging buffers and two streams for the chunked pipeline
@@ -170,6 +173,12 @@ __device__ __forceinline__ uint2 ld_u2_policy(const uint2 *ptr, uint64_t pol) {
 __device__ __forceinline__ int2 ld_i2_policy(const int2 *ptr, uint64_t pol) {
     int2 v;
     asm volatile("ld.global.nc.L2::cache_hint.v2.s32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int4 ld_i4_policy(const int4 *ptr, uint64_t pol) {
+    int4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr), "l"(pol));
     return v;
 }
 __device__ __forceinline__ int32_t ld_i32_policy(const int32_t *ptr, uint64_t pol) {

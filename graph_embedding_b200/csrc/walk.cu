@@ -241,8 +241,8 @@ int gw_node2vec_walks_dev(gw_graph *g, double p, double q, int32_t walk_length, 
     if (weighted && !g->d_anJ) GW_TRY(gw_alias_nodes(g, nullptr, nullptr));
     // production path: exact mixture sampling on common-neighbour counts (walk_cn.cu)
     const char *force = getenv("GW_WALKER");
-    if (!weighted && !directed && !(p == 1.0 && q == 1.0) && !(force && !strcmp(force, "rejection"))) {
-        int rc = ensure_common_counts(g, (cudaStream_t)stream);
+    if (!weighted && !directed && !(force && !strcmp(force, "rejection"))) {
+        int rc = ensure_common_counts(g, (cudaStream_t)stream, !(p == 1.0 && q == 1.0));   // first order: no counts
         if (rc == GW_OK)
             return launch_walk_cn(g, p, q, walk_length, d_starts, n_starts, seed, walk_id_base, d_out_walks, d_out_lens,
                                   (cudaStream_t)stream);
@@ -310,8 +310,8 @@ int gw_node2vec_walks(gw_graph *g, double p, double q, int32_t walk_length, cons
         }
     }
     // one-off preprocessing (common-neighbour counts) must not race with the two streams
-    if (!(g->flags & (GW_F_DIRECTED | GW_F_WEIGHTED)) && !(p == 1.0 && q == 1.0)) {
-        int rc = ensure_common_counts(g, g->ws_stream[0]);
+    if (!(g->flags & (GW_F_DIRECTED | GW_F_WEIGHTED))) {
+        int rc = ensure_common_counts(g, g->ws_stream[0], !(p == 1.0 && q == 1.0));
         if (rc != GW_OK && rc != GW_E_STATE) return rc;
     }
     if ((g->flags & GW_F_WEIGHTED) && !g->d_anJ) GW_TRY(gw_alias_nodes(g, nullptr, nullptr));
@@ -382,6 +382,26 @@ int gw_graph_prepare_walks(gw_graph *g, double *build_ms) {
         if (rc != GW_OK && rc != GW_E_STATE) return rc;
     }
     if (build_ms) *build_ms = g->common_build_ms;
+    return GW_OK;
+}
+
+int gw_node2vec_walk_traffic_dev(gw_graph *g, double p, double q, int32_t walk_length, const int64_t *d_starts,
+                                 int64_t n_starts, uint64_t seed, uint64_t walk_id_base, int64_t *stats4, void *stream) {
+    if (!g || !stats4 || (n_starts > 0 && !d_starts)) return fail(GW_E_INVALID, "bad arguments");
+    if (g->flags & (GW_F_DIRECTED | GW_F_WEIGHTED | GW_F_MULTI))
+        return fail(GW_E_STATE, "traffic counting mode exists for the mixture walker only (undirected, unweighted)");
+    GW_CUDA(cudaSetDevice(g->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_common_counts(g, st, !(p == 1.0 && q == 1.0));
+    if (rc != GW_OK) return rc == GW_E_STATE ? fail(GW_E_STATE, "graph has self loops: mixture walker not applicable") : rc;
+    DevBuf<unsigned long long> acc;
+    GW_CUDA(acc.alloc(4));
+    GW_CUDA(cudaMemsetAsync(acc.p, 0, 4 * sizeof(unsigned long long), st));
+    if (n_starts > 0) GW_TRY(count_walk_cn(g, p, q, walk_length, d_starts, n_starts, seed, walk_id_base, acc.p, st));
+    unsigned long long h[4];
+    GW_CUDA(cudaMemcpyAsync(h, acc.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    GW_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < 4; i++) stats4[i] = (int64_t)h[i];
     return GW_OK;
 }
 

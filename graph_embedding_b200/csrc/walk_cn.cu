@@ -12,8 +12,9 @@
 // needed in O, and C is resolved by a WARP-COOPERATIVE sorted-list intersection: the 32 lanes
 // stream the shorter row in coalesced 128-byte lines, each lane binary-searches its element in the
 // other row, a ballot/popc/fns picks the j-th match.  c(prev,cur) is symmetric and rides in the
-// same 8-byte entry as the neighbour id ({nbr, cnt} pairs, `colc`), so reading the next vertex
-// also reads the next step's count: ONE random 32-byte sector per step in component A.
+// same 16-byte entry as the neighbour id AND the neighbour's row descriptor ({nbr, cnt, offset,
+// degree} quads, `nbr4`), so reading the next vertex also reads the next step's count and the next
+// row's bounds: ONE random 32-byte sector per step in component A, and no dependent meta[] load.
 //
 // This replaces preprocess_transition_probs' sum(deg^2) alias_edges by a sum-over-edges
 // intersection pass (k_common_counts), the only preprocessing that fits HBM at scale.
@@ -34,10 +35,20 @@ __device__ __forceinline__ bool sorted_contains(const int32_t *__restrict__ row,
     return lo < d && __ldg(row + lo) == x;
 }
 
-// one warp per directed entry e = (u -> v): colc[e] = {v, |N(u) & N(v)|}
+// first-order walks need no counts: nbr4[e] = {v, 0, offset(v), degree(v)}
+__global__ void k_nbr4_nocount(const uint2 *__restrict__ meta, const int32_t *__restrict__ col, int64_t nnz,
+                               int4 *__restrict__ nbr4) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    int32_t v = __ldg(col + e);
+    uint2 mv = __ldg(meta + v);
+    nbr4[e] = make_int4(v, 0, (int)mv.x, (int)mv.y);
+}
+
+// one warp per directed entry e = (u -> v): nbr4[e] = {v, |N(u) & N(v)|, offset(v), degree(v)}
 __global__ void __launch_bounds__(256) k_common_counts(const uint2 *__restrict__ meta, const int32_t *__restrict__ col,
                                                         const int64_t *__restrict__ row_ptr, int64_t n, int64_t nnz,
-                                                        int2 *__restrict__ colc, int *__restrict__ self_loops) {
+                                                        int4 *__restrict__ nbr4, int *__restrict__ self_loops) {
     const int lane = threadIdx.x & 31;
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -49,20 +60,21 @@ __global__ void __launch_bounds__(256) k_common_counts(const uint2 *__restrict__
         }
         const int32_t u = (int32_t)lo, v = __ldg(col + e);
         if (u == v && lane == 0) atomicExch(self_loops, 1);
-        uint2 ms = __ldg(meta + u), ml = __ldg(meta + v);
+        const uint2 mv = __ldg(meta + v);
+        uint2 ms = __ldg(meta + u), ml = mv;
         if (ms.y > ml.y) { uint2 t = ms; ms = ml; ml = t; }
         int cnt = 0;
         for (uint32_t i = lane; i < ms.y; i += 32)
             cnt += sorted_contains(col + ml.x, ml.y, __ldg(col + ms.x + i)) ? 1 : 0;
         for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (lane == 0) colc[e] = make_int2(v, cnt);
+        if (lane == 0) nbr4[e] = make_int4(v, cnt, (int)mv.x, (int)mv.y);
     }
 }
 
 struct CnParams {
     const uint2 *meta;
     const int32_t *col;
-    const int2 *colc;
+    const int4 *nbr4;
     const int64_t *starts;
     int64_t n_walks;
     int32_t L;
@@ -72,11 +84,13 @@ struct CnParams {
     uint64_t walk_id_base;
     int32_t *out;
     int32_t *lens;
+    unsigned long long *stats;   // COUNT mode: [0] steps, [1] bytes, [2] intersections, [3] extra proposals
 };
 
 __device__ __forceinline__ float unit24(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }
 
-template <bool VEC8>
+// COUNT = byte-model mode: same walks, no corpus stores, per-step algorithmic bytes summed.
+template <bool VEC8, bool COUNT>
 __global__ void __launch_bounds__(256) k_walk_cn(CnParams P) {
     const int lane = threadIdx.x & 31;
     const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
@@ -87,6 +101,7 @@ __global__ void __launch_bounds__(256) k_walk_cn(CnParams P) {
     int32_t cur = valid ? (int32_t)P.starts[wi] : 0;
     int32_t prev = -1;
     uint2 mprev = make_uint2(0, 0);
+    uint2 m = valid ? ld_u2_policy(P.meta + cur, pol_keep) : make_uint2(0, 0);   // the only meta[] load of the walk
     int32_t c = 0;                       // |N(prev) & N(cur)|
     bool alive = valid;
     int32_t len = 1;
@@ -94,7 +109,8 @@ __global__ void __launch_bounds__(256) k_walk_cn(CnParams P) {
 #pragma unroll
     for (int i = 0; i < 8; i++) buf[i] = -1;
     buf[0] = cur;
-    if (!VEC8 && valid) o[0] = cur;
+    if (!VEC8 && !COUNT && valid) o[0] = cur;
+    unsigned long long st_steps = 0, st_bytes = 0, st_isect = 0, st_prop = 0;
 
     // positions are produced in blocks of 8 so that the staging buffer is indexed statically
     for (int32_t base = 0; base < P.L; base += 8) {
@@ -104,19 +120,19 @@ __global__ void __launch_bounds__(256) k_walk_cn(CnParams P) {
             if (pos == 0) continue;                   // the start node
             if (pos >= P.L) break;                    // uniform across the grid
             int32_t nxt = -1, cn = 0;
-            uint2 m = make_uint2(0, 0);
+            uint2 mn = make_uint2(0, 0);                 // row descriptor of nxt
             bool want_isect = false;
             uint32_t jsel = 0;
             if (alive) {
-                m = ld_u2_policy(P.meta + cur, pol_keep);
                 const uint32_t d = m.y;
                 if (d == 0) {
                     alive = false;
                 } else {
                     uint4 rnd = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, 0u), P.key);
+                    if (COUNT) { st_steps++; if (prev < 0) st_bytes += 36; }
                     if (prev < 0) {                                   // first step: alias_nodes law = uniform
-                        int2 e = ld_i2_policy(P.colc + m.x + scale_u32(rnd.y, d), pol_stream);
-                        nxt = e.x; cn = e.y;
+                        int4 e = ld_i4_policy(P.nbr4 + m.x + scale_u32(rnd.y, d), pol_stream);
+                        nxt = e.x; cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w);
                     } else {
                         const float dm1 = (float)(d - 1);
                         const float MR = P.r - P.r0;
@@ -131,26 +147,35 @@ __global__ void __launch_bounds__(256) k_walk_cn(CnParams P) {
                         else if (haveC && (u < MR + MA + MC || !haveO)) comp = 2;
                         else if (haveO) comp = 3;
                         else comp = 1;
+                        if (COUNT) st_bytes += (comp == 0) ? 4 : 36;      // store (+ one {nbr,cnt} sector)
                         if (comp == 0) {                              // R: return
-                            nxt = prev; cn = c;
+                            nxt = prev; cn = c; mn = mprev;
                         } else if (comp == 1) {                       // A: uniform over N(cur), prev thinned
                             uint32_t rk = rnd.y, ra = rnd.z, att = 0;
                             for (;;) {
-                                int2 e = ld_i2_policy(P.colc + m.x + scale_u32(rk, d), pol_stream);
-                                if (e.x != prev || unit24(ra) * P.lo < P.r0) { nxt = e.x; cn = e.y; break; }
+                                int4 e = ld_i4_policy(P.nbr4 + m.x + scale_u32(rk, d), pol_stream);
+                                if (e.x != prev || unit24(ra) * P.lo < P.r0) { nxt = e.x; cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w); break; }
                                 uint4 r2 = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, ++att), P.key);
                                 rk = r2.x; ra = r2.y;
+                                if (COUNT) { st_bytes += 32; st_prop++; }
                             }
                         } else if (comp == 2) {                       // C: uniform over N(cur) & N(prev)
                             want_isect = true;
                             jsel = scale_u32(rnd.y, (uint32_t)c);
+                            if (COUNT) {   // both rows read once, in whole sectors
+                                st_bytes += 32ull * ((d * 4 + 31) / 32) + 32ull * ((mprev.y * 4 + 31) / 32);
+                                st_isect++;
+                            }
                         } else {                                      // O: uniform over N(cur) \ N(prev) \ {prev}
                             uint32_t rk = rnd.y, att = 0;
+                            const uint32_t ssec = 32u * (uint32_t)max(1, (32 - __clz(mprev.y)) - 2);   // S(d_prev) sectors
+                            if (COUNT) st_bytes += ssec;
                             for (;;) {
-                                int2 e = ld_i2_policy(P.colc + m.x + scale_u32(rk, d), pol_stream);
-                                if (e.x != prev && !sorted_contains(P.col + mprev.x, mprev.y, e.x)) { nxt = e.x; cn = e.y; break; }
+                                int4 e = ld_i4_policy(P.nbr4 + m.x + scale_u32(rk, d), pol_stream);
+                                if (e.x != prev && !sorted_contains(P.col + mprev.x, mprev.y, e.x)) { nxt = e.x; cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w); break; }
                                 uint4 r2 = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, ++att), P.key);
                                 rk = r2.x;
+                                if (COUNT) { st_bytes += 32 + ssec; st_prop++; }
                             }
                         }
                     }
@@ -186,7 +211,7 @@ __global__ void __launch_bounds__(256) k_walk_cn(CnParams P) {
                 }
                 if (lane == src) {
                     if (xsel < 0) {                   // counts and rows disagree: cannot happen; stay exact-ish
-                        nxt = prev; cn = c;
+                        nxt = prev; cn = c; mn = mprev;
                     } else {
                         uint32_t idx = isel;          // index of xsel inside N(cur)
                         if (!scan_cur) {
@@ -198,24 +223,33 @@ __global__ void __launch_bounds__(256) k_walk_cn(CnParams P) {
                             idx = lo2;
                         }
                         nxt = xsel;
-                        cn = __ldg(P.colc + c_off + idx).y;
+                        int4 e = __ldg(P.nbr4 + c_off + idx);
+                        cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w);
                     }
                 }
             }
             if (alive) {
                 buf[s] = nxt;
-                if (!VEC8) o[pos] = nxt;
-                prev = cur; mprev = m; cur = nxt; c = cn;
+                if (!VEC8 && !COUNT) o[pos] = nxt;
+                prev = cur; mprev = m; cur = nxt; c = cn; m = mn;
                 len = pos + 1;
             }
         }
-        if (VEC8 && valid) {      // one full 32-byte sector per 8 steps, no read-modify-write in L2/DRAM
+        if (VEC8 && !COUNT && valid) {      // one full 32-byte sector per 8 steps, no read-modify-write in L2/DRAM
             int4 *dst = reinterpret_cast<int4 *>(o + base);
             dst[0] = make_int4(buf[0], buf[1], buf[2], buf[3]);
             dst[1] = make_int4(buf[4], buf[5], buf[6], buf[7]);
         }
 #pragma unroll
         for (int i = 0; i < 8; i++) buf[i] = -1;
+    }
+    if (COUNT) {
+        for (int o2 = 16; o2; o2 >>= 1) {
+            st_steps += __shfl_xor_sync(0xffffffffu, st_steps, o2); st_bytes += __shfl_xor_sync(0xffffffffu, st_bytes, o2);
+            st_isect += __shfl_xor_sync(0xffffffffu, st_isect, o2); st_prop += __shfl_xor_sync(0xffffffffu, st_prop, o2);
+        }
+        if (lane == 0) { atomicAdd(P.stats, st_steps); atomicAdd(P.stats + 1, st_bytes); atomicAdd(P.stats + 2, st_isect); atomicAdd(P.stats + 3, st_prop); }
+        return;
     }
     if (valid) {
         if (P.lens) P.lens[wi] = len;
@@ -224,14 +258,22 @@ __global__ void __launch_bounds__(256) k_walk_cn(CnParams P) {
     }
 }
 
-// Builds colc once per graph.  Returns GW_E_STATE (silently usable by the caller as "not
-// applicable") when the graph has self loops.
-int ensure_common_counts(gw_graph *g, cudaStream_t st) {
-    if (g->d_colc) return GW_OK;
-    if (g->has_self_loops == 1) return GW_E_STATE;
-    DevBuf<int2> colc;
+// Builds nbr4 once per graph.  need_counts = false (first-order walks) skips the intersection pass.
+// Returns GW_E_STATE (usable by the caller as "not applicable") when counts are needed and the
+// graph has self loops (c(prev,cur) is then not symmetric).
+int ensure_common_counts(gw_graph *g, cudaStream_t st, bool need_counts) {
+    if (g->d_nbr4 && (g->nbr4_has_counts || !need_counts)) return GW_OK;
+    if (need_counts && g->has_self_loops == 1) return GW_E_STATE;
+    if (!g->d_nbr4) GW_CUDA(cudaMalloc((void **)&g->d_nbr4, sizeof(int4) * (size_t)std::max<int64_t>(g->nnz, 1)));
+    if (!need_counts) {
+        if (g->nnz > 0) {
+            k_nbr4_nocount<<<(unsigned)((g->nnz + 255) / 256), 256, 0, st>>>(g->d_meta, g->d_col, g->nnz, g->d_nbr4);
+            GW_LAUNCHED();
+        }
+        GW_CUDA(cudaStreamSynchronize(st));
+        return GW_OK;
+    }
     DevBuf<int> flag;
-    GW_CUDA(colc.alloc((size_t)std::max<int64_t>(g->nnz, 1)));
     GW_CUDA(flag.alloc(1));
     GW_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
     cudaEvent_t e0, e1;
@@ -240,7 +282,7 @@ int ensure_common_counts(gw_graph *g, cudaStream_t st) {
     if (g->nnz > 0) {
         int sms = 148;
         device_info(&sms, nullptr);
-        k_common_counts<<<sms * 16, 256, 0, st>>>(g->d_meta, g->d_col, g->d_row_ptr, g->n, g->nnz, colc.p, flag.p);
+        k_common_counts<<<sms * 16, 256, 0, st>>>(g->d_meta, g->d_col, g->d_row_ptr, g->n, g->nnz, g->d_nbr4, flag.p);
         GW_LAUNCHED();
     }
     GW_CUDA(cudaEventRecord(e1, st));
@@ -252,23 +294,40 @@ int ensure_common_counts(gw_graph *g, cudaStream_t st) {
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     g->common_build_ms = ms;
     g->has_self_loops = h;
-    if (h) return GW_E_STATE;
-    g->d_colc = colc.take();
+    if (h) return GW_E_STATE;       // rows/descriptors are valid, counts unusable
+    g->nbr4_has_counts = 1;
     return GW_OK;
 }
 
 int launch_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_starts, int64_t n_starts, uint64_t seed,
                    uint64_t walk_id_base, int32_t *d_out, int32_t *d_lens, cudaStream_t st) {
     CnParams P;
-    P.meta = g->d_meta; P.col = g->d_col; P.colc = g->d_colc; P.starts = d_starts; P.n_walks = n_starts; P.L = L;
+    P.meta = g->d_meta; P.col = g->d_col; P.nbr4 = g->d_nbr4; P.starts = d_starts; P.n_walks = n_starts; P.L = L;
     P.a = (float)(1.0 / q); P.b = 1.0f; P.r = (float)(1.0 / p);
     P.lo = std::min(P.a, P.b); P.r0 = std::min(P.r, P.lo);
     P.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     P.walk_id_base = walk_id_base; P.out = d_out; P.lens = d_lens;
+    P.stats = nullptr;
     unsigned grid = (unsigned)((n_starts + 255) / 256);
     bool vec = (L % 8 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 31) == 0);
-    if (vec) k_walk_cn<true><<<grid, 256, 0, st>>>(P);
-    else k_walk_cn<false><<<grid, 256, 0, st>>>(P);
+    if (vec) k_walk_cn<true, false><<<grid, 256, 0, st>>>(P);
+    else k_walk_cn<false, false><<<grid, 256, 0, st>>>(P);
+    GW_LAUNCHED();
+    return GW_OK;
+}
+
+// Byte model of the mixture walker on the SAME walks (same seed / ids): no stores, counters only.
+int count_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_starts, int64_t n_starts, uint64_t seed,
+                  uint64_t walk_id_base, unsigned long long *d_stats, cudaStream_t st) {
+    CnParams P;
+    P.meta = g->d_meta; P.col = g->d_col; P.nbr4 = g->d_nbr4; P.starts = d_starts; P.n_walks = n_starts; P.L = L;
+    P.a = (float)(1.0 / q); P.b = 1.0f; P.r = (float)(1.0 / p);
+    P.lo = std::min(P.a, P.b); P.r0 = std::min(P.r, P.lo);
+    P.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    P.walk_id_base = walk_id_base; P.out = nullptr; P.lens = nullptr;
+    P.stats = d_stats;
+    unsigned grid = (unsigned)((n_starts + 255) / 256);
+    k_walk_cn<false, true><<<grid, 256, 0, st>>>(P);
     GW_LAUNCHED();
     return GW_OK;
 }
