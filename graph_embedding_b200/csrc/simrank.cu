@@ -34,6 +34,7 @@ constexpr double SR_FIX = 4294967296.0;   // 2^32
 struct SimrankParams {
     const uint2 *meta;
     const int32_t *col;
+    const int4 *nbr4;                // {neighbour, -, offset(nbr), degree(nbr)}: ONE random access per walk step
     const int64_t *queries;
     int64_t nq;
     int64_t n;
@@ -169,9 +170,10 @@ __device__ __forceinline__ int walk_sample(const SimrankParams &P, int32_t v, ui
     int32_t path[LEN + 1];
     uint32_t dg[LEN + 1];
     path[0] = v;
-    int32_t cur = v;
     int len = 0;
     bool alive = live;
+    uint2 m = live ? __ldg(P.meta + v) : make_uint2(0, 0);   // same word for every sample of the query: L1 hit
+    dg[0] = m.y;
     uint4 r;
 #pragma unroll
     for (int t = 0; t < LEN; t++) {
@@ -179,20 +181,19 @@ __device__ __forceinline__ int walk_sample(const SimrankParams &P, int32_t v, ui
             r = Philox::gen(make_uint4((uint32_t)qid, (uint32_t)(qid >> 32), (uint32_t)s, (uint32_t)(t >> 2)), P.key);
         uint32_t rw = (t & 3) == 0 ? r.x : (t & 3) == 1 ? r.y : (t & 3) == 2 ? r.z : r.w;
         path[t + 1] = -1;
-        dg[t] = 0;
+        dg[t + 1] = 0;
         if (alive) {
-            uint2 m = __ldg(P.meta + cur);
-            dg[t] = m.y;
-            if (m.y != 0) {                           // Graph.randNeighbor (Graph.java:69-73)
-                cur = __ldg(P.col + m.x + scale_u32(rw, m.y));
-                path[t + 1] = cur;
+            if (m.y != 0) {                               // Graph.randNeighbor (Graph.java:69-73)
+                int4 e = __ldg(P.nbr4 + m.x + scale_u32(rw, m.y));
+                path[t + 1] = e.x;
+                m = make_uint2((uint32_t)e.z, (uint32_t)e.w);   // next row descriptor rides in the same 16 bytes
+                dg[t + 1] = m.y;
                 len++;
             } else {
-                alive = false;                        // dead end: path stays truncated (:66)
+                alive = false;                            // dead end: path stays truncated (:66)
             }
         }
     }
-    dg[LEN] = alive ? __ldg(P.meta + cur).y : 0;
     // computePathSim (SingleRandomWalk.java:81-92)
 #pragma unroll
     for (int i = 1; i <= STEP; i++) {
@@ -681,7 +682,8 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
         g->simrank_layout = (uint64_t)gs * 1000003u + (uint64_t)grid;
         g->simrank_dirty = 0;
     }
-    P.meta = g->d_meta; P.col = g->d_col; P.queries = d_queries; P.nq = nq; P.n = g->n;
+    GW_TRY(ensure_common_counts(g, st, false));               // nbr4 rows (no counts needed)
+    P.meta = g->d_meta; P.col = g->d_col; P.nbr4 = g->d_nbr4; P.queries = d_queries; P.nq = nq; P.n = g->n;
     P.sample = sample; P.k = k;
     for (int i = 0; i < 16; i++) P.coef[i] = 0;
     for (int i = 1; i <= step; i++) P.coef[i] = (float)(pow(c, i) / (double)sample);   // cache[i] = Math.pow(C, i) (:34-36), / SAMPLE (:89)

@@ -20,6 +20,7 @@
 // intersection pass (k_common_counts), the only preprocessing that fits HBM at scale.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -90,8 +91,8 @@ struct CnParams {
 __device__ __forceinline__ float unit24(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }
 
 // COUNT = byte-model mode: same walks, no corpus stores, per-step algorithmic bytes summed.
-template <bool VEC8, bool COUNT>
-__global__ void __launch_bounds__(256) k_walk_cn(CnParams P) {
+template <bool VEC8, bool COUNT, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
     const int lane = threadIdx.x & 31;
     const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
     const int64_t wi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -310,8 +311,12 @@ int launch_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_
     P.stats = nullptr;
     unsigned grid = (unsigned)((n_starts + 255) / 256);
     bool vec = (L % 8 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 31) == 0);
-    if (vec) k_walk_cn<true, false><<<grid, 256, 0, st>>>(P);
-    else k_walk_cn<false, false><<<grid, 256, 0, st>>>(P);
+    const char *occ = getenv("GW_CN_MINB");     // experiment knob: resident blocks per SM the kernel is compiled for
+    int minb = occ ? atoi(occ) : 5;
+    if (!vec) k_walk_cn<false, false, 5><<<grid, 256, 0, st>>>(P);
+    else if (minb >= 8) k_walk_cn<true, false, 8><<<grid, 256, 0, st>>>(P);
+    else if (minb >= 6) k_walk_cn<true, false, 6><<<grid, 256, 0, st>>>(P);
+    else k_walk_cn<true, false, 5><<<grid, 256, 0, st>>>(P);
     GW_LAUNCHED();
     return GW_OK;
 }
@@ -327,7 +332,7 @@ int count_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_s
     P.walk_id_base = walk_id_base; P.out = nullptr; P.lens = nullptr;
     P.stats = d_stats;
     unsigned grid = (unsigned)((n_starts + 255) / 256);
-    k_walk_cn<false, true><<<grid, 256, 0, st>>>(P);
+    k_walk_cn<false, true, 5><<<grid, 256, 0, st>>>(P);
     GW_LAUNCHED();
     return GW_OK;
 }
