@@ -348,23 +348,32 @@ def main():
             tr = g.walk_traffic_dev(args.p, args.q, L, perms[last].data_ptr(), nw, seed=42,
                                     walk_id_base=(rank * 1000 + last) * nw, stream=stream)
             assert tr["steps"] == steps_exec, (tr, steps_exec)
-            alg_bytes = float(tr["bytes"])
-            kname = "k_walk_cn<true,false>"
+            # line model (main): a random access costs one 128-byte line of HBM traffic on this part
+            # (profiles/r1_gather_bench_*: 48.7 G random loads/s = 6.2 TB/s of lines for ANY load flavour)
+            alg_bytes = 128.0 * tr["random_accesses"] + tr["streamed_bytes"] + 4.0 * steps_exec
+            sector_bytes = 32.0 * tr["random_accesses"] + tr["streamed_bytes"] + 4.0 * steps_exec
+            kname = "k_walk_cn<true,false,5>"
         else:
-            alg_bytes, tr = survey_bytes, None
+            alg_bytes, tr, sector_bytes = survey_bytes, None, survey_bytes
             kname = "k_walk_free<false,false>"
         roof = {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "traffic": ncu_traffic(kname), "kernel": kname, "peak_source": peak_src,
                 "bytes_per_unit": alg_bytes / steps_exec, "units_per_launch": steps_exec, "launch_ms": kernel_ms,
-                "model": ("mixture walker: 36 B/step (one {nbr,cnt,offset,degree} sector + 4 B store; 4 B for a return step) "
-                          "+ both rows per intersection + 32*S(d_prev) per adjacency search" if mixture else
-                          "SURVEY 8(d): 68 + 32*S(d_prev) per step"),
+                "model": ("mixture walker, line model: 128 B per random access (one {nbr,cnt,offset,degree} entry per "
+                          "non-return step; S(d_prev) more per adjacency search) + streamed rows of intersections + "
+                          "4 B store per step" if mixture else "SURVEY 8(d): 68 + 32*S(d_prev) per step"),
+                "sector_model": {"bytes_per_unit": sector_bytes / steps_exec,
+                                 "frac": sector_bytes / (kernel_ms * 1e-3) / 1e9 / peak,
+                                 "note": "same accesses counted as 32-byte sectors (what the kernel consumes)"},
                 "survey_model": {"bytes_per_unit": survey_bytes / steps_exec, "mean_search_sectors": sum_s / steps_exec,
                                  "achieved": survey_bytes / (kernel_ms * 1e-3) / 1e9,
                                  "frac": survey_bytes / (kernel_ms * 1e-3) / 1e9 / peak,
                                  "roofline_steps_per_s": peak * 1e9 / (survey_bytes / steps_exec),
-                                 "note": "byte model of a binary-search walker; > 1 means the sampler needs fewer "
-                                         "bytes than that model, not that work is skipped"}}
+                                 "note": "byte model of a binary-search walker (SURVEY 8d); > 1 means the sampler needs "
+                                         "fewer bytes than that model, not that work is skipped"}}
+        if tr:
+            roof["random_accesses_per_step"] = tr["random_accesses"] / steps_exec
+            roof["random_access_rate_G_per_s"] = tr["random_accesses"] / (kernel_ms * 1e-3) / 1e9
         if tr:
             roof["intersections_per_step"] = tr["intersections"] / steps_exec
             roof["extra_proposals_per_step"] = tr["extra_proposals"] / steps_exec

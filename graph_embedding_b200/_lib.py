@@ -262,11 +262,12 @@ class GraphHandle:
         return out, ln
 
     def walk_traffic_dev(self, p, q, walk_length, d_starts, n_starts, seed=0, walk_id_base=0, stream=0):
-        out = np.zeros(4, dtype=np.int64)
+        out = np.zeros(5, dtype=np.int64)
         check(load().gw_node2vec_walk_traffic_dev(self.h, float(p), float(q), int(walk_length), c_vp(d_starts),
                                                   int(n_starts), int(seed), int(walk_id_base),
                                                   ptr(out, ctypes.c_int64), c_vp(stream) if stream else None))
-        return dict(steps=int(out[0]), bytes=int(out[1]), intersections=int(out[2]), extra_proposals=int(out[3]))
+        return dict(steps=int(out[0]), random_accesses=int(out[1]), streamed_bytes=int(out[2]),
+                    intersections=int(out[3]), extra_proposals=int(out[4]))
 
     def byte_model_dev(self, d_walks, n_walks, walk_length, second_order, stream=0):
         steps, sec = ctypes.c_int64(), ctypes.c_int64()

@@ -122,6 +122,8 @@ struct gw_graph {
     int64_t simrank_last_steps = 0;
     void *d_simrank_scratch = nullptr;
     size_t simrank_scratch_bytes = 0;
+    void *d_hybrid_scratch = nullptr;
+    size_t hybrid_scratch_bytes = 0;
     uint64_t simrank_layout = 0;
     int simrank_dirty = 0;
     int64_t simrank_last_slow = 0;   // queries of the last call that went through the hash kernel

@@ -244,6 +244,110 @@ __device__ __forceinline__ void emit_ranked(const Sh &S, uint32_t C, uint32_t K,
     for (uint32_t r = C + tid; r < K; r += SR_BLOCK) { oid[r] = -1; osc[r] = 0.0; }
 }
 
+// Phases B (dense row / top-k) and C (clear the touched slots) of the hash accumulator, shared by
+// the Monte-Carlo hash kernel and the hybrid path-tree kernel.
+__device__ __noinline__ void finish_query(SrShared &S, const SimrankParams &P, uint32_t *gkeys, unsigned long long *gval,
+                                          uint32_t *olist, int64_t qi, int tid) {
+    __syncthreads();
+    const uint32_t M = min(S.ocount, P.olist_cap);
+
+    if (P.out_dense) {
+        // ---------------- dense row (getResult()) ----------------
+        double *row = P.out_dense + (size_t)qi * (size_t)P.n;
+        for (uint32_t e = tid; e < M; e += SR_BLOCK) {
+            uint32_t id; unsigned long long sc;
+            read_entry(S, gkeys, gval, olist[e], id, sc);
+            row[id] = (double)sc * (1.0 / SR_FIX);
+        }
+    }
+    if (P.out_ids) {
+        // ---------------- phase B: top-k ----------------
+        const uint32_t K = (uint32_t)P.k;
+        for (int i = tid; i < SR_BINS; i += SR_BLOCK) S.hist[i] = 0;
+        __syncthreads();
+        // histogram over tier-1 entries only: their k-th largest score is a lower bound of
+        // the final k-th largest
+        uint32_t n_t1 = 0;
+        for (uint32_t e = tid; e < M; e += SR_BLOCK) {
+            uint32_t o = olist[e];
+            if (!(o & 0x80000000u)) {
+                unsigned long long sc = ((unsigned long long)S.hi[o] << 32) | S.lo[o];
+                atomicAdd(&S.hist[score_bin(sc)], 1u);
+                n_t1++;
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {
+            uint32_t thr = threshold_bin(S.hist, K, tid);
+            if (tid == 0) { S.thr_bin = thr; S.ccount = 0; }
+        }
+        __syncthreads();
+        const uint32_t thr = S.thr_bin;
+        for (uint32_t e = tid; e < M; e += SR_BLOCK) {
+            uint32_t id; unsigned long long sc;
+            read_entry(S, gkeys, gval, olist[e], id, sc);
+            if (sc != 0 && score_bin(sc) >= thr) {
+                uint32_t c = atomicAdd(&S.ccount, 1u);
+                if (c < SR_CAND) { S.cand_score[c] = sc; S.cand_id[c] = id; }
+            }
+        }
+        __syncthreads();
+        const uint32_t C = S.ccount;
+        int32_t *oid = P.out_ids + (size_t)qi * K;
+        double *osc = P.out_scores + (size_t)qi * K;
+        if (C <= SR_CAND) {
+            emit_ranked(S, C, K, oid, osc, tid);
+        } else {
+            // fallback (mass ties at the threshold): K rounds of block arg-max over all entries
+            unsigned long long last_s = ~0ull;
+            uint32_t last_i = 0;
+            bool first = true;
+            for (uint32_t r = 0; r < K; r++) {
+                unsigned long long bs = 0; uint32_t bi = SR_EMPTY;
+                for (uint32_t e = tid; e < M; e += SR_BLOCK) {
+                    uint32_t id; unsigned long long sc;
+                    read_entry(S, gkeys, gval, olist[e], id, sc);
+                    if (sc == 0) continue;
+                    if (!first && !better(last_s, last_i, sc, id)) continue;   // already emitted
+                    if (bi == SR_EMPTY || better(sc, id, bs, bi)) { bs = sc; bi = id; }
+                }
+                for (int o = 16; o; o >>= 1) {
+                    unsigned long long s2 = __shfl_xor_sync(0xffffffffu, bs, o);
+                    uint32_t i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (i2 != SR_EMPTY && (bi == SR_EMPTY || better(s2, i2, bs, bi))) { bs = s2; bi = i2; }
+                }
+                if ((tid & 31) == 0) { S.red_score[tid >> 5] = bs; S.red_id[tid >> 5] = bi; }
+                __syncthreads();
+                if (tid == 0) {
+                    unsigned long long fs = 0; uint32_t fi = SR_EMPTY;
+                    for (int w = 0; w < SR_BLOCK / 32; w++) {
+                        uint32_t i2 = S.red_id[w];
+                        if (i2 != SR_EMPTY && (fi == SR_EMPTY || better(S.red_score[w], i2, fs, fi))) { fs = S.red_score[w]; fi = i2; }
+                    }
+                    S.sel_score = fs; S.sel_id = fi;
+                    if (fi != SR_EMPTY) { oid[r] = (int32_t)fi; osc[r] = (double)fs * (1.0 / SR_FIX); }
+                    else { oid[r] = -1; osc[r] = 0.0; }
+                }
+                __syncthreads();
+                last_s = S.sel_score; last_i = S.sel_id; first = false;
+                if (last_i == SR_EMPTY) {   // exhausted: pad the rest
+                    for (uint32_t r2 = r + 1 + tid; r2 < K; r2 += SR_BLOCK) { oid[r2] = -1; osc[r2] = 0.0; }
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---------------- phase C: clear only the touched slots ----------------
+    for (uint32_t e = tid; e < M; e += SR_BLOCK) {
+        uint32_t o = olist[e];
+        if (o & 0x80000000u) { uint32_t s = o & 0x7FFFFFFFu; gkeys[s] = SR_EMPTY; gval[s] = 0ull; }
+        else { S.keys[o] = SR_EMPTY; S.lo[o] = 0; S.hi[o] = 0; }
+    }
+    if (tid == 0) { S.ocount = 0; S.ccount = 0; }
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------------------
 // hash kernel: two-tier hash accumulator (tier 2 in global memory).  Exact for every input;
 // used for dense rows and as the slow path of the log kernel below.
@@ -280,107 +384,166 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_mc(SimrankParams P) {
                     acc_add_warp(S, P, gkeys, gval, olist, ok, target, to_fixed(x));
                 });
         }
-        __syncthreads();
-        const uint32_t M = min(S.ocount, P.olist_cap);
-
-        if (P.out_dense) {
-            // ---------------- dense row (getResult()) ----------------
-            double *row = P.out_dense + (size_t)qi * (size_t)P.n;
-            for (uint32_t e = tid; e < M; e += SR_BLOCK) {
-                uint32_t id; unsigned long long sc;
-                read_entry(S, gkeys, gval, olist[e], id, sc);
-                row[id] = (double)sc * (1.0 / SR_FIX);
-            }
-        }
-        if (P.out_ids) {
-            // ---------------- phase B: top-k ----------------
-            const uint32_t K = (uint32_t)P.k;
-            for (int i = tid; i < SR_BINS; i += SR_BLOCK) S.hist[i] = 0;
-            __syncthreads();
-            // histogram over tier-1 entries only: their k-th largest score is a lower bound of
-            // the final k-th largest
-            uint32_t n_t1 = 0;
-            for (uint32_t e = tid; e < M; e += SR_BLOCK) {
-                uint32_t o = olist[e];
-                if (!(o & 0x80000000u)) {
-                    unsigned long long sc = ((unsigned long long)S.hi[o] << 32) | S.lo[o];
-                    atomicAdd(&S.hist[score_bin(sc)], 1u);
-                    n_t1++;
-                }
-            }
-            __syncthreads();
-            if (tid < 32) {
-                uint32_t thr = threshold_bin(S.hist, K, tid);
-                if (tid == 0) { S.thr_bin = thr; S.ccount = 0; }
-            }
-            __syncthreads();
-            const uint32_t thr = S.thr_bin;
-            for (uint32_t e = tid; e < M; e += SR_BLOCK) {
-                uint32_t id; unsigned long long sc;
-                read_entry(S, gkeys, gval, olist[e], id, sc);
-                if (sc != 0 && score_bin(sc) >= thr) {
-                    uint32_t c = atomicAdd(&S.ccount, 1u);
-                    if (c < SR_CAND) { S.cand_score[c] = sc; S.cand_id[c] = id; }
-                }
-            }
-            __syncthreads();
-            const uint32_t C = S.ccount;
-            int32_t *oid = P.out_ids + (size_t)qi * K;
-            double *osc = P.out_scores + (size_t)qi * K;
-            if (C <= SR_CAND) {
-                emit_ranked(S, C, K, oid, osc, tid);
-            } else {
-                // fallback (mass ties at the threshold): K rounds of block arg-max over all entries
-                unsigned long long last_s = ~0ull;
-                uint32_t last_i = 0;
-                bool first = true;
-                for (uint32_t r = 0; r < K; r++) {
-                    unsigned long long bs = 0; uint32_t bi = SR_EMPTY;
-                    for (uint32_t e = tid; e < M; e += SR_BLOCK) {
-                        uint32_t id; unsigned long long sc;
-                        read_entry(S, gkeys, gval, olist[e], id, sc);
-                        if (sc == 0) continue;
-                        if (!first && !better(last_s, last_i, sc, id)) continue;   // already emitted
-                        if (bi == SR_EMPTY || better(sc, id, bs, bi)) { bs = sc; bi = id; }
-                    }
-                    for (int o = 16; o; o >>= 1) {
-                        unsigned long long s2 = __shfl_xor_sync(0xffffffffu, bs, o);
-                        uint32_t i2 = __shfl_xor_sync(0xffffffffu, bi, o);
-                        if (i2 != SR_EMPTY && (bi == SR_EMPTY || better(s2, i2, bs, bi))) { bs = s2; bi = i2; }
-                    }
-                    if ((tid & 31) == 0) { S.red_score[tid >> 5] = bs; S.red_id[tid >> 5] = bi; }
-                    __syncthreads();
-                    if (tid == 0) {
-                        unsigned long long fs = 0; uint32_t fi = SR_EMPTY;
-                        for (int w = 0; w < SR_BLOCK / 32; w++) {
-                            uint32_t i2 = S.red_id[w];
-                            if (i2 != SR_EMPTY && (fi == SR_EMPTY || better(S.red_score[w], i2, fs, fi))) { fs = S.red_score[w]; fi = i2; }
-                        }
-                        S.sel_score = fs; S.sel_id = fi;
-                        if (fi != SR_EMPTY) { oid[r] = (int32_t)fi; osc[r] = (double)fs * (1.0 / SR_FIX); }
-                        else { oid[r] = -1; osc[r] = 0.0; }
-                    }
-                    __syncthreads();
-                    last_s = S.sel_score; last_i = S.sel_id; first = false;
-                    if (last_i == SR_EMPTY) {   // exhausted: pad the rest
-                        for (uint32_t r2 = r + 1 + tid; r2 < K; r2 += SR_BLOCK) { oid[r2] = -1; osc[r2] = 0.0; }
-                        break;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        // ---------------- phase C: clear only the touched slots ----------------
-        for (uint32_t e = tid; e < M; e += SR_BLOCK) {
-            uint32_t o = olist[e];
-            if (o & 0x80000000u) { uint32_t s = o & 0x7FFFFFFFu; gkeys[s] = SR_EMPTY; gval[s] = 0ull; }
-            else { S.keys[o] = SR_EMPTY; S.lo[o] = 0; S.hi[o] = 0; }
-        }
-        if (tid == 0) { S.ocount = 0; S.ccount = 0; }
-        __syncthreads();
+        finish_query(S, P, gkeys, gval, olist, qi, tid);
     }
     for (int o = 16; o; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
     if ((tid & 31) == 0 && my_steps && !P.qlist) atomicAdd(P.steps, my_steps);   // handed-over queries were counted by the log kernel
+}
+
+// ---------------------------------------------------------------------------------------------
+// hybrid kernel: TopSim_singleSample.walk (simrank/TopSim_singleSample.java:62-203).  A level-
+// synchronous weighted path tree per query: a path of weight w at a vertex of degree d is split
+// into all d neighbours with weight w/d when w >= d (:99-125), otherwise into ceil(w) random
+// neighbours with weight w/ceil(w) (:126-149); at every even level 2i each path adds
+// w * C^i * deg(path[i]) / deg(path[2i]) to sim[source][path[2i]] when it is a first meeting
+// (:167-203; scores stay x SAMPLE as in the reference).  Paths live in a per-CTA structure-of-
+// arrays double buffer in global memory (history column per level, fp64 weights); children are
+// allocated with a block scan and written with one thread per CHILD, so a hub that fans out into
+// thousands of children does not serialise a lane.  paths(l) <= 1 + l*SAMPLE (weights are
+// conserved and a path has at most w+1 children), which sizes the buffers.
+// ---------------------------------------------------------------------------------------------
+struct HybridParams {
+    int32_t *vbuf;        // [grid][2][LEN+1][cap]
+    double *wbuf;         // [grid][2][cap]
+    uint32_t cap;
+    double cpow[16];      // C^i
+};
+
+struct HyShared {
+    SrShared acc;
+    uint32_t ofs[SR_BLOCK + 1];
+    uint32_t roff[SR_BLOCK];
+    uint32_t rdeg[SR_BLOCK];
+    uint32_t enumerate[SR_BLOCK];
+    double cw[SR_BLOCK];
+    uint32_t warp_tot[SR_BLOCK / 32];
+    uint32_t n_in, n_out;
+};
+
+template <int STEP>
+__global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, HybridParams H) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HyShared &Y = *reinterpret_cast<HyShared *>(smem_raw);
+    SrShared &S = Y.acc;
+    constexpr int LEN = 2 * STEP;
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const size_t gs = (size_t)P.gs_mask + 1;
+    uint32_t *gkeys = P.gkeys + blockIdx.x * gs;
+    unsigned long long *gval = P.gval + blockIdx.x * gs;
+    uint32_t *olist = P.olist + (size_t)blockIdx.x * P.olist_cap;
+    const size_t cap = H.cap;
+    int32_t *vb = H.vbuf + (size_t)blockIdx.x * 2 * (LEN + 1) * cap;
+    double *wb = H.wbuf + (size_t)blockIdx.x * 2 * cap;
+
+    for (int i = tid; i < SR_HS; i += SR_BLOCK) { S.keys[i] = SR_EMPTY; S.lo[i] = 0; S.hi[i] = 0; }
+    if (tid == 0) { S.ocount = 0; S.ccount = 0; }
+    __syncthreads();
+    unsigned long long my_steps = 0;
+
+    for (int64_t qi = blockIdx.x; qi < P.nq; qi += gridDim.x) {
+        const int32_t v = (int32_t)P.queries[qi];
+        const uint64_t qid = P.query_id_base + (uint64_t)qi;
+        if (tid == 0) { vb[0] = v; wb[0] = (double)P.sample; Y.n_in = 1; }
+        __syncthreads();
+        for (int l = 0; l <= LEN; l++) {
+            const int b = l & 1;
+            const int32_t *vin = vb + (size_t)b * (LEN + 1) * cap;
+            const double *win = wb + (size_t)b * cap;
+            int32_t *vout = vb + (size_t)(b ^ 1) * (LEN + 1) * cap;
+            double *wout = wb + (size_t)(b ^ 1) * cap;
+            const uint32_t n_in = Y.n_in;
+            // ---- computePathSim at even levels (i = l/2), :80-83 and :157 ----
+            if (l >= 2 && (l & 1) == 0) {
+                const int i = l >> 1;
+                for (uint32_t base = 0; base < n_in; base += SR_BLOCK) {
+                    const uint32_t p = base + tid;
+                    bool ok = p < n_in;
+                    int32_t target = -1;
+                    unsigned long long fx = 0;
+                    if (ok) {
+                        target = vin[(size_t)l * cap + p];
+                        ok = target != v && target >= 0;                          // :184-185
+                        for (int j = 0; j < i && ok; j++)                         // isFirstMeet :211-218
+                            ok = vin[(size_t)j * cap + p] != vin[(size_t)(l - j) * cap + p];
+                        if (ok) {
+                            const int32_t inter = vin[(size_t)i * cap + p];
+                            const double val = win[p] * H.cpow[i] * (double)__ldg(P.meta + inter).y /
+                                               (double)__ldg(P.meta + target).y;   // :189
+                            fx = __double2ull_rn(val * SR_FIX);
+                        }
+                    }
+                    acc_add_warp(S, P, gkeys, gval, olist, ok, (uint32_t)target, fx);
+                }
+            }
+            if (l == LEN) break;
+            // ---- expand level l -> l+1 ----
+            if (tid == 0) Y.n_out = 0;
+            __syncthreads();
+            for (uint32_t base = 0; base < n_in; base += SR_BLOCK) {
+                const uint32_t p = base + tid;
+                uint32_t nchild = 0;
+                if (p < n_in) {
+                    const int32_t cur = vin[(size_t)l * cap + p];
+                    const double w = win[p];
+                    const uint2 m = __ldg(P.meta + cur);
+                    Y.roff[tid] = m.x; Y.rdeg[tid] = m.y;
+                    if (m.y != 0 && w >= (double)m.y) {                           // :99-125 enumerate
+                        nchild = m.y;
+                        Y.enumerate[tid] = 1;
+                        Y.cw[tid] = w / (double)m.y;
+                    } else if (m.y != 0) {                                        // :126-149 sample ceil(w)
+                        int number = ((double)(int)w == w) ? (int)w : (int)w + 1;
+                        nchild = (uint32_t)max(number, 0);
+                        Y.enumerate[tid] = 0;
+                        Y.cw[tid] = nchild ? w / (double)number : 0.0;
+                    }                                                             // degree 0: randNeighbor == -1, no child
+                }
+                // block exclusive scan of nchild
+                uint32_t incl = nchild;
+                for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                if (lane == 31) Y.warp_tot[wrp] = incl;
+                __syncthreads();
+                if (wrp == 0) {
+                    uint32_t t = lane < SR_BLOCK / 32 ? Y.warp_tot[lane] : 0, inc2 = t;
+                    for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, inc2, o); if (lane >= o) inc2 += u; }
+                    if (lane < SR_BLOCK / 32) Y.warp_tot[lane] = inc2 - t;
+                    if (lane == SR_BLOCK / 32 - 1) Y.ofs[SR_BLOCK] = inc2;
+                }
+                __syncthreads();
+                Y.ofs[tid] = Y.warp_tot[wrp] + incl - nchild;
+                __syncthreads();
+                const uint32_t T = Y.ofs[SR_BLOCK];
+                const uint32_t out_base = Y.n_out;
+                if (out_base + (uint64_t)T > cap) { if (tid == 0) atomicExch(P.err, 3); break; }
+                // one thread per child
+                for (uint32_t c = tid; c < T; c += SR_BLOCK) {
+                    uint32_t lo2 = 0, hi2 = SR_BLOCK;                  // last slot t with ofs[t] <= c
+                    while (hi2 - lo2 > 1) { uint32_t mid = (lo2 + hi2) >> 1; if (Y.ofs[mid] <= c) lo2 = mid; else hi2 = mid; }
+                    const uint32_t t = lo2, j = c - Y.ofs[t], parent = base + t, oi = out_base + c;
+                    int32_t child;
+                    if (Y.enumerate[t]) {
+                        child = __ldg(P.col + Y.roff[t] + j);
+                    } else {
+                        uint4 r = Philox::gen(make_uint4((uint32_t)qid, (uint32_t)(qid >> 32), (uint32_t)(l + 1), oi), P.key);
+                        child = __ldg(P.col + Y.roff[t] + scale_u32(r.x, Y.rdeg[t]));
+                    }
+                    for (int pos = 0; pos <= l; pos++) vout[(size_t)pos * cap + oi] = vin[(size_t)pos * cap + parent];
+                    vout[(size_t)(l + 1) * cap + oi] = child;
+                    wout[oi] = Y.cw[t];
+                    my_steps++;
+                }
+                __syncthreads();
+                if (tid == 0) Y.n_out = out_base + T;
+                __syncthreads();
+            }
+            __syncthreads();
+            if (tid == 0) Y.n_in = Y.n_out;
+            __syncthreads();
+        }
+        finish_query(S, P, gkeys, gval, olist, qi, tid);
+    }
+    for (int o = 16; o; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
+    if (lane == 0 && my_steps) atomicAdd(P.steps, my_steps);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -633,17 +796,19 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     if (sample < 1) return fail(GW_E_INVALID, "sample must be positive");
     if (!(c > 0) || !(c < 1)) return fail(GW_E_INVALID, "decay c must be in (0,1)");
     if (d_out_ids && (k < 1 || k > SR_LCAND / 2)) return fail(GW_E_INVALID, "k must be in 1..%d", SR_LCAND / 2);
-    if (mode != GW_SIMRANK_MC) return fail(GW_E_INVALID, "estimator mode %d is not built yet (GW_SIMRANK_MC only)", mode);
+    if (mode != GW_SIMRANK_MC && mode != GW_SIMRANK_HYBRID) return fail(GW_E_INVALID, "unknown estimator mode %d", mode);
     if (nq == 0) return GW_OK;
     if (nq >= ((int64_t)1 << 31)) return fail(GW_E_TOO_LARGE, "more than 2^31-1 queries in one call");
     GW_CUDA(cudaSetDevice(g->device));
     int sms = 0;
     GW_TRY(device_info(&sms, nullptr));
-    const int grid = (int)std::min<int64_t>(nq, (int64_t)sms * 2);
+    const bool hybrid = mode == GW_SIMRANK_HYBRID;
+    const int grid = (int)std::min<int64_t>(nq, (int64_t)sms * (hybrid ? 1 : 2));
     const char *force = getenv("GW_SIMRANK");
-    const bool use_log = d_out_ids && !d_out_dense && !(force && !strcmp(force, "hash"));
+    const bool use_log = !hybrid && d_out_ids && !d_out_dense && !(force && !strcmp(force, "hash"));
     // hash-kernel tier-2 table: >= 2x the distinct targets one query can produce
-    const int64_t distinct = std::min<int64_t>((int64_t)sample * step, g->n);
+    // (hybrid: every path of every even level may add a target, paths(l) <= 1 + l*SAMPLE)
+    const int64_t distinct = std::min<int64_t>(hybrid ? (int64_t)sample * step * (step + 1) + step : (int64_t)sample * step, g->n);
     uint32_t gs = 1024;
     while ((int64_t)gs < 2 * distinct) gs <<= 1;
     const uint32_t ocap = (uint32_t)distinct + 1;
@@ -691,6 +856,30 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     P.query_id_base = query_id_base;
     P.gs_mask = gs - 1; P.olist_cap = ocap;
     P.out_ids = d_out_ids; P.out_scores = d_out_scores; P.out_dense = d_out_dense;
+    if (hybrid) {
+        HybridParams H;
+        H.cap = (uint32_t)std::min<int64_t>((int64_t)2 * step * sample + 1, (int64_t)0x7FFFFFFF);
+        size_t vb = (size_t)grid * 2 * (2 * step + 1) * H.cap * sizeof(int32_t);
+        size_t wbb = (size_t)grid * 2 * H.cap * sizeof(double);
+        if (g->hybrid_scratch_bytes < vb + wbb + 16) {
+            cudaFree(g->d_hybrid_scratch);
+            g->d_hybrid_scratch = nullptr; g->hybrid_scratch_bytes = 0;
+            if (cudaMalloc(&g->d_hybrid_scratch, vb + wbb + 16) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(GW_E_TOO_LARGE, "hybrid estimator needs %zu bytes of path buffers", vb + wbb);
+            }
+            g->hybrid_scratch_bytes = vb + wbb + 16;
+        }
+        H.wbuf = (double *)g->d_hybrid_scratch;
+        H.vbuf = (int32_t *)((unsigned char *)g->d_hybrid_scratch + wbb);
+        for (int i = 0; i < 16; i++) H.cpow[i] = i <= step ? pow(c, i) : 0.0;
+        size_t smem = sizeof(HyShared);
+#define GW_HY(N) case N: GW_CUDA(cudaFuncSetAttribute(k_topsim_hybrid<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                         k_topsim_hybrid<N><<<grid, SR_BLOCK, smem, st>>>(P, H); break;
+        switch (step) { GW_HY(1) GW_HY(2) GW_HY(3) GW_HY(4) GW_HY(5) GW_HY(6) GW_HY(7) GW_HY(8) GW_HY(9) default: GW_HY(10) }
+#undef GW_HY
+        GW_LAUNCHED();
+    } else
     switch (step) {
         case 1: GW_TRY(launch_kernels<1>(P, grid, use_log, st)); break;
         case 2: GW_TRY(launch_kernels<2>(P, grid, use_log, st)); break;

@@ -386,8 +386,8 @@ int gw_graph_prepare_walks(gw_graph *g, double *build_ms) {
 }
 
 int gw_node2vec_walk_traffic_dev(gw_graph *g, double p, double q, int32_t walk_length, const int64_t *d_starts,
-                                 int64_t n_starts, uint64_t seed, uint64_t walk_id_base, int64_t *stats4, void *stream) {
-    if (!g || !stats4 || (n_starts > 0 && !d_starts)) return fail(GW_E_INVALID, "bad arguments");
+                                 int64_t n_starts, uint64_t seed, uint64_t walk_id_base, int64_t *stats5, void *stream) {
+    if (!g || !stats5 || (n_starts > 0 && !d_starts)) return fail(GW_E_INVALID, "bad arguments");
     if (g->flags & (GW_F_DIRECTED | GW_F_WEIGHTED | GW_F_MULTI))
         return fail(GW_E_STATE, "traffic counting mode exists for the mixture walker only (undirected, unweighted)");
     GW_CUDA(cudaSetDevice(g->device));
@@ -395,13 +395,13 @@ int gw_node2vec_walk_traffic_dev(gw_graph *g, double p, double q, int32_t walk_l
     int rc = ensure_common_counts(g, st, !(p == 1.0 && q == 1.0));
     if (rc != GW_OK) return rc == GW_E_STATE ? fail(GW_E_STATE, "graph has self loops: mixture walker not applicable") : rc;
     DevBuf<unsigned long long> acc;
-    GW_CUDA(acc.alloc(4));
-    GW_CUDA(cudaMemsetAsync(acc.p, 0, 4 * sizeof(unsigned long long), st));
+    GW_CUDA(acc.alloc(5));
+    GW_CUDA(cudaMemsetAsync(acc.p, 0, 5 * sizeof(unsigned long long), st));
     if (n_starts > 0) GW_TRY(count_walk_cn(g, p, q, walk_length, d_starts, n_starts, seed, walk_id_base, acc.p, st));
-    unsigned long long h[4];
+    unsigned long long h[5];
     GW_CUDA(cudaMemcpyAsync(h, acc.p, sizeof(h), cudaMemcpyDeviceToHost, st));
     GW_CUDA(cudaStreamSynchronize(st));
-    for (int i = 0; i < 4; i++) stats4[i] = (int64_t)h[i];
+    for (int i = 0; i < 5; i++) stats5[i] = (int64_t)h[i];
     return GW_OK;
 }
 

@@ -85,7 +85,7 @@ struct CnParams {
     uint64_t walk_id_base;
     int32_t *out;
     int32_t *lens;
-    unsigned long long *stats;   // COUNT mode: [0] steps, [1] bytes, [2] intersections, [3] extra proposals
+    unsigned long long *stats;   // COUNT mode: [0] steps, [1] random accesses, [2] streamed row bytes, [3] intersections, [4] extra proposals
 };
 
 __device__ __forceinline__ float unit24(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
     for (int i = 0; i < 8; i++) buf[i] = -1;
     buf[0] = cur;
     if (!VEC8 && !COUNT && valid) o[0] = cur;
-    unsigned long long st_steps = 0, st_bytes = 0, st_isect = 0, st_prop = 0;
+    unsigned long long st_steps = 0, st_acc = 0, st_bytes = 0, st_isect = 0, st_prop = 0;
 
     // positions are produced in blocks of 8 so that the staging buffer is indexed statically
     for (int32_t base = 0; base < P.L; base += 8) {
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                     alive = false;
                 } else {
                     uint4 rnd = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, 0u), P.key);
-                    if (COUNT) { st_steps++; if (prev < 0) st_bytes += 36; }
+                    if (COUNT) { st_steps++; if (prev < 0) st_acc++; }
                     if (prev < 0) {                                   // first step: alias_nodes law = uniform
                         int4 e = ld_i4_policy(P.nbr4 + m.x + scale_u32(rnd.y, d), pol_stream);
                         nxt = e.x; cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w);
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                         else if (haveC && (u < MR + MA + MC || !haveO)) comp = 2;
                         else if (haveO) comp = 3;
                         else comp = 1;
-                        if (COUNT) st_bytes += (comp == 0) ? 4 : 36;      // store (+ one {nbr,cnt} sector)
+                        if (COUNT && comp != 0) st_acc++;                  // one random {nbr,cnt,off,deg} access
                         if (comp == 0) {                              // R: return
                             nxt = prev; cn = c; mn = mprev;
                         } else if (comp == 1) {                       // A: uniform over N(cur), prev thinned
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                                 if (e.x != prev || unit24(ra) * P.lo < P.r0) { nxt = e.x; cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w); break; }
                                 uint4 r2 = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, ++att), P.key);
                                 rk = r2.x; ra = r2.y;
-                                if (COUNT) { st_bytes += 32; st_prop++; }
+                                if (COUNT) { st_acc++; st_prop++; }
                             }
                         } else if (comp == 2) {                       // C: uniform over N(cur) & N(prev)
                             want_isect = true;
@@ -169,14 +169,14 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                             }
                         } else {                                      // O: uniform over N(cur) \ N(prev) \ {prev}
                             uint32_t rk = rnd.y, att = 0;
-                            const uint32_t ssec = 32u * (uint32_t)max(1, (32 - __clz(mprev.y)) - 2);   // S(d_prev) sectors
-                            if (COUNT) st_bytes += ssec;
+                            const uint32_t ssec = (uint32_t)max(1, (32 - __clz(mprev.y)) - 2);   // S(d_prev) random sectors per search
+                            if (COUNT) st_acc += ssec;
                             for (;;) {
                                 int4 e = ld_i4_policy(P.nbr4 + m.x + scale_u32(rk, d), pol_stream);
                                 if (e.x != prev && !sorted_contains(P.col + mprev.x, mprev.y, e.x)) { nxt = e.x; cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w); break; }
                                 uint4 r2 = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, ++att), P.key);
                                 rk = r2.x;
-                                if (COUNT) { st_bytes += 32 + ssec; st_prop++; }
+                                if (COUNT) { st_acc += 1 + ssec; st_prop++; }
                             }
                         }
                     }
@@ -247,9 +247,10 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
     if (COUNT) {
         for (int o2 = 16; o2; o2 >>= 1) {
             st_steps += __shfl_xor_sync(0xffffffffu, st_steps, o2); st_bytes += __shfl_xor_sync(0xffffffffu, st_bytes, o2);
+            st_acc += __shfl_xor_sync(0xffffffffu, st_acc, o2);
             st_isect += __shfl_xor_sync(0xffffffffu, st_isect, o2); st_prop += __shfl_xor_sync(0xffffffffu, st_prop, o2);
         }
-        if (lane == 0) { atomicAdd(P.stats, st_steps); atomicAdd(P.stats + 1, st_bytes); atomicAdd(P.stats + 2, st_isect); atomicAdd(P.stats + 3, st_prop); }
+        if (lane == 0) { atomicAdd(P.stats, st_steps); atomicAdd(P.stats + 1, st_acc); atomicAdd(P.stats + 2, st_bytes); atomicAdd(P.stats + 3, st_isect); atomicAdd(P.stats + 4, st_prop); }
         return;
     }
     if (valid) {

@@ -137,11 +137,12 @@ int gw_node2vec_walks_replay(gw_graph *g, int32_t walk_length, const int64_t *st
                              int64_t n_starts, const double *uniforms, int64_t n_uniforms,
                              const int64_t *draw_offset, int32_t *out_walks, int32_t *out_lens);
 /* Byte model of the production (mixture) walker, measured by re-running the SAME walks (same
- * seed / walk ids) in a counting mode that stores no corpus: stats4 = {steps, algorithmic HBM
- * bytes, warp-cooperative intersections, extra proposals}. */
+ * seed / walk ids) in a counting mode that stores no corpus: stats5 = {steps, random accesses
+ * ({nbr,cnt,offset,degree} loads + search sectors), streamed row bytes, warp-cooperative
+ * intersections, extra proposals}  (DESIGN.md §4). */
 int gw_node2vec_walk_traffic_dev(gw_graph *g, double p, double q, int32_t walk_length,
                                  const int64_t *d_starts, int64_t n_starts, uint64_t seed,
-                                 uint64_t walk_id_base, int64_t *stats4, void *stream);
+                                 uint64_t walk_id_base, int64_t *stats5, void *stream);
 /* Byte model of SURVEY.md §8(d) evaluated on a device-resident corpus: number of executed
  * steps and sum over steps of S(d_prev) (0 for first steps). */
 int gw_walks_byte_model_dev(const gw_graph *g, const int32_t *d_walks, int64_t n_walks,

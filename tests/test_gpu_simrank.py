@@ -220,3 +220,54 @@ def test_barabasi_albert_generator():
     assert deg.max() > 150                                       # heavy tail
     ids, sc = h.simrank_topk(np.arange(100, dtype=np.int64), 0.6, 5, 2000, 20, seed=1)
     assert (sc[:, 0] > 0).all()
+
+
+# ---------------- TopSim_singleSample (hybrid enumerate-or-sample path tree) ----------------
+def test_hybrid_is_deterministic_enumeration_when_weight_exceeds_degree():
+    """karate, STEP=2: with SAMPLE >= maxdeg^4 every level enumerates (TopSim_singleSample.java:99-125),
+    so the result is exactly SAMPLE x truncated SimRank — and equals the oracle's restatement."""
+    gk = sr.Graph(os.path.join(DATA, "karate.edgelist"), 35, separator=" ")
+    s, d = S.read_edge_file(os.path.join(DATA, "karate.edgelist"), " ")
+    ok = S.build_multigraph(s, d, 35)
+    sample, step = 200000, 2
+    exact = S.simrank_exact_matrix(ok, 0.6, step)
+    q = np.arange(35, dtype=np.int64)
+    rows = gk.handle.simrank_rows(q, 0.6, step, sample, mode=_lib.GW_SIMRANK_HYBRID, seed=1)
+    assert np.abs(rows / sample - exact).max() < 1e-8
+    for v in (1, 12, 34):
+        ref, _, _ = S.topsim_row(ok, v, sample, step, 0.6, mode=0, max_paths=1 << 21)
+        assert np.abs(rows[v] - ref).max() < 1e-4 * sample * 1e-3 + 1e-3      # fixed-point resolution only
+
+
+@pytest.mark.parametrize("step", [3, 5])
+def test_hybrid_converges_and_beats_pure_monte_carlo(g333, o333, step):
+    sample = 10000
+    exact = S.simrank_exact_matrix(o333, 0.6, step)
+    q = np.array([0, 5, 17, 100, 200, 332], dtype=np.int64)
+    hyb = g333.handle.simrank_rows(q, 0.6, step, sample, mode=_lib.GW_SIMRANK_HYBRID, seed=3) / sample
+    mc = g333.handle.simrank_rows(q, 0.6, step, sample, mode=_lib.GW_SIMRANK_MC, seed=3)
+    e_h, e_m = [], []
+    for r, v in enumerate(q):
+        top = np.argsort(-exact[v])[:20]
+        e_h.append(np.sqrt(np.mean((hyb[r][top] - exact[v][top]) ** 2)))
+        e_m.append(np.sqrt(np.mean((mc[r][top] - exact[v][top]) ** 2)))
+        assert hyb[r][v] == 0.0
+        assert abs(hyb[r].sum() - exact[v].sum()) <= 0.03 * exact[v].sum() + 1e-3
+    assert np.mean(e_h) <= 3e-3
+    assert np.mean(e_h) < np.mean(e_m)          # enumeration removes the variance of the first levels
+    # same estimator as the CPU restatement (independent RNG): agreement within noise
+    ref, _, _ = S.topsim_row(o333, 5, sample, step, 0.6, mode=0, seed_state=S.java_seed(9))
+    top = np.argsort(-exact[5])[:20]
+    assert np.sqrt(np.mean((hyb[1][top] - ref[top] / sample) ** 2)) <= 4e-3
+
+
+def test_hybrid_topk_and_class_mirror(g333):
+    ts = sr.TopSim_singleSample(g333, 5000, 5, seed=2)
+    ids, sc = ts.topk(20, queries=np.arange(40))
+    rows = ts.compute(queries=np.arange(40)).getResult()
+    for v in range(40):
+        order = np.lexsort((np.arange(333), -rows[v]))[:20]
+        order = order[rows[v][order] > 0]
+        assert ids[v, :len(order)].tolist() == order.tolist()
+        assert sc[v, :len(order)].tobytes() == rows[v][order].tobytes()
+    assert sc.max() > 1.0                       # unnormalised (x SAMPLE), as TopSim_singleSample.java:189
