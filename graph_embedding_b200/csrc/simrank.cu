@@ -602,22 +602,30 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_log(SimrankParams P) {
                     const unsigned long long fx = to_fixed(x);
                     const uint32_t h = hash32(key);
                     bool pending = ok;
-                    uint32_t slot = h & (SR_HS - 1);
-#pragma unroll 1
-                    for (int pr = 0; pr < SR_T1_PROBES; pr++) {
-                        if (!__any_sync(0xffffffffu, pending)) break;
-                        if (pending) {
-                            uint32_t k0 = ((volatile uint32_t *)S.keys)[slot];
-                            if (k0 == SR_EMPTY) {
-                                k0 = atomicCAS(&S.keys[slot], SR_EMPTY, key);
-                                if (k0 == SR_EMPTY) k0 = key;
+                    if (pending) {
+                        // 4-key buckets: ONE 16-byte shared load sees every slot the key may live in.
+                        // Slots of a bucket fill in order and never empty during a query, so "first empty
+                        // slot of my view + CAS" places a key exactly once (a stale view only makes the CAS
+                        // return the occupant, after which the bucket is re-read).
+                        const uint32_t b0 = (h & (SR_HS / 4 - 1)) * 4;
+                        for (int attempt = 0; attempt < 5; attempt++) {
+                            uint4 kk;
+                            asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(kk.x), "=r"(kk.y), "=r"(kk.z), "=r"(kk.w)
+                                         : "r"((uint32_t)__cvta_generic_to_shared(&S.keys[b0])));
+                            int j = kk.x == key ? 0 : kk.y == key ? 1 : kk.z == key ? 2 : kk.w == key ? 3 : -1;
+                            if (j < 0) {
+                                int e = kk.x == SR_EMPTY ? 0 : kk.y == SR_EMPTY ? 1 : kk.z == SR_EMPTY ? 2 : kk.w == SR_EMPTY ? 3 : -1;
+                                if (e < 0) break;                               // bucket full of other keys: log
+                                uint32_t k0 = atomicCAS(&S.keys[b0 + e], SR_EMPTY, key);
+                                if (k0 == SR_EMPTY || k0 == key) j = e;
                             }
-                            if (k0 == key) {
-                                uint32_t vl = (uint32_t)fx, old = atomicAdd(&S.lo[slot], vl);
-                                if (old + vl < old || (fx >> 32)) S.slow = 1;       // score >= 1.0: exact path
+                            if (j >= 0) {
+                                uint32_t vl = (uint32_t)fx, old = atomicAdd(&S.lo[b0 + j], vl);
+                                if (old + vl < old || (fx >> 32)) S.slow = 1;   // score >= 1.0: exact path
                                 pending = false;
+                                break;
                             }
-                            else slot = (slot + 1) & (SR_HS - 1);
                         }
                     }
                     // overflow: append to the log, one shared-memory atomic per warp
