@@ -87,7 +87,7 @@ def load():
     if not os.path.exists(LIB_PATH):
         from . import build as _build
         _build.build()
-    L = ctypes.CDLL(LIB_PATH)
+    L = ctypes.CDLL(os.environ.get("GW_LIB_OVERRIDE") or LIB_PATH)    # override: kernel-variant experiments (tools/)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(L, name)          # AttributeError here = header/library mismatch: fail loudly
         fn.restype = res

@@ -118,6 +118,9 @@ struct gw_graph {
     void *ws_lens[2] = {nullptr, nullptr}; size_t ws_lens_bytes = 0;
     cudaStream_t ws_stream[2] = {nullptr, nullptr};
     cudaEvent_t ws_event = nullptr;
+    // SimRank host-API workspace (grow-only): device queries / ids / scores and a pinned staging block
+    void *ws_sr_dev = nullptr; size_t ws_sr_dev_bytes = 0;
+    void *ws_sr_pin = nullptr; size_t ws_sr_pin_bytes = 0;
     // SimRank bookkeeping
     int64_t simrank_last_steps = 0;
     void *d_simrank_scratch = nullptr;

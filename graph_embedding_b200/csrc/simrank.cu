@@ -23,7 +23,13 @@
 
 namespace gw {
 
-constexpr int SR_BLOCK = 512;
+#ifndef SR_BLOCK_THREADS
+#define SR_BLOCK_THREADS 512
+#endif
+constexpr int SR_BLOCK = SR_BLOCK_THREADS;
+#ifndef SR_ILP
+#define SR_ILP 1                     // samples walked in lock step per thread (independent loads in flight)
+#endif
 constexpr int SR_HS = 8192;          // tier-1 slots (shared memory)
 constexpr int SR_T1_PROBES = 8;      // bounded probing in tier 1, then fall through to tier 2
 constexpr int SR_BINS = 1024;
@@ -60,6 +66,7 @@ struct SimrankParams {
     int32_t *qlist_out;              // written by the log kernel
     const int32_t *qlist;            // read by the hash kernel (NULL = all queries)
     uint32_t *qcount;
+    unsigned long long *prof;        // SR_PROFILE builds: per-phase clock64 totals of CTA 0
 };
 
 struct SrShared {
@@ -160,51 +167,77 @@ __device__ __forceinline__ void read_entry(const SrShared &S, const uint32_t *gk
     }
 }
 
-// One sample: 2*STEP uniform steps from v with the whole path in registers, then the first-meet
-// contributions (SingleRandomWalk.java:53-92).  emit(ok, target, fx) is called STEP times by
-// every lane (lock-step), fx = C^i * deg(path[i]) / deg(path[2i]) / SAMPLE in 32.32 fixed point.
-template <int STEP, typename Emit>
-__device__ __forceinline__ int walk_sample(const SimrankParams &P, int32_t v, uint64_t qid, int32_t s, bool live,
-                                           Emit &&emit) {
+// The 16-byte neighbour entry of one walk step.  asm volatile pins the ISSUE point: the loads of a
+// step go out before the accumulator code that overlaps their latency.
+__device__ __forceinline__ int4 ld_nbr4(const int4 *ptr) {
+    int4 v;
+    asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+    return v;
+}
+
+// ILP samples per thread (samples g*ILP .. g*ILP+ILP-1), walked in lock step: 2*STEP uniform steps
+// from v with the whole paths in registers (SingleRandomWalk.java:53-72), ILP independent random
+// loads in flight per thread.  The first-meet contribution of level i (computePathSim, :81-92)
+// is emitted as soon as path[2i] is known, AFTER the loads of step 2i have been issued, so the
+// accumulator work hides under the memory latency of the next step.  emit(ok, target, x) is
+// called STEP*ILP times by every lane (lock-step), x = C^i * deg(path[i]) / deg(path[2i]) / SAMPLE.
+// Sample s draws word (t & 3) of Philox(qid, s, t >> 2) at step t: paths do not depend on ILP,
+// block size or grid.
+template <int STEP, int ILP, typename Emit>
+__device__ __forceinline__ int walk_group(const SimrankParams &P, int32_t v, uint2 mv, uint64_t qid, int32_t g,
+                                          Emit &&emit) {
     constexpr int LEN = 2 * STEP;
-    int32_t path[LEN + 1];
-    uint32_t dg[LEN + 1];
-    path[0] = v;
-    int len = 0;
-    bool alive = live;
-    uint2 m = live ? __ldg(P.meta + v) : make_uint2(0, 0);   // same word for every sample of the query: L1 hit
-    dg[0] = m.y;
-    uint4 r;
+    int32_t path[ILP][LEN + 1];
+    uint32_t dmid[ILP][STEP + 1];           // deg(path[i]), i <= STEP
+    uint2 m[ILP];                           // row descriptor of the current vertex
+    bool alive[ILP];
+    uint4 r[ILP];
+    int steps = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; k++) {
+        path[k][0] = v;
+        dmid[k][0] = 0;
+        m[k] = mv;
+        alive[k] = g * ILP + k < P.sample;
+    }
+    auto emit_level = [&](int i, int k) {
+        const int32_t target = path[k][2 * i];          // -1 when the walk ended before 2i steps (:66)
+        bool ok = target >= 0 && target != v;
+#pragma unroll
+        for (int j = 0; j < i; j++) ok &= (path[k][j] != path[k][2 * i - j]);   // isFirstMeet :100-106
+        // m[k] still describes path[2i]: its degree is the divisor
+        const float x = __fdividef(P.coef[i] * (float)dmid[k][i], (float)max(m[k].y, 1u));
+        emit(ok, (uint32_t)target, x);
+    };
 #pragma unroll
     for (int t = 0; t < LEN; t++) {
-        if ((t & 3) == 0)
-            r = Philox::gen(make_uint4((uint32_t)qid, (uint32_t)(qid >> 32), (uint32_t)s, (uint32_t)(t >> 2)), P.key);
-        uint32_t rw = (t & 3) == 0 ? r.x : (t & 3) == 1 ? r.y : (t & 3) == 2 ? r.z : r.w;
-        path[t + 1] = -1;
-        dg[t + 1] = 0;
-        if (alive) {
-            if (m.y != 0) {                               // Graph.randNeighbor (Graph.java:69-73)
-                int4 e = __ldg(P.nbr4 + m.x + scale_u32(rw, m.y));
-                path[t + 1] = e.x;
-                m = make_uint2((uint32_t)e.z, (uint32_t)e.w);   // next row descriptor rides in the same 16 bytes
-                dg[t + 1] = m.y;
-                len++;
-            } else {
-                alive = false;                            // dead end: path stays truncated (:66)
+        int4 e[ILP];
+#pragma unroll
+        for (int k = 0; k < ILP; k++) {
+            if ((t & 3) == 0)
+                r[k] = Philox::gen(make_uint4((uint32_t)qid, (uint32_t)(qid >> 32), (uint32_t)(g * ILP + k), (uint32_t)(t >> 2)), P.key);
+            const uint32_t rw = (t & 3) == 0 ? r[k].x : (t & 3) == 1 ? r[k].y : (t & 3) == 2 ? r[k].z : r[k].w;
+            alive[k] = alive[k] && m[k].y != 0;        // Graph.randNeighbor == -1 on a dead end (Graph.java:69-73)
+            e[k] = make_int4(-1, 0, 0, 0);
+            if (alive[k]) e[k] = ld_nbr4(P.nbr4 + m[k].x + scale_u32(rw, m[k].y));
+        }
+        if (t >= 2 && (t & 1) == 0) {
+#pragma unroll
+            for (int k = 0; k < ILP; k++) emit_level(t >> 1, k);
+        }
+#pragma unroll
+        for (int k = 0; k < ILP; k++) {
+            path[k][t + 1] = e[k].x;
+            if (alive[k]) {
+                m[k] = make_uint2((uint32_t)e[k].z, (uint32_t)e[k].w);   // next row descriptor rides in the same 16 bytes
+                steps++;
             }
+            if (t + 1 <= STEP) dmid[k][t + 1] = (uint32_t)e[k].w;
         }
     }
-    // computePathSim (SingleRandomWalk.java:81-92)
 #pragma unroll
-    for (int i = 1; i <= STEP; i++) {
-        int32_t target = path[2 * i];
-        bool ok = (2 * i <= len) && target != v;
-#pragma unroll
-        for (int j = 0; j < i; j++) ok &= (path[j] != path[2 * i - j]);   // isFirstMeet :100-106
-        float x = __fdividef(P.coef[i] * (float)dg[i], (float)max(dg[2 * i], 1u));
-        emit(ok, (uint32_t)target, x);
-    }
-    return len;
+    for (int k = 0; k < ILP; k++) emit_level(STEP, k);
+    return steps;
 }
 
 __device__ __forceinline__ unsigned long long to_fixed(float x) { return __float2ull_rn(x * 4294967296.0f); }
@@ -377,9 +410,10 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_mc(SimrankParams P) {
 
         // ---------------- phase A: walk + first-meet accumulation ----------------
         // warp-uniform trip count: every lane runs every round, lanes past SAMPLE are masked
-        for (int32_t s0 = tid - (tid & 31); s0 < P.sample; s0 += SR_BLOCK) {
-            const int32_t s = s0 + (tid & 31);
-            my_steps += (unsigned long long)walk_sample<STEP>(P, v, qid, s, s < P.sample,
+        const uint2 mv = __ldg(P.meta + v);
+        const int32_t ngroups = (P.sample + SR_ILP - 1) / SR_ILP;
+        for (int32_t g0 = tid - (tid & 31); g0 < ngroups; g0 += SR_BLOCK) {
+            my_steps += (unsigned long long)walk_group<STEP, SR_ILP>(P, v, mv, qid, g0 + (tid & 31),
                 [&](bool ok, uint32_t target, float x) {
                     acc_add_warp(S, P, gkeys, gval, olist, ok, target, to_fixed(x));
                 });
@@ -557,8 +591,20 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
 // saturation, too many survivors) is flagged and re-run by the hash kernel; both kernels add the
 // same 32.32 fixed-point integers, so the result does not depend on which one produced it.
 // ---------------------------------------------------------------------------------------------
-constexpr int SR_SKETCH = 8192;
-constexpr int SR_T3 = 512;
+#ifndef SR_SKETCH_CELLS
+#define SR_SKETCH_CELLS 16384
+#endif
+constexpr int SR_SKETCH = SR_SKETCH_CELLS;
+#ifndef SR_RING_STAGES
+#define SR_RING_STAGES 2
+#endif
+#ifndef SR_WILP
+#define SR_WILP 1                            // samples walked in lock step per walker thread of the log kernel
+#endif
+#ifndef SR_T3_SLOTS
+#define SR_T3_SLOTS 512
+#endif
+constexpr int SR_T3 = SR_T3_SLOTS;
 constexpr int SR_LCAND = 256;
 
 struct SrLogShared {
@@ -576,98 +622,239 @@ struct SrLogShared {
     uint32_t slow;                       // this query needs the hash kernel
 };
 
+// walker -> accumulator hand-over: one single-producer single-consumer ring per warp pair, a stage =
+// the WILP * STEP (key, x) contributions of WILP samples per lane; full/empty mbarriers per stage
+constexpr int SR_PAIRS = 16;                 // walker warps = accumulator warps per CTA (1024 threads, one CTA per SM)
+constexpr int SR_ABLOCK = SR_PAIRS * 32;     // accumulator threads (phases B and C run on them alone)
+static_assert(SR_ABLOCK == SR_BLOCK, "phase B/C strides assume SR_BLOCK accumulator threads");
 template <int STEP>
-__global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_log(SimrankParams P) {
+struct SrRing {
+    static constexpr int WILP = STEP <= 5 ? SR_WILP : 1;     // samples in flight per walker thread
+    static constexpr int STAGES = STEP <= 5 ? SR_RING_STAGES : SR_RING_STAGES / 2;   // walkers run this far ahead of phase B
+    uint2 slot[SR_PAIRS][STAGES][WILP * STEP * 32];
+    unsigned long long full[SR_PAIRS][STAGES];
+    unsigned long long empty[SR_PAIRS][STAGES];
+};
+__device__ __forceinline__ void acc_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(SR_ABLOCK) : "memory"); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {      // release.cta: my stores before it are visible to the waiter
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE;\nbra LAB_WAIT;\nDONE:\n}"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+// The STEP contributions of one sample per lane into the query's accumulator, batched so that the
+// shared-memory round trips of the levels overlap instead of chaining: all bucket loads first, then
+// all adds (return values consumed at the very end), ONE log reservation per warp for every level.
+// 4-key buckets: one 16-byte shared load sees every slot a key may live in.  Slots of a bucket fill
+// in order and never empty during a query, so "first empty slot of my view + CAS" places a key
+// exactly once (a stale view only makes the CAS return the occupant, after which the bucket is
+// re-read).  What does not fit goes to the per-CTA log + sketch.  Called by all 32 lanes together.
+template <int STEP>
+__device__ __forceinline__ void log_insert_chunk(SrLogShared &S, const SimrankParams &P, uint2 *log, int lane,
+                                                 const uint32_t *key, const float *x) {
+    uint4 kk[STEP];
+    uint32_t b0[STEP];
+    bool pending[STEP];
+    uint32_t wrapped = 0;
+#pragma unroll
+    for (int i = 0; i < STEP; i++) {
+        b0[i] = (hash32(key[i]) & (SR_HS / 4 - 1)) * 4;
+        pending[i] = key[i] != SR_EMPTY;
+        kk[i] = make_uint4(0, 0, 0, 0);
+        if (pending[i])
+            asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(kk[i].x), "=r"(kk[i].y), "=r"(kk[i].z), "=r"(kk[i].w)
+                         : "r"((uint32_t)__cvta_generic_to_shared(&S.keys[b0[i]])));
+    }
+    uint32_t old[STEP];
+#pragma unroll
+    for (int i = 0; i < STEP; i++) {
+        const unsigned long long fx = to_fixed(x[i]);
+        const uint32_t vl = (uint32_t)fx;
+        old[i] = 0;
+        if (pending[i]) {
+            if (fx >> 32) wrapped = 1;                          // single contribution >= 1.0: exact path
+            uint4 v = kk[i];
+            for (int attempt = 0; attempt < 5; attempt++) {
+                int j = v.x == key[i] ? 0 : v.y == key[i] ? 1 : v.z == key[i] ? 2 : v.w == key[i] ? 3 : -1;
+                if (j < 0) {
+                    int e = v.x == SR_EMPTY ? 0 : v.y == SR_EMPTY ? 1 : v.z == SR_EMPTY ? 2 : v.w == SR_EMPTY ? 3 : -1;
+                    if (e < 0) break;                           // bucket full of other keys: log
+                    uint32_t k0 = atomicCAS(&S.keys[b0[i] + e], SR_EMPTY, key[i]);
+                    if (k0 == SR_EMPTY || k0 == key[i]) j = e;
+                }
+                if (j >= 0) {
+                    old[i] = atomicAdd(&S.lo[b0[i] + j], vl);
+                    pending[i] = false;
+                    break;
+                }
+                asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                             : "r"((uint32_t)__cvta_generic_to_shared(&S.keys[b0[i]])));
+            }
+        }
+    }
+    // overflow: append to the log, one shared-memory atomic per warp for all levels
+    uint32_t mask[STEP], total = 0;
+#pragma unroll
+    for (int i = 0; i < STEP; i++) { mask[i] = __ballot_sync(0xffffffffu, pending[i]); total += __popc(mask[i]); }
+    if (total) {
+        uint32_t basep = 0;
+        if (lane == 0) basep = atomicAdd(&S.lcount, total);
+        basep = __shfl_sync(0xffffffffu, basep, 0);
+        uint32_t sold[STEP], sadd[STEP];
+#pragma unroll
+        for (int i = 0; i < STEP; i++) {
+            sold[i] = 0; sadd[i] = 0;
+            if (pending[i]) {
+                const uint32_t pos = basep + __popc(mask[i] & ((1u << lane) - 1));
+                if (pos < P.log_cap) log[pos] = make_uint2(key[i], __float_as_uint(x[i]));
+                sadd[i] = (uint32_t)min((to_fixed(x[i]) >> 8) + 1ull, 0xFFFFFFFFull);
+                sold[i] = atomicAdd(&S.sketch[(hash32(key[i]) >> 13) & (SR_SKETCH - 1)], sadd[i]);
+            }
+            basep += __popc(mask[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < STEP; i++) if (sold[i] + sadd[i] < sold[i]) wrapped = 1;    // sketch cell wrapped
+    }
+#pragma unroll
+    for (int i = 0; i < STEP; i++) if (old[i] + (uint32_t)to_fixed(x[i]) < old[i]) wrapped = 1;   // score >= 1.0: exact path
+    if (wrapped) S.slow = 1;
+}
+
+template <int STEP>
+__device__ __forceinline__ void log_insert_batch(SrLogShared &S, const SimrankParams &P, uint2 *log, int lane,
+                                                 const uint32_t (&key)[STEP], const float (&x)[STEP]) {
+    constexpr int C0 = STEP <= 5 ? STEP : 5;            // at most 5 levels in flight (registers)
+    log_insert_chunk<C0>(S, P, log, lane, key, x);
+    if (STEP > C0) log_insert_chunk<(STEP > C0 ? STEP - C0 : 1)>(S, P, log, lane, key + C0, x + C0);
+}
+
+// One CTA of 1024 threads per SM, split by role.  Warps [0, SR_PAIRS) are WALKERS: they do nothing but
+// walk (WILP samples in flight per thread) and hand the (key, x) contributions of every sample to
+// their partner through a shared-memory ring.  Warps [SR_PAIRS, 2*SR_PAIRS) are ACCUMULATORS: they
+// drain the rings into the query's hash table / log, and run top-k (phase B) and the reset (phase C)
+// among themselves behind a named barrier.  The walkers never meet a CTA-wide barrier: while the
+// accumulators rank query q the walkers are already walking query q+1, so the random loads keep the
+// memory system at its ceiling all the time instead of alternating with the shared-memory work.
+// (The unsplit kernel ran phase A as "10 dependent loads, then STEP inserts" in every warp, in step
+// with every other warp: walk time and accumulate time added up, 6.1 ms where the walks alone take
+// 3.9 ms -- profiles/README.md.)
+#ifdef SR_PROFILE
+#define SR_TICK(slot) do { if (prof_on) { long long t_ = clock64(); atomicAdd(P.prof + (slot), (unsigned long long)(t_ - t_last)); t_last = t_; } } while (0)
+#else
+#define SR_TICK(slot) do { } while (0)
+#endif
+
+template <int STEP>
+__global__ void __launch_bounds__(2 * SR_ABLOCK, 1) k_simrank_log(SimrankParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SrLogShared &S = *reinterpret_cast<SrLogShared *>(smem_raw);
-    const int tid = threadIdx.x, lane = threadIdx.x & 31;
+    using Ring = SrRing<STEP>;
+    constexpr int WILP = Ring::WILP;
+    Ring &R = *reinterpret_cast<Ring *>(smem_raw + ((sizeof(SrLogShared) + 15) & ~(size_t)15));
+    const int tid = threadIdx.x, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     uint2 *log = P.log + (size_t)blockIdx.x * P.log_cap;
     uint32_t *t3keys = S.hist;
 
-    for (int i = tid; i < SR_HS; i += SR_BLOCK) { S.keys[i] = SR_EMPTY; S.lo[i] = 0; }
-    for (int i = tid; i < SR_SKETCH; i += SR_BLOCK) S.sketch[i] = 0;
+    if (tid < SR_PAIRS * Ring::STAGES) {
+        mbar_init(&R.full[tid / Ring::STAGES][tid % Ring::STAGES], 32);
+        mbar_init(&R.empty[tid / Ring::STAGES][tid % Ring::STAGES], 32);
+    }
+    for (int i = tid; i < SR_HS; i += 2 * SR_ABLOCK) { S.keys[i] = SR_EMPTY; S.lo[i] = 0; }
+    for (int i = tid; i < SR_SKETCH; i += 2 * SR_ABLOCK) S.sketch[i] = 0;
     if (tid == 0) { S.lcount = 0; S.ccount = 0; S.t3count = 0; S.slow = 0; }
     __syncthreads();
-    unsigned long long my_steps = 0;
+    uint32_t stage_no = 0;                   // stages handed over so far by this warp pair (same count on both sides)
+    const int32_t ngroups = (P.sample + WILP - 1) / WILP;
+#ifdef SR_PROFILE
+    const bool prof_on = blockIdx.x == 0 && lane == 0 && (wrp == 0 || wrp == SR_PAIRS);
+    long long t_last = clock64();
+#endif
 
-    for (int64_t qi = blockIdx.x; qi < P.nq; qi += gridDim.x) {
-        const int32_t v = (int32_t)P.queries[qi];
-        const uint64_t qid = P.query_id_base + (uint64_t)qi;
-
-        // ---------------- phase A ----------------
-        for (int32_t s0 = tid - lane; s0 < P.sample; s0 += SR_BLOCK) {
-            const int32_t s = s0 + lane;
-            my_steps += (unsigned long long)walk_sample<STEP>(P, v, qid, s, s < P.sample,
-                [&](bool ok, uint32_t key, float x) {
-                    const unsigned long long fx = to_fixed(x);
-                    const uint32_t h = hash32(key);
-                    bool pending = ok;
-                    if (pending) {
-                        // 4-key buckets: ONE 16-byte shared load sees every slot the key may live in.
-                        // Slots of a bucket fill in order and never empty during a query, so "first empty
-                        // slot of my view + CAS" places a key exactly once (a stale view only makes the CAS
-                        // return the occupant, after which the bucket is re-read).
-                        const uint32_t b0 = (h & (SR_HS / 4 - 1)) * 4;
-                        for (int attempt = 0; attempt < 5; attempt++) {
-                            uint4 kk;
-                            asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                         : "=r"(kk.x), "=r"(kk.y), "=r"(kk.z), "=r"(kk.w)
-                                         : "r"((uint32_t)__cvta_generic_to_shared(&S.keys[b0])));
-                            int j = kk.x == key ? 0 : kk.y == key ? 1 : kk.z == key ? 2 : kk.w == key ? 3 : -1;
-                            if (j < 0) {
-                                int e = kk.x == SR_EMPTY ? 0 : kk.y == SR_EMPTY ? 1 : kk.z == SR_EMPTY ? 2 : kk.w == SR_EMPTY ? 3 : -1;
-                                if (e < 0) break;                               // bucket full of other keys: log
-                                uint32_t k0 = atomicCAS(&S.keys[b0 + e], SR_EMPTY, key);
-                                if (k0 == SR_EMPTY || k0 == key) j = e;
-                            }
-                            if (j >= 0) {
-                                uint32_t vl = (uint32_t)fx, old = atomicAdd(&S.lo[b0 + j], vl);
-                                if (old + vl < old || (fx >> 32)) S.slow = 1;   // score >= 1.0: exact path
-                                pending = false;
-                                break;
-                            }
-                        }
-                    }
-                    // overflow: append to the log, one shared-memory atomic per warp
-                    uint32_t mask = __ballot_sync(0xffffffffu, pending);
-                    if (mask) {
-                        uint32_t basep = 0;
-                        if (lane == __ffs(mask) - 1) basep = atomicAdd(&S.lcount, (uint32_t)__popc(mask));
-                        basep = __shfl_sync(0xffffffffu, basep, __ffs(mask) - 1);
-                        if (pending) {
-                            uint32_t pos = basep + __popc(mask & ((1u << lane) - 1));
-                            if (pos < P.log_cap) log[pos] = make_uint2(key, __float_as_uint(x));
-                            uint32_t add = (uint32_t)min((fx >> 8) + 1ull, 0xFFFFFFFFull);
-                            uint32_t old = atomicAdd(&S.sketch[(h >> 13) & (SR_SKETCH - 1)], add);
-                            if (old + add < old) S.slow = 1;          // sketch cell wrapped
-                        }
-                    }
-                });
+    if (wrp < SR_PAIRS) {
+        // =============================== walkers ===============================
+        unsigned long long my_steps = 0;
+        for (int64_t qi = blockIdx.x; qi < P.nq; qi += gridDim.x) {
+            const int32_t v = (int32_t)P.queries[qi];
+            const uint64_t qid = P.query_id_base + (uint64_t)qi;
+            const uint2 mv = __ldg(P.meta + v);
+            for (int32_t g0 = wrp * 32; g0 < ngroups; g0 += SR_PAIRS * 32, stage_no++) {
+                const uint32_t st = stage_no % Ring::STAGES, ph = (stage_no / Ring::STAGES) & 1;
+                SR_TICK(0);                                    // walker: walking
+                mbar_wait(&R.empty[wrp][st], ph ^ 1);          // the accumulator has taken the stage's previous content
+                SR_TICK(1);                                    // walker: waiting for a free stage
+                uint2 *slot = R.slot[wrp][st];
+                int cnt = 0;                                   // emit order: level-major, sample-minor (walk_group)
+                my_steps += (unsigned long long)walk_group<STEP, WILP>(P, v, mv, qid, g0 + lane,
+                    [&](bool ok, uint32_t key, float x) {
+                        slot[cnt * 32 + lane] = make_uint2(ok ? key : SR_EMPTY, __float_as_uint(x));
+                        cnt++;
+                    });
+                mbar_arrive(&R.full[wrp][st]);
+            }
         }
-        __syncthreads();
+        for (int o = 16; o; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
+        if (lane == 0 && my_steps) atomicAdd(P.steps, my_steps);
+        return;
+    }
+
+    // =============================== accumulators ===============================
+    const int pw = wrp - SR_PAIRS, atid = tid - SR_ABLOCK;
+    for (int64_t qi = blockIdx.x; qi < P.nq; qi += gridDim.x) {
+        // ---------------- phase A: drain my walker's ring ----------------
+        for (int32_t g0 = pw * 32; g0 < ngroups; g0 += SR_PAIRS * 32, stage_no++) {
+            const uint32_t st = stage_no % Ring::STAGES, ph = (stage_no / Ring::STAGES) & 1;
+            SR_TICK(2);                                        // accumulator: inserting
+            mbar_wait(&R.full[pw][st], ph);
+            SR_TICK(3);                                        // accumulator: waiting for its walker
+#pragma unroll
+            for (int k = 0; k < WILP; k++) {
+                uint32_t ek[STEP];
+                float ex[STEP];
+#pragma unroll
+                for (int i = 0; i < STEP; i++) {
+                    const uint2 en = R.slot[pw][st][(i * WILP + k) * 32 + lane];
+                    ek[i] = en.x; ex[i] = __uint_as_float(en.y);
+                }
+                if (k == WILP - 1) mbar_arrive(&R.empty[pw][st]);          // stage is in registers: give it back
+                log_insert_batch<STEP>(S, P, log, lane, ek, ex);
+            }
+        }
+        SR_TICK(2);
+        acc_barrier();
+        SR_TICK(4);                                            // waiting for the other accumulators' last stages
         const uint32_t Lc = min(S.lcount, P.log_cap);
-        if (S.lcount > P.log_cap && tid == 0) S.slow = 1;
+        if (S.lcount > P.log_cap && atid == 0) S.slow = 1;
 
         // ---------------- phase B: top-k ----------------
         const uint32_t K = (uint32_t)P.k;
-        for (int i = tid; i < SR_BINS; i += SR_BLOCK) S.hist[i] = 0;
-        __syncthreads();
-        for (int i = tid; i < SR_HS; i += SR_BLOCK) {
+        {
+        for (int i = atid; i < SR_BINS; i += SR_BLOCK) S.hist[i] = 0;
+        acc_barrier();
+        for (int i = atid; i < SR_HS; i += SR_BLOCK) {
             if (S.keys[i] != SR_EMPTY) {
                 unsigned long long sc = S.lo[i];
                 if (sc) atomicAdd(&S.hist[score_bin(sc)], 1u);
             }
         }
-        __syncthreads();
-        if (tid < 32) {
-            uint32_t thr = threshold_bin(S.hist, K, tid);
-            if (tid == 0) { S.thr_bin = thr; S.ccount = 0; S.t3count = 0; }
+        acc_barrier();
+        SR_TICK(5);                                            // histogram of table scores
+        if (atid < 32) {
+            uint32_t thr = threshold_bin(S.hist, K, atid);
+            if (atid == 0) { S.thr_bin = thr; S.ccount = 0; S.t3count = 0; }
         }
-        __syncthreads();
+        acc_barrier();
         const uint32_t thr = S.thr_bin;
-        if (thr == 0 && Lc > 0 && tid == 0) S.slow = 1;   // no usable lower bound: every logged key could matter
-        for (int i = tid; i < SR_T3; i += SR_BLOCK) { t3keys[i] = SR_EMPTY; S.t3lo[i] = 0; S.t3hi[i] = 0; }
-        for (int i = tid; i < SR_HS; i += SR_BLOCK) {     // table candidates
+        if (thr == 0 && Lc > 0 && atid == 0) S.slow = 1;   // no usable lower bound: every logged key could matter
+        for (int i = atid; i < SR_T3; i += SR_BLOCK) { t3keys[i] = SR_EMPTY; S.t3lo[i] = 0; S.t3hi[i] = 0; }
+        for (int i = atid; i < SR_HS; i += SR_BLOCK) {     // table candidates
             uint32_t id = S.keys[i];
             if (id != SR_EMPTY) {
                 unsigned long long sc = S.lo[i];
@@ -677,11 +864,22 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_log(SimrankParams P) {
                 }
             }
         }
-        __syncthreads();
+        acc_barrier();
+        SR_TICK(6);                                            // threshold + table candidates
         if (thr != 0) {
             // one streaming pass over the log; survivors are summed exactly in tier 3
-            for (uint32_t e = tid; e < Lc; e += SR_BLOCK) {
-                uint2 en = log[e];
+            // (8 independent loads in flight per thread: the pass is L2-latency bound otherwise)
+            for (uint32_t e0 = atid; e0 < Lc; e0 += SR_BLOCK * 8) {
+              uint2 ens[8];
+#pragma unroll
+              for (int u = 0; u < 8; u++) {
+                  const uint32_t e = e0 + u * SR_BLOCK;
+                  ens[u] = e < Lc ? __ldcg(log + e) : make_uint2(SR_EMPTY, 0u);
+              }
+#pragma unroll
+              for (int u = 0; u < 8; u++) {
+                const uint2 en = ens[u];
+                if (en.x == SR_EMPTY) continue;
                 uint32_t cell = S.sketch[(hash32(en.x) >> 13) & (SR_SKETCH - 1)];
                 if (score_bin((unsigned long long)cell << 8) >= thr) {
                     uint32_t slot = (hash32(en.x) >> 4) & (SR_T3 - 1);
@@ -700,9 +898,11 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_log(SimrankParams P) {
                     }
                     if (!done) S.slow = 1;
                 }
+              }
             }
-            __syncthreads();
-            for (int i = tid; i < SR_T3; i += SR_BLOCK) {
+            acc_barrier();
+            SR_TICK(7);                                        // log pass
+            for (int i = atid; i < SR_T3; i += SR_BLOCK) {
                 uint32_t id = t3keys[i];
                 if (id != SR_EMPTY) {
                     unsigned long long sc = ((unsigned long long)S.t3hi[i] << 32) | S.t3lo[i];
@@ -713,26 +913,28 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_log(SimrankParams P) {
                 }
             }
         }
-        __syncthreads();
+        acc_barrier();
+        SR_TICK(8);                                            // tier-3 candidates
         const uint32_t C = S.ccount;
         int32_t *oid = P.out_ids + (size_t)qi * K;
         double *osc = P.out_scores + (size_t)qi * K;
         const bool slow = S.slow != 0 || C > SR_LCAND;
         if (!slow) {
-            emit_ranked(S, C, K, oid, osc, tid);
-        } else if (tid == 0) {
+            emit_ranked(S, C, K, oid, osc, atid);
+        } else if (atid == 0) {
             uint32_t w = atomicAdd(P.qcount, 1u);     // hand the query to the hash kernel
             P.qlist_out[w] = (int32_t)qi;
         }
-        __syncthreads();
+        }
+        acc_barrier();
+        SR_TICK(9);                                            // ranking
         // ---------------- phase C: reset ----------------
-        for (int i = tid; i < SR_HS; i += SR_BLOCK) { S.keys[i] = SR_EMPTY; S.lo[i] = 0; }
-        for (int i = tid; i < SR_SKETCH; i += SR_BLOCK) S.sketch[i] = 0;
-        if (tid == 0) { S.lcount = 0; S.ccount = 0; S.t3count = 0; S.slow = 0; }
-        __syncthreads();
+        for (int i = atid; i < SR_HS; i += SR_BLOCK) { S.keys[i] = SR_EMPTY; S.lo[i] = 0; }
+        for (int i = atid; i < SR_SKETCH; i += SR_BLOCK) S.sketch[i] = 0;
+        if (atid == 0) { S.lcount = 0; S.ccount = 0; S.t3count = 0; S.slow = 0; }
+        acc_barrier();
+        SR_TICK(10);                                           // reset
     }
-    for (int o = 16; o; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
-    if (lane == 0 && my_steps) atomicAdd(P.steps, my_steps);
 }
 
 // ---------------- exact SimRank (SimRank.java:36-77) as dense sweeps ----------------
@@ -778,11 +980,11 @@ __global__ void k_gather_rows_zero_diag(const double *__restrict__ A, int64_t n,
 using namespace gw;
 
 template <int STEP>
-static int launch_kernels(const SimrankParams &P, int grid, bool use_log, cudaStream_t st) {
+static int launch_kernels(const SimrankParams &P, int grid, int log_grid, bool use_log, cudaStream_t st) {
     if (use_log) {
-        size_t smem = sizeof(SrLogShared);
+        size_t smem = ((sizeof(SrLogShared) + 15) & ~(size_t)15) + sizeof(SrRing<STEP>);
         GW_CUDA(cudaFuncSetAttribute(k_simrank_log<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_simrank_log<STEP><<<grid, SR_BLOCK, smem, st>>>(P);
+        k_simrank_log<STEP><<<log_grid, 2 * SR_ABLOCK, smem, st>>>(P);
         GW_LAUNCHED();
     }
     // hash kernel: everything (dense rows / forced) or only the queries the log kernel handed over
@@ -812,6 +1014,7 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     GW_TRY(device_info(&sms, nullptr));
     const bool hybrid = mode == GW_SIMRANK_HYBRID;
     const int grid = (int)std::min<int64_t>(nq, (int64_t)sms * (hybrid ? 1 : 2));
+    const int log_grid = (int)std::min<int64_t>(nq, (int64_t)sms);      // log kernel: one 1024-thread CTA per SM
     const char *force = getenv("GW_SIMRANK");
     const bool use_log = !hybrid && d_out_ids && !d_out_dense && !(force && !strcmp(force, "hash"));
     // hash-kernel tier-2 table: >= 2x the distinct targets one query can produce
@@ -822,7 +1025,7 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     const uint32_t ocap = (uint32_t)distinct + 1;
     const uint32_t log_cap = (uint32_t)std::min<int64_t>((int64_t)sample * step, (int64_t)0x7FFFFFFF);
     // layout: [64 B header][gval u64 grid*gs][gkeys u32 grid*gs][olist u32 grid*ocap][log uint2 grid*log_cap][qlist i32 nq]
-    size_t off_gval = 64;
+    size_t off_gval = 256;
     size_t off_gkeys = off_gval + (size_t)grid * gs * 8;
     size_t off_olist = off_gkeys + (size_t)grid * gs * 4;
     size_t off_log = (off_olist + (size_t)grid * ocap * 4 + 15) & ~(size_t)15;
@@ -848,7 +1051,8 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     P.qlist_out = (int32_t *)(base + off_qlist);
     P.qlist = nullptr;
     P.log_cap = log_cap;
-    GW_CUDA(cudaMemsetAsync(base, 0, 64, st));
+    GW_CUDA(cudaMemsetAsync(base, 0, 256, st));
+    P.prof = (unsigned long long *)(base + 64);
     if (fresh || g->simrank_dirty) {   // the hash kernel leaves its tables clean; only (re)initialise when the layout changes
         GW_CUDA(cudaMemsetAsync(P.gval, 0, (size_t)grid * gs * 8, st));
         GW_CUDA(cudaMemsetAsync(P.gkeys, 0xFF, (size_t)grid * gs * 4, st));
@@ -889,16 +1093,16 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
         GW_LAUNCHED();
     } else
     switch (step) {
-        case 1: GW_TRY(launch_kernels<1>(P, grid, use_log, st)); break;
-        case 2: GW_TRY(launch_kernels<2>(P, grid, use_log, st)); break;
-        case 3: GW_TRY(launch_kernels<3>(P, grid, use_log, st)); break;
-        case 4: GW_TRY(launch_kernels<4>(P, grid, use_log, st)); break;
-        case 5: GW_TRY(launch_kernels<5>(P, grid, use_log, st)); break;
-        case 6: GW_TRY(launch_kernels<6>(P, grid, use_log, st)); break;
-        case 7: GW_TRY(launch_kernels<7>(P, grid, use_log, st)); break;
-        case 8: GW_TRY(launch_kernels<8>(P, grid, use_log, st)); break;
-        case 9: GW_TRY(launch_kernels<9>(P, grid, use_log, st)); break;
-        default: GW_TRY(launch_kernels<10>(P, grid, use_log, st)); break;
+        case 1: GW_TRY(launch_kernels<1>(P, grid, log_grid, use_log, st)); break;
+        case 2: GW_TRY(launch_kernels<2>(P, grid, log_grid, use_log, st)); break;
+        case 3: GW_TRY(launch_kernels<3>(P, grid, log_grid, use_log, st)); break;
+        case 4: GW_TRY(launch_kernels<4>(P, grid, log_grid, use_log, st)); break;
+        case 5: GW_TRY(launch_kernels<5>(P, grid, log_grid, use_log, st)); break;
+        case 6: GW_TRY(launch_kernels<6>(P, grid, log_grid, use_log, st)); break;
+        case 7: GW_TRY(launch_kernels<7>(P, grid, log_grid, use_log, st)); break;
+        case 8: GW_TRY(launch_kernels<8>(P, grid, log_grid, use_log, st)); break;
+        case 9: GW_TRY(launch_kernels<9>(P, grid, log_grid, use_log, st)); break;
+        default: GW_TRY(launch_kernels<10>(P, grid, log_grid, use_log, st)); break;
     }
     if (sync_steps) {
         unsigned long long hs = 0;
@@ -939,14 +1143,40 @@ int gw_simrank_topk(gw_graph *g, const int64_t *queries, int64_t nq, double c, i
     GW_TRY(check_queries_host(g, queries, nq));
     if (nq == 0) return GW_OK;
     GW_CUDA(cudaSetDevice(g->device));
-    DevBuf<int64_t> dq;
-    DevBuf<int32_t> di;
-    DevBuf<double> dsc;
-    GW_CUDA(dq.alloc((size_t)nq)); GW_CUDA(di.alloc((size_t)nq * k)); GW_CUDA(dsc.alloc((size_t)nq * k));
-    GW_CUDA(cudaMemcpy(dq.p, queries, sizeof(int64_t) * (size_t)nq, cudaMemcpyHostToDevice));
-    GW_TRY(simrank_run(g, dq.p, nq, c, step, sample, k, mode, seed, query_id_base, di.p, dsc.p, nullptr, nullptr, true));
-    GW_CUDA(cudaMemcpy(out_ids, di.p, sizeof(int32_t) * (size_t)nq * k, cudaMemcpyDeviceToHost));
-    GW_CUDA(cudaMemcpy(out_scores, dsc.p, sizeof(double) * (size_t)nq * k, cudaMemcpyDeviceToHost));
+    // one device block {queries | ids | scores} and one pinned block of the same layout, both kept in the
+    // handle: repeated calls touch neither cudaMalloc nor the driver's pageable-copy staging
+    const size_t bq = sizeof(int64_t) * (size_t)nq, bs = sizeof(double) * (size_t)nq * k, bi = sizeof(int32_t) * (size_t)nq * k;
+    const size_t off_s = (bq + 255) & ~(size_t)255, off_i = (off_s + bs + 255) & ~(size_t)255, total = off_i + bi;
+    if (g->ws_sr_dev_bytes < total) {
+        cudaFree(g->ws_sr_dev); g->ws_sr_dev = nullptr; g->ws_sr_dev_bytes = 0;
+        GW_CUDA(cudaMalloc(&g->ws_sr_dev, total));
+        g->ws_sr_dev_bytes = total;
+    }
+    if (g->ws_sr_pin_bytes < total) {
+        if (g->ws_sr_pin) cudaFreeHost(g->ws_sr_pin);
+        g->ws_sr_pin = nullptr; g->ws_sr_pin_bytes = 0;
+        GW_CUDA(cudaMallocHost(&g->ws_sr_pin, total));
+        g->ws_sr_pin_bytes = total;
+    }
+    unsigned char *dv = (unsigned char *)g->ws_sr_dev, *pin = (unsigned char *)g->ws_sr_pin;
+    memcpy(pin, queries, bq);
+    GW_CUDA(cudaMemcpyAsync(dv, pin, bq, cudaMemcpyHostToDevice, nullptr));
+    GW_TRY(simrank_run(g, (const int64_t *)dv, nq, c, step, sample, k, mode, seed, query_id_base, (int32_t *)(dv + off_i),
+                       (double *)(dv + off_s), nullptr, nullptr, false));
+    GW_CUDA(cudaMemcpyAsync(pin + off_s, dv + off_s, total - off_s, cudaMemcpyDeviceToHost, nullptr));
+    unsigned long long hs = 0;
+    int herr = 0;
+    uint32_t nslow = 0;
+    unsigned char *hdr = (unsigned char *)g->d_simrank_scratch;
+    GW_CUDA(cudaMemcpyAsync(&hs, hdr, sizeof(hs), cudaMemcpyDeviceToHost, nullptr));
+    GW_CUDA(cudaMemcpyAsync(&herr, hdr + 16, sizeof(herr), cudaMemcpyDeviceToHost, nullptr));
+    GW_CUDA(cudaMemcpyAsync(&nslow, hdr + 32, sizeof(nslow), cudaMemcpyDeviceToHost, nullptr));
+    GW_CUDA(cudaStreamSynchronize(nullptr));
+    g->simrank_last_steps = (int64_t)hs;
+    g->simrank_last_slow = (int64_t)nslow;
+    if (herr) { g->simrank_dirty = 1; return fail(GW_E_STATE, "SimRank accumulator overflow (code %d)", herr); }
+    memcpy(out_scores, pin + off_s, bs);
+    memcpy(out_ids, pin + off_i, bi);
     return GW_OK;
 }
 
@@ -990,6 +1220,13 @@ int gw_simrank_last_slow_queries(const gw_graph *g, int64_t *count) {
         GW_CUDA(cudaDeviceSynchronize());
         GW_CUDA(cudaMemcpy(&h, (unsigned char *)g->d_simrank_scratch + 32, sizeof(h), cudaMemcpyDeviceToHost));
         *count = (int64_t)h;
+#ifdef SR_PROFILE
+        unsigned long long pr[16];
+        GW_CUDA(cudaMemcpy(pr, (unsigned char *)g->d_simrank_scratch + 64, sizeof(pr), cudaMemcpyDeviceToHost));
+        const char *nm[11] = {"walker walking", "walker waiting for a stage", "acc inserting", "acc waiting for walker", "acc barrier after A",
+                              "B histogram", "B threshold+table candidates", "B log pass", "B tier-3 scan", "B ranking", "C reset"};
+        for (int i = 0; i < 11; i++) fprintf(stderr, "SR_PROFILE %-30s %12llu cycles\n", nm[i], pr[i]);
+#endif
     }
     return GW_OK;
 }

@@ -132,19 +132,41 @@ def test_tiny_sample_many_ties_uses_fallback(g333):
 
 
 def test_log_kernel_and_hash_kernel_agree_bit_for_bit(monkeypatch):
-    """The production (log-structured) kernel and the exact hash kernel add the same 32.32
-    fixed-point integers: identical ids and scores on a graph large enough to overflow tier 1."""
+    """The production (log-structured, warp-specialised) kernel and the exact hash kernel add the
+    same 32.32 fixed-point integers: identical ids and scores on a graph large enough to overflow
+    the shared-memory table, whichever kernel finished a query."""
     h = _lib.GraphHandle.barabasi_albert(200000, 8, seed=3)
     q = np.random.RandomState(5).choice(h.n, 96, replace=False).astype(np.int64)
     q[:4] = [0, 1, 2, 3]                                         # hubs: many single-hit ties
-    a_ids, a_sc = h.simrank_topk(q, 0.6, 5, 10000, 20, seed=21)
-    slow = h.simrank_last_slow_queries()
-    steps = h.simrank_last_steps()
-    monkeypatch.setenv("GW_SIMRANK", "hash")
-    b_ids, b_sc = h.simrank_topk(q, 0.6, 5, 10000, 20, seed=21)
-    assert np.array_equal(a_ids, b_ids) and a_sc.tobytes() == b_sc.tobytes()
-    assert steps == h.simrank_last_steps() == 96 * 10000 * 10
-    assert 0 < slow < 48                                         # hubs go through the hash kernel, the bulk does not
+    handed_over = 0
+    for sample, k in ((10000, 20), (10001, 20), (3000, 100), (10000, 128)):   # odd SAMPLE: ragged last walker round
+        monkeypatch.delenv("GW_SIMRANK", raising=False)
+        a_ids, a_sc = h.simrank_topk(q, 0.6, 5, sample, k, seed=21)
+        slow = h.simrank_last_slow_queries()
+        steps = h.simrank_last_steps()
+        monkeypatch.setenv("GW_SIMRANK", "hash")
+        b_ids, b_sc = h.simrank_topk(q, 0.6, 5, sample, k, seed=21)
+        assert np.array_equal(a_ids, b_ids) and a_sc.tobytes() == b_sc.tobytes(), (sample, k)
+        assert steps == h.simrank_last_steps() == 96 * sample * 10
+        if k == 20:
+            assert slow < 48, (sample, k, slow)                  # the bulk never needs the hash kernel
+        handed_over += slow
+    assert handed_over > 0                                       # ... but the hand-over path is exercised (k = 128: the
+                                                                 # threshold sits at the single-hit level, every logged key survives)
+
+
+def test_log_kernel_other_step_counts(monkeypatch):
+    """STEP != 5 instantiations of the walker/accumulator kernel (ring depth and level chunking differ)."""
+    h = _lib.GraphHandle.barabasi_albert(50000, 8, seed=4)
+    q = np.random.RandomState(6).choice(h.n, 40, replace=False).astype(np.int64)
+    for step in (1, 2, 3, 7, 10):
+        monkeypatch.delenv("GW_SIMRANK", raising=False)
+        a_ids, a_sc = h.simrank_topk(q, 0.6, step, 4000, 20, seed=3)
+        steps = h.simrank_last_steps()
+        monkeypatch.setenv("GW_SIMRANK", "hash")
+        b_ids, b_sc = h.simrank_topk(q, 0.6, step, 4000, 20, seed=3)
+        assert np.array_equal(a_ids, b_ids) and a_sc.tobytes() == b_sc.tobytes(), step
+        assert steps == h.simrank_last_steps() == 40 * 4000 * 2 * step
 
 
 def test_java_shaped_driver_and_wire_format(tmp_path, g333, o333):

@@ -17,7 +17,12 @@ __device__ __forceinline__ int4 load16(const int4 *p, uint64_t pol) {
     else if (MODE == 3) v = __ldcs(p);                       // ld.global.cs (streaming)
     else if (MODE == 4) asm volatile("ld.global.nc.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
     else if (MODE == 5) asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    else asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    else if (MODE == 6) asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    else if (MODE == 7) asm volatile("ld.global.nc.L2::64B.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else if (MODE == 8) asm volatile("ld.global.nc.L2::128B.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else if (MODE == 9) asm volatile("ld.global.nc.L2::256B.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else if (MODE == 10) asm volatile("ld.global.L1::no_allocate.L2::64B.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else asm volatile("ld.volatile.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
 
@@ -32,6 +37,47 @@ __global__ void k_chain(const int4 *__restrict__ a, uint32_t mask, int steps, ui
         int4 v = load16<MODE>(a + i, pol);
         acc += v.y;
         i = mix((uint32_t)v.x + s) & mask;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+// pair mode: every step loads the random entry AND its partner at byte distance `dist` (same naturally
+// aligned 2*dist block).  If pairs run at the single-load rate the ceiling is a DRAM activate / L2-miss
+// REQUEST rate that locality can amortise, not bytes.
+__global__ void k_pair(const int4 *__restrict__ a, uint32_t mask, int steps, uint32_t dist16, uint32_t *out) {
+    uint32_t i = mix(blockIdx.x * blockDim.x + threadIdx.x) & mask;
+    uint32_t acc = 0;
+    for (int s = 0; s < steps; s++) {
+        int4 v = __ldg(a + i);
+        int4 w = __ldg(a + (i ^ dist16));
+        acc += v.y + w.y;
+        i = mix((uint32_t)v.x + s) & mask;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+// strided-footprint mode: random entries, but only one 128-byte line out of every `stride` lines is ever
+// touched: footprint = n/stride lines (L2 resident when small) spread over the whole address range (every
+// 2 MB page is touched).  Separates "L2 capacity" from "TLB reach".
+__global__ void k_strided(const int4 *__restrict__ a, uint32_t mask_lines, uint32_t stride_lines, int steps, uint32_t *out) {
+    uint32_t i = mix(blockIdx.x * blockDim.x + threadIdx.x) & mask_lines;
+    uint32_t acc = 0;
+    for (int s = 0; s < steps; s++) {
+        int4 v = __ldg(a + (size_t)i * stride_lines * 8);
+        acc += v.y;
+        i = mix((uint32_t)v.x + s + acc) & mask_lines;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+template <int MODE>
+__global__ void k_chain_mod(const int4 *__restrict__ a, uint32_t n, int steps, uint32_t *out) {
+    uint32_t i = mix(blockIdx.x * blockDim.x + threadIdx.x) % n;
+    uint32_t acc = 0;
+    for (int s = 0; s < steps; s++) {
+        int4 v = load16<MODE>(a + i, 0);
+        acc += v.y;
+        i = __umulhi(mix((uint32_t)v.x + s), n);
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
@@ -98,24 +144,112 @@ int main(int argc, char **argv) {
         printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
         return 0;
     }
+    if (argc > 1 && atoi(argv[1]) == -4) {   // mode 6: dense arrays on a fine size grid, default vs L2::64B loads
+        uint32_t *out; int nthreads = 1 << 22, steps = 80;
+        cudaMalloc(&out, nthreads * 4);
+        int sizes[] = {64, 96, 128, 192, 256, 320, 384, 512, 768, 1024, 1536, 2048, 4096};
+        for (int si = 0; si < 13; si++) {
+            size_t n = ((size_t)sizes[si] << 20) / 16; int4 *a;
+            cudaMalloc(&a, n * sizeof(int4));
+            k_fill<<<(unsigned)((n + 255) / 256), 256>>>(a, n);
+            // non power-of-two sizes: the chain kernels mask with the next power of two minus one, so use a
+            // modulo variant here
+            float m0, m1;
+            {
+                cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+                k_chain_mod<1><<<nthreads / 256, 256>>>(a, (uint32_t)n, steps, out);
+                cudaEventRecord(e0);
+                k_chain_mod<1><<<nthreads / 256, 256>>>(a, (uint32_t)n, steps, out);
+                cudaEventRecord(e1); cudaEventSynchronize(e1);
+                cudaEventElapsedTime(&m0, e0, e1);
+                k_chain_mod<7><<<nthreads / 256, 256>>>(a, (uint32_t)n, steps, out);
+                cudaEventRecord(e0);
+                k_chain_mod<7><<<nthreads / 256, 256>>>(a, (uint32_t)n, steps, out);
+                cudaEventRecord(e1); cudaEventSynchronize(e1);
+                cudaEventElapsedTime(&m1, e0, e1);
+            }
+            printf("dense %5d MiB: default %7.3f ms %6.1f G loads/s | L2::64B %7.3f ms %6.1f G loads/s\n", sizes[si], m0,
+                   (double)nthreads * steps / m0 / 1e6, m1, (double)nthreads * steps / m1 / 1e6);
+            cudaFree(a);
+        }
+        printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
+        return 0;
+    }
+    if (argc > 1 && atoi(argv[1]) == -2) {   // mode 4: fixed 64 MiB footprint spread over growing address ranges
+        uint32_t *out; int nthreads = 1 << 22, steps = 80;
+        cudaMalloc(&out, nthreads * 4);
+        for (int lg = 22; lg <= 29; lg++) {          // array of 2^lg int4 = 64 MiB .. 8 GiB
+            size_t n = (size_t)1 << lg; int4 *a;
+            if (cudaMalloc(&a, n * sizeof(int4)) != cudaSuccess) break;
+            k_fill<<<(unsigned)((n + 255) / 256), 256>>>(a, n);
+            uint32_t lines = (uint32_t)(n / 8), foot_lines = 1u << 19;    // 2^19 lines x 128 B = 64 MiB touched
+            uint32_t stride = lines / foot_lines;
+            cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+            k_strided<<<nthreads / 256, 256>>>(a, foot_lines - 1, stride, steps, out);
+            cudaEventRecord(e0);
+            k_strided<<<nthreads / 256, 256>>>(a, foot_lines - 1, stride, steps, out);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            printf("64 MiB footprint over %6.0f MiB (stride %4u lines): %7.3f ms  %6.1f G loads/s\n", n * 16.0 / (1 << 20), stride, ms, (double)nthreads * steps / ms / 1e6);
+            cudaFree(a);
+        }
+        printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
+        return 0;
+    }
+    if (argc > 1 && atoi(argv[1]) == -3) {   // mode 5: occupancy sweep (resident threads per SM), one wave, long chains
+        size_t n = (size_t)1 << 27; int4 *a; uint32_t *out; int steps = 4000;
+        cudaMalloc(&a, n * sizeof(int4)); cudaMalloc(&out, 148 * 2048 * 4);
+        k_fill<<<(unsigned)((n + 255) / 256), 256>>>(a, n);
+        for (int tpsm = 64; tpsm <= 2048; tpsm *= 2) {
+            int bs = tpsm < 256 ? tpsm : 256, grid = 148 * (tpsm / bs);
+            cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+            k_chain<1><<<grid, bs>>>(a, (uint32_t)(n - 1), 100, out);
+            cudaEventRecord(e0);
+            k_chain<1><<<grid, bs>>>(a, (uint32_t)(n - 1), steps, out);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            printf("%4d threads/SM: %8.3f ms  %6.1f G loads/s  latency/load %.0f ns\n", tpsm, ms, (double)grid * bs * steps / ms / 1e6, ms * 1e6 / steps);
+        }
+        printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
+        return 0;
+    }
+    if (argc > 1 && atoi(argv[1]) < 0) {   // mode 3: paired loads at growing distance
+        size_t n = (size_t)1 << 27; int4 *a; uint32_t *out; int nthreads = 1 << 22, steps = 80;
+        cudaMalloc(&a, n * sizeof(int4)); cudaMalloc(&out, nthreads * 4);
+        k_fill<<<(unsigned)((n + 255) / 256), 256>>>(a, n);
+        for (uint32_t dist = 16; dist <= (1u << 22); dist <<= 1) {
+            cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+            k_pair<<<nthreads / 256, 256>>>(a, (uint32_t)(n - 1), steps, dist / 16, out);
+            cudaEventRecord(e0);
+            k_pair<<<nthreads / 256, 256>>>(a, (uint32_t)(n - 1), steps, dist / 16, out);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            printf("pair distance %8u B: %7.3f ms  %6.1f G pairs/s  %6.1f G loads/s\n", dist, ms, (double)nthreads * steps / ms / 1e6, 2.0 * nthreads * steps / ms / 1e6);
+        }
+        printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
+        return 0;
+    }
     int logn = argc > 1 ? atoi(argv[1]) : 27;            // 2^27 x 16 B = 2 GiB
     size_t n = (size_t)1 << logn;
     int4 *a; uint32_t *out;
     int nthreads = 1 << 22, steps = 80;
     cudaMalloc(&a, n * sizeof(int4)); cudaMalloc(&out, nthreads * 4);
     k_fill<<<(unsigned)((n + 255) / 256), 256>>>(a, n);
-    const char *names[] = {"ld.global", "ld.global.nc", "ld.global.cg", "ld.global.cs", "nc+L2 evict_first hint", "nc+L1::no_allocate", "nc+L1::no_allocate+L2 hint"};
+    const char *names[] = {"ld.global", "ld.global.nc", "ld.global.cg", "ld.global.cs", "nc+L2 evict_first hint", "nc+L1::no_allocate", "nc+L1::no_allocate+L2 hint", "nc.L2::64B", "nc.L2::128B", "nc.L2::256B", "L1::no_allocate.L2::64B", "ld.volatile"};
     for (int gran = 0; gran < 3; gran++) {
         size_t g = gran == 0 ? 0 : (gran == 1 ? 32 : 128);
         if (g) { cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g); printf("set L2 fetch granularity %zu: %s\n", g, cudaGetErrorString(e)); }
         size_t cur = 0; cudaDeviceGetLimit(&cur, cudaLimitMaxL2FetchGranularity);
         printf("-- L2 fetch granularity limit = %zu B, array %.1f GiB, %d threads x %d dependent loads\n", cur, n * 16.0 / (1 << 30), nthreads, steps);
-        float ms[7];
+        float ms[12];
         ms[0] = run<0>(a, (uint32_t)(n - 1), nthreads, steps, out); ms[1] = run<1>(a, (uint32_t)(n - 1), nthreads, steps, out);
         ms[2] = run<2>(a, (uint32_t)(n - 1), nthreads, steps, out); ms[3] = run<3>(a, (uint32_t)(n - 1), nthreads, steps, out);
         ms[4] = run<4>(a, (uint32_t)(n - 1), nthreads, steps, out); ms[5] = run<5>(a, (uint32_t)(n - 1), nthreads, steps, out);
         ms[6] = run<6>(a, (uint32_t)(n - 1), nthreads, steps, out);
-        for (int m = 0; m < 7; m++)
+        ms[7] = run<7>(a, (uint32_t)(n - 1), nthreads, steps, out); ms[8] = run<8>(a, (uint32_t)(n - 1), nthreads, steps, out);
+        ms[9] = run<9>(a, (uint32_t)(n - 1), nthreads, steps, out); ms[10] = run<10>(a, (uint32_t)(n - 1), nthreads, steps, out);
+        ms[11] = run<11>(a, (uint32_t)(n - 1), nthreads, steps, out);
+        for (int m = 0; m < 12; m++)
             printf("   %-30s %7.3f ms  %6.1f G loads/s  (%.2f TB/s of 32 B sectors)\n", names[m], ms[m], (double)nthreads * steps / ms[m] / 1e6, (double)nthreads * steps * 32 / ms[m] / 1e9);
     }
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
