@@ -110,6 +110,10 @@ struct gw_graph {
     // unweighted, loop-free graphs only)
     int4 *d_nbr4 = nullptr;        // {neighbour, |N(u) & N(v)|, offset(v), degree(v)} per directed entry
     int nbr4_has_counts = 0;
+    // word-blocked Bloom filter over the undirected edge set (lazy; q < 1 walks): "x not adjacent to prev" in
+    // ONE random 8-byte access instead of a binary search over N(prev); positives are verified exactly
+    unsigned long long *d_bloom = nullptr;
+    uint64_t bloom_words = 0;
     int has_self_loops = -1;       // -1 unknown
     double common_build_ms = 0;
     // host-API workspace (grow-only): staging buffers and two streams for the chunked pipeline

@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -34,6 +35,35 @@ __device__ __forceinline__ bool sorted_contains(const int32_t *__restrict__ row,
         if (v < x) lo = mid + 1; else hi = mid;
     }
     return lo < d && __ldg(row + lo) == x;
+}
+
+// ---- edge Bloom filter: 16 bits per undirected edge, 4 bits of one 64-bit word per key ----------
+__device__ __forceinline__ uint64_t edge_hash(int32_t a, int32_t b) {      // unordered pair
+    uint64_t k = a < b ? ((uint64_t)(uint32_t)a << 32) | (uint32_t)b : ((uint64_t)(uint32_t)b << 32) | (uint32_t)a;
+    k ^= k >> 30; k *= 0xBF58476D1CE4E5B9ull; k ^= k >> 27; k *= 0x94D049BB133111EBull; k ^= k >> 31;     // splitmix64 finaliser
+    return k;
+}
+__device__ __forceinline__ unsigned long long bloom_mask(uint64_t h) {
+    return (1ull << (h & 63)) | (1ull << ((h >> 6) & 63)) | (1ull << ((h >> 12) & 63)) | (1ull << ((h >> 18) & 63));
+}
+__device__ __forceinline__ uint64_t bloom_word(uint64_t h, uint64_t nwords) { return __umul64hi(h, nwords); }
+
+__global__ void k_bloom_build(const uint2 *__restrict__ meta, const int32_t *__restrict__ col, int64_t n,
+                              unsigned long long *__restrict__ bloom, uint64_t nwords) {
+    // one warp per row: entries (u, v) with u < v set their 4 bits
+    const int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t u = warp; u < n; u += nwarps) {
+        const uint2 m = __ldg(meta + u);
+        for (uint32_t i = lane; i < m.y; i += 32) {
+            const int32_t v = __ldg(col + m.x + i);
+            if ((int64_t)v > u) {
+                const uint64_t h = edge_hash((int32_t)u, v);
+                atomicOr(bloom + bloom_word(h, nwords), bloom_mask(h));
+            }
+        }
+    }
 }
 
 // first-order walks need no counts: nbr4[e] = {v, 0, offset(v), degree(v)}
@@ -76,6 +106,8 @@ struct CnParams {
     const uint2 *meta;
     const int32_t *col;
     const int4 *nbr4;
+    const unsigned long long *bloom;   // edge Bloom filter (component O), may be NULL
+    uint64_t bloom_words;
     const int64_t *starts;
     int64_t n_walks;
     int32_t L;
@@ -170,13 +202,28 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                         } else {                                      // O: uniform over N(cur) \ N(prev) \ {prev}
                             uint32_t rk = rnd.y, att = 0;
                             const uint32_t ssec = (uint32_t)max(1, (32 - __clz(mprev.y)) - 2);   // S(d_prev) random sectors per search
-                            if (COUNT) st_acc += ssec;
                             for (;;) {
                                 int4 e = ld_i4_policy(P.nbr4 + m.x + scale_u32(rk, d), pol_stream);
-                                if (e.x != prev && !sorted_contains(P.col + mprev.x, mprev.y, e.x)) { nxt = e.x; cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w); break; }
+                                bool take = e.x != prev;
+                                if (take) {
+                                    // "not adjacent to prev": one 8-byte Bloom word says so for ~99 % of the
+                                    // non-neighbours; only positives pay for the exact search over N(prev)
+                                    bool maybe = true;
+                                    if (P.bloom) {
+                                        const uint64_t h = edge_hash(prev, e.x);
+                                        const unsigned long long w = __ldg(P.bloom + bloom_word(h, P.bloom_words)), bm = bloom_mask(h);
+                                        maybe = (w & bm) == bm;
+                                        if (COUNT) st_acc++;
+                                    }
+                                    if (maybe) {
+                                        if (COUNT) st_acc += ssec;
+                                        take = !sorted_contains(P.col + mprev.x, mprev.y, e.x);
+                                    }
+                                }
+                                if (take) { nxt = e.x; cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w); break; }
                                 uint4 r2 = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, ++att), P.key);
                                 rk = r2.x;
-                                if (COUNT) { st_acc += 1 + ssec; st_prop++; }
+                                if (COUNT) { st_acc++; st_prop++; }
                             }
                         }
                     }
@@ -301,10 +348,29 @@ int ensure_common_counts(gw_graph *g, cudaStream_t st, bool need_counts) {
     return GW_OK;
 }
 
+// Lazy Bloom filter over the edge set (16 bits per undirected edge, power-of-two-free sizing).
+static int ensure_bloom(gw_graph *g, cudaStream_t st) {
+    if (g->d_bloom) return GW_OK;
+    const char *off = getenv("GW_BLOOM");
+    if (off && !strcmp(off, "0")) return GW_OK;             // experiment knob: exact searches only
+    uint64_t nwords = std::max<uint64_t>(1024, (uint64_t)(g->nnz / 2) / 4 + 1);     // 64 bits per 4 edges
+    if (cudaMalloc((void **)&g->d_bloom, nwords * 8) != cudaSuccess) { cudaGetLastError(); g->d_bloom = nullptr; return GW_OK; }   // optional
+    g->bloom_words = nwords;
+    GW_CUDA(cudaMemsetAsync(g->d_bloom, 0, nwords * 8, st));
+    int sms = 148;
+    device_info(&sms, nullptr);
+    k_bloom_build<<<sms * 16, 256, 0, st>>>(g->d_meta, g->d_col, g->n, g->d_bloom, nwords);
+    GW_LAUNCHED();
+    GW_CUDA(cudaStreamSynchronize(st));
+    return GW_OK;
+}
+
 int launch_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_starts, int64_t n_starts, uint64_t seed,
                    uint64_t walk_id_base, int32_t *d_out, int32_t *d_lens, cudaStream_t st) {
     CnParams P;
+    if (q < 1.0) GW_TRY(ensure_bloom(g, st));
     P.meta = g->d_meta; P.col = g->d_col; P.nbr4 = g->d_nbr4; P.starts = d_starts; P.n_walks = n_starts; P.L = L;
+    P.bloom = g->d_bloom; P.bloom_words = g->bloom_words;
     P.a = (float)(1.0 / q); P.b = 1.0f; P.r = (float)(1.0 / p);
     P.lo = std::min(P.a, P.b); P.r0 = std::min(P.r, P.lo);
     P.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
@@ -326,7 +392,9 @@ int launch_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_
 int count_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_starts, int64_t n_starts, uint64_t seed,
                   uint64_t walk_id_base, unsigned long long *d_stats, cudaStream_t st) {
     CnParams P;
+    if (q < 1.0) GW_TRY(ensure_bloom(g, st));
     P.meta = g->d_meta; P.col = g->d_col; P.nbr4 = g->d_nbr4; P.starts = d_starts; P.n_walks = n_starts; P.L = L;
+    P.bloom = g->d_bloom; P.bloom_words = g->bloom_words;
     P.a = (float)(1.0 / q); P.b = 1.0f; P.r = (float)(1.0 / p);
     P.lo = std::min(P.a, P.b); P.r0 = std::min(P.r, P.lo);
     P.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));

@@ -136,6 +136,25 @@ def test_walks_independent_of_batch_split(walker, monkeypatch):
     assert not np.array_equal(whole, other)
 
 
+def test_bloom_filter_does_not_change_walks(monkeypatch):
+    """q < 1: the edge Bloom filter only short-cuts adjacency tests whose answer is "not adjacent";
+    positives are verified exactly, so the walks are identical with the filter switched off."""
+    monkeypatch.setenv("GW_BLOOM", "0")
+    h0 = _lib.GraphHandle.rmat(14, 16 << 14, seed=3)
+    starts = h0.nonisolated()
+    w0, _ = h0.walks(4.0, 0.5, 40, starts, seed=5)
+    import torch
+    d_starts = torch.from_numpy(starts).cuda()
+    t0 = h0.walk_traffic_dev(4.0, 0.5, 40, d_starts.data_ptr(), len(starts), seed=5)
+    monkeypatch.delenv("GW_BLOOM")
+    h1 = _lib.GraphHandle.rmat(14, 16 << 14, seed=3)
+    w1, _ = h1.walks(4.0, 0.5, 40, starts, seed=5)
+    assert np.array_equal(w0, w1)
+    assert len(np.unique(w1[:, 1:])) > 1000
+    t1 = h1.walk_traffic_dev(4.0, 0.5, 40, d_starts.data_ptr(), len(starts), seed=5)
+    assert t1["steps"] == t0["steps"] and t1["random_accesses"] < t0["random_accesses"]   # the byte model sees the saving
+
+
 def test_dead_ends_and_errors():
     meta = case("wdir_p05_q2")
     h = open_graph(meta)
