@@ -106,11 +106,35 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def ncu_traffic(kernel):
-    """dram__bytes_read+write per launch of the named kernel from the committed ncu capture."""
+def ncu_traffic(kernel, units=None):
+    """dram__bytes_read+write per launch of the named kernel from the committed ncu capture
+    (profiles/traffic.json); scaled to `units` per launch when the capture used another batch."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(p)).get(kernel)
+        t = json.load(open(p))
+        v = t.get(kernel)
+        per = t.get(kernel + "_queries_per_launch")
+        if v is not None and per and units:
+            v = v * units / per
+        return v
+    except Exception:
+        return None
+
+
+def gather_ceiling(array_bytes):
+    """Measured ceiling of dependent random accesses/s for an array of this size (profiles/gather_ceiling.json,
+    tools/gather_bench.cu): the bound a one-access-per-step walker actually runs against on this part."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "gather_ceiling.json")))
+        xs, ys = t["array_MiB"], t["G_loads_per_s"]
+        mib = array_bytes / float(1 << 20)
+        if mib <= xs[0]:
+            return ys[0]
+        for i in range(1, len(xs)):
+            if mib <= xs[i]:
+                f = (np.log(mib) - np.log(xs[i - 1])) / (np.log(xs[i]) - np.log(xs[i - 1]))
+                return ys[i - 1] + f * (ys[i] - ys[i - 1])
+        return ys[-1]
     except Exception:
         return None
 
@@ -372,20 +396,21 @@ def measure(args, rank, world, local):
             tr = g.walk_traffic_dev(args.p, args.q, L, perms[last].data_ptr(), nw, seed=42,
                                     walk_id_base=(rank * 1000 + last) * nw, stream=stream)
             assert tr["steps"] == steps_exec, (tr, steps_exec)
-            # line model (main): a random access costs one 128-byte line of HBM traffic on this part
-            # (profiles/r1_gather_bench_*: 48.7 G random loads/s = 6.2 TB/s of lines for ANY load flavour)
-            alg_bytes = 128.0 * tr["random_accesses"] + tr["streamed_bytes"] + 4.0 * steps_exec
+            # atom model (main): a random access moves one 64-byte HBM atom (the walkers load with L2::64B; ncu:
+            # 61 B of dram__bytes_read per access, profiles/r1_gather_flavours_ncu.csv) + streamed rows + 4 B store
+            alg_bytes = 64.0 * tr["random_accesses"] + tr["streamed_bytes"] + 4.0 * steps_exec
             sector_bytes = 32.0 * tr["random_accesses"] + tr["streamed_bytes"] + 4.0 * steps_exec
             kname = "k_walk_cn<true,false,5>"
         else:
             alg_bytes, tr, sector_bytes = survey_bytes, None, survey_bytes
             kname = "k_walk_free<false,false>"
         roof = {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "traffic": ncu_traffic(kname), "kernel": kname, "peak_source": peak_src,
+                "traffic": ncu_traffic(kname) if (args.scale == 22 and args.p == 0.25 and args.q == 4.0) else None,
+                "kernel": kname, "peak_source": peak_src,
                 "bytes_per_unit": alg_bytes / steps_exec, "units_per_launch": steps_exec, "launch_ms": kernel_ms,
-                "model": ("mixture walker, line model: 128 B per random access (one {nbr,cnt,offset,degree} entry per "
-                          "non-return step; S(d_prev) more per adjacency search) + streamed rows of intersections + "
-                          "4 B store per step" if mixture else "SURVEY 8(d): 68 + 32*S(d_prev) per step"),
+                "model": ("mixture walker, atom model: 64 B per random access (one {nbr,cnt,offset,degree} entry per "
+                          "non-return step; one Bloom word and, on a positive, S(d_prev) more per adjacency test) + streamed "
+                          "rows of intersections + 4 B store per step" if mixture else "SURVEY 8(d): 68 + 32*S(d_prev) per step"),
                 "sector_model": {"bytes_per_unit": sector_bytes / steps_exec,
                                  "frac": sector_bytes / (kernel_ms * 1e-3) / 1e9 / peak,
                                  "note": "same accesses counted as 32-byte sectors (what the kernel consumes)"},
@@ -396,9 +421,13 @@ def measure(args, rank, world, local):
                                  "note": "byte model of a binary-search walker (SURVEY 8d); > 1 means the sampler needs "
                                          "fewer bytes than that model, not that work is skipped"}}
         if tr:
+            rate = tr["random_accesses"] / (kernel_ms * 1e-3) / 1e9
+            ceil = gather_ceiling(16.0 * g.nnz)
             roof["random_accesses_per_step"] = tr["random_accesses"] / steps_exec
-            roof["random_access_rate_G_per_s"] = tr["random_accesses"] / (kernel_ms * 1e-3) / 1e9
-        if tr:
+            roof["access_rate"] = {"achieved_G_per_s": rate, "ceiling_G_per_s": ceil, "frac": (rate / ceil) if ceil else None,
+                                   "note": "dependent random loads/s over an array of nbr4's size, measured by tools/gather_bench.cu "
+                                           "on this pool (profiles/gather_ceiling.json): translation-bound, independent of bytes per "
+                                           "access -- the ceiling the byte roofline cannot see"}
             roof["intersections_per_step"] = tr["intersections"] / steps_exec
             roof["extra_proposals_per_step"] = tr["extra_proposals"] / steps_exec
         roof["frac"] = roof["achieved"] / peak
@@ -468,10 +497,18 @@ def measure(args, rank, world, local):
         extra["slow_path_queries_last_step"] = g.simrank_last_slow_queries()
         kernel_ms = float(np.mean(per_launch_ms))
         alg_bytes = walk_steps * 64.0 + nq * args.topk * 12.0
+        kname = "k_simrank_log<%d>" % args.sr_step
+        rate = walk_steps / (kernel_ms * 1e-3) / 1e9
+        ceil = gather_ceiling(16.0 * g.nnz)
         roof = {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "traffic": ncu_traffic("k_simrank_log<%d>" % args.sr_step), "kernel": "k_simrank_log<%d>" % args.sr_step, "peak_source": peak_src,
+                "traffic": ncu_traffic(kname, nq) if (args.ba_nodes == 10_000_000 and args.sample == 10000 and args.sr_step == 5) else None,
+                "kernel": kname, "peak_source": peak_src,
                 "bytes_per_unit": alg_bytes / nq, "units_per_launch": nq, "launch_ms": kernel_ms,
-                "walk_steps_per_s": walk_steps / (kernel_ms * 1e-3)}
+                "model": "SURVEY 8(d): 64 B per walk step (here ONE random 16-byte entry = one 64-byte HBM atom) + 12 B per result slot",
+                "walk_steps_per_s": walk_steps / (kernel_ms * 1e-3),
+                "access_rate": {"achieved_G_per_s": rate, "ceiling_G_per_s": ceil, "frac": (rate / ceil) if ceil else None,
+                                "note": "one dependent random load per walk step; ceiling measured by tools/gather_bench.cu for an array "
+                                        "of nbr4's size (profiles/gather_ceiling.json)"}}
         roof["frac"] = roof["achieved"] / peak
         e2e = None
         if not args.no_e2e:

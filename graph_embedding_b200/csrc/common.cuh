@@ -184,9 +184,14 @@ __device__ __forceinline__ int2 ld_i2_policy(const int2 *ptr, uint64_t pol) {
     asm volatile("ld.global.nc.L2::cache_hint.v2.s32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(ptr), "l"(pol));
     return v;
 }
+// L2::64B: a random 16-byte entry pulls 64 bytes from HBM instead of the default 128 (ncu: 61 B vs 120 B of
+// dram__bytes_read per access, same access rate -- profiles/README.md)
+#ifndef GW_LD_PREFETCH
+#define GW_LD_PREFETCH ".L2::64B"
+#endif
 __device__ __forceinline__ int4 ld_i4_policy(const int4 *ptr, uint64_t pol) {
     int4 v;
-    asm volatile("ld.global.nc.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;"
+    asm volatile("ld.global.nc.L2::cache_hint" GW_LD_PREFETCH ".v4.s32 {%0, %1, %2, %3}, [%4], %5;"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr), "l"(pol));
     return v;
 }

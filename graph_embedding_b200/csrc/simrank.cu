@@ -171,7 +171,7 @@ __device__ __forceinline__ void read_entry(const SrShared &S, const uint32_t *gk
 // step go out before the accumulator code that overlaps their latency.
 __device__ __forceinline__ int4 ld_nbr4(const int4 *ptr) {
     int4 v;
-    asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+    asm volatile("ld.global.nc" GW_LD_PREFETCH ".v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
     return v;
 }
 

@@ -211,7 +211,9 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                                     bool maybe = true;
                                     if (P.bloom) {
                                         const uint64_t h = edge_hash(prev, e.x);
-                                        const unsigned long long w = __ldg(P.bloom + bloom_word(h, P.bloom_words)), bm = bloom_mask(h);
+                                        unsigned long long w;
+                                        asm volatile("ld.global.nc" GW_LD_PREFETCH ".u64 %0, [%1];" : "=l"(w) : "l"(P.bloom + bloom_word(h, P.bloom_words)));
+                                        const unsigned long long bm = bloom_mask(h);
                                         maybe = (w & bm) == bm;
                                         if (COUNT) st_acc++;
                                     }
