@@ -60,6 +60,55 @@ def test_alias_tables_bit_exact(meta):
     assert q.tobytes() == z["ae_q"].tobytes()
 
 
+def test_alias_edges_large_tables_bit_exact():
+    """Tables of every size class of the warp-per-table builder (<= 32 one thread per table; 256 / 1024 /
+    4096 / 18000-entry shared-memory stages), weighted so that the fp64 operation order matters:
+    sampled tables must equal get_alias_edge + alias_setup of the oracle bit for bit."""
+    rs = np.random.RandomState(11)
+    hubs = {0: 5000, 1: 1500, 2: 400, 3: 100}                 # hub id -> degree
+    n = 6000
+    src, dst = [], []
+    for hub, d in hubs.items():
+        leaves = rs.choice(np.arange(10, n), size=d, replace=False)
+        src += [hub] * d
+        dst += leaves.tolist()
+    extra = rs.randint(10, n, size=(4000, 2))
+    extra = extra[extra[:, 0] != extra[:, 1]]
+    src += extra[:, 0].tolist() + [0, 0, 1]
+    dst += extra[:, 1].tolist() + [1, 2, 2]                     # hub-hub edges: common neighbours exist
+    src, dst = np.array(src, dtype=np.int64), np.array(dst, dtype=np.int64)
+    key = np.minimum(src, dst) * n + np.maximum(src, dst)      # one line per undirected pair
+    _, first = np.unique(key, return_index=True)
+    src, dst = src[np.sort(first)], dst[np.sort(first)]
+    w = rs.rand(len(src)) * 3.0 + 0.1
+    src = np.concatenate([src, np.arange(n)[:-1]]); dst = np.concatenate([dst, np.arange(n)[1:]])   # a path keeps every id present
+    w = np.concatenate([w, rs.rand(n - 1) + 0.5])
+    key = np.minimum(src, dst) * n + np.maximum(src, dst)
+    _, first = np.unique(key, return_index=True)
+    keep = np.sort(first)
+    src, dst, w = src[keep], dst[keep], w[keep]
+    g = O.build_simple_graph(src, dst, w, directed=False)
+    h = _lib.GraphHandle.from_edges(src, dst, w)
+    c = h.csr(weights=True)
+    assert np.array_equal(c["row_ptr"], g["row_ptr"]) and np.array_equal(c["col_idx"], g["col_idx"])
+    assert c["weights"].tobytes() == g["weights"].tobytes()
+    p, q = 0.7, 1.9
+    off, J, Q = h.alias_edges(p, q, budget_bytes=8 << 30)
+    deg = np.diff(g["row_ptr"])
+    assert off[-1] == int((deg[g["col_idx"]].astype(np.int64)).sum())
+    rows = np.repeat(np.arange(n), deg)
+    checked = set()
+    for target in (0, 1, 2, 3, int(g["col_idx"][g["row_ptr"][0]]), 4000):        # tables INTO the hubs and into small vertices
+        ent = np.nonzero(g["col_idx"] == target)[0]
+        for e in ent[[0, len(ent) // 2, -1]].tolist():
+            u = int(rows[e])
+            j, qq = O.alias_setup(O.edge_probs(g, u, target, p, q))
+            assert np.array_equal(J[off[e]:off[e + 1]], j), (u, target)
+            assert Q[off[e]:off[e + 1]].tobytes() == np.asarray(qq, dtype=np.float64).tobytes(), (u, target)
+            checked.add(int(off[e + 1] - off[e]))
+    assert max(checked) > 4096 and any(1024 < k <= 4096 for k in checked) and any(256 < k <= 1024 for k in checked)
+
+
 @pytest.mark.parametrize("meta", CASES, ids=[c["name"] for c in CASES])
 def test_replay_walks_bit_exact(meta):
     z = load_npz(meta)
