@@ -381,7 +381,7 @@ int launch_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_
     unsigned grid = (unsigned)((n_starts + 255) / 256);
     bool vec = (L % 8 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 31) == 0);
     const char *occ = getenv("GW_CN_MINB");     // experiment knob: resident blocks per SM the kernel is compiled for
-    int minb = occ ? atoi(occ) : 5;
+    int minb = occ ? atoi(occ) : (q < 1.0 ? 6 : 5);   // q < 1 chains two dependent accesses per O step: more walks in flight pay (R-MAT-24: 24.1 -> 25.6 G steps/s); q >= 1 loses 7 % at 6
     if (!vec) k_walk_cn<false, false, 5><<<grid, 256, 0, st>>>(P);
     else if (minb >= 8) k_walk_cn<true, false, 8><<<grid, 256, 0, st>>>(P);
     else if (minb >= 6) k_walk_cn<true, false, 6><<<grid, 256, 0, st>>>(P);
