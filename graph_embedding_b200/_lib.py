@@ -71,6 +71,8 @@ SIGNATURES = {
                                            ctypes.c_uint64, c_vp, c_vp, c_vp]),
     "gw_simrank_rows": (ctypes.c_int, [c_vp, c_i64p, ctypes.c_int64, ctypes.c_double, ctypes.c_int32,
                                        ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64, c_f64p]),
+    "gw_simrank_rows_javarng": (ctypes.c_int, [c_vp, c_i64p, ctypes.c_int64, ctypes.c_double, ctypes.c_int32,
+                                               ctypes.c_int32, ctypes.POINTER(ctypes.c_uint64), c_f64p]),
     "gw_simrank_last_steps": (ctypes.c_int, [c_vp, c_i64p]),
     "gw_simrank_last_slow_queries": (ctypes.c_int, [c_vp, c_i64p]),
     "gw_simrank_exact": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_int32, c_i64p, ctypes.c_int64, c_f64p]),
@@ -299,6 +301,17 @@ class GraphHandle:
                                      int(sample), int(mode), int(seed), int(query_id_base),
                                      ptr(out, ctypes.c_double)))
         return out
+
+    def simrank_rows_javarng(self, queries, c, step, sample, rng_states):
+        """Replay mode: java.util.Random per query from the given 48-bit states; returns (rows, states after)."""
+        queries = as_c(queries, np.int64)
+        st = np.ascontiguousarray(np.asarray(rng_states, dtype=np.uint64)).copy()
+        if len(st) != len(queries):
+            raise ValueError("one rng state per query")
+        out = np.empty((len(queries), self.n), dtype=np.float64)
+        check(load().gw_simrank_rows_javarng(self.h, ptr(queries, ctypes.c_int64), len(queries), float(c), int(step),
+                                             int(sample), ptr(st, ctypes.c_uint64), ptr(out, ctypes.c_double)))
+        return out, st
 
     def simrank_last_steps(self):
         s = ctypes.c_int64()

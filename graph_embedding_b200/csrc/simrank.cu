@@ -937,6 +937,68 @@ __global__ void __launch_bounds__(2 * SR_ABLOCK, 1) k_simrank_log(SimrankParams 
     }
 }
 
+// ---------------- replay mode: java.util.Random on the device ----------------
+// java.util.Random (JDK): seed = (seed * 0x5DEECE66D + 0xB) mod 2^48, next(bits) = (int)(seed >>> (48 - bits));
+// nextInt(bound): power of two -> (bound * next(31)) >> 31, else u % bound with the int-overflow rejection test.
+__device__ __forceinline__ int32_t jr_next(uint64_t &seed, int bits) {
+    seed = (seed * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
+    return (int32_t)((int64_t)seed >> (48 - bits));
+}
+__device__ __forceinline__ int32_t jr_next_int(uint64_t &seed, int32_t bound) {
+    int32_t v = jr_next(seed, 31);
+    const int32_t m = bound - 1;
+    if ((bound & m) == 0) return (int32_t)(((int64_t)bound * (int64_t)v) >> 31);
+    int32_t u = v;
+    for (;;) {
+        v = u % bound;
+        if ((int32_t)((uint32_t)u - (uint32_t)v + (uint32_t)m) >= 0) break;      // u - r + m < 0 in Java int arithmetic
+        u = jr_next(seed, 31);
+    }
+    return v;
+}
+
+// One thread per query, samples in order, fp64 accumulation in the reference's operation order
+// (SingleRandomWalk.java:89: cache[i] * deg(inter) / deg(target) / SAMPLE, left to right).
+__global__ void k_simrank_javarng(const uint2 *__restrict__ meta, const int32_t *__restrict__ col,
+                                  const int64_t *__restrict__ queries, int64_t nq, int64_t n, int32_t sample, int32_t step,
+                                  const double *__restrict__ cache, uint64_t *__restrict__ states, double *__restrict__ out,
+                                  unsigned long long *__restrict__ steps_out) {
+    const int64_t qi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    const int32_t v = (int32_t)queries[qi];
+    double *row = out + (size_t)qi * (size_t)n;
+    uint64_t seed = states[qi];
+    const int max_step = 2 * step;
+    int32_t path[21];
+    unsigned long long steps = 0;
+    for (int32_t s = 0; s < sample; s++) {
+        int len = 0;
+        path[0] = v;
+        int32_t cur = v;
+        while (len < max_step) {                                   // :64-68
+            const uint2 m = meta[cur];
+            if (m.y == 0) break;                                   // randNeighbor == -1
+            cur = col[m.x + (uint32_t)jr_next_int(seed, (int32_t)m.y)];
+            path[++len] = cur;
+            steps++;
+        }
+        if (len == 0) continue;                                    // :82
+        for (int i = 1; i <= step && 2 * i <= len; i++) {          // :84-91
+            const int32_t inter = path[i], target = path[2 * i];
+            if (target == v) continue;
+            bool first = true;
+            for (int j = 0; j < i; j++) first &= (path[j] != path[2 * i - j]);
+            if (first) {
+                const double x = __ddiv_rn(__ddiv_rn(__dmul_rn(cache[i], (double)meta[inter].y), (double)meta[target].y), (double)sample);
+                row[target] = __dadd_rn(row[target], x);
+            }
+        }
+    }
+    row[v] = 0.0;                                                  // :43
+    states[qi] = seed;
+    atomicAdd(steps_out, steps);
+}
+
 // ---------------- exact SimRank (SimRank.java:36-77) as dense sweeps ----------------
 // T[i][:] = mean over a in N(i) of S[a][:]   (rows of degree 0 -> 0)
 __global__ void k_row_average(const uint2 *__restrict__ meta, const int32_t *__restrict__ col, int64_t n,
@@ -1194,6 +1256,40 @@ int gw_simrank_rows(gw_graph *g, const int64_t *queries, int64_t nq, double c, i
     GW_CUDA(cudaMemset(dd.p, 0, sizeof(double) * (size_t)nq * (size_t)g->n));
     GW_TRY(simrank_run(g, dq.p, nq, c, step, sample, 0, mode, seed, query_id_base, nullptr, nullptr, dd.p, nullptr, true));
     GW_CUDA(cudaMemcpy(out_dense, dd.p, sizeof(double) * (size_t)nq * (size_t)g->n, cudaMemcpyDeviceToHost));
+    return GW_OK;
+}
+
+int gw_simrank_rows_javarng(gw_graph *g, const int64_t *queries, int64_t nq, double c, int32_t step, int32_t sample,
+                            uint64_t *rng_state, double *out_dense) {
+    if (!g) return fail(GW_E_INVALID, "graph is NULL");
+    if (g->flags & GW_F_DIRECTED) return fail(GW_E_INVALID, "SimRank path is defined on undirected graphs (structures/Graph.java)");
+    if (nq < 0 || (nq > 0 && (!queries || !rng_state || !out_dense))) return fail(GW_E_INVALID, "bad arguments");
+    if (step < 1 || step > 10) return fail(GW_E_INVALID, "step must be in 1..10");
+    if (sample < 1) return fail(GW_E_INVALID, "sample must be positive");
+    GW_TRY(check_queries_host(g, queries, nq));
+    if (nq == 0) return GW_OK;
+    GW_CUDA(cudaSetDevice(g->device));
+    double cache[16] = {0};
+    for (int i = 1; i <= step; i++) cache[i] = pow(c, i);          // Math.pow(C, i), :34-36
+    DevBuf<int64_t> dq;
+    DevBuf<double> dd, dc;
+    DevBuf<unsigned long long> ds, dsteps;
+    GW_CUDA(dq.alloc((size_t)nq)); GW_CUDA(dd.alloc((size_t)nq * (size_t)g->n)); GW_CUDA(dc.alloc(16));
+    GW_CUDA(ds.alloc((size_t)nq)); GW_CUDA(dsteps.alloc(1));
+    GW_CUDA(cudaMemcpy(dq.p, queries, sizeof(int64_t) * (size_t)nq, cudaMemcpyHostToDevice));
+    GW_CUDA(cudaMemcpy(dc.p, cache, sizeof(cache), cudaMemcpyHostToDevice));
+    GW_CUDA(cudaMemcpy(ds.p, rng_state, sizeof(uint64_t) * (size_t)nq, cudaMemcpyHostToDevice));
+    GW_CUDA(cudaMemset(dd.p, 0, sizeof(double) * (size_t)nq * (size_t)g->n));
+    GW_CUDA(cudaMemset(dsteps.p, 0, sizeof(unsigned long long)));
+    k_simrank_javarng<<<(unsigned)((nq + 31) / 32), 32>>>(g->d_meta, g->d_col, dq.p, nq, g->n, sample, step, dc.p,
+                                                        (uint64_t *)ds.p, dd.p, dsteps.p);
+    GW_LAUNCHED();
+    unsigned long long hs = 0;
+    GW_CUDA(cudaMemcpy(out_dense, dd.p, sizeof(double) * (size_t)nq * (size_t)g->n, cudaMemcpyDeviceToHost));
+    GW_CUDA(cudaMemcpy(rng_state, ds.p, sizeof(uint64_t) * (size_t)nq, cudaMemcpyDeviceToHost));
+    GW_CUDA(cudaMemcpy(&hs, dsteps.p, sizeof(hs), cudaMemcpyDeviceToHost));
+    g->simrank_last_steps = (int64_t)hs;
+    if (g->d_simrank_scratch) GW_CUDA(cudaMemcpy(g->d_simrank_scratch, &hs, sizeof(hs), cudaMemcpyHostToDevice));   // gw_simrank_last_steps reads it there
     return GW_OK;
 }
 

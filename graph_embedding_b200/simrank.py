@@ -81,12 +81,29 @@ class Graph:
         return self.eCount
 
 
+_JR_MULT, _JR_ADD, _JR_MASK = 0x5DEECE66D, 0xB, (1 << 48) - 1
+
+
+def _jr_jump(state, n):
+    """java.util.Random state after n calls of next(): s -> a^n s + c (a^n - 1)/(a - 1)  (mod 2^48)."""
+    a, c, acc_a, acc_c = _JR_MULT, _JR_ADD, 1, 0
+    while n:
+        if n & 1:
+            acc_a, acc_c = (acc_a * a) & _JR_MASK, (acc_c * a + c) & _JR_MASK
+        a, c = (a * a) & _JR_MASK, (c * a + c) & _JR_MASK
+        n >>= 1
+    return (acc_a * state + acc_c) & _JR_MASK
+
+
 class SingleRandomWalk:
     """simrank/SingleRandomWalk.java: pure Monte-Carlo single-walk estimator (scores / SAMPLE)."""
     MODE = _lib.GW_SIMRANK_MC
     SAMPLE = 10000
 
-    def __init__(self, g, sample, step, seed=None):
+    def __init__(self, g, sample, step, seed=None, java_seed=None):
+        """seed: Philox key of the production kernels.  java_seed: replay mode -- the walks are drawn from
+        java.util.Random(java_seed) exactly as a JVM whose `Graph.rand` (structures/Graph.java:17) was
+        seeded that way would draw them, one stream shared by all queries in order."""
         self.topk_k = MyConfiguration.TOPK
         self.STEP = step
         self.SAMPLE = sample
@@ -94,13 +111,40 @@ class SingleRandomWalk:
         self.COUNT = g.getVCount()
         self.sim = None
         self.seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
+        self.java_state = None if java_seed is None else (int(java_seed) ^ _JR_MULT) & _JR_MASK
 
     def compute(self, queries=None):
         """compute() (:39-45): every vertex 0..COUNT-1 is a query; dense result like double[][]."""
         q = np.arange(self.COUNT, dtype=np.int64) if queries is None else np.asarray(queries, dtype=np.int64)
         self._queries = q
+        if self.java_state is not None and self.MODE == _lib.GW_SIMRANK_MC:
+            self.sim = self._compute_java_stream(q)
+            return self
         self.sim = self.g.handle.simrank_rows(q, MyConfiguration.C, self.STEP, self.SAMPLE, self.MODE, self.seed)
         return self
+
+    def _compute_java_stream(self, q):
+        """All queries share ONE sequential java.util.Random stream.  A query normally consumes exactly
+        SAMPLE * 2 * STEP draws, so the state in front of every query is predicted by an LCG jump and all
+        queries replay in parallel; where the prediction fails (nextInt's rejection loop fired, or the
+        vertex is isolated and drew nothing) the tail is replayed again from the true state."""
+        out = np.zeros((len(q), self.COUNT), dtype=np.float64)
+        state, lo = self.java_state, 0
+        per_query = self.SAMPLE * 2 * self.STEP
+        while lo < len(q):
+            states = [state]
+            for _ in range(lo + 1, len(q)):
+                states.append(_jr_jump(states[-1], per_query))
+            rows, after = self.g.handle.simrank_rows_javarng(q[lo:], MyConfiguration.C, self.STEP, self.SAMPLE, states)
+            after = [int(x) for x in after]
+            good = 1                                             # rows[0] started from a true state
+            while good < len(states) and after[good - 1] == states[good]:
+                good += 1
+            out[lo:lo + good] = rows[:good]
+            state = after[good - 1]
+            lo += good
+        self.java_state = state
+        return out
 
     def getResult(self):
         return self.sim

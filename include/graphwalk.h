@@ -165,6 +165,14 @@ int gw_simrank_topk_dev(gw_graph *g, const int64_t *d_queries, int64_t nq, doubl
 int gw_simrank_rows(gw_graph *g, const int64_t *queries, int64_t nq, double c, int32_t step,
                     int32_t sample, int32_t mode, uint64_t seed, uint64_t query_id_base,
                     double *out_dense);
+/* Replay mode of SingleRandomWalk (SingleRandomWalk.java:39-106 with structures/Graph.java:69-73): every
+ * query is walked SEQUENTIALLY by one thread with java.util.Random itself (48-bit LCG, nextInt(bound)
+ * with its rejection loop), starting from rng_state[i] (the scrambled 48-bit seed), and accumulated
+ * in fp64 in the reference's operation order: out[nq*n] is what the Java code leaves in sim[v][*]
+ * when its static Random is in that state, and rng_state[i] is updated to the state after the query
+ * (feed it to the next query to replay a whole compute()).  Parity path, not the fast path. */
+int gw_simrank_rows_javarng(gw_graph *g, const int64_t *queries, int64_t nq, double c, int32_t step,
+                            int32_t sample, uint64_t *rng_state, double *out_dense);
 /* Total walk steps executed by the last gw_simrank_* call on this graph. */
 int gw_simrank_last_steps(const gw_graph *g, int64_t *steps);
 /* Queries of the last gw_simrank_topk* call that were finished by the exact hash-table kernel

@@ -213,6 +213,53 @@ def test_precision_grows_with_sample(g333):
     assert p2 > p1 and p2 > 0.9
 
 
+def test_replay_with_java_util_random_is_bit_exact(g333, o333):
+    """Replay mode (gw_simrank_rows_javarng): the device walks every query with java.util.Random itself and
+    accumulates in fp64 in SingleRandomWalk.java:89's operation order.  Fed the states the oracle's
+    sequential run went through, it must return the oracle's rows bit for bit and the same states after."""
+    qs = [0, 5, 17, 100, 332, 5]
+    st = S.java_seed(20260101)
+    states, rows = [], []
+    for v in qs:                                                 # one static Random shared by all queries (Graph.java:17)
+        states.append(st)
+        row, steps, st = S.single_random_walk_row(o333, v, 3000, 5, 0.6, st)
+        rows.append(row)
+    got, after = g333.handle.simrank_rows_javarng(qs, 0.6, 5, 3000, states)
+    assert got.tobytes() == np.asarray(rows).tobytes()
+    assert after.tolist() == states[1:] + [st]
+    assert g333.handle.simrank_last_steps() == len(qs) * 3000 * 10
+    # full-size graph with an isolated slot (zero-length paths), hubs and power-of-two degrees
+    path = os.path.join(DATA, "blog.txt.gz")
+    g = sr.Graph(path, 10313)
+    og = S.load_multigraph(path, 10313, ",")
+    deg = np.diff(og["row_ptr"])
+    pow2 = int(np.nonzero(deg == 64)[0][0])
+    qs = [0, int(np.argmax(deg)), pow2, 777]
+    st = S.java_seed(7)
+    states, rows = [], []
+    for v in qs:
+        states.append(st)
+        row, steps, st = S.single_random_walk_row(og, v, 2000, 4, 0.8, st)
+        rows.append(row)
+    got, after = g.handle.simrank_rows_javarng(qs, 0.8, 4, 2000, states)
+    assert got.tobytes() == np.asarray(rows).tobytes() and after.tolist() == states[1:] + [st]
+    assert not got[0].any() and after[0] == states[0]            # isolated vertex: no draw consumed
+
+
+def test_seeded_jvm_run_is_reproduced_by_the_mirror_class(g333, o333):
+    """SingleRandomWalk(g, sample, step, java_seed=s).compute(): the whole compute() loop of a JVM whose
+    Graph.rand was seeded with s -- one stream across all 333 queries -- equals the oracle's sequential run."""
+    st = S.java_seed(99)
+    want = np.zeros((333, 333))
+    for v in range(333):
+        want[v], _, st = S.single_random_walk_row(o333, v, 400, 5, 0.6, st)
+    srw = sr.SingleRandomWalk(g333, 400, 5, java_seed=99)
+    got = srw.compute().getResult()
+    assert got.tobytes() == want.tobytes()
+    assert srw.java_state == st
+    assert sr._jr_jump(S.java_seed(5), 0) == S.java_seed(5)
+
+
 def test_blog_graph_full_size_properties():
     """Config 2 (blog.txt, V = 10313): size-independent checks at full size."""
     g = sr.Graph(os.path.join(DATA, "blog.txt.gz"), 10313)
