@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--workload", default="node2vec", choices=["node2vec", "simrank"])
     ap.add_argument("--scale", type=int, default=22)
     ap.add_argument("--edge-factor", type=int, default=16)
+    ap.add_argument("--rmat-abc", default="0.45,0.15,0.15", help="R-MAT quadrant probabilities a,b,c (d = 1-a-b-c); "
+                    "default = the reference generator's (RMATGraphGenerator.java:179-182); Graph500: 0.57,0.19,0.19")
     ap.add_argument("--p", type=float, default=0.25)
     ap.add_argument("--q", type=float, default=4.0)
     ap.add_argument("--walk-length", type=int, default=80)
@@ -278,9 +280,10 @@ def metric_unit(args):
 
 def config_of(args):
     if args.workload == "node2vec":
-        return {"workload": "node2vec on synthetic R-MAT scale-%d (%d*2^%d tuples, a,b,c,d=.45/.15/.15/.25), p=%g q=%g, "
+        abc = "a,b,c,d=.45/.15/.15/.25" if args.rmat_abc == "0.45,0.15,0.15" else "a,b,c=" + args.rmat_abc
+        return {"workload": "node2vec on synthetic R-MAT scale-%d (%d*2^%d tuples, %s), p=%g q=%g, "
                             "walk_length=%d, one step = one walk per non-isolated vertex" %
-                            (args.scale, args.edge_factor, args.scale, args.p, args.q, args.walk_length),
+                            (args.scale, args.edge_factor, args.scale, abc, args.p, args.q, args.walk_length),
                 "cache": "inputs larger than L2 (col_idx %.0f MB, corpus %.0f MB per step)" %
                          (4.0 * 2 * args.edge_factor * (1 << args.scale) / 1e6,
                           4.0 * args.walk_length * (1 << args.scale) / 1e6),
@@ -350,7 +353,8 @@ def measure(args, rank, world, local):
     if args.workload == "node2vec":
         L = args.walk_length
         t0 = time.perf_counter()
-        g = _lib.GraphHandle.rmat(args.scale, args.edge_factor << args.scale, seed=1)
+        ra, rb, rc = [float(x) for x in args.rmat_abc.split(",")]
+        g = _lib.GraphHandle.rmat(args.scale, args.edge_factor << args.scale, a=ra, b=rb, c=rc, seed=1)
         starts_np = g.nonisolated()
         extra["graph_build_s"] = round(time.perf_counter() - t0, 3)
         extra["walk_preprocess_ms"] = round(g.prepare_walks(), 3)      # per-edge common-neighbour counts, one-off
@@ -400,12 +404,12 @@ def measure(args, rank, world, local):
             # 61 B of dram__bytes_read per access, profiles/r1_gather_flavours_ncu.csv) + streamed rows + 4 B store
             alg_bytes = 64.0 * tr["random_accesses"] + tr["streamed_bytes"] + 4.0 * steps_exec
             sector_bytes = 32.0 * tr["random_accesses"] + tr["streamed_bytes"] + 4.0 * steps_exec
-            kname = "k_walk_cn<true,false,5>"
+            kname = "k_walk_cn<true,false,5>"   # traffic.json key (flat-degree instantiation)
         else:
             alg_bytes, tr, sector_bytes = survey_bytes, None, survey_bytes
             kname = "k_walk_free<false,false>"
         roof = {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "traffic": ncu_traffic(kname) if (args.scale == 22 and args.p == 0.25 and args.q == 4.0) else None,
+                "traffic": ncu_traffic(kname) if (args.scale == 22 and args.p == 0.25 and args.q == 4.0 and args.rmat_abc == "0.45,0.15,0.15") else None,
                 "kernel": kname, "peak_source": peak_src,
                 "bytes_per_unit": alg_bytes / steps_exec, "units_per_launch": steps_exec, "launch_ms": kernel_ms,
                 "model": ("mixture walker, atom model: 64 B per random access (one {nbr,cnt,offset,degree} entry per "

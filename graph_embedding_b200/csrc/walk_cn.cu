@@ -122,8 +122,88 @@ struct CnParams {
 
 __device__ __forceinline__ float unit24(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }
 
+// Uniform draw from N(cur) & N(prev) by rejection: x uniform over the SHORTER row S, accepted iff it is in
+// the other row T (uniform over S, conditioned on membership, is uniform over S & T).  The membership test
+// is one Bloom word; only a positive pays for the binary search over T, which also yields x's position.
+// Kept out of line: it is the rare path of heavy-tailed graphs and must not cost the common path registers.
+// Returns x's nbr4 entry inside N(cur).
+__device__ __noinline__ int4 common_by_rejection(const CnParams &P, uint2 m, uint2 mprev, bool cur_short, int32_t owner_t,
+                                                 uint64_t wid, int32_t pos, uint32_t rk, unsigned long long *acc,
+                                                 unsigned long long *prop) {
+    const uint32_t s_off = cur_short ? m.x : mprev.x, s_deg = cur_short ? m.y : mprev.y;
+    const uint32_t t_off = cur_short ? mprev.x : m.x, t_deg = cur_short ? mprev.y : m.y;
+    const uint32_t tsec = (uint32_t)max(1, (32 - __clz(t_deg)) - 2);
+    uint32_t att = 0;                                        // owner_t: the vertex whose row is T (Bloom keys are edges)
+    for (;;) {
+        const uint32_t k = scale_u32(rk, s_deg);
+        const int32_t x = __ldg(P.col + s_off + k);
+        if (acc) (*acc)++;
+        bool maybe = true;
+        if (P.bloom) {
+            const uint64_t h = edge_hash(owner_t, x);
+            maybe = (__ldg(P.bloom + bloom_word(h, P.bloom_words)) & bloom_mask(h)) == bloom_mask(h);
+            if (acc) (*acc)++;
+        }
+        if (maybe) {
+            uint32_t lo2 = 0, hi2 = t_deg;                   // lower bound of x in T
+            while (lo2 < hi2) {
+                const uint32_t mid = (lo2 + hi2) >> 1;
+                if (__ldg(P.col + t_off + mid) < x) lo2 = mid + 1; else hi2 = mid;
+            }
+            if (acc) (*acc) += tsec;
+            if (lo2 < t_deg && __ldg(P.col + t_off + lo2) == x) {
+                if (acc) (*acc)++;
+                return __ldg(P.nbr4 + m.x + (cur_short ? k : lo2));      // x's entry inside N(cur)
+            }
+        }
+        uint4 r2 = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, ++att), P.key);
+        rk = r2.x;
+        if (prop) (*prop)++;
+    }
+}
+
+// Whole second-order step by rejection, for contexts where BOTH rows are long (heavy-tailed graphs, q > 1):
+// an exact common-neighbour draw would stream a long row, this costs a bounded number of accesses.
+// Return with probability r / (r + W'), W' = a (d-1-c) + b c (exact, c is known); otherwise propose x uniform
+// over N(cur), drop prev, accept with w(x) / max(a, b) where w = b for common neighbours and a otherwise.
+// "u < min(a, b)" accepts without looking; else one Bloom word decides "not common" and only positives are
+// verified by the search over N(prev).  Returns x's nbr4 entry, or .x == -2 for the return step.
+__device__ __noinline__ int4 step_by_rejection(const CnParams &P, uint2 m, uint2 mprev, int32_t prev, int32_t c, uint64_t wid,
+                                               int32_t pos, uint4 rnd, unsigned long long *acc, unsigned long long *prop) {
+    const uint32_t d = m.y;
+    const float Wp = P.a * ((float)(d - 1) - (float)c) + P.b * (float)c;
+    if (d == 1 || unit24(rnd.x) * (P.r + Wp) < P.r) return make_int4(-2, 0, 0, 0);
+    const float hi = fmaxf(P.a, P.b), lo = fminf(P.a, P.b);
+    const uint32_t ssec = (uint32_t)max(1, (32 - __clz(mprev.y)) - 2);
+    uint32_t rk = rnd.y, ra = rnd.z, att = 0;
+    for (;;) {
+        const int4 e = __ldg(P.nbr4 + m.x + scale_u32(rk, d));
+        if (acc) (*acc)++;
+        if (e.x != prev) {
+            const float u = unit24(ra) * hi;
+            bool take = u < lo;
+            if (!take) {                                       // the class of x matters
+                const uint64_t h = edge_hash(prev, e.x);
+                bool common = (__ldg(P.bloom + bloom_word(h, P.bloom_words)) & bloom_mask(h)) == bloom_mask(h);
+                if (acc) (*acc)++;
+                if (common) {
+                    common = sorted_contains(P.col + mprev.x, mprev.y, e.x);
+                    if (acc) (*acc) += ssec;
+                }
+                take = u < (common ? P.b : P.a);
+            }
+            if (take) return e;
+        }
+        const uint4 r2 = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, ++att), P.key);
+        rk = r2.x; ra = r2.y;
+        if (prop) (*prop)++;
+    }
+}
+
 // COUNT = byte-model mode: same walks, no corpus stores, per-step algorithmic bytes summed.
-template <bool VEC8, bool COUNT, int MINB>
+// HUB = the graph has rows longer than 2048 entries: common-neighbour draws of long rows go through
+// common_by_rejection (compiled out otherwise: the call costs the common path 8 % on flat-degree graphs).
+template <bool VEC8, bool COUNT, int MINB, bool HUB>
 __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
     const int lane = threadIdx.x & 31;
     const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
@@ -166,6 +246,13 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                     if (prev < 0) {                                   // first step: alias_nodes law = uniform
                         int4 e = ld_i4_policy(P.nbr4 + m.x + scale_u32(rnd.y, d), pol_stream);
                         nxt = e.x; cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w);
+                    } else if (HUB && P.bloom != nullptr && P.b > P.a && min(d, mprev.y) > 256u) {
+                        unsigned long long racc = 0, rprop = 0;
+                        const int4 e = step_by_rejection(P, m, mprev, prev, c, wid, pos, rnd, COUNT ? &racc : nullptr,
+                                                         COUNT ? &rprop : nullptr);
+                        if (e.x == -2) { nxt = prev; cn = c; mn = mprev; }
+                        else { nxt = e.x; cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w); }
+                        if (COUNT) { st_acc += racc; st_prop += rprop; }
                     } else {
                         const float dm1 = (float)(d - 1);
                         const float MR = P.r - P.r0;
@@ -193,11 +280,24 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                                 if (COUNT) { st_acc++; st_prop++; }
                             }
                         } else if (comp == 2) {                       // C: uniform over N(cur) & N(prev)
-                            want_isect = true;
-                            jsel = scale_u32(rnd.y, (uint32_t)c);
-                            if (COUNT) {   // both rows read once, in whole sectors
-                                st_bytes += 32ull * ((d * 4 + 31) / 32) + 32ull * ((mprev.y * 4 + 31) / 32);
-                                st_isect++;
+                            const bool cur_short = d <= mprev.y;
+                            const uint32_t s_deg = cur_short ? d : mprev.y, t_deg = cur_short ? mprev.y : d;
+                            if (HUB && s_deg > 64u && c >= 16) {
+                                // (per-lane rejection: ~2 dependent accesses per proposal, |S|/c proposals; the warp-
+                                // cooperative stream: ~17 cached loads per 32 elements -> rejection wins from c ~ 13 up)
+                                // long rows that share many neighbours (hub pairs of heavy-tailed graphs)
+                                unsigned long long racc = 0, rprop = 0;
+                                const int4 e = common_by_rejection(P, m, mprev, cur_short, cur_short ? prev : cur, wid, pos, rnd.y,
+                                                                   COUNT ? &racc : nullptr, COUNT ? &rprop : nullptr);
+                                nxt = e.x; cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w);
+                                if (COUNT) { st_acc += racc; st_prop += rprop; }
+                            } else {
+                                want_isect = true;
+                                jsel = scale_u32(rnd.y, (uint32_t)c);
+                                if (COUNT) {   // both rows read once, in whole sectors
+                                    st_bytes += 32ull * ((d * 4 + 31) / 32) + 32ull * ((mprev.y * 4 + 31) / 32);
+                                    st_isect++;
+                                }
                             }
                         } else {                                      // O: uniform over N(cur) \ N(prev) \ {prev}
                             uint32_t rk = rnd.y, att = 0;
@@ -242,13 +342,22 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                 const bool scan_cur = c_deg <= p_deg;          // stream the shorter row
                 const uint32_t s_off = scan_cur ? c_off : p_off, s_deg = scan_cur ? c_deg : p_deg;
                 const uint32_t t_off = scan_cur ? p_off : c_off, t_deg = scan_cur ? p_deg : c_deg;
+                // long target rows (HUB graphs): one Bloom word answers "not in T" for ~99 % of the streamed
+                // elements; only positives pay for the binary search
+                const bool use_bloom = HUB && P.bloom != nullptr && t_deg > 256u;
+                const int32_t owner_t = __shfl_sync(0xffffffffu, scan_cur ? prev : cur, src);
                 uint32_t seen = 0;
                 int32_t xsel = -1;
                 uint32_t isel = 0;
                 for (uint32_t b0 = 0; b0 < s_deg; b0 += 32) {
                     const uint32_t i = b0 + lane;
                     int32_t x = (i < s_deg) ? __ldg(P.col + s_off + i) : -1;
-                    bool f = (i < s_deg) && sorted_contains(P.col + t_off, t_deg, x);
+                    bool f = i < s_deg;
+                    if (f && use_bloom) {
+                        const uint64_t h = edge_hash(owner_t, x);
+                        f = (__ldg(P.bloom + bloom_word(h, P.bloom_words)) & bloom_mask(h)) == bloom_mask(h);
+                    }
+                    f = f && sorted_contains(P.col + t_off, t_deg, x);
                     uint32_t bal = __ballot_sync(0xffffffffu, f);
                     uint32_t nb = __popc(bal);
                     if (seen + nb > j) {
@@ -370,7 +479,7 @@ static int ensure_bloom(gw_graph *g, cudaStream_t st) {
 int launch_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_starts, int64_t n_starts, uint64_t seed,
                    uint64_t walk_id_base, int32_t *d_out, int32_t *d_lens, cudaStream_t st) {
     CnParams P;
-    if (q < 1.0) GW_TRY(ensure_bloom(g, st));
+    if (!(p == 1.0 && q == 1.0)) GW_TRY(ensure_bloom(g, st));
     P.meta = g->d_meta; P.col = g->d_col; P.nbr4 = g->d_nbr4; P.starts = d_starts; P.n_walks = n_starts; P.L = L;
     P.bloom = g->d_bloom; P.bloom_words = g->bloom_words;
     P.a = (float)(1.0 / q); P.b = 1.0f; P.r = (float)(1.0 / p);
@@ -382,10 +491,15 @@ int launch_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_
     bool vec = (L % 8 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 31) == 0);
     const char *occ = getenv("GW_CN_MINB");     // experiment knob: resident blocks per SM the kernel is compiled for
     int minb = occ ? atoi(occ) : (q < 1.0 ? 6 : 5);   // q < 1 chains two dependent accesses per O step: more walks in flight pay (R-MAT-24: 24.1 -> 25.6 G steps/s); q >= 1 loses 7 % at 6
-    if (!vec) k_walk_cn<false, false, 5><<<grid, 256, 0, st>>>(P);
-    else if (minb >= 8) k_walk_cn<true, false, 8><<<grid, 256, 0, st>>>(P);
-    else if (minb >= 6) k_walk_cn<true, false, 6><<<grid, 256, 0, st>>>(P);
-    else k_walk_cn<true, false, 5><<<grid, 256, 0, st>>>(P);
+    const bool hub = g->max_degree > 2048 || getenv("GW_CN_HUB") != nullptr;    // env: test knob for small graphs
+    if (!vec) { if (hub) k_walk_cn<false, false, 5, true><<<grid, 256, 0, st>>>(P); else k_walk_cn<false, false, 5, false><<<grid, 256, 0, st>>>(P); }
+    else if (hub) {
+        if (minb >= 6) k_walk_cn<true, false, 6, true><<<grid, 256, 0, st>>>(P);
+        else k_walk_cn<true, false, 5, true><<<grid, 256, 0, st>>>(P);
+    }
+    else if (minb >= 8) k_walk_cn<true, false, 8, false><<<grid, 256, 0, st>>>(P);
+    else if (minb >= 6) k_walk_cn<true, false, 6, false><<<grid, 256, 0, st>>>(P);
+    else k_walk_cn<true, false, 5, false><<<grid, 256, 0, st>>>(P);
     GW_LAUNCHED();
     return GW_OK;
 }
@@ -394,7 +508,7 @@ int launch_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_
 int count_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_starts, int64_t n_starts, uint64_t seed,
                   uint64_t walk_id_base, unsigned long long *d_stats, cudaStream_t st) {
     CnParams P;
-    if (q < 1.0) GW_TRY(ensure_bloom(g, st));
+    if (!(p == 1.0 && q == 1.0)) GW_TRY(ensure_bloom(g, st));
     P.meta = g->d_meta; P.col = g->d_col; P.nbr4 = g->d_nbr4; P.starts = d_starts; P.n_walks = n_starts; P.L = L;
     P.bloom = g->d_bloom; P.bloom_words = g->bloom_words;
     P.a = (float)(1.0 / q); P.b = 1.0f; P.r = (float)(1.0 / p);
@@ -403,7 +517,8 @@ int count_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_s
     P.walk_id_base = walk_id_base; P.out = nullptr; P.lens = nullptr;
     P.stats = d_stats;
     unsigned grid = (unsigned)((n_starts + 255) / 256);
-    k_walk_cn<false, true, 5><<<grid, 256, 0, st>>>(P);
+    if (g->max_degree > 2048 || getenv("GW_CN_HUB") != nullptr) k_walk_cn<false, true, 5, true><<<grid, 256, 0, st>>>(P);
+    else k_walk_cn<false, true, 5, false><<<grid, 256, 0, st>>>(P);
     GW_LAUNCHED();
     return GW_OK;
 }

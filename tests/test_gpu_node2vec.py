@@ -170,6 +170,38 @@ def test_free_running_chi_square(name, reps, pq, walker, monkeypatch):
         assert stats.chi2.sf(chi2w, dfw) < 1e-6
 
 
+def test_hub_pairs_chi_square(monkeypatch):
+    """Heavy-tailed shape: hubs that share most of their (long) rows.  The common-neighbour draw of such
+    pairs goes through per-lane rejection instead of the warp-cooperative intersection; the transition
+    frequencies must still follow get_alias_edge's law (pooled chi-square, alpha = 1e-4)."""
+    monkeypatch.setenv("GW_CN_HUB", "1")          # the kernel instantiation graphs with rows > 2048 entries get
+    n_leaf = 330                                  # hub rows ~285 entries: both rows > 256 -> whole-step rejection (hub-hub), shorter -> mixture
+    hubs = [0, 1, 2]
+    src, dst = [], []
+    for h_ in hubs:
+        for leaf in range(3, 3 + n_leaf):
+            if (leaf + h_) % 7:                                   # rows differ a little: common counts < degree
+                src.append(h_); dst.append(leaf)
+    src += [0, 0, 1]; dst += [1, 2, 2]                            # hub-hub edges
+    for leaf in range(3, 3 + n_leaf - 1, 2):
+        src.append(leaf); dst.append(leaf + 1)                    # some leaf-leaf edges
+    src, dst = np.array(src, dtype=np.int64), np.array(dst, dtype=np.int64)
+    g = O.build_simple_graph(src, dst, np.ones(len(src)), directed=False)
+    h = _lib.GraphHandle.from_edges(src, dst)
+    deg = np.diff(g["row_ptr"])
+    assert deg[:3].min() > 256                                    # long enough for both rejection paths
+    for p, q in ((0.25, 4.0), (2.0, 3.0)):
+        starts = np.tile(np.arange(h.n, dtype=np.int64), 400)
+        walks, lens = h.walks(p, q, 30, starts, seed=77)
+        chi2, df = chi2_transitions(walks, lens, g, lambda c: O.first_step_law(g, c),
+                                    lambda a, b: O.second_order_law(g, a, b, p, q))
+        pval = stats.chi2.sf(chi2, df)
+        assert df > 300 and pval > 1e-4, (p, q, chi2, df, pval)
+        bad, dfb = chi2_transitions(walks, lens, g, lambda c: O.first_step_law(g, c),
+                                    lambda a, b: O.second_order_law(g, a, b, p * 1.5, q / 1.5))
+        assert stats.chi2.sf(bad, dfb) < 1e-6                     # power: a nearby law is rejected
+
+
 @pytest.mark.parametrize("walker", ["mixture", "rejection"])
 def test_walks_independent_of_batch_split(walker, monkeypatch):
     if walker == "rejection":
