@@ -114,6 +114,9 @@ struct gw_graph {
     // ONE random 8-byte access instead of a binary search over N(prev); positives are verified exactly
     unsigned long long *d_bloom = nullptr;
     uint64_t bloom_words = 0;
+    // per-row hash sets for LONG rows of heavy-tailed graphs (lazy): row v with degree > 256 owns the 2*deg
+    // slots rowhash[2*off(v) ...]; membership in a 100k-entry row costs 1-2 accesses instead of 17
+    int32_t *d_rowhash = nullptr;
     int has_self_loops = -1;       // -1 unknown
     double common_build_ms = 0;
     // host-API workspace (grow-only): staging buffers and two streams for the chunked pipeline

@@ -404,7 +404,7 @@ int gw_graph_free(gw_graph *g) {
     cudaSetDevice(g->device);
     cudaFree(g->d_meta); cudaFree(g->d_col); cudaFree(g->d_w); cudaFree(g->d_row_ptr);
     cudaFree(g->d_anJ); cudaFree(g->d_anq); cudaFree(g->d_aeoff); cudaFree(g->d_aeJ); cudaFree(g->d_aeq);
-    cudaFree(g->d_simrank_scratch); cudaFree(g->d_nbr4); cudaFree(g->d_bloom); cudaFree(g->d_hybrid_scratch);
+    cudaFree(g->d_simrank_scratch); cudaFree(g->d_nbr4); cudaFree(g->d_bloom); cudaFree(g->d_rowhash); cudaFree(g->d_hybrid_scratch);
     cudaFree(g->ws_starts); cudaFree(g->ws_sr_dev);
     if (g->ws_sr_pin) cudaFreeHost(g->ws_sr_pin);
     for (int i = 0; i < 2; i++) { cudaFree(g->ws_out[i]); cudaFree(g->ws_lens[i]); if (g->ws_stream[i]) cudaStreamDestroy(g->ws_stream[i]); }

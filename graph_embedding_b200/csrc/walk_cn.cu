@@ -37,6 +37,50 @@ __device__ __forceinline__ bool sorted_contains(const int32_t *__restrict__ row,
     return lo < d && __ldg(row + lo) == x;
 }
 
+// ---- per-row hash sets of long rows (heavy-tailed graphs) ----------------------------------------
+constexpr uint32_t ROWHASH_MIN_DEG = 256;      // rows longer than this own 2*deg open-addressing slots at rowhash[2*off]
+__device__ __forceinline__ uint32_t rowhash_slot(int32_t x, uint32_t size) {
+    uint32_t h = (uint32_t)x;
+    h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+    return __umulhi(h, size);
+}
+// x in N(row)?  Long rows with a hash set: linear probing from the hashed slot (load factor 1/2); others:
+// binary search over the sorted row.
+__device__ __forceinline__ bool row_contains(const int32_t *__restrict__ col, const int32_t *__restrict__ rowhash, uint2 mrow,
+                                             int32_t x) {
+    if (rowhash != nullptr && mrow.y > ROWHASH_MIN_DEG) {
+        const uint32_t size = 2u * mrow.y;
+        const int32_t *tab = rowhash + 2ull * mrow.x;
+        uint32_t s = rowhash_slot(x, size);
+        for (;;) {
+            const int32_t v = __ldg(tab + s);
+            if (v == x) return true;
+            if (v < 0) return false;
+            s = s + 1 == size ? 0 : s + 1;
+        }
+    }
+    return sorted_contains(col + mrow.x, mrow.y, x);
+}
+__global__ void k_rowhash_build(const uint2 *__restrict__ meta, const int32_t *__restrict__ col, int64_t n,
+                                int32_t *__restrict__ rowhash) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t v = warp; v < n; v += nwarps) {
+        const uint2 m = __ldg(meta + v);
+        if (m.y <= ROWHASH_MIN_DEG) continue;
+        const uint32_t size = 2u * m.y;
+        int32_t *tab = rowhash + 2ull * m.x;
+        for (uint32_t i = lane; i < size; i += 32) tab[i] = -1;
+        __syncwarp();
+        for (uint32_t i = lane; i < m.y; i += 32) {
+            const int32_t x = __ldg(col + m.x + i);
+            uint32_t s = rowhash_slot(x, size);
+            while (atomicCAS(tab + s, -1, x) != -1) s = s + 1 == size ? 0 : s + 1;     // sorted SIMPLE rows hold no duplicates
+        }
+    }
+}
+
 // ---- edge Bloom filter: 16 bits per undirected edge, 4 bits of one 64-bit word per key ----------
 __device__ __forceinline__ uint64_t edge_hash(int32_t a, int32_t b) {      // unordered pair
     uint64_t k = a < b ? ((uint64_t)(uint32_t)a << 32) | (uint32_t)b : ((uint64_t)(uint32_t)b << 32) | (uint32_t)a;
@@ -108,6 +152,7 @@ struct CnParams {
     const int4 *nbr4;
     const unsigned long long *bloom;   // edge Bloom filter (component O), may be NULL
     uint64_t bloom_words;
+    const int32_t *rowhash;            // hash sets of long rows (HUB graphs), may be NULL
     const int64_t *starts;
     int64_t n_walks;
     int32_t L;
@@ -138,22 +183,40 @@ __device__ __noinline__ int4 common_by_rejection(const CnParams &P, uint2 m, uin
         const uint32_t k = scale_u32(rk, s_deg);
         const int32_t x = __ldg(P.col + s_off + k);
         if (acc) (*acc)++;
-        bool maybe = true;
-        if (P.bloom) {
-            const uint64_t h = edge_hash(owner_t, x);
-            maybe = (__ldg(P.bloom + bloom_word(h, P.bloom_words)) & bloom_mask(h)) == bloom_mask(h);
+        if (P.rowhash != nullptr && t_deg > ROWHASH_MIN_DEG) {           // exact membership in 1-2 accesses
             if (acc) (*acc)++;
-        }
-        if (maybe) {
-            uint32_t lo2 = 0, hi2 = t_deg;                   // lower bound of x in T
-            while (lo2 < hi2) {
-                const uint32_t mid = (lo2 + hi2) >> 1;
-                if (__ldg(P.col + t_off + mid) < x) lo2 = mid + 1; else hi2 = mid;
-            }
-            if (acc) (*acc) += tsec;
-            if (lo2 < t_deg && __ldg(P.col + t_off + lo2) == x) {
+            if (row_contains(P.col, P.rowhash, make_uint2(t_off, t_deg), x)) {
+                uint32_t idx = k;
+                if (!cur_short) {                                          // x's position inside N(cur) = T: one search per ACCEPTED draw
+                    uint32_t lo2 = 0, hi2 = t_deg;
+                    while (lo2 < hi2) {
+                        const uint32_t mid = (lo2 + hi2) >> 1;
+                        if (__ldg(P.col + t_off + mid) < x) lo2 = mid + 1; else hi2 = mid;
+                    }
+                    idx = lo2;
+                    if (acc) (*acc) += tsec;
+                }
                 if (acc) (*acc)++;
-                return __ldg(P.nbr4 + m.x + (cur_short ? k : lo2));      // x's entry inside N(cur)
+                return __ldg(P.nbr4 + m.x + idx);
+            }
+        } else {
+            bool maybe = true;
+            if (P.bloom) {
+                const uint64_t h = edge_hash(owner_t, x);
+                maybe = (__ldg(P.bloom + bloom_word(h, P.bloom_words)) & bloom_mask(h)) == bloom_mask(h);
+                if (acc) (*acc)++;
+            }
+            if (maybe) {
+                uint32_t lo2 = 0, hi2 = t_deg;                   // lower bound of x in T
+                while (lo2 < hi2) {
+                    const uint32_t mid = (lo2 + hi2) >> 1;
+                    if (__ldg(P.col + t_off + mid) < x) lo2 = mid + 1; else hi2 = mid;
+                }
+                if (acc) (*acc) += tsec;
+                if (lo2 < t_deg && __ldg(P.col + t_off + lo2) == x) {
+                    if (acc) (*acc)++;
+                    return __ldg(P.nbr4 + m.x + (cur_short ? k : lo2));      // x's entry inside N(cur)
+                }
             }
         }
         uint4 r2 = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, ++att), P.key);
@@ -183,12 +246,18 @@ __device__ __noinline__ int4 step_by_rejection(const CnParams &P, uint2 m, uint2
             const float u = unit24(ra) * hi;
             bool take = u < lo;
             if (!take) {                                       // the class of x matters
-                const uint64_t h = edge_hash(prev, e.x);
-                bool common = (__ldg(P.bloom + bloom_word(h, P.bloom_words)) & bloom_mask(h)) == bloom_mask(h);
-                if (acc) (*acc)++;
-                if (common) {
-                    common = sorted_contains(P.col + mprev.x, mprev.y, e.x);
-                    if (acc) (*acc) += ssec;
+                bool common;
+                if (P.rowhash) {                               // exact, 1-2 accesses (both rows are long here)
+                    common = row_contains(P.col, P.rowhash, mprev, e.x);
+                    if (acc) (*acc)++;
+                } else {
+                    const uint64_t h = edge_hash(prev, e.x);
+                    common = (__ldg(P.bloom + bloom_word(h, P.bloom_words)) & bloom_mask(h)) == bloom_mask(h);
+                    if (acc) (*acc)++;
+                    if (common) {
+                        common = sorted_contains(P.col + mprev.x, mprev.y, e.x);
+                        if (acc) (*acc) += ssec;
+                    }
                 }
                 take = u < (common ? P.b : P.a);
             }
@@ -319,7 +388,7 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                                     }
                                     if (maybe) {
                                         if (COUNT) st_acc += ssec;
-                                        take = !sorted_contains(P.col + mprev.x, mprev.y, e.x);
+                                        take = !row_contains(P.col, HUB ? P.rowhash : nullptr, mprev, e.x);
                                     }
                                 }
                                 if (take) { nxt = e.x; cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w); break; }
@@ -357,7 +426,7 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                         const uint64_t h = edge_hash(owner_t, x);
                         f = (__ldg(P.bloom + bloom_word(h, P.bloom_words)) & bloom_mask(h)) == bloom_mask(h);
                     }
-                    f = f && sorted_contains(P.col + t_off, t_deg, x);
+                    f = f && row_contains(P.col, HUB ? P.rowhash : nullptr, make_uint2(t_off, t_deg), x);
                     uint32_t bal = __ballot_sync(0xffffffffu, f);
                     uint32_t nb = __popc(bal);
                     if (seen + nb > j) {
@@ -476,12 +545,30 @@ static int ensure_bloom(gw_graph *g, cudaStream_t st) {
     return GW_OK;
 }
 
+// Lazy hash sets of the long rows (heavy-tailed graphs only): 2 slots per directed entry, 8 bytes per entry.
+static int ensure_rowhash(gw_graph *g, cudaStream_t st) {
+    if (g->d_rowhash || g->nnz == 0) return GW_OK;
+    const char *off = getenv("GW_ROWHASH");
+    if (off && !strcmp(off, "0")) return GW_OK;             // experiment knob: binary searches only
+    if (cudaMalloc((void **)&g->d_rowhash, sizeof(int32_t) * 2 * (size_t)g->nnz) != cudaSuccess) {
+        cudaGetLastError(); g->d_rowhash = nullptr; return GW_OK;                       // optional
+    }
+    int sms = 148;
+    device_info(&sms, nullptr);
+    k_rowhash_build<<<sms * 16, 256, 0, st>>>(g->d_meta, g->d_col, g->n, g->d_rowhash);
+    GW_LAUNCHED();
+    GW_CUDA(cudaStreamSynchronize(st));
+    return GW_OK;
+}
+static bool is_hub_graph(const gw_graph *g) { return g->max_degree > 2048 || getenv("GW_CN_HUB") != nullptr; }   // env: test knob for small graphs
+
 int launch_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_starts, int64_t n_starts, uint64_t seed,
                    uint64_t walk_id_base, int32_t *d_out, int32_t *d_lens, cudaStream_t st) {
     CnParams P;
     if (!(p == 1.0 && q == 1.0)) GW_TRY(ensure_bloom(g, st));
+    if (!(p == 1.0 && q == 1.0) && is_hub_graph(g)) GW_TRY(ensure_rowhash(g, st));
     P.meta = g->d_meta; P.col = g->d_col; P.nbr4 = g->d_nbr4; P.starts = d_starts; P.n_walks = n_starts; P.L = L;
-    P.bloom = g->d_bloom; P.bloom_words = g->bloom_words;
+    P.bloom = g->d_bloom; P.bloom_words = g->bloom_words; P.rowhash = g->d_rowhash;
     P.a = (float)(1.0 / q); P.b = 1.0f; P.r = (float)(1.0 / p);
     P.lo = std::min(P.a, P.b); P.r0 = std::min(P.r, P.lo);
     P.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
@@ -491,7 +578,7 @@ int launch_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_
     bool vec = (L % 8 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 31) == 0);
     const char *occ = getenv("GW_CN_MINB");     // experiment knob: resident blocks per SM the kernel is compiled for
     int minb = occ ? atoi(occ) : (q < 1.0 ? 6 : 5);   // q < 1 chains two dependent accesses per O step: more walks in flight pay (R-MAT-24: 24.1 -> 25.6 G steps/s); q >= 1 loses 7 % at 6
-    const bool hub = g->max_degree > 2048 || getenv("GW_CN_HUB") != nullptr;    // env: test knob for small graphs
+    const bool hub = is_hub_graph(g);
     if (!vec) { if (hub) k_walk_cn<false, false, 5, true><<<grid, 256, 0, st>>>(P); else k_walk_cn<false, false, 5, false><<<grid, 256, 0, st>>>(P); }
     else if (hub) {
         if (minb >= 6) k_walk_cn<true, false, 6, true><<<grid, 256, 0, st>>>(P);
@@ -509,15 +596,16 @@ int count_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_s
                   uint64_t walk_id_base, unsigned long long *d_stats, cudaStream_t st) {
     CnParams P;
     if (!(p == 1.0 && q == 1.0)) GW_TRY(ensure_bloom(g, st));
+    if (!(p == 1.0 && q == 1.0) && is_hub_graph(g)) GW_TRY(ensure_rowhash(g, st));
     P.meta = g->d_meta; P.col = g->d_col; P.nbr4 = g->d_nbr4; P.starts = d_starts; P.n_walks = n_starts; P.L = L;
-    P.bloom = g->d_bloom; P.bloom_words = g->bloom_words;
+    P.bloom = g->d_bloom; P.bloom_words = g->bloom_words; P.rowhash = g->d_rowhash;
     P.a = (float)(1.0 / q); P.b = 1.0f; P.r = (float)(1.0 / p);
     P.lo = std::min(P.a, P.b); P.r0 = std::min(P.r, P.lo);
     P.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     P.walk_id_base = walk_id_base; P.out = nullptr; P.lens = nullptr;
     P.stats = d_stats;
     unsigned grid = (unsigned)((n_starts + 255) / 256);
-    if (g->max_degree > 2048 || getenv("GW_CN_HUB") != nullptr) k_walk_cn<false, true, 5, true><<<grid, 256, 0, st>>>(P);
+    if (is_hub_graph(g)) k_walk_cn<false, true, 5, true><<<grid, 256, 0, st>>>(P);
     else k_walk_cn<false, true, 5, false><<<grid, 256, 0, st>>>(P);
     GW_LAUNCHED();
     return GW_OK;
