@@ -73,6 +73,9 @@ SIGNATURES = {
                                        ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64, c_f64p]),
     "gw_simrank_rows_javarng": (ctypes.c_int, [c_vp, c_i64p, ctypes.c_int64, ctypes.c_double, ctypes.c_int32,
                                                ctypes.c_int32, ctypes.POINTER(ctypes.c_uint64), c_f64p]),
+    "gw_topsim_rows_javarng": (ctypes.c_int, [c_vp, c_i64p, ctypes.c_int64, ctypes.c_double, ctypes.c_int32,
+                                              ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
+                                              ctypes.POINTER(ctypes.c_uint64), c_f64p]),
     "gw_simrank_last_steps": (ctypes.c_int, [c_vp, c_i64p]),
     "gw_simrank_last_slow_queries": (ctypes.c_int, [c_vp, c_i64p]),
     "gw_simrank_exact": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_int32, c_i64p, ctypes.c_int64, c_f64p]),
@@ -311,6 +314,20 @@ class GraphHandle:
         out = np.empty((len(queries), self.n), dtype=np.float64)
         check(load().gw_simrank_rows_javarng(self.h, ptr(queries, ctypes.c_int64), len(queries), float(c), int(step),
                                              int(sample), ptr(st, ctypes.c_uint64), ptr(out, ctypes.c_double)))
+        return out, st
+
+    def topsim_rows_javarng(self, queries, c, step, sample, rng_states, mode=0, max_paths=0):
+        """Replay mode of TopSim_singleSample (mode 0) / TopSim_Enumerate (mode 1); returns (rows x SAMPLE, states after)."""
+        queries = as_c(queries, np.int64)
+        st = np.ascontiguousarray(np.asarray(rng_states, dtype=np.uint64)).copy()
+        if len(st) != len(queries):
+            raise ValueError("one rng state per query")
+        if max_paths <= 0:
+            max_paths = 2 * int(step) * int(sample) + 1           # paths(l) <= 1 + l * SAMPLE for the hybrid tree
+        out = np.empty((len(queries), self.n), dtype=np.float64)
+        check(load().gw_topsim_rows_javarng(self.h, ptr(queries, ctypes.c_int64), len(queries), float(c), int(step),
+                                            int(sample), int(mode), int(max_paths), ptr(st, ctypes.c_uint64),
+                                            ptr(out, ctypes.c_double)))
         return out, st
 
     def simrank_last_steps(self):

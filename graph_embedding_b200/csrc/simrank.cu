@@ -999,6 +999,91 @@ __global__ void k_simrank_javarng(const uint2 *__restrict__ meta, const int32_t 
     atomicAdd(steps_out, steps);
 }
 
+// Replay of the path-tree estimators: one thread per query walks the reference's FIFO queue level by level
+// (TopSim_singleSample.java:62-158 / TopSim_Enumerate.java:61-130) in two global-memory level buffers:
+// vb[level parity][position 0..2*STEP][cap] (structure of arrays), wb[level parity][cap].
+__global__ void k_topsim_javarng(const uint2 *__restrict__ meta, const int32_t *__restrict__ col,
+                                 const int64_t *__restrict__ queries, int64_t nq, int64_t n, int32_t sample, int32_t step,
+                                 int32_t mode, const double *__restrict__ cache, int64_t cap, int32_t *__restrict__ vbuf,
+                                 double *__restrict__ wbuf, uint64_t *__restrict__ states, double *__restrict__ out,
+                                 int *__restrict__ err) {
+    const int64_t qi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    const int32_t v = (int32_t)queries[qi];
+    const int max_step = 2 * step, LEN1 = max_step + 1;
+    double *row = out + (size_t)qi * (size_t)n;
+    int32_t *vb = vbuf + (size_t)qi * 2 * LEN1 * cap;
+    double *wb = wbuf + (size_t)qi * 2 * cap;
+    uint64_t seed = states[qi];
+    int64_t n0 = 1;
+    for (int i = 0; i <= max_step; i++) vb[(size_t)i * cap] = -1;
+    vb[0] = v; wb[0] = (double)sample;
+    int path_len = 0, topsim = 1;
+    bool overflow = false;
+    for (;;) {
+        const int b = path_len & 1;
+        const int32_t *vin = vb + (size_t)b * LEN1 * cap;
+        const double *win = wb + (size_t)b * cap;
+        int32_t *vout = vb + (size_t)(b ^ 1) * LEN1 * cap;
+        double *wout = wb + (size_t)(b ^ 1) * cap;
+        const bool last = path_len >= max_step;
+        if (last || path_len / 2 == topsim) {                       // computePathSim, :80-83 and :157
+            const int start = topsim;
+            if (path_len != 0) {
+                for (int64_t k = 0; k < n0; k++) {
+                    for (int i = start; i <= step && 2 * i <= path_len; i++) {          // :180-192
+                        const int32_t inter = vin[(size_t)i * cap + k], target = vin[(size_t)(2 * i) * cap + k];
+                        if (target == v || target == -1) continue;
+                        bool first = true;
+                        for (int j = 0; j < i; j++) first &= (vin[(size_t)j * cap + k] != vin[(size_t)(2 * i - j) * cap + k]);
+                        if (first)
+                            row[target] = __dadd_rn(row[target], __ddiv_rn(__dmul_rn(__dmul_rn(win[k], cache[i]), (double)meta[inter].y),
+                                                                          (double)meta[target].y));   // :189
+                    }
+                }
+            }
+            if (!last) topsim++;
+        }
+        if (last) break;
+        int64_t n1 = 0;
+        for (int64_t k = 0; k < n0 && !overflow; k++) {
+            const int32_t c = vin[(size_t)path_len * cap + k];
+            const double wt = win[k];
+            const uint2 m = meta[c];
+            const int d = (int)m.y;
+            if (d != 0 && (mode == 1 || wt >= (double)d)) {          // :99-125 enumerate
+                const double ns = __ddiv_rn(wt, (double)d);
+                if (n1 + d > cap) { overflow = true; break; }
+                for (int j = 0; j < d; j++) {
+                    for (int pos = 0; pos <= path_len; pos++) vout[(size_t)pos * cap + n1] = vin[(size_t)pos * cap + k];
+                    for (int pos = path_len + 2; pos <= max_step; pos++) vout[(size_t)pos * cap + n1] = -1;
+                    vout[(size_t)(path_len + 1) * cap + n1] = col[m.x + j];
+                    wout[n1] = ns;
+                    n1++;
+                }
+            } else if (mode == 0) {                                  // :126-149 ceil(weight) random children
+                const int number = ((double)(int)wt == wt) ? (int)wt : (int)wt + 1;
+                for (int j = 0; j < number; j++) {
+                    if (d == 0) break;                               // randNeighbor == -1
+                    const int32_t nb = col[m.x + (uint32_t)jr_next_int(seed, d)];
+                    if (n1 + 1 > cap) { overflow = true; break; }
+                    for (int pos = 0; pos <= path_len; pos++) vout[(size_t)pos * cap + n1] = vin[(size_t)pos * cap + k];
+                    for (int pos = path_len + 2; pos <= max_step; pos++) vout[(size_t)pos * cap + n1] = -1;
+                    vout[(size_t)(path_len + 1) * cap + n1] = nb;
+                    wout[n1] = __ddiv_rn(wt, (double)number);
+                    n1++;
+                }
+            }
+        }
+        if (overflow) break;
+        n0 = n1;
+        path_len++;
+    }
+    if (overflow) atomicExch(err, 1);
+    row[v] = 0.0;
+    states[qi] = seed;
+}
+
 // ---------------- exact SimRank (SimRank.java:36-77) as dense sweeps ----------------
 // T[i][:] = mean over a in N(i) of S[a][:]   (rows of degree 0 -> 0)
 __global__ void k_row_average(const uint2 *__restrict__ meta, const int32_t *__restrict__ col, int64_t n,
@@ -1290,6 +1375,47 @@ int gw_simrank_rows_javarng(gw_graph *g, const int64_t *queries, int64_t nq, dou
     GW_CUDA(cudaMemcpy(&hs, dsteps.p, sizeof(hs), cudaMemcpyDeviceToHost));
     g->simrank_last_steps = (int64_t)hs;
     if (g->d_simrank_scratch) GW_CUDA(cudaMemcpy(g->d_simrank_scratch, &hs, sizeof(hs), cudaMemcpyHostToDevice));   // gw_simrank_last_steps reads it there
+    return GW_OK;
+}
+
+int gw_topsim_rows_javarng(gw_graph *g, const int64_t *queries, int64_t nq, double c, int32_t step, int32_t sample,
+                           int32_t mode, int64_t max_paths, uint64_t *rng_state, double *out_dense) {
+    if (!g) return fail(GW_E_INVALID, "graph is NULL");
+    if (g->flags & GW_F_DIRECTED) return fail(GW_E_INVALID, "SimRank path is defined on undirected graphs (structures/Graph.java)");
+    if (nq < 0 || (nq > 0 && (!queries || !rng_state || !out_dense))) return fail(GW_E_INVALID, "bad arguments");
+    if (step < 1 || step > 10) return fail(GW_E_INVALID, "step must be in 1..10");
+    if (sample < 1 || max_paths < 1) return fail(GW_E_INVALID, "sample and max_paths must be positive");
+    if (mode != 0 && mode != 1) return fail(GW_E_INVALID, "mode must be 0 (TopSim_singleSample) or 1 (TopSim_Enumerate)");
+    GW_TRY(check_queries_host(g, queries, nq));
+    if (nq == 0) return GW_OK;
+    GW_CUDA(cudaSetDevice(g->device));
+    double cache[16] = {0};
+    for (int i = 1; i <= step; i++) cache[i] = pow(c, i);          // Math.pow(C, i)
+    const size_t LEN1 = 2 * (size_t)step + 1;
+    DevBuf<int64_t> dq;
+    DevBuf<double> dd, dc, dw;
+    DevBuf<int32_t> dv;
+    DevBuf<unsigned long long> ds;
+    DevBuf<int> derr;
+    if (dv.alloc((size_t)nq * 2 * LEN1 * (size_t)max_paths) != cudaSuccess || dw.alloc((size_t)nq * 2 * (size_t)max_paths) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(GW_E_TOO_LARGE, "path buffers for %lld queries x %lld paths do not fit", (long long)nq, (long long)max_paths);
+    }
+    GW_CUDA(dq.alloc((size_t)nq)); GW_CUDA(dd.alloc((size_t)nq * (size_t)g->n)); GW_CUDA(dc.alloc(16));
+    GW_CUDA(ds.alloc((size_t)nq)); GW_CUDA(derr.alloc(1));
+    GW_CUDA(cudaMemcpy(dq.p, queries, sizeof(int64_t) * (size_t)nq, cudaMemcpyHostToDevice));
+    GW_CUDA(cudaMemcpy(dc.p, cache, sizeof(cache), cudaMemcpyHostToDevice));
+    GW_CUDA(cudaMemcpy(ds.p, rng_state, sizeof(uint64_t) * (size_t)nq, cudaMemcpyHostToDevice));
+    GW_CUDA(cudaMemset(dd.p, 0, sizeof(double) * (size_t)nq * (size_t)g->n));
+    GW_CUDA(cudaMemset(derr.p, 0, sizeof(int)));
+    k_topsim_javarng<<<(unsigned)((nq + 31) / 32), 32>>>(g->d_meta, g->d_col, dq.p, nq, g->n, sample, step, mode, dc.p, max_paths, dv.p,
+                                                       dw.p, (uint64_t *)ds.p, dd.p, derr.p);
+    GW_LAUNCHED();
+    int herr = 0;
+    GW_CUDA(cudaMemcpy(&herr, derr.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (herr) return fail(GW_E_TOO_LARGE, "a level of the path tree exceeded max_paths = %lld", (long long)max_paths);
+    GW_CUDA(cudaMemcpy(out_dense, dd.p, sizeof(double) * (size_t)nq * (size_t)g->n, cudaMemcpyDeviceToHost));
+    GW_CUDA(cudaMemcpy(rng_state, ds.p, sizeof(uint64_t) * (size_t)nq, cudaMemcpyDeviceToHost));
     return GW_OK;
 }
 

@@ -158,8 +158,42 @@ class SingleRandomWalk:
 
 class TopSim_singleSample(SingleRandomWalk):
     """simrank/TopSim_singleSample.java: hybrid enumerate-while-weight>=degree else sample
-    (scores x SAMPLE, unnormalised, as the reference :189)."""
+    (scores x SAMPLE, unnormalised, as the reference :189).  java_seed: replay mode -- the reference's queue
+    order with java.util.Random(java_seed), one stream over all queries (sequential, parity path)."""
     MODE = _lib.GW_SIMRANK_HYBRID
+
+    def compute(self, queries=None):
+        if self.java_state is None:
+            return super().compute(queries)
+        q = np.arange(self.COUNT, dtype=np.int64) if queries is None else np.asarray(queries, dtype=np.int64)
+        self._queries = q
+        out = np.zeros((len(q), self.COUNT), dtype=np.float64)
+        for i, v in enumerate(q.tolist()):                       # draws per query vary: the stream is chained query by query
+            row, after = self.g.handle.topsim_rows_javarng([v], MyConfiguration.C, self.STEP, self.SAMPLE, [self.java_state], mode=0)
+            out[i] = row[0]
+            self.java_state = int(after[0])
+        self.sim = out
+        return self
+
+
+class TopSim_Enumerate(SingleRandomWalk):
+    """simrank/TopSim_Enumerate.java: the path tree with EVERY path split into all neighbours (deterministic;
+    equals SAMPLE x SimRank truncated at STEP sweeps).  The reference runs it for vertex 0 only (:47); level
+    sizes are products of degrees, so `max_paths` bounds the queue (MemoryError beyond)."""
+
+    def __init__(self, g, sample, step, max_paths=1 << 22):
+        super().__init__(g, sample, step, seed=0)
+        self.max_paths = max_paths
+
+    def compute(self, queries=None):
+        q = np.array([0], dtype=np.int64) if queries is None else np.asarray(queries, dtype=np.int64)
+        self._queries = q
+        self.sim, _ = self.g.handle.topsim_rows_javarng(q, MyConfiguration.C, self.STEP, self.SAMPLE, [0] * len(q), mode=1,
+                                                        max_paths=self.max_paths)
+        return self
+
+    def topk(self, k=None, queries=None):
+        raise NotImplementedError("TopSim_Enumerate is the deterministic parity path; use SimRank or SingleRandomWalk.topk")
 
 
 class SimRank:

@@ -173,6 +173,14 @@ int gw_simrank_rows(gw_graph *g, const int64_t *queries, int64_t nq, double c, i
  * (feed it to the next query to replay a whole compute()).  Parity path, not the fast path. */
 int gw_simrank_rows_javarng(gw_graph *g, const int64_t *queries, int64_t nq, double c, int32_t step,
                             int32_t sample, uint64_t *rng_state, double *out_dense);
+/* Replay mode of the path-tree estimators: mode 0 = TopSim_singleSample.walk (TopSim_singleSample.java:62-203:
+ * enumerate while weight >= degree, else ceil(weight) children drawn with java.util.Random), mode 1 =
+ * TopSim_Enumerate.walk (TopSim_Enumerate.java:61-184: always enumerate, no random draw).  One thread per
+ * query runs the reference's queue in its order with fp64 in its operation order; scores are x SAMPLE as in
+ * the reference (:189).  max_paths bounds the queue of one level (GW_E_TOO_LARGE when exceeded). */
+int gw_topsim_rows_javarng(gw_graph *g, const int64_t *queries, int64_t nq, double c, int32_t step,
+                           int32_t sample, int32_t mode, int64_t max_paths, uint64_t *rng_state,
+                           double *out_dense);
 /* Total walk steps executed by the last gw_simrank_* call on this graph. */
 int gw_simrank_last_steps(const gw_graph *g, int64_t *steps);
 /* Queries of the last gw_simrank_topk* call that were finished by the exact hash-table kernel

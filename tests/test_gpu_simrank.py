@@ -246,6 +246,33 @@ def test_replay_with_java_util_random_is_bit_exact(g333, o333):
     assert not got[0].any() and after[0] == states[0]            # isolated vertex: no draw consumed
 
 
+def test_path_tree_replay_is_bit_exact(g333, o333):
+    """gw_topsim_rows_javarng: TopSim_singleSample's queue (enumerate while weight >= degree, else ceil(weight)
+    children drawn with java.util.Random) and TopSim_Enumerate's, replayed by one thread per query in the
+    reference's order: rows (x SAMPLE) and RNG states equal the oracle's bit for bit."""
+    qs = [0, 5, 17, 200]
+    for sample, step, C in ((800, 5, 0.6), (37, 3, 0.8), (5000, 2, 0.6)):
+        st = S.java_seed(31337)
+        states, rows = [], []
+        for v in qs:
+            states.append(st)
+            row, made, st = S.topsim_row(o333, v, sample, step, C, mode=0, seed_state=st)
+            rows.append(row)
+        got, after = g333.handle.topsim_rows_javarng(qs, C, step, sample, states, mode=0)
+        assert got.tobytes() == np.asarray(rows).tobytes(), (sample, step)
+        assert after.tolist() == states[1:] + [st]
+    # TopSim_Enumerate: no random draw, the level sizes are products of degrees
+    deg = np.diff(o333["row_ptr"])
+    small = [int(v) for v in np.argsort(deg)[:2]]                   # two low-degree sources keep deg^4 paths small
+    for step, srcs in ((1, qs[:2]), (2, small)):
+        rows = [S.topsim_row(o333, v, 100, step, 0.6, mode=1, max_paths=1 << 24)[0] for v in srcs]
+        got, after = g333.handle.topsim_rows_javarng(srcs, 0.6, step, 100, [1, 2], mode=1, max_paths=1 << 21)
+        assert got.tobytes() == np.asarray(rows).tobytes() and after.tolist() == [1, 2]
+        assert got.any()
+    with pytest.raises(MemoryError):
+        g333.handle.topsim_rows_javarng(qs[:1], 0.6, 3, 100, [1], mode=1, max_paths=1000)
+
+
 def test_seeded_jvm_run_is_reproduced_by_the_mirror_class(g333, o333):
     """SingleRandomWalk(g, sample, step, java_seed=s).compute(): the whole compute() loop of a JVM whose
     Graph.rand was seeded with s -- one stream across all 333 queries -- equals the oracle's sequential run."""
@@ -258,6 +285,18 @@ def test_seeded_jvm_run_is_reproduced_by_the_mirror_class(g333, o333):
     assert got.tobytes() == want.tobytes()
     assert srw.java_state == st
     assert sr._jr_jump(S.java_seed(5), 0) == S.java_seed(5)
+    # the hybrid estimator through its mirror class, same stream discipline
+    st = S.java_seed(7)
+    want = []
+    for v in (3, 4, 5):
+        row, _, st = S.topsim_row(o333, v, 300, 5, 0.6, mode=0, seed_state=st)
+        want.append(row)
+    ts = sr.TopSim_singleSample(g333, 300, 5, java_seed=7)
+    assert ts.compute([3, 4, 5]).getResult().tobytes() == np.asarray(want).tobytes() and ts.java_state == st
+    # TopSim_Enumerate (deterministic) = SAMPLE x SimRank truncated at STEP sweeps
+    en = sr.TopSim_Enumerate(g333, 100, 1).compute([0, 9]).getResult()
+    exact = g333.handle.simrank_exact(0.6, 1, rows=np.array([0, 9], dtype=np.int64))
+    assert np.abs(en - 100 * exact).max() < 1e-9
 
 
 def test_blog_graph_full_size_properties():
