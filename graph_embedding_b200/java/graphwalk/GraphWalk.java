@@ -46,6 +46,8 @@ public final class GraphWalk {
         FunctionDescriptor.of(I, P, P, J, D, I, I, I, J, J, P));
     private static final MethodHandle EXACT = h("gw_simrank_exact",
         FunctionDescriptor.of(I, P, D, I, P, J, P));
+    private static final MethodHandle ROWS_JAVARNG = h("gw_simrank_rows_javarng",
+        FunctionDescriptor.of(I, P, P, J, D, I, I, P, P));
 
     private GraphWalk() {}
 
@@ -106,6 +108,25 @@ public final class GraphWalk {
             check((int) TOPK.invokeExact(g, q, (long) queries.length, c, step, sample, k, mode, seed, 0L, ids, sc));
             MemorySegment.copy(ids, I, 0, outIds, 0, outIds.length);
             MemorySegment.copy(sc, D, 0, outScores, 0, outScores.length);
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
+    }
+
+    /**
+     * gw_simrank_rows_javarng: replay mode.  rngState[i] is the 48-bit java.util.Random state in front of query i
+     * ((seed ^ 0x5DEECE66DL) & ((1L << 48) - 1) for a fresh Random(seed)); it is updated to the state after
+     * the query, so a JVM run with a seeded Graph.rand is reproduced bit for bit.
+     */
+    public static double[][] simrankRowsJavaRng(MemorySegment g, long[] queries, int vCount, double c, int step, int sample,
+                                                long[] rngState) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment q = a.allocateFrom(J, queries);
+            MemorySegment st = a.allocateFrom(J, rngState);
+            MemorySegment out = a.allocate(D, (long) queries.length * vCount);
+            check((int) ROWS_JAVARNG.invokeExact(g, q, (long) queries.length, c, step, sample, st, out));
+            MemorySegment.copy(st, J, 0, rngState, 0, rngState.length);
+            double[][] sim = new double[queries.length][vCount];
+            for (int r = 0; r < queries.length; r++) MemorySegment.copy(out, D, (long) r * vCount * 8, sim[r], 0, vCount);
+            return sim;
         } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
     }
 
