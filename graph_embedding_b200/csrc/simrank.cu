@@ -425,20 +425,34 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_mc(SimrankParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// hybrid kernel: TopSim_singleSample.walk (simrank/TopSim_singleSample.java:62-203).  A level-
-// synchronous weighted path tree per query: a path of weight w at a vertex of degree d is split
-// into all d neighbours with weight w/d when w >= d (:99-125), otherwise into ceil(w) random
-// neighbours with weight w/ceil(w) (:126-149); at every even level 2i each path adds
-// w * C^i * deg(path[i]) / deg(path[2i]) to sim[source][path[2i]] when it is a first meeting
-// (:167-203; scores stay x SAMPLE as in the reference).  Paths live in a per-CTA structure-of-
-// arrays double buffer in global memory (history column per level, fp64 weights); children are
-// allocated with a block scan and written with one thread per CHILD, so a hub that fans out into
-// thousands of children does not serialise a lane.  paths(l) <= 1 + l*SAMPLE (weights are
-// conserved and a path has at most w+1 children), which sizes the buffers.
+// hybrid kernel: TopSim_singleSample.walk (simrank/TopSim_singleSample.java:62-203).  A weighted path
+// tree per query: a path of weight w at a vertex of degree d is split into all d neighbours with
+// weight w/d when w >= d (:99-125), otherwise into ceil(w) random neighbours with weight w/ceil(w)
+// (:126-149); at every even level 2i each path adds w * C^i * deg(path[i]) / deg(path[2i]) to
+// sim[source][path[2i]] when it is a first meeting (:167-203; scores stay x SAMPLE as in the reference).
+//
+// Once a path has been SAMPLED its children carry weight <= 1 and have exactly one child per level
+// from then on: the tree is an enumerated prefix (few, heavy paths) with independent chains hanging
+// off it.  Phase 1 expands the prefix level-synchronously (structure-of-arrays double buffer in global
+// memory, children allocated by a block scan, one thread per CHILD so that a hub does not serialise a
+// lane) and hands every path that must sample to a chain-parent list; phase 2 gives every chain to one
+// thread that copies the parent's history into registers ONCE and walks to depth 2*STEP like the
+// Monte-Carlo walker (one random 16-byte nbr4 entry per step).  Before the split every level copied
+// every path's whole history through HBM (28 % of the stall samples, 67 GB of DRAM traffic per 2048
+// queries) and paid a dozen CTA barriers per level for ~10 000 single-child paths.
+// paths(l) <= 1 + l*SAMPLE (weights are conserved and a path has at most w+1 children) sizes the buffers.
+// Chain RNG: Philox keyed by (query id, parent's index in its level buffer, level, child number): every
+// quantity is produced by deterministic scans, so results do not depend on scheduling.
 // ---------------------------------------------------------------------------------------------
 struct HybridParams {
-    int32_t *vbuf;        // [grid][2][LEN+1][cap]
+    int32_t *vbuf;        // [grid][2][LEN+1][cap]   level buffers of the enumerated prefix
     double *wbuf;         // [grid][2][cap]
+    int32_t *chist;       // [grid][LEN+1][cap]      chain parents: history up to their level
+    double *cw;           // [grid][cap]             weight of each of the parent's chains = w / ceil(w)
+    uint32_t *cnum;       // [grid][cap]             number of chains = ceil(w)
+    uint32_t *cofs;       // [grid][cap + 1]         exclusive prefix of cnum
+    uint32_t *ckey;       // [grid][cap]             (index in its level buffer << 4) | level
+    uint32_t *cpar;       // [grid][2*cap]           chain -> parent
     uint32_t cap;
     double cpow[16];      // C^i
 };
@@ -447,12 +461,30 @@ struct HyShared {
     SrShared acc;
     uint32_t ofs[SR_BLOCK + 1];
     uint32_t roff[SR_BLOCK];
-    uint32_t rdeg[SR_BLOCK];
-    uint32_t enumerate[SR_BLOCK];
     double cw[SR_BLOCK];
     uint32_t warp_tot[SR_BLOCK / 32];
-    uint32_t n_in, n_out;
+    uint32_t n_in, n_out, n_cp, scan_base;
 };
+
+// block exclusive scan of one value per thread; returns the exclusive prefix, *total = block sum
+__device__ __forceinline__ uint32_t block_scan(HyShared &Y, uint32_t val, int tid, uint32_t *total) {
+    const int lane = tid & 31, wrp = tid >> 5;
+    uint32_t incl = val;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) Y.warp_tot[wrp] = incl;
+    __syncthreads();
+    if (wrp == 0) {
+        uint32_t t = lane < SR_BLOCK / 32 ? Y.warp_tot[lane] : 0, inc2 = t;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, inc2, o); if (lane >= o) inc2 += u; }
+        if (lane < SR_BLOCK / 32) Y.warp_tot[lane] = inc2 - t;
+        if (lane == SR_BLOCK / 32 - 1) Y.ofs[SR_BLOCK] = inc2;
+    }
+    __syncthreads();
+    const uint32_t excl = Y.warp_tot[wrp] + incl - val;
+    *total = Y.ofs[SR_BLOCK];
+    __syncthreads();
+    return excl;
+}
 
 template <int STEP>
 __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, HybridParams H) {
@@ -460,7 +492,7 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
     HyShared &Y = *reinterpret_cast<HyShared *>(smem_raw);
     SrShared &S = Y.acc;
     constexpr int LEN = 2 * STEP;
-    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const size_t gs = (size_t)P.gs_mask + 1;
     uint32_t *gkeys = P.gkeys + blockIdx.x * gs;
     unsigned long long *gval = P.gval + blockIdx.x * gs;
@@ -468,6 +500,12 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
     const size_t cap = H.cap;
     int32_t *vb = H.vbuf + (size_t)blockIdx.x * 2 * (LEN + 1) * cap;
     double *wb = H.wbuf + (size_t)blockIdx.x * 2 * cap;
+    int32_t *chist = H.chist + (size_t)blockIdx.x * (LEN + 1) * cap;
+    double *cw = H.cw + (size_t)blockIdx.x * cap;
+    uint32_t *cnum = H.cnum + (size_t)blockIdx.x * cap;
+    uint32_t *cofs = H.cofs + (size_t)blockIdx.x * (cap + 1);
+    uint32_t *ckey = H.ckey + (size_t)blockIdx.x * cap;
+    uint32_t *cpar = H.cpar + (size_t)blockIdx.x * 2 * cap;
 
     for (int i = tid; i < SR_HS; i += SR_BLOCK) { S.keys[i] = SR_EMPTY; S.lo[i] = 0; S.hi[i] = 0; }
     if (tid == 0) { S.ocount = 0; S.ccount = 0; }
@@ -477,8 +515,9 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
     for (int64_t qi = blockIdx.x; qi < P.nq; qi += gridDim.x) {
         const int32_t v = (int32_t)P.queries[qi];
         const uint64_t qid = P.query_id_base + (uint64_t)qi;
-        if (tid == 0) { vb[0] = v; wb[0] = (double)P.sample; Y.n_in = 1; }
+        if (tid == 0) { vb[0] = v; wb[0] = (double)P.sample; Y.n_in = 1; Y.n_cp = 0; }
         __syncthreads();
+        // ======================= phase 1: the enumerated prefix, level by level =======================
         for (int l = 0; l <= LEN; l++) {
             const int b = l & 1;
             const int32_t *vin = vb + (size_t)b * (LEN + 1) * cap;
@@ -486,6 +525,7 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
             int32_t *vout = vb + (size_t)(b ^ 1) * (LEN + 1) * cap;
             double *wout = wb + (size_t)(b ^ 1) * cap;
             const uint32_t n_in = Y.n_in;
+            if (n_in == 0) break;                                  // every path has been handed to the chains (uniform)
             // ---- computePathSim at even levels (i = l/2), :80-83 and :157 ----
             if (l >= 2 && (l & 1) == 0) {
                 const int i = l >> 1;
@@ -510,7 +550,7 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
                 }
             }
             if (l == LEN) break;
-            // ---- expand level l -> l+1 ----
+            // ---- expand level l -> l+1: enumerating paths stay in the level buffers, sampling paths become chain parents ----
             if (tid == 0) Y.n_out = 0;
             __syncthreads();
             for (uint32_t base = 0; base < n_in; base += SR_BLOCK) {
@@ -520,33 +560,27 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
                     const int32_t cur = vin[(size_t)l * cap + p];
                     const double w = win[p];
                     const uint2 m = __ldg(P.meta + cur);
-                    Y.roff[tid] = m.x; Y.rdeg[tid] = m.y;
                     if (m.y != 0 && w >= (double)m.y) {                           // :99-125 enumerate
                         nchild = m.y;
-                        Y.enumerate[tid] = 1;
+                        Y.roff[tid] = m.x;
                         Y.cw[tid] = w / (double)m.y;
-                    } else if (m.y != 0) {                                        // :126-149 sample ceil(w)
-                        int number = ((double)(int)w == w) ? (int)w : (int)w + 1;
-                        nchild = (uint32_t)max(number, 0);
-                        Y.enumerate[tid] = 0;
-                        Y.cw[tid] = nchild ? w / (double)number : 0.0;
+                    } else if (m.y != 0) {                                        // :126-149 sample ceil(w): a chain parent
+                        const int number = ((double)(int)w == w) ? (int)w : (int)w + 1;
+                        if (number > 0) {
+                            const uint32_t k = atomicAdd(&Y.n_cp, 1u);
+                            if (k < cap) {
+                                for (int pos = 0; pos <= l; pos++) chist[(size_t)pos * cap + k] = vin[(size_t)pos * cap + p];
+                                cw[k] = w / (double)number;
+                                cnum[k] = (uint32_t)number;
+                                ckey[k] = (p << 4) | (uint32_t)l;
+                            }
+                        }
                     }                                                             // degree 0: randNeighbor == -1, no child
                 }
-                // block exclusive scan of nchild
-                uint32_t incl = nchild;
-                for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-                if (lane == 31) Y.warp_tot[wrp] = incl;
+                uint32_t T;
+                const uint32_t excl = block_scan(Y, nchild, tid, &T);
+                Y.ofs[tid] = excl;
                 __syncthreads();
-                if (wrp == 0) {
-                    uint32_t t = lane < SR_BLOCK / 32 ? Y.warp_tot[lane] : 0, inc2 = t;
-                    for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, inc2, o); if (lane >= o) inc2 += u; }
-                    if (lane < SR_BLOCK / 32) Y.warp_tot[lane] = inc2 - t;
-                    if (lane == SR_BLOCK / 32 - 1) Y.ofs[SR_BLOCK] = inc2;
-                }
-                __syncthreads();
-                Y.ofs[tid] = Y.warp_tot[wrp] + incl - nchild;
-                __syncthreads();
-                const uint32_t T = Y.ofs[SR_BLOCK];
                 const uint32_t out_base = Y.n_out;
                 if (out_base + (uint64_t)T > cap) { if (tid == 0) atomicExch(P.err, 3); break; }
                 // one thread per child
@@ -554,15 +588,8 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
                     uint32_t lo2 = 0, hi2 = SR_BLOCK;                  // last slot t with ofs[t] <= c
                     while (hi2 - lo2 > 1) { uint32_t mid = (lo2 + hi2) >> 1; if (Y.ofs[mid] <= c) lo2 = mid; else hi2 = mid; }
                     const uint32_t t = lo2, j = c - Y.ofs[t], parent = base + t, oi = out_base + c;
-                    int32_t child;
-                    if (Y.enumerate[t]) {
-                        child = __ldg(P.col + Y.roff[t] + j);
-                    } else {
-                        uint4 r = Philox::gen(make_uint4((uint32_t)qid, (uint32_t)(qid >> 32), (uint32_t)(l + 1), oi), P.key);
-                        child = __ldg(P.col + Y.roff[t] + scale_u32(r.x, Y.rdeg[t]));
-                    }
                     for (int pos = 0; pos <= l; pos++) vout[(size_t)pos * cap + oi] = vin[(size_t)pos * cap + parent];
-                    vout[(size_t)(l + 1) * cap + oi] = child;
+                    vout[(size_t)(l + 1) * cap + oi] = __ldg(P.col + Y.roff[t] + j);
                     wout[oi] = Y.cw[t];
                     my_steps++;
                 }
@@ -573,6 +600,92 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
             __syncthreads();
             if (tid == 0) Y.n_in = Y.n_out;
             __syncthreads();
+        }
+        __syncthreads();
+        // ======================= phase 2: the chains =======================
+        const uint32_t n_cp = Y.n_cp;
+        if (n_cp > cap) { if (tid == 0) atomicExch(P.err, 3); }
+        else if (n_cp > 0) {
+            // exclusive prefix of the chain counts, chain -> parent map
+            if (tid == 0) Y.scan_base = 0;
+            __syncthreads();
+            for (uint32_t base = 0; base < n_cp; base += SR_BLOCK) {
+                const uint32_t k = base + tid;
+                const uint32_t val = k < n_cp ? cnum[k] : 0u;
+                uint32_t T;
+                const uint32_t excl = block_scan(Y, val, tid, &T);
+                if (k < n_cp) cofs[k] = Y.scan_base + excl;
+                __syncthreads();
+                if (tid == 0) Y.scan_base += T;
+                __syncthreads();
+            }
+            const uint32_t n_chain = Y.scan_base;
+            if (n_chain > 2 * cap) { if (tid == 0) atomicExch(P.err, 3); }
+            else {
+                for (uint32_t k = tid; k < n_cp; k += SR_BLOCK) {
+                    const uint32_t o = cofs[k], c = cnum[k];
+                    for (uint32_t j = 0; j < c; j++) cpar[o + j] = k;
+                }
+                __syncthreads();
+                for (uint32_t t0 = (uint32_t)(tid - lane); t0 < n_chain; t0 += SR_BLOCK) {
+                    const uint32_t t = t0 + lane;
+                    const bool live = t < n_chain;
+                    int32_t path[LEN + 1];
+                    uint32_t dgs[LEN + 1];
+                    int lvl = LEN, len = 0;
+                    double wq = 0.0;
+                    uint32_t ctr_p = 0, ctr_lj = 0;
+                    uint2 m = make_uint2(0, 0);
+#pragma unroll
+                    for (int pos = 0; pos <= LEN; pos++) { path[pos] = -1; dgs[pos] = 0; }
+                    if (live) {
+                        const uint32_t k = cpar[t], key = ckey[k];
+                        lvl = (int)(key & 15u);
+                        ctr_p = key >> 4;
+                        ctr_lj = ((uint32_t)lvl << 24) | (t - cofs[k]);
+                        wq = cw[k];
+#pragma unroll
+                        for (int pos = 0; pos <= LEN; pos++) if (pos <= lvl) path[pos] = chist[(size_t)pos * cap + k];
+                        m = __ldg(P.meta + path[lvl]);
+                        len = lvl;
+                    }
+                    bool alive = live;
+                    uint4 r = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int sidx = 0; sidx < LEN; sidx++) {
+                        if (alive && sidx >= lvl) {
+                            const int off = sidx - lvl;
+                            if ((off & 3) == 0)
+                                r = Philox::gen(make_uint4((uint32_t)qid ^ (0x9E3779B9u * (uint32_t)(off >> 2)), (uint32_t)(qid >> 32), ctr_p, ctr_lj), P.key);
+                            const uint32_t rw = (off & 3) == 0 ? r.x : (off & 3) == 1 ? r.y : (off & 3) == 2 ? r.z : r.w;
+                            if (m.y == 0) alive = false;                          // randNeighbor == -1: the chain ends
+                            else {
+                                const int4 e = ld_nbr4(P.nbr4 + m.x + scale_u32(rw, m.y));
+                                path[sidx + 1] = e.x;
+                                dgs[sidx + 1] = (uint32_t)e.w;
+                                m = make_uint2((uint32_t)e.z, (uint32_t)e.w);
+                                len = sidx + 1;
+                                my_steps++;
+                            }
+                        }
+                    }
+                    // computePathSim for the levels this chain added (:167-203)
+#pragma unroll
+                    for (int i = 1; i <= STEP; i++) {
+                        const int32_t target = path[2 * i];
+                        bool ok = live && 2 * i > lvl && 2 * i <= len && target != v;
+#pragma unroll
+                        for (int j = 0; j < i; j++) ok &= (path[j] != path[2 * i - j]);
+                        unsigned long long fx = 0;
+                        if (ok) {
+                            const uint32_t dmid = i > lvl ? dgs[i] : __ldg(P.meta + path[i]).y;
+                            const double val = wq * H.cpow[i] * (double)dmid / (double)dgs[2 * i];
+                            fx = __double2ull_rn(val * SR_FIX);
+                        }
+                        acc_add_warp(S, P, gkeys, gval, olist, ok, (uint32_t)target, fx);
+                    }
+                }
+            }
         }
         finish_query(S, P, gkeys, gval, olist, qi, tid);
     }
@@ -1217,20 +1330,32 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     P.out_ids = d_out_ids; P.out_scores = d_out_scores; P.out_dense = d_out_dense;
     if (hybrid) {
         HybridParams H;
-        H.cap = (uint32_t)std::min<int64_t>((int64_t)2 * step * sample + 1, (int64_t)0x7FFFFFFF);
-        size_t vb = (size_t)grid * 2 * (2 * step + 1) * H.cap * sizeof(int32_t);
-        size_t wbb = (size_t)grid * 2 * H.cap * sizeof(double);
-        if (g->hybrid_scratch_bytes < vb + wbb + 16) {
+        H.cap = (uint32_t)std::min<int64_t>((int64_t)2 * step * sample + 1, (int64_t)0x0FFFFFFF);   // index << 4 must fit 32 bits
+        const size_t LEN1 = 2 * (size_t)step + 1, capz = H.cap;
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+        const size_t o_w = take((size_t)grid * 2 * capz * sizeof(double));
+        const size_t o_cw = take((size_t)grid * capz * sizeof(double));
+        const size_t o_v = take((size_t)grid * 2 * LEN1 * capz * sizeof(int32_t));
+        const size_t o_ch = take((size_t)grid * LEN1 * capz * sizeof(int32_t));
+        const size_t o_cn = take((size_t)grid * capz * sizeof(uint32_t));
+        const size_t o_co = take((size_t)grid * (capz + 1) * sizeof(uint32_t));
+        const size_t o_ck = take((size_t)grid * capz * sizeof(uint32_t));
+        const size_t o_cp = take((size_t)grid * 2 * capz * sizeof(uint32_t));
+        if (g->hybrid_scratch_bytes < off + 16) {
             cudaFree(g->d_hybrid_scratch);
             g->d_hybrid_scratch = nullptr; g->hybrid_scratch_bytes = 0;
-            if (cudaMalloc(&g->d_hybrid_scratch, vb + wbb + 16) != cudaSuccess) {
+            if (cudaMalloc(&g->d_hybrid_scratch, off + 16) != cudaSuccess) {
                 cudaGetLastError();
-                return fail(GW_E_TOO_LARGE, "hybrid estimator needs %zu bytes of path buffers", vb + wbb);
+                return fail(GW_E_TOO_LARGE, "hybrid estimator needs %zu bytes of path buffers", off);
             }
-            g->hybrid_scratch_bytes = vb + wbb + 16;
+            g->hybrid_scratch_bytes = off + 16;
         }
-        H.wbuf = (double *)g->d_hybrid_scratch;
-        H.vbuf = (int32_t *)((unsigned char *)g->d_hybrid_scratch + wbb);
+        unsigned char *hb = (unsigned char *)g->d_hybrid_scratch;
+        H.wbuf = (double *)(hb + o_w); H.cw = (double *)(hb + o_cw);
+        H.vbuf = (int32_t *)(hb + o_v); H.chist = (int32_t *)(hb + o_ch);
+        H.cnum = (uint32_t *)(hb + o_cn); H.cofs = (uint32_t *)(hb + o_co);
+        H.ckey = (uint32_t *)(hb + o_ck); H.cpar = (uint32_t *)(hb + o_cp);
         for (int i = 0; i < 16; i++) H.cpow[i] = i <= step ? pow(c, i) : 0.0;
         size_t smem = sizeof(HyShared);
 #define GW_HY(N) case N: GW_CUDA(cudaFuncSetAttribute(k_topsim_hybrid<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
