@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -67,6 +68,8 @@ struct SimrankParams {
     const int32_t *qlist;            // read by the hash kernel (NULL = all queries)
     uint32_t *qcount;
     unsigned long long *prof;        // SR_PROFILE builds: per-phase clock64 totals of CTA 0
+    double out_scale;                // fixed point -> score: 2^-32 (Monte Carlo), SAMPLE * 2^-32 (path tree, x SAMPLE as the reference)
+    double inv_sample;               // path tree: contributions are accumulated / SAMPLE so that they fit the 0.32 fixed-point table
 };
 
 struct SrShared {
@@ -266,13 +269,13 @@ __device__ __forceinline__ uint32_t threshold_bin(const uint32_t *hist, uint32_t
 
 // rank-by-counting among the candidates in shared memory; writes the K best (score desc, id asc)
 template <typename Sh>
-__device__ __forceinline__ void emit_ranked(const Sh &S, uint32_t C, uint32_t K, int32_t *oid, double *osc, int tid) {
+__device__ __forceinline__ void emit_ranked(const Sh &S, uint32_t C, uint32_t K, int32_t *oid, double *osc, int tid, double scale) {
     for (uint32_t a = tid; a < C; a += SR_BLOCK) {
         unsigned long long sa = S.cand_score[a];
         uint32_t ia = S.cand_id[a];
         uint32_t rank = 0;
         for (uint32_t b = 0; b < C; b++) rank += better(S.cand_score[b], S.cand_id[b], sa, ia) ? 1u : 0u;
-        if (rank < K) { oid[rank] = (int32_t)ia; osc[rank] = (double)sa * (1.0 / SR_FIX); }
+        if (rank < K) { oid[rank] = (int32_t)ia; osc[rank] = (double)sa * scale; }
     }
     for (uint32_t r = C + tid; r < K; r += SR_BLOCK) { oid[r] = -1; osc[r] = 0.0; }
 }
@@ -290,7 +293,7 @@ __device__ __noinline__ void finish_query(SrShared &S, const SimrankParams &P, u
         for (uint32_t e = tid; e < M; e += SR_BLOCK) {
             uint32_t id; unsigned long long sc;
             read_entry(S, gkeys, gval, olist[e], id, sc);
-            row[id] = (double)sc * (1.0 / SR_FIX);
+            row[id] = (double)sc * P.out_scale;
         }
     }
     if (P.out_ids) {
@@ -329,7 +332,7 @@ __device__ __noinline__ void finish_query(SrShared &S, const SimrankParams &P, u
         int32_t *oid = P.out_ids + (size_t)qi * K;
         double *osc = P.out_scores + (size_t)qi * K;
         if (C <= SR_CAND) {
-            emit_ranked(S, C, K, oid, osc, tid);
+            emit_ranked(S, C, K, oid, osc, tid, P.out_scale);
         } else {
             // fallback (mass ties at the threshold): K rounds of block arg-max over all entries
             unsigned long long last_s = ~0ull;
@@ -358,7 +361,7 @@ __device__ __noinline__ void finish_query(SrShared &S, const SimrankParams &P, u
                         if (i2 != SR_EMPTY && (fi == SR_EMPTY || better(S.red_score[w], i2, fs, fi))) { fs = S.red_score[w]; fi = i2; }
                     }
                     S.sel_score = fs; S.sel_id = fi;
-                    if (fi != SR_EMPTY) { oid[r] = (int32_t)fi; osc[r] = (double)fs * (1.0 / SR_FIX); }
+                    if (fi != SR_EMPTY) { oid[r] = (int32_t)fi; osc[r] = (double)fs * P.out_scale; }
                     else { oid[r] = -1; osc[r] = 0.0; }
                 }
                 __syncthreads();
@@ -425,6 +428,371 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_mc(SimrankParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// log kernel (production): no global atomics.  A contribution goes to the shared-memory table when
+// its key fits there; otherwise it is APPENDED to a per-CTA log (coalesced 8-byte stores) and its
+// value is added to a small shared-memory sketch cell (an upper bound of every logged key's total).
+// Top-k: threshold bin from the table (a lower bound of the k-th score), table candidates, then ONE
+// streaming pass over the log that keeps only entries whose sketch cell could reach the threshold
+// (almost none: logged keys are the single-hit tail) and sums those exactly in a tiny third table.
+// A query that cannot be finished exactly this way (threshold at the single-hit level, sketch
+// saturation, too many survivors) is flagged and re-run by the hash kernel; both kernels add the
+// same 32.32 fixed-point integers, so the result does not depend on which one produced it.
+// ---------------------------------------------------------------------------------------------
+#ifndef SR_SKETCH_CELLS
+#define SR_SKETCH_CELLS 16384
+#endif
+constexpr int SR_SKETCH = SR_SKETCH_CELLS;
+#ifndef SR_RING_STAGES
+#define SR_RING_STAGES 2
+#endif
+#ifndef SR_WILP
+#define SR_WILP 1                            // samples walked in lock step per walker thread of the log kernel
+#endif
+#ifndef SR_T3_SLOTS
+#define SR_T3_SLOTS 512
+#endif
+constexpr int SR_T3 = SR_T3_SLOTS;
+constexpr int SR_LCAND = 256;
+
+struct SrLogShared {
+    uint32_t keys[SR_HS];
+    uint32_t lo[SR_HS];                  // 0.32 fixed point; a carry out of it sends the query to the hash kernel
+    uint32_t sketch[SR_SKETCH];          // 2^-24 units, rounded up
+    uint32_t hist[SR_BINS];              // threshold histogram, then tier-3 keys (SR_T3 <= SR_BINS)
+    uint32_t t3lo[SR_T3], t3hi[SR_T3];
+    unsigned long long cand_score[SR_LCAND];
+    uint32_t cand_id[SR_LCAND];
+    uint32_t lcount;                     // log entries
+    uint32_t ccount;                     // candidates
+    uint32_t t3count;
+    uint32_t thr_bin;
+    uint32_t slow;                       // this query needs the hash kernel
+};
+
+// walker -> accumulator hand-over: one single-producer single-consumer ring per warp pair, a stage =
+// the WILP * STEP (key, x) contributions of WILP samples per lane; full/empty mbarriers per stage
+constexpr int SR_PAIRS = 16;                 // walker warps = accumulator warps per CTA (1024 threads, one CTA per SM)
+constexpr int SR_ABLOCK = SR_PAIRS * 32;     // accumulator threads (phases B and C run on them alone)
+static_assert(SR_ABLOCK == SR_BLOCK, "phase B/C strides assume SR_BLOCK accumulator threads");
+template <int STEP>
+struct SrRing {
+    static constexpr int WILP = STEP <= 5 ? SR_WILP : 1;     // samples in flight per walker thread
+    static constexpr int STAGES = STEP <= 5 ? SR_RING_STAGES : SR_RING_STAGES / 2;   // walkers run this far ahead of phase B
+    uint2 slot[SR_PAIRS][STAGES][WILP * STEP * 32];
+    unsigned long long full[SR_PAIRS][STAGES];
+    unsigned long long empty[SR_PAIRS][STAGES];
+};
+__device__ __forceinline__ void acc_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(SR_ABLOCK) : "memory"); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {      // release.cta: my stores before it are visible to the waiter
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE;\nbra LAB_WAIT;\nDONE:\n}"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+// The STEP contributions of one sample per lane into the query's accumulator, batched so that the
+// shared-memory round trips of the levels overlap instead of chaining: all bucket loads first, then
+// all adds (return values consumed at the very end), ONE log reservation per warp for every level.
+// 4-key buckets: one 16-byte shared load sees every slot a key may live in.  Slots of a bucket fill
+// in order and never empty during a query, so "first empty slot of my view + CAS" places a key
+// exactly once (a stale view only makes the CAS return the occupant, after which the bucket is
+// re-read).  What does not fit goes to the per-CTA log + sketch.  Called by all 32 lanes together.
+template <int STEP>
+__device__ __forceinline__ void log_insert_chunk(SrLogShared &S, const SimrankParams &P, uint2 *log, int lane,
+                                                 const uint32_t *key, const uint32_t *v32) {
+    uint4 kk[STEP];
+    uint32_t b0[STEP];
+    bool pending[STEP];
+    uint32_t wrapped = 0;
+#pragma unroll
+    for (int i = 0; i < STEP; i++) {
+        b0[i] = (hash32(key[i]) & (SR_HS / 4 - 1)) * 4;
+        pending[i] = key[i] != SR_EMPTY;
+        kk[i] = make_uint4(0, 0, 0, 0);
+        if (pending[i])
+            asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(kk[i].x), "=r"(kk[i].y), "=r"(kk[i].z), "=r"(kk[i].w)
+                         : "r"((uint32_t)__cvta_generic_to_shared(&S.keys[b0[i]])));
+    }
+    uint32_t old[STEP];
+#pragma unroll
+    for (int i = 0; i < STEP; i++) {
+        old[i] = 0;
+        if (pending[i]) {
+            uint4 v = kk[i];
+            for (int attempt = 0; attempt < 5; attempt++) {
+                int j = v.x == key[i] ? 0 : v.y == key[i] ? 1 : v.z == key[i] ? 2 : v.w == key[i] ? 3 : -1;
+                if (j < 0) {
+                    int e = v.x == SR_EMPTY ? 0 : v.y == SR_EMPTY ? 1 : v.z == SR_EMPTY ? 2 : v.w == SR_EMPTY ? 3 : -1;
+                    if (e < 0) break;                           // bucket full of other keys: log
+                    uint32_t k0 = atomicCAS(&S.keys[b0[i] + e], SR_EMPTY, key[i]);
+                    if (k0 == SR_EMPTY || k0 == key[i]) j = e;
+                }
+                if (j >= 0) {
+                    old[i] = atomicAdd(&S.lo[b0[i] + j], v32[i]);
+                    pending[i] = false;
+                    break;
+                }
+                asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                             : "r"((uint32_t)__cvta_generic_to_shared(&S.keys[b0[i]])));
+            }
+        }
+    }
+    // overflow: append to the log, one shared-memory atomic per warp for all levels
+    uint32_t mask[STEP], total = 0;
+#pragma unroll
+    for (int i = 0; i < STEP; i++) { mask[i] = __ballot_sync(0xffffffffu, pending[i]); total += __popc(mask[i]); }
+    if (total) {
+        uint32_t basep = 0;
+        if (lane == 0) basep = atomicAdd(&S.lcount, total);
+        basep = __shfl_sync(0xffffffffu, basep, 0);
+        uint32_t sold[STEP], sadd[STEP];
+#pragma unroll
+        for (int i = 0; i < STEP; i++) {
+            sold[i] = 0; sadd[i] = 0;
+            if (pending[i]) {
+                const uint32_t pos = basep + __popc(mask[i] & ((1u << lane) - 1));
+                if (pos < P.log_cap) log[pos] = make_uint2(key[i], v32[i]);
+                sadd[i] = (v32[i] >> 8) + 1u;
+                sold[i] = atomicAdd(&S.sketch[(hash32(key[i]) >> 13) & (SR_SKETCH - 1)], sadd[i]);
+            }
+            basep += __popc(mask[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < STEP; i++) if (sold[i] + sadd[i] < sold[i]) wrapped = 1;    // sketch cell wrapped
+    }
+#pragma unroll
+    for (int i = 0; i < STEP; i++) if (old[i] + v32[i] < old[i]) wrapped = 1;   // score >= 1.0: exact path
+    if (wrapped) S.slow = 1;
+}
+
+// key[i] == SR_EMPTY: no contribution at level i.  fx: 32.32 fixed point; a single contribution >= 1.0 sends the
+// query to the exact kernel.
+template <int STEP>
+__device__ __forceinline__ void log_insert_batch(SrLogShared &S, const SimrankParams &P, uint2 *log, int lane,
+                                                 const uint32_t (&key)[STEP], const unsigned long long (&fx)[STEP]) {
+    uint32_t v32[STEP];
+    bool big = false;
+#pragma unroll
+    for (int i = 0; i < STEP; i++) { v32[i] = (uint32_t)fx[i]; big |= (key[i] != SR_EMPTY) && (fx[i] >> 32) != 0; }
+    if (big) S.slow = 1;
+    constexpr int C0 = STEP <= 5 ? STEP : 5;            // at most 5 levels in flight (registers)
+    log_insert_chunk<C0>(S, P, log, lane, key, v32);
+    if (STEP > C0) log_insert_chunk<(STEP > C0 ? STEP - C0 : 1)>(S, P, log, lane, key + C0, v32 + C0);
+}
+
+// Phases B (top-k) and C (reset) of the log-structured accumulator, run by SR_BLOCK threads (atid = 0..SR_BLOCK-1)
+// that synchronise through bar(): the accumulator warps of k_simrank_log (named barrier) or the whole CTA of the
+// path-tree kernel (__syncthreads).  The caller has made every insert of the query visible (bar()) before.
+template <typename Bar>
+__device__ __forceinline__ void log_finish_query(SrLogShared &S, const SimrankParams &P, uint2 *log, int64_t qi, int atid, Bar bar) {
+    uint32_t *t3keys = S.hist;
+        const uint32_t Lc = min(S.lcount, P.log_cap);
+        if (S.lcount > P.log_cap && atid == 0) S.slow = 1;
+
+        // ---------------- phase B: top-k ----------------
+        const uint32_t K = (uint32_t)P.k;
+        {
+        for (int i = atid; i < SR_BINS; i += SR_BLOCK) S.hist[i] = 0;
+        bar();
+        for (int i = atid; i < SR_HS; i += SR_BLOCK) {
+            if (S.keys[i] != SR_EMPTY) {
+                unsigned long long sc = S.lo[i];
+                if (sc) atomicAdd(&S.hist[score_bin(sc)], 1u);
+            }
+        }
+        bar();
+        if (atid < 32) {
+            uint32_t thr = threshold_bin(S.hist, K, atid);
+            if (atid == 0) { S.thr_bin = thr; S.ccount = 0; S.t3count = 0; }
+        }
+        bar();
+        const uint32_t thr = S.thr_bin;
+        if (thr == 0 && Lc > 0 && atid == 0) S.slow = 1;   // no usable lower bound: every logged key could matter
+        for (int i = atid; i < SR_T3; i += SR_BLOCK) { t3keys[i] = SR_EMPTY; S.t3lo[i] = 0; S.t3hi[i] = 0; }
+        for (int i = atid; i < SR_HS; i += SR_BLOCK) {     // table candidates
+            uint32_t id = S.keys[i];
+            if (id != SR_EMPTY) {
+                unsigned long long sc = S.lo[i];
+                if (sc != 0 && score_bin(sc) >= thr) {
+                    uint32_t c = atomicAdd(&S.ccount, 1u);
+                    if (c < SR_LCAND) { S.cand_score[c] = sc; S.cand_id[c] = id; }
+                }
+            }
+        }
+        bar();
+        if (thr != 0) {
+            // one streaming pass over the log; survivors are summed exactly in tier 3
+            // (8 independent loads in flight per thread: the pass is L2-latency bound otherwise)
+            for (uint32_t e0 = atid; e0 < Lc; e0 += SR_BLOCK * 8) {
+              uint2 ens[8];
+#pragma unroll
+              for (int u = 0; u < 8; u++) {
+                  const uint32_t e = e0 + u * SR_BLOCK;
+                  ens[u] = e < Lc ? __ldcg(log + e) : make_uint2(SR_EMPTY, 0u);
+              }
+#pragma unroll
+              for (int u = 0; u < 8; u++) {
+                const uint2 en = ens[u];
+                if (en.x == SR_EMPTY) continue;
+                uint32_t cell = S.sketch[(hash32(en.x) >> 13) & (SR_SKETCH - 1)];
+                if (score_bin((unsigned long long)cell << 8) >= thr) {
+                    uint32_t slot = (hash32(en.x) >> 4) & (SR_T3 - 1);
+                    bool done = false;
+                    for (int pr = 0; pr < SR_T3 && !done; pr++) {
+                        uint32_t k0 = ((volatile uint32_t *)t3keys)[slot];
+                        if (k0 == SR_EMPTY) {
+                            k0 = atomicCAS(&t3keys[slot], SR_EMPTY, en.x);
+                            if (k0 == SR_EMPTY) {
+                                if (atomicAdd(&S.t3count, 1u) >= (uint32_t)(SR_T3 * 3 / 4)) S.slow = 1;
+                                k0 = en.x;
+                            }
+                        }
+                        if (k0 == en.x) { fixed_add(&S.t3lo[slot], &S.t3hi[slot], (unsigned long long)en.y); done = true; }
+                        else slot = (slot + 1) & (SR_T3 - 1);
+                    }
+                    if (!done) S.slow = 1;
+                }
+              }
+            }
+            bar();
+            for (int i = atid; i < SR_T3; i += SR_BLOCK) {
+                uint32_t id = t3keys[i];
+                if (id != SR_EMPTY) {
+                    unsigned long long sc = ((unsigned long long)S.t3hi[i] << 32) | S.t3lo[i];
+                    if (sc != 0 && score_bin(sc) >= thr) {
+                        uint32_t c = atomicAdd(&S.ccount, 1u);
+                        if (c < SR_LCAND) { S.cand_score[c] = sc; S.cand_id[c] = id; }
+                    }
+                }
+            }
+        }
+        bar();
+        const uint32_t C = S.ccount;
+        int32_t *oid = P.out_ids + (size_t)qi * K;
+        double *osc = P.out_scores + (size_t)qi * K;
+        const bool slow = S.slow != 0 || C > SR_LCAND;
+        if (!slow) {
+            emit_ranked(S, C, K, oid, osc, atid, P.out_scale);
+        } else if (atid == 0) {
+            uint32_t w = atomicAdd(P.qcount, 1u);     // hand the query to the hash kernel
+            P.qlist_out[w] = (int32_t)qi;
+        }
+        }
+        bar();
+        // ---------------- phase C: reset ----------------
+        for (int i = atid; i < SR_HS; i += SR_BLOCK) { S.keys[i] = SR_EMPTY; S.lo[i] = 0; }
+        for (int i = atid; i < SR_SKETCH; i += SR_BLOCK) S.sketch[i] = 0;
+        if (atid == 0) { S.lcount = 0; S.ccount = 0; S.t3count = 0; S.slow = 0; }
+        bar();
+}
+
+// One CTA of 1024 threads per SM, split by role.  Warps [0, SR_PAIRS) are WALKERS: they do nothing but
+// walk (WILP samples in flight per thread) and hand the (key, x) contributions of every sample to
+// their partner through a shared-memory ring.  Warps [SR_PAIRS, 2*SR_PAIRS) are ACCUMULATORS: they
+// drain the rings into the query's hash table / log, and run top-k (phase B) and the reset (phase C)
+// among themselves behind a named barrier.  The walkers never meet a CTA-wide barrier: while the
+// accumulators rank query q the walkers are already walking query q+1, so the random loads keep the
+// memory system at its ceiling all the time instead of alternating with the shared-memory work.
+// (The unsplit kernel ran phase A as "10 dependent loads, then STEP inserts" in every warp, in step
+// with every other warp: walk time and accumulate time added up, 6.1 ms where the walks alone take
+// 3.9 ms -- profiles/README.md.)
+#ifdef SR_PROFILE
+#define SR_TICK(slot) do { if (prof_on) { long long t_ = clock64(); atomicAdd(P.prof + (slot), (unsigned long long)(t_ - t_last)); t_last = t_; } } while (0)
+#else
+#define SR_TICK(slot) do { } while (0)
+#endif
+
+template <int STEP>
+__global__ void __launch_bounds__(2 * SR_ABLOCK, 1) k_simrank_log(SimrankParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SrLogShared &S = *reinterpret_cast<SrLogShared *>(smem_raw);
+    using Ring = SrRing<STEP>;
+    constexpr int WILP = Ring::WILP;
+    Ring &R = *reinterpret_cast<Ring *>(smem_raw + ((sizeof(SrLogShared) + 15) & ~(size_t)15));
+    const int tid = threadIdx.x, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    uint2 *log = P.log + (size_t)blockIdx.x * P.log_cap;
+    uint32_t *t3keys = S.hist;
+
+    if (tid < SR_PAIRS * Ring::STAGES) {
+        mbar_init(&R.full[tid / Ring::STAGES][tid % Ring::STAGES], 32);
+        mbar_init(&R.empty[tid / Ring::STAGES][tid % Ring::STAGES], 32);
+    }
+    for (int i = tid; i < SR_HS; i += 2 * SR_ABLOCK) { S.keys[i] = SR_EMPTY; S.lo[i] = 0; }
+    for (int i = tid; i < SR_SKETCH; i += 2 * SR_ABLOCK) S.sketch[i] = 0;
+    if (tid == 0) { S.lcount = 0; S.ccount = 0; S.t3count = 0; S.slow = 0; }
+    __syncthreads();
+    uint32_t stage_no = 0;                   // stages handed over so far by this warp pair (same count on both sides)
+    const int32_t ngroups = (P.sample + WILP - 1) / WILP;
+#ifdef SR_PROFILE
+    const bool prof_on = blockIdx.x == 0 && lane == 0 && (wrp == 0 || wrp == SR_PAIRS);
+    long long t_last = clock64();
+#endif
+
+    if (wrp < SR_PAIRS) {
+        // =============================== walkers ===============================
+        unsigned long long my_steps = 0;
+        for (int64_t qi = blockIdx.x; qi < P.nq; qi += gridDim.x) {
+            const int32_t v = (int32_t)P.queries[qi];
+            const uint64_t qid = P.query_id_base + (uint64_t)qi;
+            const uint2 mv = __ldg(P.meta + v);
+            for (int32_t g0 = wrp * 32; g0 < ngroups; g0 += SR_PAIRS * 32, stage_no++) {
+                const uint32_t st = stage_no % Ring::STAGES, ph = (stage_no / Ring::STAGES) & 1;
+                SR_TICK(0);                                    // walker: walking
+                mbar_wait(&R.empty[wrp][st], ph ^ 1);          // the accumulator has taken the stage's previous content
+                SR_TICK(1);                                    // walker: waiting for a free stage
+                uint2 *slot = R.slot[wrp][st];
+                int cnt = 0;                                   // emit order: level-major, sample-minor (walk_group)
+                my_steps += (unsigned long long)walk_group<STEP, WILP>(P, v, mv, qid, g0 + lane,
+                    [&](bool ok, uint32_t key, float x) {
+                        slot[cnt * 32 + lane] = make_uint2(ok ? key : SR_EMPTY, __float_as_uint(x));
+                        cnt++;
+                    });
+                mbar_arrive(&R.full[wrp][st]);
+            }
+        }
+        for (int o = 16; o; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
+        if (lane == 0 && my_steps) atomicAdd(P.steps, my_steps);
+        return;
+    }
+
+    // =============================== accumulators ===============================
+    const int pw = wrp - SR_PAIRS, atid = tid - SR_ABLOCK;
+    for (int64_t qi = blockIdx.x; qi < P.nq; qi += gridDim.x) {
+        // ---------------- phase A: drain my walker's ring ----------------
+        for (int32_t g0 = pw * 32; g0 < ngroups; g0 += SR_PAIRS * 32, stage_no++) {
+            const uint32_t st = stage_no % Ring::STAGES, ph = (stage_no / Ring::STAGES) & 1;
+            SR_TICK(2);                                        // accumulator: inserting
+            mbar_wait(&R.full[pw][st], ph);
+            SR_TICK(3);                                        // accumulator: waiting for its walker
+#pragma unroll
+            for (int k = 0; k < WILP; k++) {
+                uint32_t ek[STEP];
+                unsigned long long ex[STEP];
+#pragma unroll
+                for (int i = 0; i < STEP; i++) {
+                    const uint2 en = R.slot[pw][st][(i * WILP + k) * 32 + lane];
+                    ek[i] = en.x; ex[i] = to_fixed(__uint_as_float(en.y));
+                }
+                if (k == WILP - 1) mbar_arrive(&R.empty[pw][st]);          // stage is in registers: give it back
+                log_insert_batch<STEP>(S, P, log, lane, ek, ex);
+            }
+        }
+        SR_TICK(2);
+        acc_barrier();
+        SR_TICK(4);                                            // waiting for the other accumulators' last stages
+        log_finish_query(S, P, log, qi, atid, [] { acc_barrier(); });
+        SR_TICK(10);                                           // reset
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // hybrid kernel: TopSim_singleSample.walk (simrank/TopSim_singleSample.java:62-203).  A weighted path
 // tree per query: a path of weight w at a vertex of degree d is split into all d neighbours with
 // weight w/d when w >= d (:99-125), otherwise into ceil(w) random neighbours with weight w/ceil(w)
@@ -457,8 +825,9 @@ struct HybridParams {
     double cpow[16];      // C^i
 };
 
+template <bool LOGACC>
 struct HyShared {
-    SrShared acc;
+    typename std::conditional<LOGACC, SrLogShared, SrShared>::type acc;
     uint32_t ofs[SR_BLOCK + 1];
     uint32_t roff[SR_BLOCK];
     double cw[SR_BLOCK];
@@ -467,7 +836,8 @@ struct HyShared {
 };
 
 // block exclusive scan of one value per thread; returns the exclusive prefix, *total = block sum
-__device__ __forceinline__ uint32_t block_scan(HyShared &Y, uint32_t val, int tid, uint32_t *total) {
+template <typename HY>
+__device__ __forceinline__ uint32_t block_scan(HY &Y, uint32_t val, int tid, uint32_t *total) {
     const int lane = tid & 31, wrp = tid >> 5;
     uint32_t incl = val;
     for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -486,11 +856,16 @@ __device__ __forceinline__ uint32_t block_scan(HyShared &Y, uint32_t val, int ti
     return excl;
 }
 
-template <int STEP>
+// LOGACC = true: contributions go to the log-structured accumulator of the Monte-Carlo kernel (shared-memory table +
+// per-CTA log + sketch, no global atomics); a query it cannot finish exactly is handed to the LOGACC = false
+// instantiation (exact two-tier hash, also the dense-rows path).  Both add the same integers
+// round(val / SAMPLE * 2^32), so results do not depend on which one ran; scores leave x SAMPLE (P.out_scale).
+template <int STEP, bool LOGACC>
 __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, HybridParams H) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    HyShared &Y = *reinterpret_cast<HyShared *>(smem_raw);
-    SrShared &S = Y.acc;
+    HyShared<LOGACC> &Y = *reinterpret_cast<HyShared<LOGACC> *>(smem_raw);
+    auto &S = Y.acc;
+    uint2 *log = P.log + (size_t)blockIdx.x * P.log_cap;
     constexpr int LEN = 2 * STEP;
     const int tid = threadIdx.x, lane = tid & 31;
     const size_t gs = (size_t)P.gs_mask + 1;
@@ -507,12 +882,31 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
     uint32_t *ckey = H.ckey + (size_t)blockIdx.x * cap;
     uint32_t *cpar = H.cpar + (size_t)blockIdx.x * 2 * cap;
 
-    for (int i = tid; i < SR_HS; i += SR_BLOCK) { S.keys[i] = SR_EMPTY; S.lo[i] = 0; S.hi[i] = 0; }
-    if (tid == 0) { S.ocount = 0; S.ccount = 0; }
+    if constexpr (LOGACC) {
+        for (int i = tid; i < SR_HS; i += SR_BLOCK) { S.keys[i] = SR_EMPTY; S.lo[i] = 0; }
+        for (int i = tid; i < SR_SKETCH; i += SR_BLOCK) S.sketch[i] = 0;
+        if (tid == 0) { S.lcount = 0; S.ccount = 0; S.t3count = 0; S.slow = 0; }
+    } else {
+        for (int i = tid; i < SR_HS; i += SR_BLOCK) { S.keys[i] = SR_EMPTY; S.lo[i] = 0; S.hi[i] = 0; }
+        if (tid == 0) { S.ocount = 0; S.ccount = 0; }
+    }
     __syncthreads();
     unsigned long long my_steps = 0;
+    // one contribution per lane, all 32 lanes together
+    auto add = [&](bool ok, uint32_t key, unsigned long long fx) {
+        if constexpr (LOGACC) {
+            const uint32_t k1[1] = {ok ? key : SR_EMPTY};
+            const unsigned long long f1[1] = {fx};
+            log_insert_batch<1>(S, P, log, lane, k1, f1);
+        } else {
+            acc_add_warp(S, P, gkeys, gval, olist, ok, key, fx);
+        }
+    };
 
-    for (int64_t qi = blockIdx.x; qi < P.nq; qi += gridDim.x) {
+    // exact instantiation as the slow path: only the queries the log instantiation handed over (P.qlist / P.qcount)
+    const int64_t n_work = P.qlist ? (int64_t)*P.qcount : P.nq;
+    for (int64_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        const int64_t qi = P.qlist ? (int64_t)P.qlist[wi] : wi;
         const int32_t v = (int32_t)P.queries[qi];
         const uint64_t qid = P.query_id_base + (uint64_t)qi;
         if (tid == 0) { vb[0] = v; wb[0] = (double)P.sample; Y.n_in = 1; Y.n_cp = 0; }
@@ -543,10 +937,10 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
                             const int32_t inter = vin[(size_t)i * cap + p];
                             const double val = win[p] * H.cpow[i] * (double)__ldg(P.meta + inter).y /
                                                (double)__ldg(P.meta + target).y;   // :189
-                            fx = __double2ull_rn(val * SR_FIX);
+                            fx = __double2ull_rn(val * P.inv_sample * SR_FIX);
                         }
                     }
-                    acc_add_warp(S, P, gkeys, gval, olist, ok, (uint32_t)target, fx);
+                    add(ok, (uint32_t)target, fx);
                 }
             }
             if (l == LEN) break;
@@ -680,374 +1074,22 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
                         if (ok) {
                             const uint32_t dmid = i > lvl ? dgs[i] : __ldg(P.meta + path[i]).y;
                             const double val = wq * H.cpow[i] * (double)dmid / (double)dgs[2 * i];
-                            fx = __double2ull_rn(val * SR_FIX);
+                            fx = __double2ull_rn(val * P.inv_sample * SR_FIX);
                         }
-                        acc_add_warp(S, P, gkeys, gval, olist, ok, (uint32_t)target, fx);
+                        add(ok, (uint32_t)target, fx);
                     }
                 }
             }
         }
-        finish_query(S, P, gkeys, gval, olist, qi, tid);
+        if constexpr (LOGACC) {
+            __syncthreads();
+            log_finish_query(S, P, log, qi, tid, [] { __syncthreads(); });
+        } else {
+            finish_query(S, P, gkeys, gval, olist, qi, tid);
+        }
     }
     for (int o = 16; o; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
-    if (lane == 0 && my_steps) atomicAdd(P.steps, my_steps);
-}
-
-// ---------------------------------------------------------------------------------------------
-// log kernel (production): no global atomics.  A contribution goes to the shared-memory table when
-// its key fits there; otherwise it is APPENDED to a per-CTA log (coalesced 8-byte stores) and its
-// value is added to a small shared-memory sketch cell (an upper bound of every logged key's total).
-// Top-k: threshold bin from the table (a lower bound of the k-th score), table candidates, then ONE
-// streaming pass over the log that keeps only entries whose sketch cell could reach the threshold
-// (almost none: logged keys are the single-hit tail) and sums those exactly in a tiny third table.
-// A query that cannot be finished exactly this way (threshold at the single-hit level, sketch
-// saturation, too many survivors) is flagged and re-run by the hash kernel; both kernels add the
-// same 32.32 fixed-point integers, so the result does not depend on which one produced it.
-// ---------------------------------------------------------------------------------------------
-#ifndef SR_SKETCH_CELLS
-#define SR_SKETCH_CELLS 16384
-#endif
-constexpr int SR_SKETCH = SR_SKETCH_CELLS;
-#ifndef SR_RING_STAGES
-#define SR_RING_STAGES 2
-#endif
-#ifndef SR_WILP
-#define SR_WILP 1                            // samples walked in lock step per walker thread of the log kernel
-#endif
-#ifndef SR_T3_SLOTS
-#define SR_T3_SLOTS 512
-#endif
-constexpr int SR_T3 = SR_T3_SLOTS;
-constexpr int SR_LCAND = 256;
-
-struct SrLogShared {
-    uint32_t keys[SR_HS];
-    uint32_t lo[SR_HS];                  // 0.32 fixed point; a carry out of it sends the query to the hash kernel
-    uint32_t sketch[SR_SKETCH];          // 2^-24 units, rounded up
-    uint32_t hist[SR_BINS];              // threshold histogram, then tier-3 keys (SR_T3 <= SR_BINS)
-    uint32_t t3lo[SR_T3], t3hi[SR_T3];
-    unsigned long long cand_score[SR_LCAND];
-    uint32_t cand_id[SR_LCAND];
-    uint32_t lcount;                     // log entries
-    uint32_t ccount;                     // candidates
-    uint32_t t3count;
-    uint32_t thr_bin;
-    uint32_t slow;                       // this query needs the hash kernel
-};
-
-// walker -> accumulator hand-over: one single-producer single-consumer ring per warp pair, a stage =
-// the WILP * STEP (key, x) contributions of WILP samples per lane; full/empty mbarriers per stage
-constexpr int SR_PAIRS = 16;                 // walker warps = accumulator warps per CTA (1024 threads, one CTA per SM)
-constexpr int SR_ABLOCK = SR_PAIRS * 32;     // accumulator threads (phases B and C run on them alone)
-static_assert(SR_ABLOCK == SR_BLOCK, "phase B/C strides assume SR_BLOCK accumulator threads");
-template <int STEP>
-struct SrRing {
-    static constexpr int WILP = STEP <= 5 ? SR_WILP : 1;     // samples in flight per walker thread
-    static constexpr int STAGES = STEP <= 5 ? SR_RING_STAGES : SR_RING_STAGES / 2;   // walkers run this far ahead of phase B
-    uint2 slot[SR_PAIRS][STAGES][WILP * STEP * 32];
-    unsigned long long full[SR_PAIRS][STAGES];
-    unsigned long long empty[SR_PAIRS][STAGES];
-};
-__device__ __forceinline__ void acc_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(SR_ABLOCK) : "memory"); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {      // release.cta: my stores before it are visible to the waiter
-    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
-    asm volatile("{\n.reg .pred p;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE;\nbra LAB_WAIT;\nDONE:\n}"
-                 ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
-}
-
-// The STEP contributions of one sample per lane into the query's accumulator, batched so that the
-// shared-memory round trips of the levels overlap instead of chaining: all bucket loads first, then
-// all adds (return values consumed at the very end), ONE log reservation per warp for every level.
-// 4-key buckets: one 16-byte shared load sees every slot a key may live in.  Slots of a bucket fill
-// in order and never empty during a query, so "first empty slot of my view + CAS" places a key
-// exactly once (a stale view only makes the CAS return the occupant, after which the bucket is
-// re-read).  What does not fit goes to the per-CTA log + sketch.  Called by all 32 lanes together.
-template <int STEP>
-__device__ __forceinline__ void log_insert_chunk(SrLogShared &S, const SimrankParams &P, uint2 *log, int lane,
-                                                 const uint32_t *key, const float *x) {
-    uint4 kk[STEP];
-    uint32_t b0[STEP];
-    bool pending[STEP];
-    uint32_t wrapped = 0;
-#pragma unroll
-    for (int i = 0; i < STEP; i++) {
-        b0[i] = (hash32(key[i]) & (SR_HS / 4 - 1)) * 4;
-        pending[i] = key[i] != SR_EMPTY;
-        kk[i] = make_uint4(0, 0, 0, 0);
-        if (pending[i])
-            asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(kk[i].x), "=r"(kk[i].y), "=r"(kk[i].z), "=r"(kk[i].w)
-                         : "r"((uint32_t)__cvta_generic_to_shared(&S.keys[b0[i]])));
-    }
-    uint32_t old[STEP];
-#pragma unroll
-    for (int i = 0; i < STEP; i++) {
-        const unsigned long long fx = to_fixed(x[i]);
-        const uint32_t vl = (uint32_t)fx;
-        old[i] = 0;
-        if (pending[i]) {
-            if (fx >> 32) wrapped = 1;                          // single contribution >= 1.0: exact path
-            uint4 v = kk[i];
-            for (int attempt = 0; attempt < 5; attempt++) {
-                int j = v.x == key[i] ? 0 : v.y == key[i] ? 1 : v.z == key[i] ? 2 : v.w == key[i] ? 3 : -1;
-                if (j < 0) {
-                    int e = v.x == SR_EMPTY ? 0 : v.y == SR_EMPTY ? 1 : v.z == SR_EMPTY ? 2 : v.w == SR_EMPTY ? 3 : -1;
-                    if (e < 0) break;                           // bucket full of other keys: log
-                    uint32_t k0 = atomicCAS(&S.keys[b0[i] + e], SR_EMPTY, key[i]);
-                    if (k0 == SR_EMPTY || k0 == key[i]) j = e;
-                }
-                if (j >= 0) {
-                    old[i] = atomicAdd(&S.lo[b0[i] + j], vl);
-                    pending[i] = false;
-                    break;
-                }
-                asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                             : "r"((uint32_t)__cvta_generic_to_shared(&S.keys[b0[i]])));
-            }
-        }
-    }
-    // overflow: append to the log, one shared-memory atomic per warp for all levels
-    uint32_t mask[STEP], total = 0;
-#pragma unroll
-    for (int i = 0; i < STEP; i++) { mask[i] = __ballot_sync(0xffffffffu, pending[i]); total += __popc(mask[i]); }
-    if (total) {
-        uint32_t basep = 0;
-        if (lane == 0) basep = atomicAdd(&S.lcount, total);
-        basep = __shfl_sync(0xffffffffu, basep, 0);
-        uint32_t sold[STEP], sadd[STEP];
-#pragma unroll
-        for (int i = 0; i < STEP; i++) {
-            sold[i] = 0; sadd[i] = 0;
-            if (pending[i]) {
-                const uint32_t pos = basep + __popc(mask[i] & ((1u << lane) - 1));
-                if (pos < P.log_cap) log[pos] = make_uint2(key[i], __float_as_uint(x[i]));
-                sadd[i] = (uint32_t)min((to_fixed(x[i]) >> 8) + 1ull, 0xFFFFFFFFull);
-                sold[i] = atomicAdd(&S.sketch[(hash32(key[i]) >> 13) & (SR_SKETCH - 1)], sadd[i]);
-            }
-            basep += __popc(mask[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < STEP; i++) if (sold[i] + sadd[i] < sold[i]) wrapped = 1;    // sketch cell wrapped
-    }
-#pragma unroll
-    for (int i = 0; i < STEP; i++) if (old[i] + (uint32_t)to_fixed(x[i]) < old[i]) wrapped = 1;   // score >= 1.0: exact path
-    if (wrapped) S.slow = 1;
-}
-
-template <int STEP>
-__device__ __forceinline__ void log_insert_batch(SrLogShared &S, const SimrankParams &P, uint2 *log, int lane,
-                                                 const uint32_t (&key)[STEP], const float (&x)[STEP]) {
-    constexpr int C0 = STEP <= 5 ? STEP : 5;            // at most 5 levels in flight (registers)
-    log_insert_chunk<C0>(S, P, log, lane, key, x);
-    if (STEP > C0) log_insert_chunk<(STEP > C0 ? STEP - C0 : 1)>(S, P, log, lane, key + C0, x + C0);
-}
-
-// One CTA of 1024 threads per SM, split by role.  Warps [0, SR_PAIRS) are WALKERS: they do nothing but
-// walk (WILP samples in flight per thread) and hand the (key, x) contributions of every sample to
-// their partner through a shared-memory ring.  Warps [SR_PAIRS, 2*SR_PAIRS) are ACCUMULATORS: they
-// drain the rings into the query's hash table / log, and run top-k (phase B) and the reset (phase C)
-// among themselves behind a named barrier.  The walkers never meet a CTA-wide barrier: while the
-// accumulators rank query q the walkers are already walking query q+1, so the random loads keep the
-// memory system at its ceiling all the time instead of alternating with the shared-memory work.
-// (The unsplit kernel ran phase A as "10 dependent loads, then STEP inserts" in every warp, in step
-// with every other warp: walk time and accumulate time added up, 6.1 ms where the walks alone take
-// 3.9 ms -- profiles/README.md.)
-#ifdef SR_PROFILE
-#define SR_TICK(slot) do { if (prof_on) { long long t_ = clock64(); atomicAdd(P.prof + (slot), (unsigned long long)(t_ - t_last)); t_last = t_; } } while (0)
-#else
-#define SR_TICK(slot) do { } while (0)
-#endif
-
-template <int STEP>
-__global__ void __launch_bounds__(2 * SR_ABLOCK, 1) k_simrank_log(SimrankParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SrLogShared &S = *reinterpret_cast<SrLogShared *>(smem_raw);
-    using Ring = SrRing<STEP>;
-    constexpr int WILP = Ring::WILP;
-    Ring &R = *reinterpret_cast<Ring *>(smem_raw + ((sizeof(SrLogShared) + 15) & ~(size_t)15));
-    const int tid = threadIdx.x, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    uint2 *log = P.log + (size_t)blockIdx.x * P.log_cap;
-    uint32_t *t3keys = S.hist;
-
-    if (tid < SR_PAIRS * Ring::STAGES) {
-        mbar_init(&R.full[tid / Ring::STAGES][tid % Ring::STAGES], 32);
-        mbar_init(&R.empty[tid / Ring::STAGES][tid % Ring::STAGES], 32);
-    }
-    for (int i = tid; i < SR_HS; i += 2 * SR_ABLOCK) { S.keys[i] = SR_EMPTY; S.lo[i] = 0; }
-    for (int i = tid; i < SR_SKETCH; i += 2 * SR_ABLOCK) S.sketch[i] = 0;
-    if (tid == 0) { S.lcount = 0; S.ccount = 0; S.t3count = 0; S.slow = 0; }
-    __syncthreads();
-    uint32_t stage_no = 0;                   // stages handed over so far by this warp pair (same count on both sides)
-    const int32_t ngroups = (P.sample + WILP - 1) / WILP;
-#ifdef SR_PROFILE
-    const bool prof_on = blockIdx.x == 0 && lane == 0 && (wrp == 0 || wrp == SR_PAIRS);
-    long long t_last = clock64();
-#endif
-
-    if (wrp < SR_PAIRS) {
-        // =============================== walkers ===============================
-        unsigned long long my_steps = 0;
-        for (int64_t qi = blockIdx.x; qi < P.nq; qi += gridDim.x) {
-            const int32_t v = (int32_t)P.queries[qi];
-            const uint64_t qid = P.query_id_base + (uint64_t)qi;
-            const uint2 mv = __ldg(P.meta + v);
-            for (int32_t g0 = wrp * 32; g0 < ngroups; g0 += SR_PAIRS * 32, stage_no++) {
-                const uint32_t st = stage_no % Ring::STAGES, ph = (stage_no / Ring::STAGES) & 1;
-                SR_TICK(0);                                    // walker: walking
-                mbar_wait(&R.empty[wrp][st], ph ^ 1);          // the accumulator has taken the stage's previous content
-                SR_TICK(1);                                    // walker: waiting for a free stage
-                uint2 *slot = R.slot[wrp][st];
-                int cnt = 0;                                   // emit order: level-major, sample-minor (walk_group)
-                my_steps += (unsigned long long)walk_group<STEP, WILP>(P, v, mv, qid, g0 + lane,
-                    [&](bool ok, uint32_t key, float x) {
-                        slot[cnt * 32 + lane] = make_uint2(ok ? key : SR_EMPTY, __float_as_uint(x));
-                        cnt++;
-                    });
-                mbar_arrive(&R.full[wrp][st]);
-            }
-        }
-        for (int o = 16; o; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
-        if (lane == 0 && my_steps) atomicAdd(P.steps, my_steps);
-        return;
-    }
-
-    // =============================== accumulators ===============================
-    const int pw = wrp - SR_PAIRS, atid = tid - SR_ABLOCK;
-    for (int64_t qi = blockIdx.x; qi < P.nq; qi += gridDim.x) {
-        // ---------------- phase A: drain my walker's ring ----------------
-        for (int32_t g0 = pw * 32; g0 < ngroups; g0 += SR_PAIRS * 32, stage_no++) {
-            const uint32_t st = stage_no % Ring::STAGES, ph = (stage_no / Ring::STAGES) & 1;
-            SR_TICK(2);                                        // accumulator: inserting
-            mbar_wait(&R.full[pw][st], ph);
-            SR_TICK(3);                                        // accumulator: waiting for its walker
-#pragma unroll
-            for (int k = 0; k < WILP; k++) {
-                uint32_t ek[STEP];
-                float ex[STEP];
-#pragma unroll
-                for (int i = 0; i < STEP; i++) {
-                    const uint2 en = R.slot[pw][st][(i * WILP + k) * 32 + lane];
-                    ek[i] = en.x; ex[i] = __uint_as_float(en.y);
-                }
-                if (k == WILP - 1) mbar_arrive(&R.empty[pw][st]);          // stage is in registers: give it back
-                log_insert_batch<STEP>(S, P, log, lane, ek, ex);
-            }
-        }
-        SR_TICK(2);
-        acc_barrier();
-        SR_TICK(4);                                            // waiting for the other accumulators' last stages
-        const uint32_t Lc = min(S.lcount, P.log_cap);
-        if (S.lcount > P.log_cap && atid == 0) S.slow = 1;
-
-        // ---------------- phase B: top-k ----------------
-        const uint32_t K = (uint32_t)P.k;
-        {
-        for (int i = atid; i < SR_BINS; i += SR_BLOCK) S.hist[i] = 0;
-        acc_barrier();
-        for (int i = atid; i < SR_HS; i += SR_BLOCK) {
-            if (S.keys[i] != SR_EMPTY) {
-                unsigned long long sc = S.lo[i];
-                if (sc) atomicAdd(&S.hist[score_bin(sc)], 1u);
-            }
-        }
-        acc_barrier();
-        SR_TICK(5);                                            // histogram of table scores
-        if (atid < 32) {
-            uint32_t thr = threshold_bin(S.hist, K, atid);
-            if (atid == 0) { S.thr_bin = thr; S.ccount = 0; S.t3count = 0; }
-        }
-        acc_barrier();
-        const uint32_t thr = S.thr_bin;
-        if (thr == 0 && Lc > 0 && atid == 0) S.slow = 1;   // no usable lower bound: every logged key could matter
-        for (int i = atid; i < SR_T3; i += SR_BLOCK) { t3keys[i] = SR_EMPTY; S.t3lo[i] = 0; S.t3hi[i] = 0; }
-        for (int i = atid; i < SR_HS; i += SR_BLOCK) {     // table candidates
-            uint32_t id = S.keys[i];
-            if (id != SR_EMPTY) {
-                unsigned long long sc = S.lo[i];
-                if (sc != 0 && score_bin(sc) >= thr) {
-                    uint32_t c = atomicAdd(&S.ccount, 1u);
-                    if (c < SR_LCAND) { S.cand_score[c] = sc; S.cand_id[c] = id; }
-                }
-            }
-        }
-        acc_barrier();
-        SR_TICK(6);                                            // threshold + table candidates
-        if (thr != 0) {
-            // one streaming pass over the log; survivors are summed exactly in tier 3
-            // (8 independent loads in flight per thread: the pass is L2-latency bound otherwise)
-            for (uint32_t e0 = atid; e0 < Lc; e0 += SR_BLOCK * 8) {
-              uint2 ens[8];
-#pragma unroll
-              for (int u = 0; u < 8; u++) {
-                  const uint32_t e = e0 + u * SR_BLOCK;
-                  ens[u] = e < Lc ? __ldcg(log + e) : make_uint2(SR_EMPTY, 0u);
-              }
-#pragma unroll
-              for (int u = 0; u < 8; u++) {
-                const uint2 en = ens[u];
-                if (en.x == SR_EMPTY) continue;
-                uint32_t cell = S.sketch[(hash32(en.x) >> 13) & (SR_SKETCH - 1)];
-                if (score_bin((unsigned long long)cell << 8) >= thr) {
-                    uint32_t slot = (hash32(en.x) >> 4) & (SR_T3 - 1);
-                    bool done = false;
-                    for (int pr = 0; pr < SR_T3 && !done; pr++) {
-                        uint32_t k0 = ((volatile uint32_t *)t3keys)[slot];
-                        if (k0 == SR_EMPTY) {
-                            k0 = atomicCAS(&t3keys[slot], SR_EMPTY, en.x);
-                            if (k0 == SR_EMPTY) {
-                                if (atomicAdd(&S.t3count, 1u) >= (uint32_t)(SR_T3 * 3 / 4)) S.slow = 1;
-                                k0 = en.x;
-                            }
-                        }
-                        if (k0 == en.x) { fixed_add(&S.t3lo[slot], &S.t3hi[slot], to_fixed(__uint_as_float(en.y))); done = true; }
-                        else slot = (slot + 1) & (SR_T3 - 1);
-                    }
-                    if (!done) S.slow = 1;
-                }
-              }
-            }
-            acc_barrier();
-            SR_TICK(7);                                        // log pass
-            for (int i = atid; i < SR_T3; i += SR_BLOCK) {
-                uint32_t id = t3keys[i];
-                if (id != SR_EMPTY) {
-                    unsigned long long sc = ((unsigned long long)S.t3hi[i] << 32) | S.t3lo[i];
-                    if (sc != 0 && score_bin(sc) >= thr) {
-                        uint32_t c = atomicAdd(&S.ccount, 1u);
-                        if (c < SR_LCAND) { S.cand_score[c] = sc; S.cand_id[c] = id; }
-                    }
-                }
-            }
-        }
-        acc_barrier();
-        SR_TICK(8);                                            // tier-3 candidates
-        const uint32_t C = S.ccount;
-        int32_t *oid = P.out_ids + (size_t)qi * K;
-        double *osc = P.out_scores + (size_t)qi * K;
-        const bool slow = S.slow != 0 || C > SR_LCAND;
-        if (!slow) {
-            emit_ranked(S, C, K, oid, osc, atid);
-        } else if (atid == 0) {
-            uint32_t w = atomicAdd(P.qcount, 1u);     // hand the query to the hash kernel
-            P.qlist_out[w] = (int32_t)qi;
-        }
-        }
-        acc_barrier();
-        SR_TICK(9);                                            // ranking
-        // ---------------- phase C: reset ----------------
-        for (int i = atid; i < SR_HS; i += SR_BLOCK) { S.keys[i] = SR_EMPTY; S.lo[i] = 0; }
-        for (int i = atid; i < SR_SKETCH; i += SR_BLOCK) S.sketch[i] = 0;
-        if (atid == 0) { S.lcount = 0; S.ccount = 0; S.t3count = 0; S.slow = 0; }
-        acc_barrier();
-        SR_TICK(10);                                           // reset
-    }
+    if (lane == 0 && my_steps && !P.qlist) atomicAdd(P.steps, my_steps);   // handed-over queries were counted by the log instantiation
 }
 
 // ---------------- replay mode: java.util.Random on the device ----------------
@@ -1283,7 +1325,9 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     uint32_t gs = 1024;
     while ((int64_t)gs < 2 * distinct) gs <<= 1;
     const uint32_t ocap = (uint32_t)distinct + 1;
-    const uint32_t log_cap = (uint32_t)std::min<int64_t>((int64_t)sample * step, (int64_t)0x7FFFFFFF);
+    // log capacity = the most contributions one query can make (path tree: every path of every even level)
+    const uint32_t log_cap = (uint32_t)std::min<int64_t>(hybrid ? (int64_t)sample * step * (step + 1) + step : (int64_t)sample * step,
+                                                         (int64_t)0x7FFFFFFF);
     // layout: [64 B header][gval u64 grid*gs][gkeys u32 grid*gs][olist u32 grid*ocap][log uint2 grid*log_cap][qlist i32 nq]
     size_t off_gval = 256;
     size_t off_gkeys = off_gval + (size_t)grid * gs * 8;
@@ -1322,6 +1366,8 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     GW_TRY(ensure_common_counts(g, st, false));               // nbr4 rows (no counts needed)
     P.meta = g->d_meta; P.col = g->d_col; P.nbr4 = g->d_nbr4; P.queries = d_queries; P.nq = nq; P.n = g->n;
     P.sample = sample; P.k = k;
+    P.out_scale = hybrid ? (double)sample / SR_FIX : 1.0 / SR_FIX;
+    P.inv_sample = 1.0 / (double)sample;
     for (int i = 0; i < 16; i++) P.coef[i] = 0;
     for (int i = 1; i <= step; i++) P.coef[i] = (float)(pow(c, i) / (double)sample);   // cache[i] = Math.pow(C, i) (:34-36), / SAMPLE (:89)
     P.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
@@ -1357,9 +1403,19 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
         H.cnum = (uint32_t *)(hb + o_cn); H.cofs = (uint32_t *)(hb + o_co);
         H.ckey = (uint32_t *)(hb + o_ck); H.cpar = (uint32_t *)(hb + o_cp);
         for (int i = 0; i < 16; i++) H.cpow[i] = i <= step ? pow(c, i) : 0.0;
-        size_t smem = sizeof(HyShared);
-#define GW_HY(N) case N: GW_CUDA(cudaFuncSetAttribute(k_topsim_hybrid<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                         k_topsim_hybrid<N><<<grid, SR_BLOCK, smem, st>>>(P, H); break;
+        // top-k: log-structured instantiation first, then the exact one over the queries it handed over;
+        // dense rows: the exact instantiation alone
+        const bool hy_log = d_out_ids && !d_out_dense && !(force && !strcmp(force, "hash"));
+        SimrankParams Q = P;
+        if (hy_log) Q.qlist = P.qlist_out;
+#define GW_HY(N) case N: \
+            if (hy_log) { \
+                GW_CUDA(cudaFuncSetAttribute(k_topsim_hybrid<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HyShared<true>))); \
+                k_topsim_hybrid<N, true><<<grid, SR_BLOCK, sizeof(HyShared<true>), st>>>(P, H); \
+                GW_LAUNCHED(); \
+            } \
+            GW_CUDA(cudaFuncSetAttribute(k_topsim_hybrid<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HyShared<false>))); \
+            k_topsim_hybrid<N, false><<<grid, SR_BLOCK, sizeof(HyShared<false>), st>>>(Q, H); break;
         switch (step) { GW_HY(1) GW_HY(2) GW_HY(3) GW_HY(4) GW_HY(5) GW_HY(6) GW_HY(7) GW_HY(8) GW_HY(9) default: GW_HY(10) }
 #undef GW_HY
         GW_LAUNCHED();
