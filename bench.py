@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--sample", type=int, default=10000)
     ap.add_argument("--sr-step", type=int, default=5)
     ap.add_argument("--topk", type=int, default=20)
+    ap.add_argument("--estimator", default="mc", choices=["mc", "hybrid"],
+                    help="simrank workload: mc = SingleRandomWalk (headline), hybrid = TopSim_singleSample path tree")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -289,8 +291,9 @@ def config_of(args):
                           4.0 * args.walk_length * (1 << args.scale) / 1e6),
                 "sharding": "graph replicated per GPU, disjoint walk ids per rank, no data-path collective"}
     return {"workload": "TopSim SimRank top-%d on synthetic Barabasi-Albert n=%d m=%d, c=0.6 STEP=%d SAMPLE=%d, "
-                        "one step = %d queries" % (args.topk, args.ba_nodes, args.ba_m, args.sr_step, args.sample,
-                                                   args.queries_per_step),
+                        "one step = %d queries%s" % (args.topk, args.ba_nodes, args.ba_m, args.sr_step, args.sample,
+                                                     args.queries_per_step,
+                                                     "" if getattr(args, "estimator", "mc") == "mc" else ", estimator TopSim_singleSample (path tree)"),
             "cache": "inputs larger than L2 (col_idx %.0f MB)" % (4.0 * 2 * args.ba_m * args.ba_nodes / 1e6),
             "sharding": "graph replicated per GPU, disjoint query slices per rank, no data-path collective"}
 
@@ -468,6 +471,7 @@ def measure(args, rank, world, local):
         extra["graph_build_s"] = round(time.perf_counter() - t0, 3)
         extra["graph"] = {"nodes": g.n, "directed_entries": g.nnz, "max_degree": g.max_degree}
         nq = args.queries_per_step
+        sr_mode = _lib.GW_SIMRANK_HYBRID if args.estimator == "hybrid" else _lib.GW_SIMRANK_MC
         rs = np.random.RandomState(2)
         total_q = nq * (args.warmup + args.steps) * world
         allq = rs.choice(g.n, size=min(total_q, g.n), replace=False).astype(np.int64)
@@ -478,8 +482,8 @@ def measure(args, rank, world, local):
 
         def step(i):
             g.simrank_topk_dev(d_q.data_ptr() + 8 * nq * i, nq, 0.6, args.sr_step, args.sample, args.topk,
-                               d_ids.data_ptr(), d_sc.data_ptr(), seed=7, query_id_base=(rank * 100000 + i) * nq,
-                               stream=stream)
+                               d_ids.data_ptr(), d_sc.data_ptr(), mode=sr_mode, seed=7,
+                               query_id_base=(rank * 100000 + i) * nq, stream=stream)
         for i in range(args.warmup):
             step(i)
         barrier()
@@ -501,11 +505,11 @@ def measure(args, rank, world, local):
         extra["slow_path_queries_last_step"] = g.simrank_last_slow_queries()
         kernel_ms = float(np.mean(per_launch_ms))
         alg_bytes = walk_steps * 64.0 + nq * args.topk * 12.0
-        kname = "k_simrank_log<%d>" % args.sr_step
+        kname = ("k_simrank_log<%d>" if args.estimator == "mc" else "k_topsim_hybrid<%d,true>") % args.sr_step
         rate = walk_steps / (kernel_ms * 1e-3) / 1e9
         ceil = gather_ceiling(16.0 * g.nnz)
         roof = {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "traffic": ncu_traffic(kname, nq) if (args.ba_nodes == 10_000_000 and args.sample == 10000 and args.sr_step == 5) else None,
+                "traffic": ncu_traffic(kname, nq) if (args.ba_nodes == 10_000_000 and args.sample == 10000 and args.sr_step == 5 and args.estimator == "mc") else None,
                 "kernel": kname, "peak_source": peak_src,
                 "bytes_per_unit": alg_bytes / nq, "units_per_launch": nq, "launch_ms": kernel_ms,
                 "model": "SURVEY 8(d): 64 B per walk step (here ONE random 16-byte entry = one 64-byte HBM atom) + 12 B per result slot",
@@ -517,12 +521,12 @@ def measure(args, rank, world, local):
         e2e = None
         if not args.no_e2e:
             hq = myq[:nq].copy()
-            g.simrank_topk(hq, 0.6, args.sr_step, args.sample, args.topk, seed=8)
+            g.simrank_topk(hq, 0.6, args.sr_step, args.sample, args.topk, mode=sr_mode, seed=8)
             barrier()
             n_e2e = max(3, min(args.steps, 5))
             t0 = time.perf_counter()
             for i in range(n_e2e):
-                g.simrank_topk(hq, 0.6, args.sr_step, args.sample, args.topk, seed=9 + i)
+                g.simrank_topk(hq, 0.6, args.sr_step, args.sample, args.topk, mode=sr_mode, seed=9 + i)
             dt = time.perf_counter() - t0
             tt = torch.tensor([dt], device=dev)
             if world > 1:
