@@ -217,6 +217,40 @@ def test_walks_independent_of_batch_split(walker, monkeypatch):
     assert not np.array_equal(whole, other)
 
 
+def test_large_edgelist_is_parsed_in_parallel_chunks(tmp_path):
+    """Files above 1 MB are cut at line boundaries and parsed by several host threads: same CSR and same
+    first-appearance order as the edge arrays, comments / blank lines / CRLF handled per line, and an error
+    deep in the file is reported with the file's line number."""
+    rs = np.random.RandomState(5)
+    m = 400000
+    src = rs.randint(0, 50000, m); dst = rs.randint(0, 50000, m)
+    keep = src != dst
+    src, dst = src[keep].astype(np.int64), dst[keep].astype(np.int64)
+    lines = []
+    for i, (u, v) in enumerate(zip(src.tolist(), dst.tolist())):
+        if i % 1000 == 0:
+            lines.append("# comment %d" % i)
+        if i % 1777 == 0:
+            lines.append("")
+        lines.append("%d %d%s" % (u, v, "\r" if i % 3 == 0 else ""))
+    path = str(tmp_path / "big.edgelist")
+    with open(path, "w", newline="") as f:
+        f.write("\n".join(lines) + "\n")
+    assert os.path.getsize(path) > 3 << 20
+    h = _lib.GraphHandle.from_file(path, delimiter=" ")
+    g = _lib.GraphHandle.from_edges(src, dst)
+    a, b = h.csr(), g.csr()
+    for k in ("node_ids", "first_seen", "row_ptr", "col_idx"):
+        assert np.array_equal(a[k], b[k]), k
+    bad_line = len(lines) - 5
+    lines[bad_line - 1] = "12 notanumber"
+    with open(path, "w", newline="") as f:
+        f.write("\n".join(lines) + "\n")
+    with pytest.raises(IOError) as ei:
+        _lib.GraphHandle.from_file(path, delimiter=" ")
+    assert ":%d:" % bad_line in str(ei.value)
+
+
 def test_bloom_filter_does_not_change_walks(monkeypatch):
     """q < 1: the edge Bloom filter only short-cuts adjacency tests whose answer is "not adjacent";
     positives are verified exactly, so the walks are identical with the filter switched off."""
