@@ -121,5 +121,42 @@ while time.perf_counter() - t0 < 10.0:
 t_cpu = time.perf_counter() - t0
 out["a9_a12_cpu_port_blog"] = {"seconds": t_cpu, "queries": nqd, "queries_per_s": nqd / t_cpu, "cores": 1,
                                "what": "oracle/simrank_oracle.c SingleRandomWalk.walk + FixedMaxPQ on blog.txt"}
+# CPU: the other rows' oracle routines on bounded samples (1 core each)
+t0 = time.perf_counter()
+nq2 = 0
+st = S.java_seed(2)
+while time.perf_counter() - t0 < 5.0:
+    row, made, st = S.topsim_row(ogb, int(qs[nq2 % len(qs)]), 10000, 5, 0.6, mode=0, seed_state=st)
+    S.fixedmaxpq_topk(row, 20)
+    nq2 += 1
+t_cpu = time.perf_counter() - t0
+out["a11_cpu_port_blog"] = {"seconds": t_cpu, "queries": nq2, "queries_per_s": nq2 / t_cpu, "cores": 1,
+                            "what": "oracle/simrank_oracle.c TopSim_singleSample path tree + FixedMaxPQ on blog.txt"}
+o333 = S.load_multigraph(os.path.join(DATA, "0_333_5038.txt"), 333, " ")
+t0 = time.perf_counter()
+S.simrank_exact_matrix(o333, 0.6, 5)
+t_cpu = time.perf_counter() - t0
+t_g333, _ = timed(lambda: _lib.GraphHandle.from_file(os.path.join(DATA, "0_333_5038.txt"), delimiter=" ", mode=_lib.GW_MODE_MULTI,
+                                                      n_slots=333).simrank_exact(0.6, 5), reps=2)
+out["a13_exact_simrank_g333"] = {"gpu_seconds": t_g333, "cpu_port_seconds": t_cpu, "n": 333, "iters": 5,
+                                 "what": "SimRank.compute on 0_333_5038.txt: device sweeps (incl. loading the file) vs the oracle's C restatement"}
+t0 = time.perf_counter()
+og2 = O.load_graph(tmp.name, ",")
+t_cpu = time.perf_counter() - t0
+out["a1_cpu_port_blog"] = {"seconds": t_cpu, "edges_per_s": 333983 / t_cpu, "cores": 1,
+                           "what": "oracle/n2v_oracle.py parse_edgelist + build_simple_graph (networkx semantics) on blog.txt"}
+an = O.alias_nodes_flat(og)
+ae = O.alias_edges_flat(og, 0.25, 4.0)
+rng = np.random.RandomState(1)
+t0 = time.perf_counter()
+steps_cpu = 0
+i = 0
+while time.perf_counter() - t0 < 5.0:
+    wlk, _ = O.walk_replay(og, an, ae, 80, i % 333, rng.rand(2 * 79), 0)
+    steps_cpu += len(wlk) - 1
+    i += 1
+t_cpu = time.perf_counter() - t0
+out["a5_a7_cpu_port_g333"] = {"seconds": t_cpu, "walk_steps": steps_cpu, "steps_per_s": steps_cpu / t_cpu, "cores": 1,
+                              "what": "oracle/n2v_oracle.py node2vec_walk/alias_draw on 0_333_5038.txt (materialised alias tables)"}
 os.unlink(tmp.name)
 print(json.dumps(out, indent=1))
