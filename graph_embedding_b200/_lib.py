@@ -76,6 +76,14 @@ SIGNATURES = {
     "gw_topsim_rows_javarng": (ctypes.c_int, [c_vp, c_i64p, ctypes.c_int64, ctypes.c_double, ctypes.c_int32,
                                               ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
                                               ctypes.POINTER(ctypes.c_uint64), c_f64p]),
+    "gw_simrank_cache_javarng": (ctypes.c_int, [c_vp, c_i64p, ctypes.c_int64, ctypes.c_double, ctypes.c_int32,
+                                                ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
+                                                ctypes.POINTER(ctypes.c_uint64), c_i32p,
+                                                ctypes.POINTER(ctypes.c_float), c_i32p]),
+    "gw_double_walk_paths": (ctypes.c_int, [c_vp, c_i64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                            ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), c_i32p]),
+    "gw_double_walk_sims": (ctypes.c_int, [c_vp, c_i32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                           ctypes.c_double, c_i64p, ctypes.c_int64, ctypes.c_int32, c_f64p]),
     "gw_simrank_last_steps": (ctypes.c_int, [c_vp, c_i64p]),
     "gw_simrank_last_slow_queries": (ctypes.c_int, [c_vp, c_i64p]),
     "gw_simrank_exact": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_int32, c_i64p, ctypes.c_int64, c_f64p]),
@@ -329,6 +337,49 @@ class GraphHandle:
                                             int(sample), int(mode), int(max_paths), ptr(st, ctypes.c_uint64),
                                             ptr(out, ctypes.c_double)))
         return out, st
+
+    def simrank_cache_javarng(self, queries, c, step, sample, capacity, rng_states, mode=0, max_paths=0):
+        """Replay mode of SingleRandomWalk_M (mode 0) / TopSim_singleSample_M (mode 1): per query the heap arrays of its
+        FixedCacheMap(capacity).  Returns (list of (keys, float32 values) in heap order, states after)."""
+        queries = as_c(queries, np.int64)
+        st = np.ascontiguousarray(np.asarray(rng_states, dtype=np.uint64)).copy()
+        if len(st) != len(queries):
+            raise ValueError("one rng state per query")
+        if max_paths <= 0:
+            max_paths = 2 * int(step) * int(sample) + 1
+        keys = np.zeros((len(queries), capacity), dtype=np.int32)
+        vals = np.zeros((len(queries), capacity), dtype=np.float32)
+        sizes = np.zeros(len(queries), dtype=np.int32)
+        check(load().gw_simrank_cache_javarng(self.h, ptr(queries, ctypes.c_int64), len(queries), float(c), int(step),
+                                              int(sample), int(mode), int(capacity), int(max_paths),
+                                              ptr(st, ctypes.c_uint64), ptr(keys, ctypes.c_int32),
+                                              ptr(vals, ctypes.c_float), ptr(sizes, ctypes.c_int32)))
+        return [(keys[i, :sizes[i]].copy(), vals[i, :sizes[i]].copy()) for i in range(len(queries))], st
+
+    def double_walk_paths(self, vertices, sample, step, seed=0, rng_states=None):
+        """DoubleRandomWalk.samplePaths: int32 [nv, sample, step]; with rng_states (one 48-bit java.util.Random state per
+        vertex) the replay kernel runs and the states after are returned too."""
+        vertices = as_c(vertices, np.int64)
+        out = np.zeros((len(vertices), sample, step), dtype=np.int32)
+        st = None
+        if rng_states is not None:
+            st = np.ascontiguousarray(np.asarray(rng_states, dtype=np.uint64)).copy()
+            if len(st) != len(vertices):
+                raise ValueError("one rng state per vertex")
+        check(load().gw_double_walk_paths(self.h, ptr(vertices, ctypes.c_int64), len(vertices), int(sample), int(step),
+                                          int(seed), ptr(st, ctypes.c_uint64), ptr(out, ctypes.c_int32)))
+        return out if st is None else (out, st)
+
+    def double_walk_sims(self, paths, c, rows=None, exact_order=False):
+        """DoubleRandomWalk.getSim over a path set [nv, sample, step]: rows x nv fp64."""
+        paths = as_c(paths, np.int32)
+        nv, sample, step = paths.shape
+        rows = np.arange(nv, dtype=np.int64) if rows is None else as_c(rows, np.int64)
+        out = np.empty((len(rows), nv), dtype=np.float64)
+        check(load().gw_double_walk_sims(self.h, ptr(paths, ctypes.c_int32), nv, sample, step, float(c),
+                                         ptr(rows, ctypes.c_int64), len(rows), int(bool(exact_order)),
+                                         ptr(out, ctypes.c_double)))
+        return out
 
     def simrank_last_steps(self):
         s = ctypes.c_int64()

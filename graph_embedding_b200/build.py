@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["graph.cu", "alias.cu", "walk.cu", "walk_cn.cu", "simrank.cu"]
+SOURCES = ["graph.cu", "alias.cu", "walk.cu", "walk_cn.cu", "simrank.cu", "doublewalk.cu"]
 LIB = os.path.join(HERE, "libgraphwalk.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "-Xcudafe",

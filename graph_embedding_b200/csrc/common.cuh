@@ -204,6 +204,25 @@ __device__ __forceinline__ int32_t ld_i32_policy(const int32_t *ptr, uint64_t po
     return v;
 }
 #endif
+#ifdef __CUDACC__
+// java.util.Random on the device (replay kernels): next(bits) and nextInt(bound) with its rejection loop
+__device__ __forceinline__ int32_t jr_next(uint64_t &seed, int bits) {
+    seed = (seed * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
+    return (int32_t)((int64_t)seed >> (48 - bits));
+}
+__device__ __forceinline__ int32_t jr_next_int(uint64_t &seed, int32_t bound) {
+    int32_t v = jr_next(seed, 31);
+    const int32_t m = bound - 1;
+    if ((bound & m) == 0) return (int32_t)(((int64_t)bound * (int64_t)v) >> 31);
+    int32_t u = v;
+    for (;;) {
+        v = u % bound;
+        if ((int32_t)((uint32_t)u - (uint32_t)v + (uint32_t)m) >= 0) break;      // u - r + m < 0 in Java int arithmetic
+        u = jr_next(seed, 31);
+    }
+    return v;
+}
+#endif
 // uniform index in [0,d) from 32 random bits (bias <= d / 2^32)
 __host__ __device__ static inline uint32_t scale_u32(uint32_t r, uint32_t d) {
 #ifdef __CUDA_ARCH__

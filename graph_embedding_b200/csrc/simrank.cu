@@ -1095,33 +1095,58 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
 // ---------------- replay mode: java.util.Random on the device ----------------
 // java.util.Random (JDK): seed = (seed * 0x5DEECE66D + 0xB) mod 2^48, next(bits) = (int)(seed >>> (48 - bits));
 // nextInt(bound): power of two -> (bound * next(31)) >> 31, else u % bound with the int-overflow rejection test.
-__device__ __forceinline__ int32_t jr_next(uint64_t &seed, int bits) {
-    seed = (seed * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
-    return (int32_t)((int64_t)seed >> (48 - bits));
-}
-__device__ __forceinline__ int32_t jr_next_int(uint64_t &seed, int32_t bound) {
-    int32_t v = jr_next(seed, 31);
-    const int32_t m = bound - 1;
-    if ((bound & m) == 0) return (int32_t)(((int64_t)bound * (int64_t)v) >> 31);
-    int32_t u = v;
-    for (;;) {
-        v = u % bound;
-        if ((int32_t)((uint32_t)u - (uint32_t)v + (uint32_t)m) >= 0) break;      // u - r + m < 0 in Java int arithmetic
-        u = jr_next(seed, 31);
+// (jr_next / jr_next_int live in common.cuh: doublewalk.cu replays with them too)
+
+// lxctools/FixedCacheMap.java:26-100 on the device, one instance per replayed query: 1-based binary min-heap on float
+// values (keys/vals [nmax+1]) and the key -> heap slot map as a dense pos[n] array (0 = absent; the reference keeps a
+// HashMap<Integer, Short>, same contents for nmax <= 32767, which the entry point enforces).
+struct DevCacheMap {
+    int32_t *keys; float *vals; int32_t *pos; int nmax, n;
+    __device__ __forceinline__ bool greater(int a, int b) const { return vals[a] > vals[b]; }
+    __device__ __forceinline__ void exch(int a, int b) {
+        pos[keys[a]] = b; pos[keys[b]] = a;
+        const int32_t tk = keys[a]; keys[a] = keys[b]; keys[b] = tk;
+        const float tv = vals[a]; vals[a] = vals[b]; vals[b] = tv;
     }
-    return v;
-}
+    __device__ void sink(int i) {
+        while (2 * i <= n) {
+            int j = 2 * i;
+            if (j < n && greater(j, j + 1)) j++;
+            if (!greater(i, j)) break;
+            exch(i, j);
+            i = j;
+        }
+    }
+    __device__ void swim(int i) {
+        while (i > 1 && greater(i / 2, i)) { exch(i, i / 2); i = i / 2; }
+    }
+    __device__ void put(int32_t key, float value) {               // :32-50
+        const int idx = pos[key];
+        if (idx != 0) { vals[idx] = __fadd_rn(vals[idx], value); sink(idx); }
+        else if (n < nmax) { n++; keys[n] = key; vals[n] = value; pos[key] = n; swim(n); }
+        else if (value > vals[1]) { pos[keys[1]] = 0; keys[1] = key; vals[1] = value; pos[key] = 1; sink(1); }
+    }
+};
+struct ReplaySink {          // where a replayed path's contribution goes: dense double rows or one DevCacheMap per query
+    double *dense; int32_t *ckeys; float *cvals; int32_t *cpos; int32_t *csize; int32_t cap;
+};
 
 // One thread per query, samples in order, fp64 accumulation in the reference's operation order
 // (SingleRandomWalk.java:89: cache[i] * deg(inter) / deg(target) / SAMPLE, left to right).
+// CACHE: SingleRandomWalk_M.java:81-94 -- the same walks, the increment cast to float and put() into the query's cache.
+template <bool CACHE>
 __global__ void k_simrank_javarng(const uint2 *__restrict__ meta, const int32_t *__restrict__ col,
                                   const int64_t *__restrict__ queries, int64_t nq, int64_t n, int32_t sample, int32_t step,
-                                  const double *__restrict__ cache, uint64_t *__restrict__ states, double *__restrict__ out,
+                                  const double *__restrict__ cache, uint64_t *__restrict__ states, ReplaySink sk,
                                   unsigned long long *__restrict__ steps_out) {
     const int64_t qi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (qi >= nq) return;
     const int32_t v = (int32_t)queries[qi];
-    double *row = out + (size_t)qi * (size_t)n;
+    double *row = CACHE ? nullptr : sk.dense + (size_t)qi * (size_t)n;
+    DevCacheMap cm{nullptr, nullptr, nullptr, 0, 0};
+    if constexpr (CACHE)
+        cm = DevCacheMap{sk.ckeys + (size_t)qi * (size_t)(sk.cap + 1), sk.cvals + (size_t)qi * (size_t)(sk.cap + 1),
+                         sk.cpos + (size_t)qi * (size_t)n, sk.cap, 0};
     uint64_t seed = states[qi];
     const int max_step = 2 * step;
     int32_t path[21];
@@ -1145,11 +1170,13 @@ __global__ void k_simrank_javarng(const uint2 *__restrict__ meta, const int32_t 
             for (int j = 0; j < i; j++) first &= (path[j] != path[2 * i - j]);
             if (first) {
                 const double x = __ddiv_rn(__ddiv_rn(__dmul_rn(cache[i], (double)meta[inter].y), (double)meta[target].y), (double)sample);
-                row[target] = __dadd_rn(row[target], x);
+                if constexpr (CACHE) cm.put(target, __double2float_rn(x));
+                else row[target] = __dadd_rn(row[target], x);
             }
         }
     }
-    row[v] = 0.0;                                                  // :43
+    if constexpr (CACHE) sk.csize[qi] = cm.n;
+    else row[v] = 0.0;                                             // :43
     states[qi] = seed;
     atomicAdd(steps_out, steps);
 }
@@ -1157,16 +1184,22 @@ __global__ void k_simrank_javarng(const uint2 *__restrict__ meta, const int32_t 
 // Replay of the path-tree estimators: one thread per query walks the reference's FIFO queue level by level
 // (TopSim_singleSample.java:62-158 / TopSim_Enumerate.java:61-130) in two global-memory level buffers:
 // vb[level parity][position 0..2*STEP][cap] (structure of arrays), wb[level parity][cap].
+// CACHE: TopSim_singleSample_M.java:224-225 -- increment / SAMPLE cast to float and put() into the query's cache.
+template <bool CACHE>
 __global__ void k_topsim_javarng(const uint2 *__restrict__ meta, const int32_t *__restrict__ col,
                                  const int64_t *__restrict__ queries, int64_t nq, int64_t n, int32_t sample, int32_t step,
                                  int32_t mode, const double *__restrict__ cache, int64_t cap, int32_t *__restrict__ vbuf,
-                                 double *__restrict__ wbuf, uint64_t *__restrict__ states, double *__restrict__ out,
+                                 double *__restrict__ wbuf, uint64_t *__restrict__ states, ReplaySink sk,
                                  int *__restrict__ err) {
     const int64_t qi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (qi >= nq) return;
     const int32_t v = (int32_t)queries[qi];
     const int max_step = 2 * step, LEN1 = max_step + 1;
-    double *row = out + (size_t)qi * (size_t)n;
+    double *row = CACHE ? nullptr : sk.dense + (size_t)qi * (size_t)n;
+    DevCacheMap cm{nullptr, nullptr, nullptr, 0, 0};
+    if constexpr (CACHE)
+        cm = DevCacheMap{sk.ckeys + (size_t)qi * (size_t)(sk.cap + 1), sk.cvals + (size_t)qi * (size_t)(sk.cap + 1),
+                         sk.cpos + (size_t)qi * (size_t)n, sk.cap, 0};
     int32_t *vb = vbuf + (size_t)qi * 2 * LEN1 * cap;
     double *wb = wbuf + (size_t)qi * 2 * cap;
     uint64_t seed = states[qi];
@@ -1191,9 +1224,11 @@ __global__ void k_topsim_javarng(const uint2 *__restrict__ meta, const int32_t *
                         if (target == v || target == -1) continue;
                         bool first = true;
                         for (int j = 0; j < i; j++) first &= (vin[(size_t)j * cap + k] != vin[(size_t)(2 * i - j) * cap + k]);
-                        if (first)
-                            row[target] = __dadd_rn(row[target], __ddiv_rn(__dmul_rn(__dmul_rn(win[k], cache[i]), (double)meta[inter].y),
-                                                                          (double)meta[target].y));   // :189
+                        if (first) {
+                            const double x = __ddiv_rn(__dmul_rn(__dmul_rn(win[k], cache[i]), (double)meta[inter].y), (double)meta[target].y);
+                            if constexpr (CACHE) cm.put(target, __double2float_rn(__ddiv_rn(x, (double)sample)));
+                            else row[target] = __dadd_rn(row[target], x);                                // :189
+                        }
                     }
                 }
             }
@@ -1235,7 +1270,8 @@ __global__ void k_topsim_javarng(const uint2 *__restrict__ meta, const int32_t *
         path_len++;
     }
     if (overflow) atomicExch(err, 1);
-    row[v] = 0.0;
+    if constexpr (CACHE) sk.csize[qi] = cm.n;
+    else row[v] = 0.0;
     states[qi] = seed;
 }
 
@@ -1547,8 +1583,8 @@ int gw_simrank_rows_javarng(gw_graph *g, const int64_t *queries, int64_t nq, dou
     GW_CUDA(cudaMemcpy(ds.p, rng_state, sizeof(uint64_t) * (size_t)nq, cudaMemcpyHostToDevice));
     GW_CUDA(cudaMemset(dd.p, 0, sizeof(double) * (size_t)nq * (size_t)g->n));
     GW_CUDA(cudaMemset(dsteps.p, 0, sizeof(unsigned long long)));
-    k_simrank_javarng<<<(unsigned)((nq + 31) / 32), 32>>>(g->d_meta, g->d_col, dq.p, nq, g->n, sample, step, dc.p,
-                                                        (uint64_t *)ds.p, dd.p, dsteps.p);
+    k_simrank_javarng<false><<<(unsigned)((nq + 31) / 32), 32>>>(g->d_meta, g->d_col, dq.p, nq, g->n, sample, step, dc.p,
+                                                               (uint64_t *)ds.p, ReplaySink{dd.p, nullptr, nullptr, nullptr, nullptr, 0}, dsteps.p);
     GW_LAUNCHED();
     unsigned long long hs = 0;
     GW_CUDA(cudaMemcpy(out_dense, dd.p, sizeof(double) * (size_t)nq * (size_t)g->n, cudaMemcpyDeviceToHost));
@@ -1589,13 +1625,74 @@ int gw_topsim_rows_javarng(gw_graph *g, const int64_t *queries, int64_t nq, doub
     GW_CUDA(cudaMemcpy(ds.p, rng_state, sizeof(uint64_t) * (size_t)nq, cudaMemcpyHostToDevice));
     GW_CUDA(cudaMemset(dd.p, 0, sizeof(double) * (size_t)nq * (size_t)g->n));
     GW_CUDA(cudaMemset(derr.p, 0, sizeof(int)));
-    k_topsim_javarng<<<(unsigned)((nq + 31) / 32), 32>>>(g->d_meta, g->d_col, dq.p, nq, g->n, sample, step, mode, dc.p, max_paths, dv.p,
-                                                       dw.p, (uint64_t *)ds.p, dd.p, derr.p);
+    k_topsim_javarng<false><<<(unsigned)((nq + 31) / 32), 32>>>(g->d_meta, g->d_col, dq.p, nq, g->n, sample, step, mode, dc.p, max_paths, dv.p,
+                                                              dw.p, (uint64_t *)ds.p, ReplaySink{dd.p, nullptr, nullptr, nullptr, nullptr, 0}, derr.p);
     GW_LAUNCHED();
     int herr = 0;
     GW_CUDA(cudaMemcpy(&herr, derr.p, sizeof(int), cudaMemcpyDeviceToHost));
     if (herr) return fail(GW_E_TOO_LARGE, "a level of the path tree exceeded max_paths = %lld", (long long)max_paths);
     GW_CUDA(cudaMemcpy(out_dense, dd.p, sizeof(double) * (size_t)nq * (size_t)g->n, cudaMemcpyDeviceToHost));
+    GW_CUDA(cudaMemcpy(rng_state, ds.p, sizeof(uint64_t) * (size_t)nq, cudaMemcpyDeviceToHost));
+    return GW_OK;
+}
+
+int gw_simrank_cache_javarng(gw_graph *g, const int64_t *queries, int64_t nq, double c, int32_t step, int32_t sample,
+                             int32_t mode, int32_t capacity, int64_t max_paths, uint64_t *rng_state, int32_t *out_keys,
+                             float *out_vals, int32_t *out_sizes) {
+    if (!g) return fail(GW_E_INVALID, "graph is NULL");
+    if (g->flags & GW_F_DIRECTED) return fail(GW_E_INVALID, "SimRank path is defined on undirected graphs (structures/Graph.java)");
+    if (nq < 0 || (nq > 0 && (!queries || !rng_state || !out_keys || !out_vals || !out_sizes))) return fail(GW_E_INVALID, "bad arguments");
+    if (step < 1 || step > 10) return fail(GW_E_INVALID, "step must be in 1..10");
+    if (sample < 1) return fail(GW_E_INVALID, "sample must be positive");
+    if (mode != 0 && mode != 1) return fail(GW_E_INVALID, "mode must be 0 (SingleRandomWalk_M) or 1 (TopSim_singleSample_M)");
+    if (capacity < 1 || capacity > 32767)
+        return fail(GW_E_INVALID, "capacity must be in 1..32767 (FixedCacheMap.java:17 stores heap slots as Short)");
+    if (mode == 1 && max_paths < 1) return fail(GW_E_INVALID, "max_paths must be positive");
+    GW_TRY(check_queries_host(g, queries, nq));
+    if (nq == 0) return GW_OK;
+    GW_CUDA(cudaSetDevice(g->device));
+    double cache[16] = {0};
+    for (int i = 1; i <= step; i++) cache[i] = pow(c, i);          // Math.pow(C, i)
+    const size_t LEN1 = 2 * (size_t)step + 1, slots = (size_t)capacity + 1;
+    DevBuf<int64_t> dq;
+    DevBuf<double> dc, dw;
+    DevBuf<int32_t> dv, dk, dpos, dsz;
+    DevBuf<float> dval;
+    DevBuf<unsigned long long> ds, dsteps;
+    DevBuf<int> derr;
+    if (dk.alloc((size_t)nq * slots) != cudaSuccess || dval.alloc((size_t)nq * slots) != cudaSuccess ||
+        dpos.alloc((size_t)nq * (size_t)g->n) != cudaSuccess ||
+        (mode == 1 && (dv.alloc((size_t)nq * 2 * LEN1 * (size_t)max_paths) != cudaSuccess || dw.alloc((size_t)nq * 2 * (size_t)max_paths) != cudaSuccess))) {
+        cudaGetLastError();
+        return fail(GW_E_TOO_LARGE, "cache / path buffers for %lld queries do not fit", (long long)nq);
+    }
+    GW_CUDA(dq.alloc((size_t)nq)); GW_CUDA(dc.alloc(16)); GW_CUDA(dsz.alloc((size_t)nq));
+    GW_CUDA(ds.alloc((size_t)nq)); GW_CUDA(derr.alloc(1)); GW_CUDA(dsteps.alloc(1));
+    GW_CUDA(cudaMemcpy(dq.p, queries, sizeof(int64_t) * (size_t)nq, cudaMemcpyHostToDevice));
+    GW_CUDA(cudaMemcpy(dc.p, cache, sizeof(cache), cudaMemcpyHostToDevice));
+    GW_CUDA(cudaMemcpy(ds.p, rng_state, sizeof(uint64_t) * (size_t)nq, cudaMemcpyHostToDevice));
+    GW_CUDA(cudaMemset(dk.p, 0, sizeof(int32_t) * (size_t)nq * slots));
+    GW_CUDA(cudaMemset(dval.p, 0, sizeof(float) * (size_t)nq * slots));
+    GW_CUDA(cudaMemset(dpos.p, 0, sizeof(int32_t) * (size_t)nq * (size_t)g->n));
+    GW_CUDA(cudaMemset(derr.p, 0, sizeof(int)));
+    GW_CUDA(cudaMemset(dsteps.p, 0, sizeof(unsigned long long)));
+    const ReplaySink sk{nullptr, dk.p, dval.p, dpos.p, dsz.p, capacity};
+    if (mode == 0)
+        k_simrank_javarng<true><<<(unsigned)((nq + 31) / 32), 32>>>(g->d_meta, g->d_col, dq.p, nq, g->n, sample, step, dc.p,
+                                                                  (uint64_t *)ds.p, sk, dsteps.p);
+    else
+        k_topsim_javarng<true><<<(unsigned)((nq + 31) / 32), 32>>>(g->d_meta, g->d_col, dq.p, nq, g->n, sample, step, 0, dc.p, max_paths,
+                                                                 dv.p, dw.p, (uint64_t *)ds.p, sk, derr.p);
+    GW_LAUNCHED();
+    int herr = 0;
+    GW_CUDA(cudaMemcpy(&herr, derr.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (herr) return fail(GW_E_TOO_LARGE, "a level of the path tree exceeded max_paths = %lld", (long long)max_paths);
+    // heap slot 0 is unused (1-based arrays): the caller receives slots 1..capacity of every query
+    GW_CUDA(cudaMemcpy2D(out_keys, sizeof(int32_t) * (size_t)capacity, dk.p + 1, sizeof(int32_t) * slots,
+                         sizeof(int32_t) * (size_t)capacity, (size_t)nq, cudaMemcpyDeviceToHost));
+    GW_CUDA(cudaMemcpy2D(out_vals, sizeof(float) * (size_t)capacity, dval.p + 1, sizeof(float) * slots,
+                         sizeof(float) * (size_t)capacity, (size_t)nq, cudaMemcpyDeviceToHost));
+    GW_CUDA(cudaMemcpy(out_sizes, dsz.p, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost));
     GW_CUDA(cudaMemcpy(rng_state, ds.p, sizeof(uint64_t) * (size_t)nq, cudaMemcpyDeviceToHost));
     return GW_OK;
 }

@@ -99,6 +99,7 @@ class SingleRandomWalk:
     """simrank/SingleRandomWalk.java: pure Monte-Carlo single-walk estimator (scores / SAMPLE)."""
     MODE = _lib.GW_SIMRANK_MC
     SAMPLE = 10000
+    JAVA_CHUNK = 4096            # queries replayed per launch in java_seed mode
 
     def __init__(self, g, sample, step, seed=None, java_seed=None):
         """seed: Philox key of the production kernels.  java_seed: replay mode -- the walks are drawn from
@@ -123,28 +124,34 @@ class SingleRandomWalk:
         self.sim = self.g.handle.simrank_rows(q, MyConfiguration.C, self.STEP, self.SAMPLE, self.MODE, self.seed)
         return self
 
-    def _compute_java_stream(self, q):
-        """All queries share ONE sequential java.util.Random stream.  A query normally consumes exactly
-        SAMPLE * 2 * STEP draws, so the state in front of every query is predicted by an LCG jump and all
-        queries replay in parallel; where the prediction fails (nextInt's rejection loop fired, or the
-        vertex is isolated and drew nothing) the tail is replayed again from the true state."""
-        out = np.zeros((len(q), self.COUNT), dtype=np.float64)
+    def _chain_java_stream(self, q, per_query, run):
+        """All queries share ONE sequential java.util.Random stream.  A query normally consumes exactly `per_query`
+        draws, so the state in front of every query is predicted by an LCG jump and all queries replay in parallel;
+        where the prediction fails (nextInt's rejection loop fired, or the vertex is isolated and drew nothing) the
+        tail is replayed again from the true state.  run(queries, states) -> (per-query results, states after)."""
+        out = [None] * len(q)
         state, lo = self.java_state, 0
-        per_query = self.SAMPLE * 2 * self.STEP
         while lo < len(q):
+            hi = min(len(q), lo + self.JAVA_CHUNK)
             states = [state]
-            for _ in range(lo + 1, len(q)):
+            for _ in range(lo + 1, hi):
                 states.append(_jr_jump(states[-1], per_query))
-            rows, after = self.g.handle.simrank_rows_javarng(q[lo:], MyConfiguration.C, self.STEP, self.SAMPLE, states)
+            res, after = run(q[lo:hi], states)
             after = [int(x) for x in after]
-            good = 1                                             # rows[0] started from a true state
+            good = 1                                             # res[0] started from a true state
             while good < len(states) and after[good - 1] == states[good]:
                 good += 1
-            out[lo:lo + good] = rows[:good]
+            out[lo:lo + good] = list(res[:good])
             state = after[good - 1]
             lo += good
         self.java_state = state
         return out
+
+    def _compute_java_stream(self, q):
+        rows = self._chain_java_stream(
+            q, self.SAMPLE * 2 * self.STEP,
+            lambda qs, st: self.g.handle.simrank_rows_javarng(qs, MyConfiguration.C, self.STEP, self.SAMPLE, st))
+        return np.asarray(rows, dtype=np.float64).reshape(len(q), self.COUNT)
 
     def getResult(self):
         return self.sim
@@ -194,6 +201,166 @@ class TopSim_Enumerate(SingleRandomWalk):
 
     def topk(self, k=None, queries=None):
         raise NotImplementedError("TopSim_Enumerate is the deterministic parity path; use SimRank or SingleRandomWalk.topk")
+
+
+class FixedCacheMap:
+    """lxctools/FixedCacheMap.java: bounded key -> float cache that evicts the entry with the MINIMUM value; 1-based
+    binary min-heap (keys/values) plus key -> slot map; float32 arithmetic as Java's `float`.  Iterating drains the
+    heap with delMin (:102-132): ascending by value, destructive -- exactly what Print.printByOrder consumes."""
+
+    def __init__(self, NMAX, keys=None, values=None):
+        self.NMAX = int(NMAX)
+        self.keys = [0] + ([] if keys is None else [int(k) for k in keys])
+        self.values = [np.float32(0)] + ([] if values is None else [np.float32(x) for x in values])
+        self.key2Index = {k: i for i, k in enumerate(self.keys) if i > 0}
+
+    def size(self):
+        return len(self.keys) - 1
+
+    def isEmpty(self):
+        return self.size() == 0
+
+    def _exch(self, a, b):
+        k, v, m = self.keys, self.values, self.key2Index
+        m[k[a]] = b
+        m[k[b]] = a
+        k[a], k[b] = k[b], k[a]
+        v[a], v[b] = v[b], v[a]
+
+    def _sink(self, i):
+        n, v = self.size(), self.values
+        while 2 * i <= n:
+            j = 2 * i
+            if j < n and v[j] > v[j + 1]:
+                j += 1
+            if not v[i] > v[j]:
+                break
+            self._exch(i, j)
+            i = j
+
+    def _swim(self, i):
+        v = self.values
+        while i > 1 and v[i // 2] > v[i]:
+            self._exch(i, i // 2)
+            i //= 2
+
+    def put(self, key, value):
+        value = np.float32(value)
+        idx = self.key2Index.get(key)
+        if idx is not None:
+            self.values[idx] = np.float32(self.values[idx] + value)
+            self._sink(idx)
+        elif self.size() < self.NMAX:
+            self.keys.append(int(key)); self.values.append(value)
+            self.key2Index[key] = self.size()
+            self._swim(self.size())
+        elif value > self.values[1]:
+            del self.key2Index[self.keys[1]]
+            self.keys[1], self.values[1] = int(key), value
+            self.key2Index[key] = 1
+            self._sink(1)
+
+    def __iter__(self):
+        while self.size() > 0:
+            kv = (self.keys[1], self.values[1])
+            self.key2Index.pop(self.keys[1], None)
+            self._exch(1, self.size())
+            self.keys.pop(); self.values.pop()
+            self._sink(1)
+            yield kv
+
+
+class SingleRandomWalk_M(SingleRandomWalk):
+    """simrank/SingleRandomWalk_M.java: the walks of SingleRandomWalk, similarities kept per vertex in a
+    FixedCacheMap(TOPK * M) as float increments; STEP is the class constant 5 (:19).  getResult() -> list of
+    FixedCacheMap.  java_seed: replay mode, bit-exact with a JVM whose Graph.rand was seeded that way (evictions
+    included).  Without it the production kernel runs: the device accumulates every target exactly (nothing is
+    evicted), and each cache receives the top min(capacity, 128) entries of that result."""
+    CACHE_MODE = 0
+
+    def __init__(self, g, M, sample, seed=None, java_seed=None):
+        super().__init__(g, sample, 5, seed=seed, java_seed=java_seed)
+        self.capacity = self.topk_k * M
+
+    def _draws_per_query(self):
+        return self.SAMPLE * 2 * self.STEP
+
+    def compute(self, queries=None):
+        q = np.arange(self.COUNT, dtype=np.int64) if queries is None else np.asarray(queries, dtype=np.int64)
+        self._queries = q
+        if self.java_state is not None:
+            heaps = self._chain_java_stream(
+                q, self._draws_per_query(),
+                lambda qs, st: self.g.handle.simrank_cache_javarng(qs, MyConfiguration.C, self.STEP, self.SAMPLE, self.capacity,
+                                                                   st, mode=self.CACHE_MODE))
+            self.sim = [FixedCacheMap(self.capacity, k, v) for k, v in heaps]
+            return self
+        k = min(self.capacity, 128)
+        ids, sc = self.g.handle.simrank_topk(q, MyConfiguration.C, self.STEP, self.SAMPLE, k, self.MODE, self.seed)
+        if self.MODE == _lib.GW_SIMRANK_HYBRID:
+            sc = sc / self.SAMPLE                                # TopSim_singleSample_M.java:224 divides by SAMPLE
+        self.sim = []
+        for r in range(len(q)):
+            m = FixedCacheMap(self.capacity)
+            for c in range(k - 1, -1, -1):                       # ascending score
+                if ids[r, c] >= 0:
+                    m.put(int(ids[r, c]), sc[r, c])
+            self.sim.append(m)
+        return self
+
+
+class TopSim_singleSample_M(SingleRandomWalk_M):
+    """simrank/TopSim_singleSample_M.java: the path tree of TopSim_singleSample with FixedCacheMap accumulation
+    (increments / SAMPLE, float).  java_seed replays the reference's queue order; the draws per query vary, so the
+    stream is chained query by query."""
+    MODE = _lib.GW_SIMRANK_HYBRID
+    CACHE_MODE = 1
+    JAVA_CHUNK = 1
+
+    def _draws_per_query(self):
+        return 0
+
+
+class DoubleRandomWalk:
+    """simrank/DoubleRandomWalk.java: SAMPLE walks of STEP steps from every vertex (samplePaths :50-65), pair score =
+    sum over all SAMPLE^2 path pairs of C^(first common position + 1) / SAMPLE^2 (getSim :77-91).
+    java_seed: replay mode -- paths from one java.util.Random(java_seed) stream over the vertices in order and fp64
+    adds in the reference's order (bit-exact).  Otherwise Philox paths and integer first-meeting counts."""
+    SAMPLE = 200
+    JAVA_CHUNK = 4096
+
+    def __init__(self, g, sample, step, seed=None, java_seed=None):
+        self.SAMPLE = sample
+        self.STEP = step
+        self.g = g
+        self.COUNT = g.getVCount()
+        self.paths = None
+        self.sim = None
+        self.seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
+        self.java_state = None if java_seed is None else (int(java_seed) ^ _JR_MULT) & _JR_MASK
+
+    def samplePaths(self):
+        verts = np.arange(self.COUNT, dtype=np.int64)
+        if self.java_state is None:
+            self.paths = self.g.handle.double_walk_paths(verts, self.SAMPLE, self.STEP, seed=self.seed)
+            return self
+        per = SingleRandomWalk._chain_java_stream(
+            self, verts, self.SAMPLE * self.STEP,
+            lambda vs, st: self.g.handle.double_walk_paths(vs, self.SAMPLE, self.STEP, rng_states=st))
+        self.paths = np.stack(per).astype(np.int32)
+        return self
+
+    def computeSims(self, rows=None):
+        self.sim = self.g.handle.double_walk_sims(self.paths, MyConfiguration.C, rows=rows,
+                                                  exact_order=self.java_state is not None)
+        return self
+
+    def compute(self):
+        self.samplePaths()
+        return self.computeSims()
+
+    def getResult(self):
+        return self.sim
 
 
 class SimRank:
@@ -300,7 +467,21 @@ class Print:
 
     @staticmethod
     def printByOrder(sim, outPath, topk, testTopK=None):
-        """utils/Print.java:25-53: `<v>,<id>,...` and `<v>,<id>:<%.6f>,...`, CRLF."""
+        """utils/Print.java:25-53: `<v>,<id>,...` and `<v>,<id>:<%.6f>,...`, CRLF.  A list of FixedCacheMap selects
+        the overload of :94-123: per vertex the LAST topk entries of the cache's ascending (destructive) iteration."""
+        if len(sim) and isinstance(sim[0], FixedCacheMap):
+            sep, kv = MyConfiguration.SEPARATOR, MyConfiguration.SEPARATOR_KV
+            with open(outPath, "w", newline="") as out, open(outPath + ".sim.txt", "w", newline="") as outsim:
+                for v in range(len(sim)):
+                    size = sim[v].size()
+                    out.write(str(v)); outsim.write(str(v))
+                    for i, (key, val) in enumerate(sim[v]):
+                        if i < size - topk:
+                            continue
+                        out.write(sep + str(key))
+                        outsim.write(sep + str(key) + kv + java_format(val, 6))
+                    out.write("\r\n"); outsim.write("\r\n")
+            return
         Print._write(sim, outPath, topk, 6)
 
     @staticmethod

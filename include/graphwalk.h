@@ -181,6 +181,30 @@ int gw_simrank_rows_javarng(gw_graph *g, const int64_t *queries, int64_t nq, dou
 int gw_topsim_rows_javarng(gw_graph *g, const int64_t *queries, int64_t nq, double c, int32_t step,
                            int32_t sample, int32_t mode, int64_t max_paths, uint64_t *rng_state,
                            double *out_dense);
+/* Replay mode of the bounded-cache estimators: mode 0 = SingleRandomWalk_M.walk (SingleRandomWalk_M.java:59-94),
+ * mode 1 = TopSim_singleSample_M.walk (TopSim_singleSample_M.java:61-239).  Same walks / path tree and
+ * java.util.Random stream as the two entry points above; each increment (/ SAMPLE in both classes) is cast to float
+ * and put() into the query's FixedCacheMap (lxctools/FixedCacheMap.java:32-50: accumulate a present key and sink it,
+ * else append and swim while not full, else replace the minimum when strictly greater) of `capacity` = topk * M
+ * slots, 1..32767 (the reference stores heap slots as Short, :17).  Output is what getResult()[v] holds: per query
+ * out_sizes[i] live entries, out_keys/out_vals[i*capacity + s] = heap slot s+1 (heap order, NOT sorted; iterate with
+ * delMin as Print.printByOrder(FixedCacheMap[], ...) does, utils/Print.java:94-123).  max_paths: mode 1 only. */
+int gw_simrank_cache_javarng(gw_graph *g, const int64_t *queries, int64_t nq, double c, int32_t step,
+                             int32_t sample, int32_t mode, int32_t capacity, int64_t max_paths,
+                             uint64_t *rng_state, int32_t *out_keys, float *out_vals, int32_t *out_sizes);
+/* DoubleRandomWalk.samplePaths (simrank/DoubleRandomWalk.java:50-65): `sample` walks of `step` steps from each of
+ * the nv vertices; out_paths is int32 [nv][sample][step] as the reference's paths[][][] (a dead end stores -1 and
+ * leaves the later slots 0).  rng_state == NULL: Philox keyed by (seed, vertex), counter (sample index, step);
+ * rng_state != NULL: replay -- vertex i is walked by one thread with java.util.Random from rng_state[i], which is
+ * updated to the state after its last draw (chain them to replay a seeded JVM). */
+int gw_double_walk_paths(gw_graph *g, const int64_t *vertices, int64_t nv, int32_t sample, int32_t step,
+                         uint64_t seed, uint64_t *rng_state, int32_t *out_paths);
+/* DoubleRandomWalk.getSim / computeSims (:67-91) over a path set [nv][sample][step]: out[nrows*nv] holds, for every
+ * requested row r (an index into the path set) and every column w != r, the score of the pair (min, max) as the
+ * reference evaluates it; the diagonal is 0.  exact_order != 0: fp64 adds in the reference's order (bit-exact);
+ * 0: integer first-meeting counts combined once (production; same value up to fp64 rounding order). */
+int gw_double_walk_sims(gw_graph *g, const int32_t *paths, int64_t nv, int32_t sample, int32_t step, double c,
+                        const int64_t *rows, int64_t nrows, int32_t exact_order, double *out_dense);
 /* Total walk steps executed by the last gw_simrank_* call on this graph. */
 int gw_simrank_last_steps(const gw_graph *g, int64_t *steps);
 /* Queries of the last gw_simrank_topk* call that were finished by the exact hash-table kernel

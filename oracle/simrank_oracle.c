@@ -7,6 +7,9 @@
  *   simrank/TopSim_Enumerate.java:61-184 full enumeration (deterministic expectation)
  *   simrank/SimRank.java:21-77           naive exact iteration
  *   lxctools/FixedMaxPQ.java:30-39,72-76 + Pair.java:78-80   top-k (java.util.PriorityQueue)
+ *   lxctools/FixedCacheMap.java:26-113   bounded evict-the-minimum cache (the `_M` estimators)
+ *   simrank/SingleRandomWalk_M.java:28-103, simrank/TopSim_singleSample_M.java:33-239
+ *   simrank/DoubleRandomWalk.java:25-91  two independent walk sets per pair
  *   java.util.Random (JDK, not in the repo): 48-bit LCG, nextInt(bound)
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
@@ -75,13 +78,87 @@ static int is_first_meet(const int32_t *path, int dst) {
     return 1;
 }
 
+
+/* ---------------- lxctools/FixedCacheMap.java ----------------
+ * 1-based binary min-heap on float values + key -> heap index map.  The reference keeps the map in a
+ * HashMap<Integer, Short> (:17; "(short) N" :40 wraps above 32767 slots -- capacities here stay below);
+ * the restatement keeps it as a dense pos[V] array (0 = absent), which has the same contents. */
+typedef struct { int nmax, n; int32_t *keys; float *vals; int32_t *pos; } fcm;
+static int fcm_greater(const fcm *m, int a, int b) { return m->vals[a] > m->vals[b]; }     /* :80-82 */
+static void fcm_exch(fcm *m, int a, int b) {                                             /* :84-96 */
+    m->pos[m->keys[a]] = b;
+    m->pos[m->keys[b]] = a;
+    int32_t tk = m->keys[a]; m->keys[a] = m->keys[b]; m->keys[b] = tk;
+    float tv = m->vals[a]; m->vals[a] = m->vals[b]; m->vals[b] = tv;
+}
+static void fcm_sink(fcm *m, int i) {                                                    /* :61-69 */
+    while (2 * i <= m->n) {
+        int j = 2 * i;
+        if (j < m->n && fcm_greater(m, j, j + 1)) j++;
+        if (!fcm_greater(m, i, j)) break;
+        fcm_exch(m, i, j);
+        i = j;
+    }
+}
+static void fcm_swim(fcm *m, int i) {                                                    /* :73-78 */
+    while (i > 1 && fcm_greater(m, i / 2, i)) { fcm_exch(m, i, i / 2); i = i / 2; }
+}
+static void fcm_put(fcm *m, int32_t key, float value) {                                  /* :32-50 */
+    int idx = m->pos[key];
+    if (idx != 0) {
+        m->vals[idx] += value;
+        fcm_sink(m, idx);
+    } else if (m->n < m->nmax) {
+        m->n++;
+        m->keys[m->n] = key;
+        m->vals[m->n] = value;
+        m->pos[key] = m->n;
+        fcm_swim(m, m->n);
+    } else if (value > m->vals[1]) {
+        m->pos[m->keys[1]] = 0;
+        m->keys[1] = key;
+        m->vals[1] = value;
+        m->pos[key] = 1;
+        fcm_sink(m, 1);
+    }
+}
+/* delMin (:102-108) until empty: the iteration order of `for (Pair p : cacheMap)` -- ascending by value,
+ * ties in heap order; destructive.  heap arrays are 1-based with n live slots; out arrays get n entries. */
+void or_fcm_drain(int32_t n, int32_t *keys /* n+1 */, float *vals /* n+1 */, int32_t *out_keys, float *out_vals) {
+    int32_t maxkey = 0;
+    for (int i = 1; i <= n; i++) if (keys[i] > maxkey) maxkey = keys[i];
+    int32_t *pos = (int32_t *)calloc((size_t)maxkey + 1, sizeof(int32_t));
+    for (int i = 1; i <= n; i++) pos[keys[i]] = i;
+    fcm m = {n, n, keys, vals, pos};
+    int k = 0;
+    while (m.n > 0) {
+        out_keys[k] = m.keys[1]; out_vals[k] = m.vals[1]; k++;
+        m.pos[m.keys[1]] = 0;
+        fcm_exch(&m, 1, m.n--);
+        fcm_sink(&m, 1);
+    }
+    free(pos);
+}
+/* test hook: a put() sequence into one cache; returns the live size, heap arrays (1-based) in hk/hv */
+int32_t or_fcm_puts(int32_t nmax, int32_t nput, const int32_t *pk, const float *pv, int32_t key_space,
+                    int32_t *hk /* nmax+1 */, float *hv /* nmax+1 */) {
+    int32_t *pos = (int32_t *)calloc((size_t)key_space, sizeof(int32_t));
+    fcm m = {nmax, 0, hk, hv, pos};
+    for (int i = 0; i < nput; i++) fcm_put(&m, pk[i], pv[i]);
+    free(pos);
+    return m.n;
+}
+
+/* where a path's contribution goes: the dense row (double[][] sim) or the vertex's FixedCacheMap */
+typedef struct { double *row; fcm *cache; } sink_t;
+
 /* SingleRandomWalk.walk + computePathSim for ONE source row (SingleRandomWalk.java:53-92).
  * row[V] is accumulated (caller zeroes); returns the number of walk steps executed.
  * seed_io: java.util.Random state carried across calls (the reference shares one static RNG). */
-int64_t or_single_random_walk_row(int64_t V, const int64_t *rp, const int32_t *col, int32_t v,
-                                  int32_t sample, int32_t step, double C, uint64_t *seed_io,
-                                  double *row) {
-    graph g = {V, rp, col};
+static int64_t single_random_walk(const graph *gp, int32_t v, int32_t sample, int32_t step, double C,
+                                  uint64_t *seed_io, sink_t sk) {
+    graph g = *gp;
+    double *row = sk.row;
     jrand r; r.seed = *seed_io;
     int max_step = 2 * step;
     double *cache = (double *)malloc(sizeof(double) * (step + 1));
@@ -103,13 +180,38 @@ int64_t or_single_random_walk_row(int64_t V, const int64_t *rp, const int32_t *c
         for (int i = 1; i <= step && 2 * i <= path_len; i++) {     /* :84-91 */
             int inter = path[i], target = path[2 * i];
             if (target == v) continue;
-            if (is_first_meet(path, 2 * i))
-                row[target] += cache[i] * deg(&g, inter) / deg(&g, target) / sample;
+            if (is_first_meet(path, 2 * i)) {
+                double incre = cache[i] * deg(&g, inter) / deg(&g, target) / sample;
+                if (sk.cache) fcm_put(sk.cache, target, (float)incre);     /* SingleRandomWalk_M.java:90-91 */
+                else row[target] += incre;                                 /* SingleRandomWalk.java:89 */
+            }
         }
     }
-    row[v] = 0;                                                    /* :43 */
+    if (row) row[v] = 0;                                           /* :43 (the _M class has no such line) */
     *seed_io = r.seed;
     free(cache); free(path);
+    return steps;
+}
+int64_t or_single_random_walk_row(int64_t V, const int64_t *rp, const int32_t *col, int32_t v,
+                                  int32_t sample, int32_t step, double C, uint64_t *seed_io,
+                                  double *row) {
+    graph g = {V, rp, col};
+    sink_t sk = {row, NULL};
+    return single_random_walk(&g, v, sample, step, C, seed_io, sk);
+}
+/* SingleRandomWalk_M.walk(v) (SingleRandomWalk_M.java:59-94; STEP is the class constant 5 there, a parameter
+ * here): same walks, increments cast to float and put() into the vertex's FixedCacheMap of `capacity` slots.
+ * hk/hv: 1-based heap arrays [capacity+1]; *size_out = live entries. */
+int64_t or_single_random_walk_cache(int64_t V, const int64_t *rp, const int32_t *col, int32_t v,
+                                    int32_t sample, int32_t step, double C, int32_t capacity,
+                                    uint64_t *seed_io, int32_t *hk, float *hv, int32_t *size_out) {
+    graph g = {V, rp, col};
+    int32_t *pos = (int32_t *)calloc((size_t)V, sizeof(int32_t));
+    fcm m = {capacity, 0, hk, hv, pos};
+    sink_t sk = {NULL, &m};
+    int64_t steps = single_random_walk(&g, v, sample, step, C, seed_io, sk);
+    *size_out = m.n;
+    free(pos);
     return steps;
 }
 
@@ -129,10 +231,10 @@ static int wp_first_meet(const wpath *p, int dst) {
  *          random children;  mode 1 = TopSim_Enumerate.walk (:61-130): always enumerate.
  * Scores are UNNORMALISED (x SAMPLE), TopSim_singleSample.java:189.
  * Returns number of child paths created (work measure), or -1 on overflow of max_paths. */
-int64_t or_topsim_row(int64_t V, const int64_t *rp, const int32_t *col, int32_t v, int32_t sample,
-                      int32_t step, double C, int32_t mode, int64_t max_paths, uint64_t *seed_io,
-                      double *row) {
-    graph g = {V, rp, col};
+static int64_t topsim(const graph *gp, int32_t v, int32_t sample, int32_t step, double C, int32_t mode,
+                      int64_t max_paths, uint64_t *seed_io, sink_t sk) {
+    graph g = *gp;
+    double *row = sk.row;
     jrand r; r.seed = *seed_io;
     int max_step = 2 * step;
     if (max_step + 1 > 22) return -2;
@@ -158,9 +260,11 @@ int64_t or_topsim_row(int64_t V, const int64_t *rp, const int32_t *col, int32_t 
                         int inter = p->cur[i], target = p->cur[2 * i];
                         if (target == v) continue;
                         if (target == -1) continue;
-                        if (wp_first_meet(p, 2 * i))
-                            row[target] += p->w * cache[i] * (double)deg(&g, inter) /
-                                           (double)deg(&g, target);
+                        if (wp_first_meet(p, 2 * i)) {
+                            double x = p->w * cache[i] * (double)deg(&g, inter) / (double)deg(&g, target);
+                            if (sk.cache) fcm_put(sk.cache, target, (float)(x / sample));   /* TopSim_singleSample_M.java:224-225 */
+                            else row[target] += x;                                          /* TopSim_singleSample.java:189 */
+                        }
                     }
                 }
             }
@@ -202,10 +306,73 @@ int64_t or_topsim_row(int64_t V, const int64_t *rp, const int32_t *col, int32_t 
         n0 = n1;
         path_len++;
     }
-    row[v] = 0;                                                    /* compute(): sim[i][i] = 0 */
+    if (row) row[v] = 0;                                           /* compute(): sim[i][i] = 0 (not in the _M class) */
     *seed_io = r.seed;
     free(q0); free(q1);
     return overflow ? -1 : made;
+}
+int64_t or_topsim_row(int64_t V, const int64_t *rp, const int32_t *col, int32_t v, int32_t sample,
+                      int32_t step, double C, int32_t mode, int64_t max_paths, uint64_t *seed_io,
+                      double *row) {
+    graph g = {V, rp, col};
+    sink_t sk = {row, NULL};
+    return topsim(&g, v, sample, step, C, mode, max_paths, seed_io, sk);
+}
+/* TopSim_singleSample_M.walk(v) (TopSim_singleSample_M.java:61-176, computePathSim :202-239): the same path
+ * tree, increments / SAMPLE cast to float and put() into the vertex's FixedCacheMap. */
+int64_t or_topsim_cache(int64_t V, const int64_t *rp, const int32_t *col, int32_t v, int32_t sample,
+                        int32_t step, double C, int32_t capacity, int64_t max_paths, uint64_t *seed_io,
+                        int32_t *hk, float *hv, int32_t *size_out) {
+    graph g = {V, rp, col};
+    int32_t *pos = (int32_t *)calloc((size_t)V, sizeof(int32_t));
+    fcm m = {capacity, 0, hk, hv, pos};
+    sink_t sk = {NULL, &m};
+    int64_t made = topsim(&g, v, sample, step, C, 0, max_paths, seed_io, sk);
+    *size_out = m.n;
+    free(pos);
+    return made;
+}
+
+/* ---------------- simrank/DoubleRandomWalk.java ----------------
+ * samplePaths (:50-65): for every vertex in order, SAMPLE walks of STEP steps, paths[v][i][step] (a dead end
+ * stores -1 and stops; later slots stay 0 as Java's int[] initialises them -- getSim stops at the -1).
+ * paths: int32 [V][sample][step], zero-initialised by the caller. */
+void or_double_walk_paths(int64_t V, const int64_t *rp, const int32_t *col, int32_t sample, int32_t step,
+                          uint64_t *seed_io, int32_t *paths) {
+    graph g = {V, rp, col};
+    jrand r; r.seed = *seed_io;
+    for (int64_t src = 0; src < V; src++)
+        for (int i = 0; i < sample; i++) {
+            int cur = (int)src;
+            for (int s = 0; s < step; s++) {
+                cur = rand_neighbor(&g, &r, cur);
+                paths[(src * sample + i) * step + s] = cur;
+                if (cur == -1) break;
+            }
+        }
+    *seed_io = r.seed;
+}
+/* getSim(v, w) (:77-91): all SAMPLE^2 path pairs, first common position counts cache[step+1]; / SAMPLE^2
+ * (int product, as the reference writes it). */
+double or_double_walk_sim(const int32_t *paths, int32_t sample, int32_t step, double C, int64_t v, int64_t w) {
+    double cache[16];
+    for (int i = 0; i <= step; i++) cache[i] = pow(C, i);          /* :33-35 */
+    const int32_t *pv = paths + v * sample * step, *pw = paths + w * sample * step;
+    double result = 0;
+    for (int i = 0; i < sample; i++)
+        for (int j = 0; j < sample; j++)
+            for (int s = 0; s < step && pv[i * step + s] != -1 && pw[j * step + s] != -1; s++)
+                if (pv[i * step + s] == pw[j * step + s]) { result += cache[s + 1]; break; }
+    return result / (sample * sample);
+}
+/* computeSims (:67-75): upper triangle, mirrored; diagonal stays 0.  sim: V*V out. */
+void or_double_walk_matrix(int64_t V, const int32_t *paths, int32_t sample, int32_t step, double C, double *sim) {
+    memset(sim, 0, sizeof(double) * (size_t)V * V);
+    for (int64_t i = 0; i < V; i++)
+        for (int64_t j = i + 1; j < V; j++) {
+            double x = or_double_walk_sim(paths, sample, step, C, i, j);
+            sim[i * V + j] = x; sim[j * V + i] = x;
+        }
 }
 
 /* ---------------- SimRank.java:36-77 (naive exact, Jacobi sweeps) ---------------- */

@@ -50,6 +50,22 @@ def lib():
                                        ctypes.c_int32, f64p]
         L.or_fixedmaxpq_topk.restype = ctypes.c_int32
         L.or_fixedmaxpq_topk.argtypes = [f64p, ctypes.c_int64, ctypes.c_int32, i32p, f64p]
+        f32p = ctypes.POINTER(ctypes.c_float)
+        L.or_fcm_drain.restype = None
+        L.or_fcm_drain.argtypes = [ctypes.c_int32, i32p, f32p, i32p, f32p]
+        L.or_fcm_puts.restype = ctypes.c_int32
+        L.or_fcm_puts.argtypes = [ctypes.c_int32, ctypes.c_int32, i32p, f32p, ctypes.c_int32, i32p, f32p]
+        L.or_single_random_walk_cache.restype = ctypes.c_int64
+        L.or_single_random_walk_cache.argtypes = [ctypes.c_int64, i64p, i32p, ctypes.c_int32, ctypes.c_int32,
+                                                  ctypes.c_int32, ctypes.c_double, ctypes.c_int32, u64p,
+                                                  i32p, f32p, i32p]
+        L.or_topsim_cache.restype = ctypes.c_int64
+        L.or_topsim_cache.argtypes = [ctypes.c_int64, i64p, i32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                      ctypes.c_double, ctypes.c_int32, ctypes.c_int64, u64p, i32p, f32p, i32p]
+        L.or_double_walk_paths.restype = None
+        L.or_double_walk_paths.argtypes = [ctypes.c_int64, i64p, i32p, ctypes.c_int32, ctypes.c_int32, u64p, i32p]
+        L.or_double_walk_matrix.restype = None
+        L.or_double_walk_matrix.argtypes = [ctypes.c_int64, i32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_double, f64p]
         L.jr_fill.restype = None
         L.jr_fill.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, i32p]
         L.or_node2vec_walks.restype = ctypes.c_int64
@@ -129,6 +145,89 @@ def topsim_row(g, v, sample, step, C=C_DEFAULT, mode=0, seed_state=None, max_pat
     if made < 0:
         raise MemoryError("path tree exceeded max_paths")
     return row, int(made), int(st.value)
+
+
+# ---------------- lxctools/FixedCacheMap.java and the _M estimators ----------------
+def fcm_puts(nmax, keys, vals, key_space=None):
+    """A put() sequence into one FixedCacheMap(nmax); returns the heap arrays (keys, float32 values) in heap
+    order (slot 1 first)."""
+    pk = np.ascontiguousarray(keys, dtype=np.int32)
+    pv = np.ascontiguousarray(vals, dtype=np.float32)
+    hk = np.zeros(nmax + 1, dtype=np.int32)
+    hv = np.zeros(nmax + 1, dtype=np.float32)
+    ks = int(pk.max()) + 1 if key_space is None and len(pk) else int(key_space or 1)
+    n = lib().or_fcm_puts(int(nmax), len(pk), _p(pk, ctypes.c_int32), _p(pv, ctypes.c_float), ks,
+                          _p(hk, ctypes.c_int32), _p(hv, ctypes.c_float))
+    return hk[1:n + 1].copy(), hv[1:n + 1].copy()
+
+
+def fcm_drain(hkeys, hvals):
+    """`for (Pair p : cacheMap)` (FixedCacheMap.java:102-132): delMin until empty -> ascending (keys, values)."""
+    n = len(hkeys)
+    hk = np.zeros(n + 1, dtype=np.int32); hk[1:] = hkeys
+    hv = np.zeros(n + 1, dtype=np.float32); hv[1:] = hvals
+    ok = np.zeros(max(n, 1), dtype=np.int32)
+    ov = np.zeros(max(n, 1), dtype=np.float32)
+    lib().or_fcm_drain(n, _p(hk, ctypes.c_int32), _p(hv, ctypes.c_float), _p(ok, ctypes.c_int32), _p(ov, ctypes.c_float))
+    return ok[:n].copy(), ov[:n].copy()
+
+
+def single_random_walk_cache(g, v, sample, step, capacity, C=C_DEFAULT, seed_state=None):
+    """SingleRandomWalk_M.walk(v): returns (heap keys, heap float32 values, steps, new_seed_state)."""
+    hk = np.zeros(capacity + 1, dtype=np.int32)
+    hv = np.zeros(capacity + 1, dtype=np.float32)
+    st = ctypes.c_uint64(java_seed(0) if seed_state is None else seed_state)
+    n = ctypes.c_int32()
+    steps = lib().or_single_random_walk_cache(g["V"], _p(g["row_ptr"], ctypes.c_int64), _p(g["col"], ctypes.c_int32),
+                                              int(v), int(sample), int(step), float(C), int(capacity),
+                                              ctypes.byref(st), _p(hk, ctypes.c_int32), _p(hv, ctypes.c_float),
+                                              ctypes.byref(n))
+    return hk[1:n.value + 1].copy(), hv[1:n.value + 1].copy(), int(steps), int(st.value)
+
+
+def topsim_cache(g, v, sample, step, capacity, C=C_DEFAULT, seed_state=None, max_paths=1 << 22):
+    """TopSim_singleSample_M.walk(v): returns (heap keys, heap float32 values, paths made, new_seed_state)."""
+    hk = np.zeros(capacity + 1, dtype=np.int32)
+    hv = np.zeros(capacity + 1, dtype=np.float32)
+    st = ctypes.c_uint64(java_seed(0) if seed_state is None else seed_state)
+    n = ctypes.c_int32()
+    made = lib().or_topsim_cache(g["V"], _p(g["row_ptr"], ctypes.c_int64), _p(g["col"], ctypes.c_int32), int(v),
+                                 int(sample), int(step), float(C), int(capacity), int(max_paths), ctypes.byref(st),
+                                 _p(hk, ctypes.c_int32), _p(hv, ctypes.c_float), ctypes.byref(n))
+    if made < 0:
+        raise MemoryError("path tree exceeded max_paths")
+    return hk[1:n.value + 1].copy(), hv[1:n.value + 1].copy(), int(made), int(st.value)
+
+
+def print_by_order_cache(caches, out_path, topk=TOPK):
+    """Print.printByOrder(FixedCacheMap[], outPath, topk) (utils/Print.java:94-123): per vertex the LAST topk
+    entries of the ascending iteration, `%.6f` of the float value."""
+    with open(out_path, "w", newline="") as out, open(out_path + ".sim.txt", "w", newline="") as outsim:
+        for v, (hk, hv) in enumerate(caches):
+            ks, vs = fcm_drain(hk, hv)
+            out.write(str(v)); outsim.write(str(v))
+            for key, val in list(zip(ks.tolist(), vs.tolist()))[max(0, len(ks) - topk):]:
+                out.write(SEPARATOR + str(key))
+                outsim.write(SEPARATOR + str(key) + SEPARATOR_KV + java_fmt(val, 6))
+            out.write("\r\n"); outsim.write("\r\n")
+
+
+# ---------------- simrank/DoubleRandomWalk.java ----------------
+def double_walk_paths(g, sample, step, seed_state):
+    """samplePaths(): int32 [V, sample, step]; returns (paths, new_seed_state)."""
+    paths = np.zeros((g["V"], sample, step), dtype=np.int32)
+    st = ctypes.c_uint64(seed_state)
+    lib().or_double_walk_paths(g["V"], _p(g["row_ptr"], ctypes.c_int64), _p(g["col"], ctypes.c_int32), int(sample),
+                               int(step), ctypes.byref(st), _p(paths, ctypes.c_int32))
+    return paths, int(st.value)
+
+
+def double_walk_matrix(paths, C=C_DEFAULT):
+    V, sample, step = paths.shape
+    sim = np.zeros((V, V), dtype=np.float64)
+    lib().or_double_walk_matrix(V, _p(np.ascontiguousarray(paths), ctypes.c_int32), sample, step, float(C),
+                                _p(sim, ctypes.c_double))
+    return sim
 
 
 def simrank_exact_naive(g, C, iters):

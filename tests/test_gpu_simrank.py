@@ -379,3 +379,111 @@ def test_hybrid_topk_and_class_mirror(g333):
         assert ids[v, :len(order)].tolist() == order.tolist()
         assert sc[v, :len(order)].tobytes() == rows[v][order].tobytes()
     assert sc.max() > 1.0                       # unnormalised (x SAMPLE), as TopSim_singleSample.java:189
+
+
+def test_cache_estimators_replay_is_bit_exact(g333, o333):
+    """gw_simrank_cache_javarng: SingleRandomWalk_M / TopSim_singleSample_M -- the walks of the dense classes, every
+    increment cast to float and put() into a FixedCacheMap(capacity) on the device (accumulate + sink, append + swim,
+    evict the minimum).  Heap arrays (keys, float values, in heap order), sizes and RNG states equal the oracle's."""
+    qs = [0, 5, 17, 100, 332, 5]
+    for mode, cap, sample, step in ((0, 40, 3000, 5), (0, 400, 500, 3), (0, 7, 200, 5), (1, 40, 800, 5), (1, 4000, 300, 5),
+                                    (1, 3, 37, 2)):
+        st = S.java_seed(424242)
+        states, want = [], []
+        for v in qs:
+            states.append(st)
+            if mode == 0:
+                hk, hv, _, st = S.single_random_walk_cache(o333, v, sample, step, cap, seed_state=st)
+            else:
+                hk, hv, _, st = S.topsim_cache(o333, v, sample, step, cap, seed_state=st)
+            want.append((hk, hv))
+        got, after = g333.handle.simrank_cache_javarng(qs, 0.6, step, sample, cap, states, mode=mode)
+        assert after.tolist() == states[1:] + [st], (mode, cap)
+        for (gk, gv), (wk, wv) in zip(got, want):
+            assert gk.tolist() == wk.tolist() and gv.tobytes() == wv.tobytes(), (mode, cap, sample)
+    with pytest.raises(ValueError):
+        g333.handle.simrank_cache_javarng(qs[:1], 0.6, 5, 10, 40000, [1])       # heap slots are Short in the reference
+
+
+def test_cache_mirror_classes_and_print_overload(tmp_path, g333, o333):
+    """SingleRandomWalk_M(g, M, sample, java_seed=s).compute() chains one java.util.Random stream over all vertices;
+    Print.printByOrder(FixedCacheMap[], out, topk) writes the last topk entries of the ascending iteration.  Files are
+    byte-identical with the oracle's restatement of utils/Print.java:94-123."""
+    sr.MyConfiguration.TOPK = 20
+    st = S.java_seed(77)
+    want = []
+    for v in range(333):
+        hk, hv, _, st = S.single_random_walk_cache(o333, v, 300, 5, 40, seed_state=st)
+        want.append((hk, hv))
+    m = sr.SingleRandomWalk_M(g333, 2, 300, java_seed=77)
+    caches = m.compute().getResult()
+    assert m.java_state == st and m.capacity == 40 and m.STEP == 5
+    for c, (wk, wv) in zip(caches, want):
+        assert c.keys[1:] == wk.tolist() and np.asarray(c.values[1:], dtype=np.float32).tobytes() == wv.tobytes()
+    a, b = str(tmp_path / "dev.txt"), str(tmp_path / "ora.txt")
+    sr.Print.printByOrder(caches, a, 20)
+    S.print_by_order_cache(want, b, 20)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    assert open(a + ".sim.txt", "rb").read() == open(b + ".sim.txt", "rb").read()
+    assert all(c.size() == 0 for c in caches)                     # the iteration is destructive, as in the reference
+    # path-tree variant through its mirror (stream chained query by query)
+    st = S.java_seed(78)
+    want = []
+    for v in (3, 4, 5):
+        hk, hv, _, st = S.topsim_cache(o333, v, 300, 5, 60, seed_state=st)
+        want.append((hk, hv))
+    t = sr.TopSim_singleSample_M(g333, 3, 300, java_seed=78)
+    caches = t.compute([3, 4, 5]).getResult()
+    assert t.java_state == st
+    for c, (wk, wv) in zip(caches, want):
+        assert c.keys[1:] == wk.tolist() and np.asarray(c.values[1:], dtype=np.float32).tobytes() == wv.tobytes()
+    # free-running mode: production kernels, exact accumulation, top min(capacity, 128) per cache
+    f = sr.SingleRandomWalk_M(g333, 2, 20000, seed=1).compute([5, 9])
+    ids, sc = g333.handle.simrank_topk([5, 9], 0.6, 5, 20000, 40, seed=1)
+    for r, c in enumerate(f.getResult()):
+        got = list(c)
+        assert (np.diff([float(v) for _, v in got]) >= 0).all()
+        want = {int(i): float(x) for i, x in zip(ids[r], sc[r]) if i >= 0}
+        assert {k for k, _ in got} == set(want)
+        assert np.allclose([float(v) for _, v in got], [want[k] for k, _ in got], rtol=1e-6)
+    h = sr.TopSim_singleSample_M(g333, 2, 2000, seed=1).compute([5]).getResult()[0]
+    exact = g333.handle.simrank_exact(0.6, 5, rows=np.array([5], dtype=np.int64))[0]
+    got = dict(h)
+    top = np.argsort(-exact)[:10]
+    assert np.abs(np.array([got.get(int(i), 0.0) for i in top]) - exact[top]).max() < 5e-3
+
+
+def test_double_random_walk_replay_and_production(g333, o333):
+    """DoubleRandomWalk: replay = paths from one java.util.Random stream over all vertices and getSim's fp64 adds in
+    the reference's order -> bit-exact with the oracle; production = Philox paths + integer first-meeting counts ->
+    same value as the exact-order kernel on the same paths up to fp64 rounding, and converging to SimRank truncated
+    at STEP sweeps."""
+    want_paths, st = S.double_walk_paths(o333, 60, 3, S.java_seed(2024))
+    want = S.double_walk_matrix(want_paths, 0.6)
+    d = sr.DoubleRandomWalk(g333, 60, 3, java_seed=2024)
+    d.samplePaths()
+    assert d.paths.tobytes() == want_paths.tobytes() and d.java_state == st
+    rows = np.array([0, 5, 100, 332], dtype=np.int64)
+    got = d.computeSims(rows).getResult()
+    assert got.tobytes() == want[rows].tobytes()
+    counted = g333.handle.double_walk_sims(d.paths, 0.6, rows=rows, exact_order=False)
+    assert np.abs(counted - got).max() < 1e-15 and (counted[np.arange(4), rows] == 0).all()
+    # a graph with dead ends: isolated slot 0 and a pendant path; -1 is stored and the later slots stay 0
+    h = _lib.GraphHandle.from_edges([1, 2, 3], [2, 3, 4], None, directed=False, mode=_lib.GW_MODE_MULTI, n_slots=6)
+    og = S.build_multigraph(np.array([1, 2, 3]), np.array([2, 3, 4]), 6)
+    wp, st2 = S.double_walk_paths(og, 9, 4, S.java_seed(3))
+    gp, after = h.double_walk_paths(np.arange(6), 9, 4, rng_states=[S.java_seed(3)] * 6)
+    assert (gp[0] == np.array([-1, 0, 0, 0])).all() and (gp[5] == np.array([-1, 0, 0, 0])).all()
+    assert after[0] == S.java_seed(3) and gp[1].tobytes() == wp[1].tobytes()      # vertex 0 drew nothing, so vertex 1 starts from the seed too
+    dd = sr.DoubleRandomWalk(sr.Graph.from_handle(h), 9, 4, java_seed=3).compute()
+    assert dd.paths.tobytes() == wp.tobytes() and dd.java_state == st2
+    assert dd.getResult().tobytes() == S.double_walk_matrix(wp, 0.6).tobytes()
+    # production: convergence on the exact top entries
+    p = sr.DoubleRandomWalk(g333, 1500, 3, seed=9).compute()
+    assert p.paths.shape == (333, 1500, 3)
+    exact = g333.handle.simrank_exact(0.6, 3)
+    np.fill_diagonal(exact, 0)
+    assert np.abs(p.getResult() - exact).max() < 6e-3
+    assert np.allclose(p.getResult(), p.getResult().T, atol=1e-15)
+    again = sr.DoubleRandomWalk(g333, 1500, 3, seed=9).samplePaths().paths
+    assert again.tobytes() == p.paths.tobytes()                  # counter-based RNG: same seed, same paths

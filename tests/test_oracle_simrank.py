@@ -126,3 +126,72 @@ def test_print_and_eval_roundtrip(tmp_path, g333):
     mean, pres = S.precision_rows(rows, rows)
     assert mean == 1.0
     assert S.java_fmt(0.0000005, 6) == "0.000001" and S.java_fmt(0.125, 2) == "0.13"
+
+
+def test_fixed_cache_map_known_answer_and_host_mirror():
+    """lxctools/FixedCacheMap.java: the put() sequence of its own main() (:134-148), traced by hand from the source
+    (capacity 3; key 3 is evicted by (4, 8), key 4 accumulates to 16, key 1 to 1.1f, (5, 1) is refused because
+    1 <= min 1.1f) -> size 3, iteration (1, 1.1) (2, 3.0) (4, 16.0), size 0 afterwards.  The host mirror class
+    (graph_embedding_b200.simrank.FixedCacheMap) must agree with the C restatement on random put sequences, heap
+    arrays included (ties and evictions exercise sink/swim order)."""
+    hk, hv = S.fcm_puts(3, [1, 2, 3, 4, 4, 1, 5], [0.5, 3, 0.1, 8, 8, 0.6, 1])
+    assert hk.tolist() == [1, 2, 4] and hv.tolist() == [np.float32(0.5) + np.float32(0.6), 3.0, 16.0]
+    ks, vs = S.fcm_drain(hk, hv)
+    assert ks.tolist() == [1, 2, 4] and vs.tolist() == [np.float32(1.1), 3.0, 16.0]
+    from graph_embedding_b200 import simrank as sr
+    rs = np.random.RandomState(3)
+    for trial in range(40):
+        cap = int(rs.randint(1, 12))
+        n = int(rs.randint(0, 80))
+        keys = rs.randint(0, 25, size=n)
+        vals = (rs.randint(1, 6, size=n) * np.float32(0.1)).astype(np.float32)       # few distinct values: many ties
+        hk, hv = S.fcm_puts(cap, keys, vals, key_space=25)
+        m = sr.FixedCacheMap(cap)
+        for k, v in zip(keys.tolist(), vals.tolist()):
+            m.put(k, v)
+        assert m.keys[1:] == hk.tolist() and [float(x) for x in m.values[1:]] == hv.tolist(), trial
+        ks, vs = S.fcm_drain(hk, hv)
+        got = list(m)
+        assert [k for k, _ in got] == ks.tolist() and [float(v) for _, v in got] == vs.tolist()
+        assert m.size() == 0
+        assert (np.diff(vs) >= 0).all()
+
+
+def test_cache_estimators_equal_dense_ones_when_nothing_is_evicted(g333):
+    """SingleRandomWalk_M / TopSim_singleSample_M with a cache as large as the graph keep every target: same RNG
+    stream as the dense classes, and each cached value is the float32 accumulation of the same increments."""
+    st0 = S.java_seed(11)
+    hk, hv, steps, st = S.single_random_walk_cache(g333, 5, 3000, 5, 333, seed_state=st0)
+    row, steps2, st2 = S.single_random_walk_row(g333, 5, 3000, 5, seed_state=st0)
+    assert (st, steps) == (st2, steps2)
+    assert sorted(hk.tolist()) == np.nonzero(row)[0].tolist()
+    assert np.abs(hv - row[hk]).max() < 2e-6
+    hk, hv, made, st = S.topsim_cache(g333, 5, 3000, 5, 333, seed_state=st0)
+    row, made2, st2 = S.topsim_row(g333, 5, 3000, 5, seed_state=st0)
+    assert (st, made) == (st2, made2)
+    assert sorted(hk.tolist()) == np.nonzero(row)[0].tolist()
+    assert np.abs(hv - row[hk] / 3000).max() < 2e-6
+    # a small cache is lossy but keeps the heavy hitters
+    hk2, hv2, _, _ = S.single_random_walk_cache(g333, 5, 3000, 5, 40, seed_state=st0)
+    assert len(hk2) == 40
+    top = np.argsort(-row)[:5]
+    assert set(top.tolist()) <= set(hk2.tolist())
+
+
+def test_double_random_walk_converges_to_truncated_exact(g333):
+    """DoubleRandomWalk.getSim is an unbiased estimator of SimRank truncated at STEP sweeps (first meeting of two
+    independent walks at position s weighs C^(s+1)); anchored on the pinned exact routine."""
+    paths, st = S.double_walk_paths(g333, 400, 3, S.java_seed(5))
+    assert paths.shape == (333, 400, 3) and paths.min() >= 0
+    pv = paths[[0, 7, 100]]
+    lib = S.lib()
+    lib.or_double_walk_sim.restype = ctypes.c_double
+    lib.or_double_walk_sim.argtypes = [ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, ctypes.c_int32, ctypes.c_double,
+                                       ctypes.c_int64, ctypes.c_int64]
+    exact = S.simrank_exact_matrix(g333, 0.6, 3)
+    pp = np.ascontiguousarray(paths)
+    errs = []
+    for v, w in [(0, 7), (7, 100), (5, 166), (5, 37), (10, 200)]:
+        est = lib.or_double_walk_sim(pp.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), 400, 3, 0.6, v, w)
+        errs.append(est - exact[v, w])
+    assert np.abs(errs).max() < 6e-3, errs
