@@ -446,11 +446,11 @@ def test_cache_mirror_classes_and_print_overload(tmp_path, g333, o333):
         want = {int(i): float(x) for i, x in zip(ids[r], sc[r]) if i >= 0}
         assert {k for k, _ in got} == set(want)
         assert np.allclose([float(v) for _, v in got], [want[k] for k, _ in got], rtol=1e-6)
-    h = sr.TopSim_singleSample_M(g333, 2, 2000, seed=1).compute([5]).getResult()[0]
+    h = sr.TopSim_singleSample_M(g333, 2, 50000, seed=1).compute([5]).getResult()[0]
     exact = g333.handle.simrank_exact(0.6, 5, rows=np.array([5], dtype=np.int64))[0]
-    got = dict(h)
+    got = dict(list(h))
     top = np.argsort(-exact)[:10]
-    assert np.abs(np.array([got.get(int(i), 0.0) for i in top]) - exact[top]).max() < 5e-3
+    assert np.abs(np.array([got.get(int(i), 0.0) for i in top]) - exact[top]).max() < 3e-3
 
 
 def test_double_random_walk_replay_and_production(g333, o333):
@@ -467,7 +467,7 @@ def test_double_random_walk_replay_and_production(g333, o333):
     got = d.computeSims(rows).getResult()
     assert got.tobytes() == want[rows].tobytes()
     counted = g333.handle.double_walk_sims(d.paths, 0.6, rows=rows, exact_order=False)
-    assert np.abs(counted - got).max() < 1e-15 and (counted[np.arange(4), rows] == 0).all()
+    assert np.abs(counted - got).max() < 1e-13 and (counted[np.arange(4), rows] == 0).all()
     # a graph with dead ends: isolated slot 0 and a pendant path; -1 is stored and the later slots stay 0
     h = _lib.GraphHandle.from_edges([1, 2, 3], [2, 3, 4], None, directed=False, mode=_lib.GW_MODE_MULTI, n_slots=6)
     og = S.build_multigraph(np.array([1, 2, 3]), np.array([2, 3, 4]), 6)
@@ -483,7 +483,8 @@ def test_double_random_walk_replay_and_production(g333, o333):
     assert p.paths.shape == (333, 1500, 3)
     exact = g333.handle.simrank_exact(0.6, 3)
     np.fill_diagonal(exact, 0)
-    assert np.abs(p.getResult() - exact).max() < 6e-3
+    err = p.getResult() - exact                                  # the CPU estimator at SAMPLE=300: rms 1.1e-3, max 0.039 (~ 1/sqrt(SAMPLE))
+    assert np.sqrt((err ** 2).mean()) < 8e-4 and np.abs(err).max() < 0.03 and abs(err.mean()) < 5e-5
     assert np.allclose(p.getResult(), p.getResult().T, atol=1e-15)
     again = sr.DoubleRandomWalk(g333, 1500, 3, seed=9).samplePaths().paths
     assert again.tobytes() == p.paths.tobytes()                  # counter-based RNG: same seed, same paths
