@@ -49,6 +49,16 @@ public final class GraphWalk {
     private static final MethodHandle ROWS_JAVARNG = h("gw_simrank_rows_javarng",
         FunctionDescriptor.of(I, P, P, J, D, I, I, P, P));
 
+    private static final ValueLayout.OfFloat F = ValueLayout.JAVA_FLOAT;
+    private static final MethodHandle TOPSIM_JAVARNG = h("gw_topsim_rows_javarng",
+        FunctionDescriptor.of(I, P, P, J, D, I, I, I, J, P, P));
+    private static final MethodHandle CACHE_JAVARNG = h("gw_simrank_cache_javarng",
+        FunctionDescriptor.of(I, P, P, J, D, I, I, I, I, J, P, P, P, P));
+    private static final MethodHandle DW_PATHS = h("gw_double_walk_paths",
+        FunctionDescriptor.of(I, P, P, J, I, I, J, P, P));
+    private static final MethodHandle DW_SIMS = h("gw_double_walk_sims",
+        FunctionDescriptor.of(I, P, P, J, I, I, D, P, J, I, P));
+
     private GraphWalk() {}
 
     static void check(int rc) {
@@ -153,6 +163,63 @@ public final class GraphWalk {
             check((int) EXACT.invokeExact(g, c, iters, r, (long) vCount, out));
             double[][] sim = new double[vCount][vCount];
             for (int i = 0; i < vCount; i++) MemorySegment.copy(out, D, (long) i * vCount * 8, sim[i], 0, vCount);
+            return sim;
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
+    }
+
+    /** gw_topsim_rows_javarng: replay of TopSim_singleSample (mode 0) / TopSim_Enumerate (mode 1); rows x SAMPLE. */
+    public static double[][] topsimRowsJavaRng(MemorySegment g, long[] queries, int vCount, double c, int step, int sample,
+                                               int mode, long maxPaths, long[] rngState) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment q = a.allocateFrom(J, queries), st = a.allocateFrom(J, rngState);
+            MemorySegment out = a.allocate(D, (long) queries.length * vCount);
+            check((int) TOPSIM_JAVARNG.invokeExact(g, q, (long) queries.length, c, step, sample, mode, maxPaths, st, out));
+            MemorySegment.copy(st, J, 0, rngState, 0, rngState.length);
+            double[][] sim = new double[queries.length][vCount];
+            for (int r = 0; r < queries.length; r++) MemorySegment.copy(out, D, (long) r * vCount * 8, sim[r], 0, vCount);
+            return sim;
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
+    }
+
+    /**
+     * gw_simrank_cache_javarng: replay of SingleRandomWalk_M (mode 0) / TopSim_singleSample_M (mode 1).  keys/vals
+     * [nq * capacity] receive heap slots 1..capacity of every query's FixedCacheMap, sizes[nq] the live entries.
+     */
+    public static void simrankCacheJavaRng(MemorySegment g, long[] queries, double c, int step, int sample, int mode,
+                                           int capacity, long maxPaths, long[] rngState, int[] keys, float[] vals, int[] sizes) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment q = a.allocateFrom(J, queries), st = a.allocateFrom(J, rngState);
+            MemorySegment k = a.allocate(I, keys.length), v = a.allocate(F, vals.length), z = a.allocate(I, sizes.length);
+            check((int) CACHE_JAVARNG.invokeExact(g, q, (long) queries.length, c, step, sample, mode, capacity, maxPaths, st, k, v, z));
+            MemorySegment.copy(st, J, 0, rngState, 0, rngState.length);
+            MemorySegment.copy(k, I, 0, keys, 0, keys.length);
+            MemorySegment.copy(v, F, 0, vals, 0, vals.length);
+            MemorySegment.copy(z, I, 0, sizes, 0, sizes.length);
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
+    }
+
+    /** gw_double_walk_paths: paths[v][i][step] flattened; rngState == null -> Philox(seed), else java.util.Random replay. */
+    public static int[] doubleWalkPaths(MemorySegment g, long[] vertices, int sample, int step, long seed, long[] rngState) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment v = a.allocateFrom(J, vertices);
+            MemorySegment st = rngState == null ? MemorySegment.NULL : a.allocateFrom(J, rngState);
+            long total = (long) vertices.length * sample * step;
+            MemorySegment out = a.allocate(I, total);
+            check((int) DW_PATHS.invokeExact(g, v, (long) vertices.length, sample, step, seed, st, out));
+            if (rngState != null) MemorySegment.copy(st, J, 0, rngState, 0, rngState.length);
+            return out.toArray(I);
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
+    }
+
+    /** gw_double_walk_sims: sim[row][*] of DoubleRandomWalk.getSim over a path set of nv vertices. */
+    public static double[][] doubleWalkSims(MemorySegment g, int[] paths, int nv, int sample, int step, double c, long[] rows,
+                                            boolean exactOrder) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment p = a.allocateFrom(I, paths), r = a.allocateFrom(J, rows);
+            MemorySegment out = a.allocate(D, (long) rows.length * nv);
+            check((int) DW_SIMS.invokeExact(g, p, (long) nv, sample, step, c, r, (long) rows.length, exactOrder ? 1 : 0, out));
+            double[][] sim = new double[rows.length][nv];
+            for (int i = 0; i < rows.length; i++) MemorySegment.copy(out, D, (long) i * nv * 8, sim[i], 0, nv);
             return sim;
         } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
     }

@@ -62,6 +62,32 @@ def read_list(file_path):
     return walks
 
 
+def save_word2vec_format(file_path, words, vectors):
+    """The `.emb` file node2vec/src/main.py:98 writes (gensim 0.13.3 `save_word2vec_format`, text mode): header
+    `<count> <dimensions>`, then one `<word> <%f> <%f> ...` line per vector (node2vec/emb/karate.emb).  Walk
+    generation ends before Word2Vec; the format is kept so a trainer fed with this engine's corpus stays a drop-in."""
+    with open(file_path, "w") as f:
+        f.write("%d %d\n" % (len(words), len(vectors[0]) if len(words) else 0))
+        for w, row in zip(words, vectors):
+            f.write("%s %s\n" % (w, " ".join("%f" % float(x) for x in row)))
+
+
+def load_word2vec_format(file_path):
+    """-> (list of words as strings, float32 array [count, dimensions]); the reader side of the same format
+    (node2vec/src/classify.py loads it through gensim)."""
+    import numpy as np
+    with open(file_path, "r") as f:
+        count, dim = (int(x) for x in f.readline().split())
+        words, vecs = [], np.zeros((count, dim), dtype=np.float32)
+        for i in range(count):
+            tok = f.readline().rstrip("\n").split(" ")
+            if len(tok) != dim + 1:
+                raise ValueError("line %d of %s has %d fields, expected %d" % (i + 2, file_path, len(tok), dim + 1))
+            words.append(tok[0])
+            vecs[i] = [float(x) for x in tok[1:]]
+    return words, vecs
+
+
 def main(args):
     nx_G = read_graph(args)
     G = node2vec.Graph(nx_G, args.directed, args.p, args.q)

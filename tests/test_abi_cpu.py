@@ -61,3 +61,16 @@ def test_host_side_java_heap_and_format():
         assert [g[0] for g in got] == ids.tolist() and [g[1] for g in got] == vals.tolist()
     for x, d in [(0.0000005, 6), (0.125, 2), (0.05161244, 8), (1e-9, 6), (0.8, 8)]:
         assert sr.java_format(x, d) == S.java_fmt(x, d)
+
+
+def test_emb_wire_format_round_trips_the_shipped_file(tmp_path):
+    """node2vec/emb/karate.emb (word2vec text format written by main.py:98): reading it and writing it back through
+    the host shim reproduces the file byte for byte."""
+    from conftest import DATA
+    from graph_embedding_b200 import main as cli
+    src = os.path.join(DATA, "karate.emb")
+    words, vecs = cli.load_word2vec_format(src)
+    assert len(words) == 34 and vecs.shape == (34, 128) and words[:2] == ["34", "33"]
+    out = str(tmp_path / "k.emb")
+    cli.save_word2vec_format(out, words, vecs)
+    assert open(out, "rb").read() == open(src, "rb").read()
