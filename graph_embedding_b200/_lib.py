@@ -84,6 +84,10 @@ SIGNATURES = {
                                             ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), c_i32p]),
     "gw_double_walk_sims": (ctypes.c_int, [c_vp, c_i32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                            ctypes.c_double, c_i64p, ctypes.c_int64, ctypes.c_int32, c_f64p]),
+    "gw_topsim_mass": (ctypes.c_int, [c_vp, c_i64p, ctypes.c_int64, ctypes.c_double, ctypes.c_int32, ctypes.c_int64,
+                                      ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), c_f64p]),
+    "gw_topsim_mass_sims": (ctypes.c_int, [c_vp, c_f64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_double, c_i64p,
+                                           c_i64p, ctypes.c_int64, ctypes.c_int32, c_f64p]),
     "gw_simrank_last_steps": (ctypes.c_int, [c_vp, c_i64p]),
     "gw_simrank_last_slow_queries": (ctypes.c_int, [c_vp, c_i64p]),
     "gw_simrank_exact": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_int32, c_i64p, ctypes.c_int64, c_f64p]),
@@ -379,6 +383,32 @@ class GraphHandle:
         check(load().gw_double_walk_sims(self.h, ptr(paths, ctypes.c_int32), nv, sample, step, float(c),
                                          ptr(rows, ctypes.c_int64), len(rows), int(bool(exact_order)),
                                          ptr(out, ctypes.c_double)))
+        return out
+
+    def topsim_mass(self, sources, weight, step, seed=0, call_id_base=0, rng_states=None, max_paths=0):
+        """TopSim_doubleSample.sample / TopSim_Dev.sample: fp64 [ns, n, step+1] path masses (-1 = unset); with rng_states
+        (one java.util.Random state per tree) the replay kernel runs and the states after are returned too."""
+        sources = as_c(sources, np.int64)
+        if max_paths <= 0:
+            max_paths = max(int(step) * (int(weight) + 2) + 1, self.max_degree + 1)
+        st = None
+        if rng_states is not None:
+            st = np.ascontiguousarray(np.asarray(rng_states, dtype=np.uint64)).copy()
+            if len(st) != len(sources):
+                raise ValueError("one rng state per tree")
+        out = np.empty((len(sources), self.n, step + 1), dtype=np.float64)
+        check(load().gw_topsim_mass(self.h, ptr(sources, ctypes.c_int64), len(sources), float(weight), int(step),
+                                    int(max_paths), int(seed), int(call_id_base), ptr(st, ctypes.c_uint64),
+                                    ptr(out, ctypes.c_double)))
+        return out if st is None else (out, st)
+
+    def topsim_mass_sims(self, mass, c, pair_a, pair_b, exact_order=False):
+        mass = as_c(mass, np.float64)
+        ns, n, s1 = mass.shape
+        pa, pb = as_c(pair_a, np.int64), as_c(pair_b, np.int64)
+        out = np.empty(len(pa), dtype=np.float64)
+        check(load().gw_topsim_mass_sims(self.h, ptr(mass, ctypes.c_double), ns, s1 - 1, float(c), ptr(pa, ctypes.c_int64),
+                                         ptr(pb, ctypes.c_int64), len(pa), int(bool(exact_order)), ptr(out, ctypes.c_double)))
         return out
 
     def simrank_last_steps(self):

@@ -363,6 +363,119 @@ class DoubleRandomWalk:
         return self.sim
 
 
+class TopSim_doubleSample:
+    """simrank/TopSim_doubleSample.java: one enumerate-or-sample path-mass tree of STEP levels per vertex (sample :66-151,
+    computePath :153-178), pair score = sum over targets and levels of C^level * mass_i * mass_j (getSim :189-199;
+    unnormalised, x SAMPLE^2).  java_seed: replay mode -- one java.util.Random stream over the vertices in order
+    (draws per tree vary, so trees are chained one by one) and getSim's fp64 order; otherwise Philox trees, all in one
+    launch, and the warp-parallel product kernel."""
+    SAMPLE = 200
+
+    def __init__(self, g, sample, step, seed=None, java_seed=None):
+        self.SAMPLE = sample
+        self.STEP = step
+        self.g = g
+        self.COUNT = g.getVCount()
+        self.paths = None
+        self.sim = None
+        self.seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
+        self.java_state = None if java_seed is None else (int(java_seed) ^ _JR_MULT) & _JR_MASK
+
+    def samplePaths(self):
+        verts = np.arange(self.COUNT, dtype=np.int64)
+        if self.java_state is None:
+            self.paths = self.g.handle.topsim_mass(verts, self.SAMPLE, self.STEP, seed=self.seed)
+            return self
+        self.paths = np.empty((self.COUNT, self.COUNT, self.STEP + 1), dtype=np.float64)
+        for v in range(self.COUNT):
+            m, after = self.g.handle.topsim_mass([v], self.SAMPLE, self.STEP, rng_states=[self.java_state])
+            self.paths[v] = m[0]
+            self.java_state = int(after[0])
+        return self
+
+    def computeSims(self):
+        n = self.COUNT
+        iu, ju = np.triu_indices(n, 1)
+        vals = self.g.handle.topsim_mass_sims(self.paths, MyConfiguration.C, iu, ju, exact_order=self.java_state is not None)
+        self.sim = np.zeros((n, n), dtype=np.float64)
+        self.sim[iu, ju] = vals
+        self.sim[ju, iu] = vals
+        return self
+
+    def compute(self):
+        self.samplePaths()
+        return self.computeSims()
+
+    def getResult(self):
+        return self.sim
+
+
+class TopSim_Dev:
+    """simrank/TopSim_Dev.java: two-stage refinement.  For every vertex i: one path-mass tree from i, then for each of
+    the `topK` best candidates j of candidate[i] (>= MIN, FixedMaxPQ order, :72-83) one tree from j and
+    sim[i][j] = getSim (:233-244).  The per-tree weight is the constructor's
+    (int)((step - singleStep) * sample * 2.0 / (step * (topK + 1.0))) (:35).  java_seed: replay of a seeded JVM (one
+    stream through i and its candidates in order); otherwise Philox trees in one launch."""
+
+    def __init__(self, g, sample, step, topK, singleStep, seed=None, java_seed=None):
+        self.SAMPLE = int(((step - singleStep) * sample * 2.0) / (float(step) * (topK + 1.0)))
+        self.STEP = step
+        self.singleK = topK
+        self.g = g
+        self.COUNT = g.getVCount()
+        self.sim = None
+        self.seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
+        self.java_state = None if java_seed is None else (int(java_seed) ^ _JR_MULT) & _JR_MASK
+
+    def _candidates(self, row):
+        pq = FixedMaxPQ(self.singleK)
+        for j in np.nonzero(np.asarray(row) >= MyConfiguration.MIN)[0].tolist():
+            pq.offer(j, float(row[j]))
+        return [k for k, _ in pq.sortedElement()]
+
+    def compute(self, candidate, rows=None):
+        n = self.COUNT
+        rows = range(n) if rows is None else list(rows)
+        self.sim = np.zeros((n, n), dtype=np.float64)
+        cands = {i: self._candidates(candidate[i]) for i in rows}
+        h = self.g.handle
+        if self.java_state is not None:
+            for i in rows:
+                m0, after = h.topsim_mass([i], self.SAMPLE, self.STEP, rng_states=[self.java_state])
+                self.java_state = int(after[0])
+                for j in cands[i]:
+                    m1, after = h.topsim_mass([j], self.SAMPLE, self.STEP, rng_states=[self.java_state])
+                    self.java_state = int(after[0])
+                    self.sim[i, j] = h.topsim_mass_sims(np.concatenate([m0, m1]), MyConfiguration.C, [0], [1], exact_order=True)[0]
+                self.sim[i, i] = 0
+            return self
+        budget = max(1, (1 << 28) // (n * (self.STEP + 1) * 8))      # trees per launch (256 MB of mass rows)
+        srcs, pa, pb, where = [], [], [], []
+        def flush():
+            if not srcs:
+                return
+            m = h.topsim_mass(srcs, self.SAMPLE, self.STEP, seed=self.seed, call_id_base=flush.base)
+            flush.base += len(srcs)
+            vals = h.topsim_mass_sims(m, MyConfiguration.C, pa, pb)
+            for (i, j), x in zip(where, vals):
+                self.sim[i, j] = x
+            del srcs[:], pa[:], pb[:], where[:]
+        flush.base = 0
+        for i in rows:
+            if len(srcs) + 1 + len(cands[i]) > budget:
+                flush()
+            a = len(srcs)
+            srcs.append(i)
+            for j in cands[i]:
+                pa.append(a); pb.append(len(srcs)); where.append((i, j))
+                srcs.append(j)
+        flush()
+        return self
+
+    def getResult(self):
+        return self.sim
+
+
 class SimRank:
     """simrank/SimRank.java: naive exact SimRank, STEP Jacobi sweeps (STEP = 3 as committed)."""
 

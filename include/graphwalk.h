@@ -205,6 +205,21 @@ int gw_double_walk_paths(gw_graph *g, const int64_t *vertices, int64_t nv, int32
  * 0: integer first-meeting counts combined once (production; same value up to fp64 rounding order). */
 int gw_double_walk_sims(gw_graph *g, const int32_t *paths, int64_t nv, int32_t sample, int32_t step, double c,
                         const int64_t *rows, int64_t nrows, int32_t exact_order, double *out_dense);
+/* TopSim_doubleSample.sample / TopSim_Dev.sample + computePath (simrank/TopSim_doubleSample.java:66-178,
+ * simrank/TopSim_Dev.java:104-226): ns independent path-mass trees (sources may repeat), each started with `weight`
+ * (SAMPLE) and `step` levels deep; out_mass is fp64 [ns][n][step+1] as the reference's paths[src][target][level]
+ * (-1 = not reached; level 0 unused; a target reached by several paths of a level keeps the LAST one's weight).
+ * rng_state == NULL: Philox keyed by (seed, call_id_base + i); else java.util.Random replay from rng_state[i]
+ * (updated).  max_paths bounds one level of one tree (GW_E_TOO_LARGE when exceeded). */
+int gw_topsim_mass(gw_graph *g, const int64_t *sources, int64_t ns, double weight, int32_t step,
+                   int64_t max_paths, uint64_t seed, uint64_t call_id_base, uint64_t *rng_state,
+                   double *out_mass);
+/* getSim of both classes (TopSim_doubleSample.java:189-199, TopSim_Dev.java:233-244) for npairs (a, b) index pairs
+ * into a mass set [ns][n][step+1]: sum over targets and levels of c^level * mass_a * mass_b where both are set.
+ * exact_order != 0: the reference's loop and fp64 operation order (bit-exact); 0: warp-parallel reduction. */
+int gw_topsim_mass_sims(gw_graph *g, const double *mass, int64_t ns, int32_t step, double c,
+                        const int64_t *pair_a, const int64_t *pair_b, int64_t npairs, int32_t exact_order,
+                        double *out);
 /* Total walk steps executed by the last gw_simrank_* call on this graph. */
 int gw_simrank_last_steps(const gw_graph *g, int64_t *steps);
 /* Queries of the last gw_simrank_topk* call that were finished by the exact hash-table kernel

@@ -10,6 +10,7 @@
  *   lxctools/FixedCacheMap.java:26-113   bounded evict-the-minimum cache (the `_M` estimators)
  *   simrank/SingleRandomWalk_M.java:28-103, simrank/TopSim_singleSample_M.java:33-239
  *   simrank/DoubleRandomWalk.java:25-91  two independent walk sets per pair
+ *   simrank/TopSim_doubleSample.java:66-200, simrank/TopSim_Dev.java:104-244   path-mass trees and their products
  *   java.util.Random (JDK, not in the repo): 48-bit LCG, nextInt(bound)
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
@@ -375,6 +376,70 @@ void or_double_walk_matrix(int64_t V, const int32_t *paths, int32_t sample, int3
         }
 }
 
+/* ---------------- TopSim_doubleSample.sample / TopSim_Dev.sample (same code: TopSim_doubleSample.java:66-151,
+ * TopSim_Dev.java:104-199) + computePath (:153-178 / :200-226) ----------------
+ * The enumerate-or-sample tree of TopSim_singleSample, STEP levels deep, started with weight `weight0`; after each
+ * level l = 1..STEP computePath stores mass[target][l] = weight of the path standing on `target` -- an OVERWRITE in
+ * queue order (the last path wins), skipped when target == source.  Only the last vertex and the weight of a path
+ * are ever read, so the queue holds (cur, w) pairs.  mass: V*(step+1) doubles, -1 = unset (caller fills).
+ * Returns paths created, -1 when a level exceeds max_paths. */
+int64_t or_mass_tree(int64_t V, const int64_t *rp, const int32_t *col, int32_t src, double weight0, int32_t step,
+                     int64_t max_paths, uint64_t *seed_io, double *mass) {
+    graph g = {V, rp, col};
+    jrand r; r.seed = *seed_io;
+    int32_t *c0 = (int32_t *)malloc(sizeof(int32_t) * (size_t)max_paths), *c1 = (int32_t *)malloc(sizeof(int32_t) * (size_t)max_paths);
+    double *w0 = (double *)malloc(sizeof(double) * (size_t)max_paths), *w1 = (double *)malloc(sizeof(double) * (size_t)max_paths);
+    int64_t n0 = 1, made = 0;
+    int overflow = 0;
+    c0[0] = src; w0[0] = weight0;
+    for (int path_len = 0; path_len < step && !overflow; path_len++) {
+        int64_t n1 = 0;
+        for (int64_t k = 0; k < n0 && !overflow; k++) {
+            int c = c0[k];
+            double wt = w0[k];
+            int d = deg(&g, c);
+            if (d != 0 && wt >= d) {
+                double ns = wt / (double)d;
+                if (n1 + d > max_paths) { overflow = 1; break; }
+                for (int j = 0; j < d; j++) { c1[n1] = g.col[g.rp[c] + j]; w1[n1] = ns; n1++; made++; }
+            } else {
+                int number = ((double)(int)wt == wt) ? (int)wt : (int)wt + 1;
+                for (int j = 0; j < number; j++) {
+                    int nb = rand_neighbor(&g, &r, c);
+                    if (nb == -1) break;
+                    if (n1 + 1 > max_paths) { overflow = 1; break; }
+                    c1[n1] = nb; w1[n1] = wt / (double)number; n1++; made++;
+                }
+            }
+        }
+        if (overflow) break;
+        int32_t *tc = c0; c0 = c1; c1 = tc;
+        double *tw = w0; w0 = w1; w1 = tw;
+        n0 = n1;
+        int level = path_len + 1;                                  /* computePath(queue, level, level) */
+        for (int64_t k = 0; k < n0; k++) {
+            if (c0[k] == src) continue;
+            mass[(int64_t)c0[k] * (step + 1) + level] = w0[k];
+        }
+    }
+    *seed_io = r.seed;
+    free(c0); free(c1); free(w0); free(w1);
+    return overflow ? -1 : made;
+}
+/* getSim (TopSim_doubleSample.java:189-199, TopSim_Dev.java:233-244): sum over targets i and levels of
+ * cache[level] * a * b where both masses are set (>= 0), in that loop order. */
+double or_mass_sim(const double *ma, const double *mb, int64_t V, int32_t step, double C) {
+    double cache[16];
+    for (int i = 0; i <= step; i++) cache[i] = pow(C, i);
+    double result = 0;
+    for (int64_t i = 0; i < V; i++)
+        for (int s = 1; s <= step; s++) {
+            double a = ma[i * (step + 1) + s], b = mb[i * (step + 1) + s];
+            if (a >= 0 && b >= 0) result += cache[s] * a * b;
+        }
+    return result;
+}
+
 /* ---------------- SimRank.java:36-77 (naive exact, Jacobi sweeps) ---------------- */
 void or_simrank_exact(int64_t V, const int64_t *rp, const int32_t *col, double C, int32_t iters,
                       double *sim /* V*V, out */) {
@@ -430,11 +495,19 @@ static void sift_down(pr *q, int size, int k, pr x) {
 }
 /* returns number of elements written (min(k, n)); descending, ties in heap-array order
  * (Collections.sort is stable). */
+int32_t or_fixedmaxpq_topk_min(const double *row, int64_t n, int32_t k, double min_value, int32_t *out_ids,
+                               double *out_vals);
 int32_t or_fixedmaxpq_topk(const double *row, int64_t n, int32_t k, int32_t *out_ids,
                            double *out_vals) {
+    return or_fixedmaxpq_topk_min(row, n, k, -INFINITY, out_ids, out_vals);
+}
+/* min_value: only entries >= min_value are offered (TopSim_Dev.java:76-83 filters candidate >= MIN) */
+int32_t or_fixedmaxpq_topk_min(const double *row, int64_t n, int32_t k, double min_value, int32_t *out_ids,
+                               double *out_vals) {
     pr *q = (pr *)malloc(sizeof(pr) * (size_t)(k > 0 ? k : 1));
     int size = 0;
     for (int64_t i = 0; i < n; i++) {
+        if (!(row[i] >= min_value)) continue;
         pr e = {(int32_t)i, row[i]};
         if (size < k) { sift_up(q, size, e); size++; }            /* pq.offer */
         else if (k > 0 && pr_cmp(&q[0], &e) < 0) {                 /* peek().compareTo(e) < 0 */

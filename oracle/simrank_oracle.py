@@ -66,6 +66,13 @@ def lib():
         L.or_double_walk_paths.argtypes = [ctypes.c_int64, i64p, i32p, ctypes.c_int32, ctypes.c_int32, u64p, i32p]
         L.or_double_walk_matrix.restype = None
         L.or_double_walk_matrix.argtypes = [ctypes.c_int64, i32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_double, f64p]
+        L.or_mass_tree.restype = ctypes.c_int64
+        L.or_mass_tree.argtypes = [ctypes.c_int64, i64p, i32p, ctypes.c_int32, ctypes.c_double, ctypes.c_int32,
+                                   ctypes.c_int64, u64p, f64p]
+        L.or_mass_sim.restype = ctypes.c_double
+        L.or_mass_sim.argtypes = [f64p, f64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_double]
+        L.or_fixedmaxpq_topk_min.restype = ctypes.c_int32
+        L.or_fixedmaxpq_topk_min.argtypes = [f64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_double, i32p, f64p]
         L.jr_fill.restype = None
         L.jr_fill.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, i32p]
         L.or_node2vec_walks.restype = ctypes.c_int64
@@ -228,6 +235,70 @@ def double_walk_matrix(paths, C=C_DEFAULT):
     lib().or_double_walk_matrix(V, _p(np.ascontiguousarray(paths), ctypes.c_int32), sample, step, float(C),
                                 _p(sim, ctypes.c_double))
     return sim
+
+
+# ---------------- simrank/TopSim_doubleSample.java, simrank/TopSim_Dev.java ----------------
+def mass_tree(g, src, weight0, step, seed_state, max_paths=1 << 22):
+    """sample(src) + computePath: mass[V, step+1] (-1 = unset), new rng state."""
+    mass = np.full((g["V"], step + 1), -1.0, dtype=np.float64)
+    st = ctypes.c_uint64(seed_state)
+    made = lib().or_mass_tree(g["V"], _p(g["row_ptr"], ctypes.c_int64), _p(g["col"], ctypes.c_int32), int(src),
+                              float(weight0), int(step), int(max_paths), ctypes.byref(st), _p(mass, ctypes.c_double))
+    if made < 0:
+        raise MemoryError("path tree exceeded max_paths")
+    return mass, int(st.value)
+
+
+def mass_sim(ma, mb, C=C_DEFAULT):
+    V, s1 = ma.shape
+    return float(lib().or_mass_sim(_p(np.ascontiguousarray(ma), ctypes.c_double), _p(np.ascontiguousarray(mb), ctypes.c_double),
+                                   V, s1 - 1, float(C)))
+
+
+def topsim_double_sample(g, sample, step, seed_state, C=C_DEFAULT):
+    """TopSim_doubleSample.compute(): samplePaths over all vertices in order (one RNG stream), then getSim for
+    i < j, mirrored; the diagonal stays 0.  Returns (sim, masses [V, V, step+1], new rng state)."""
+    V = g["V"]
+    masses = np.empty((V, V, step + 1), dtype=np.float64)
+    st = seed_state
+    for v in range(V):
+        masses[v], st = mass_tree(g, v, float(sample), step, st)
+    sim = np.zeros((V, V), dtype=np.float64)
+    for i in range(V):
+        for j in range(i + 1, V):
+            sim[i, j] = sim[j, i] = mass_sim(masses[i], masses[j], C)
+    return sim, masses, st
+
+
+def fixedmaxpq_topk_min(row, k, min_value):
+    row = np.ascontiguousarray(row, dtype=np.float64)
+    ids = np.zeros(max(k, 1), dtype=np.int32)
+    vals = np.zeros(max(k, 1), dtype=np.float64)
+    n = lib().or_fixedmaxpq_topk_min(_p(row, ctypes.c_double), len(row), int(k), float(min_value),
+                                     _p(ids, ctypes.c_int32), _p(vals, ctypes.c_double))
+    return ids[:n].copy(), vals[:n].copy()
+
+
+def topsim_dev_sample_count(sample, step, topK, singleStep):
+    """TopSim_Dev constructor (:35-36)."""
+    return int(((step - singleStep) * sample * 2.0) / (float(step) * (topK + 1.0)))
+
+
+def topsim_dev(g, candidate, sample, step, topK, singleStep, seed_state, C=C_DEFAULT, rows=None):
+    """TopSim_Dev.compute(candidate) (:57-98): per vertex i one tree from i, then for each of the top `topK`
+    candidates j (candidate[i][j] >= MIN, FixedMaxPQ order) one tree from j and sim[i][j] = getSim; one RNG stream."""
+    V = g["V"]
+    S_ = topsim_dev_sample_count(sample, step, topK, singleStep)
+    sim = np.zeros((V, V), dtype=np.float64)
+    st = seed_state
+    for i in (range(V) if rows is None else rows):
+        m0, st = mass_tree(g, i, float(S_), step, st)
+        ids, _ = fixedmaxpq_topk_min(candidate[i], topK, MIN)
+        for j in ids.tolist():
+            m1, st = mass_tree(g, j, float(S_), step, st)
+            sim[i, j] = mass_sim(m0, m1, C)
+        sim[i, i] = 0
+    return sim, st
 
 
 def simrank_exact_naive(g, C, iters):

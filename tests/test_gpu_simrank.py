@@ -488,3 +488,51 @@ def test_double_random_walk_replay_and_production(g333, o333):
     assert np.allclose(p.getResult(), p.getResult().T, atol=1e-15)
     again = sr.DoubleRandomWalk(g333, 1500, 3, seed=9).samplePaths().paths
     assert again.tobytes() == p.paths.tobytes()                  # counter-based RNG: same seed, same paths
+
+
+def test_path_mass_estimators_replay_is_bit_exact(g333, o333):
+    """TopSim_doubleSample and TopSim_Dev: the path-mass trees (enumerate-or-sample, per level the LAST path on a
+    target wins) and getSim's fp64 products.  Replay: masses, RNG states and scores equal the oracle bit for bit;
+    production: Philox trees give the same deterministic masses wherever the tree only enumerates."""
+    # single trees across the regimes: pure enumeration (weight >> degree^step), mixed, pure sampling, weight 0
+    for weight, step in ((2.0e6, 2), (3000.0, 3), (40.0, 4), (1.0, 3), (0.0, 2)):
+        st = S.java_seed(5150)
+        srcs, states, want = [0, 5, 100, 5], [], []
+        for v in srcs:
+            states.append(st)
+            m, st = S.mass_tree(o333, v, weight, step, st)
+            want.append(m)
+        got, after = g333.handle.topsim_mass(srcs, weight, step, rng_states=states, max_paths=1 << 18)
+        assert got.tobytes() == np.asarray(want).tobytes(), (weight, step)
+        assert after.tolist() == states[1:] + [st]
+    with pytest.raises(MemoryError):
+        g333.handle.topsim_mass([0], 2.0e6, 2, rng_states=[1], max_paths=100)
+    # TopSim_doubleSample through its mirror: one stream over all vertices
+    want_sim, want_mass, st = S.topsim_double_sample(o333, 500, 2, S.java_seed(31))
+    d = sr.TopSim_doubleSample(g333, 500, 2, java_seed=31).compute()
+    assert d.paths.tobytes() == want_mass.tobytes() and d.java_state == st
+    assert d.getResult().tobytes() == want_sim.tobytes()
+    fast = g333.handle.topsim_mass_sims(d.paths, 0.6, [0, 5, 7], [5, 9, 300])
+    assert np.allclose(fast, want_sim[[0, 5, 7], [5, 9, 300]], rtol=1e-12, atol=0)
+    # production trees: level 1 is enumerated whenever SAMPLE >= degree, so it is deterministic and equals the replay's
+    p = sr.TopSim_doubleSample(g333, 500, 2, seed=4).samplePaths()
+    deg = np.diff(o333["row_ptr"])
+    en = np.nonzero(deg <= 500)[0]
+    assert (p.paths[en][:, :, 1] == want_mass[en][:, :, 1]).all()
+    assert p.paths.shape == want_mass.shape and ((p.paths >= 0) == (p.paths != -1)).all()
+    p.computeSims()
+    assert np.allclose(p.getResult(), p.getResult().T) and not np.diag(p.getResult()).any()
+    again = sr.TopSim_doubleSample(g333, 500, 2, seed=4).samplePaths()
+    assert again.paths.tobytes() == p.paths.tobytes()
+    # TopSim_Dev: candidates from TopSim_singleSample rows (the reference driver, Test_u_u_TopSim_Dev.java:47-62)
+    cand = sr.TopSim_singleSample(g333, 2000, 1, java_seed=3).compute().getResult()
+    rows = [0, 5, 17, 332]
+    want, st = S.topsim_dev(o333, cand, 10000, 3, 20, 1, S.java_seed(8), rows=rows)
+    dev = sr.TopSim_Dev(g333, 10000, 3, 20, 1, java_seed=8)
+    assert dev.SAMPLE == S.topsim_dev_sample_count(10000, 3, 20, 1) == 634
+    got = dev.compute(cand, rows=rows).getResult()
+    assert got.tobytes() == want.tobytes() and dev.java_state == st and got[rows].any()
+    free = sr.TopSim_Dev(g333, 10000, 3, 20, 1, seed=2).compute(cand, rows=rows).getResult()
+    assert ((free != 0) == (want != 0)).all()                       # same candidate sets; values differ by sampling only
+    nz = want != 0
+    assert np.abs(free[nz] / want[nz] - 1).mean() < 0.2
