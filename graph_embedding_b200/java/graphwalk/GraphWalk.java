@@ -58,6 +58,10 @@ public final class GraphWalk {
         FunctionDescriptor.of(I, P, P, J, I, I, J, P, P));
     private static final MethodHandle DW_SIMS = h("gw_double_walk_sims",
         FunctionDescriptor.of(I, P, P, J, I, I, D, P, J, I, P));
+    private static final MethodHandle MASS = h("gw_topsim_mass",
+        FunctionDescriptor.of(I, P, P, J, D, I, J, J, J, P, P));
+    private static final MethodHandle MASS_SIMS = h("gw_topsim_mass_sims",
+        FunctionDescriptor.of(I, P, P, J, I, D, P, P, J, I, P));
 
     private GraphWalk() {}
 
@@ -221,6 +225,30 @@ public final class GraphWalk {
             double[][] sim = new double[rows.length][nv];
             for (int i = 0; i < rows.length; i++) MemorySegment.copy(out, D, (long) i * nv * 8, sim[i], 0, nv);
             return sim;
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
+    }
+
+    /** gw_topsim_mass: path-mass trees of TopSim_doubleSample / TopSim_Dev, [ns][n][step+1] flattened (-1 = unset). */
+    public static double[] topsimMass(MemorySegment g, long[] sources, int vCount, double weight, int step, long maxPaths,
+                                      long seed, long callIdBase, long[] rngState) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment s = a.allocateFrom(J, sources);
+            MemorySegment st = rngState == null ? MemorySegment.NULL : a.allocateFrom(J, rngState);
+            MemorySegment out = a.allocate(D, (long) sources.length * vCount * (step + 1));
+            check((int) MASS.invokeExact(g, s, (long) sources.length, weight, step, maxPaths, seed, callIdBase, st, out));
+            if (rngState != null) MemorySegment.copy(st, J, 0, rngState, 0, rngState.length);
+            return out.toArray(D);
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
+    }
+
+    /** gw_topsim_mass_sims: getSim for (a, b) index pairs into a mass set of ns trees. */
+    public static double[] topsimMassSims(MemorySegment g, double[] mass, long ns, int step, double c, long[] pairA, long[] pairB,
+                                          boolean exactOrder) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment m = a.allocateFrom(D, mass), pa = a.allocateFrom(J, pairA), pb = a.allocateFrom(J, pairB);
+            MemorySegment out = a.allocate(D, pairA.length);
+            check((int) MASS_SIMS.invokeExact(g, m, ns, step, c, pa, pb, (long) pairA.length, exactOrder ? 1 : 0, out));
+            return out.toArray(D);
         } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
     }
 }
