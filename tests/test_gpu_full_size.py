@@ -1,0 +1,94 @@
+"""BASELINE.json's full-size shapes through size-independent properties (the CPU oracle cannot finish these):
+R-MAT scale-22 node2vec (configs[2]) and Barabasi-Albert n = 10^7 TopSim top-20 (configs[4]).  Checked: generator
+determinism and invariants, every walk step follows an edge, no dead ends on an undirected graph, results independent
+of how the walks / queries are split across calls (the multi-GPU sharding rule), production kernel == exact hash
+kernel bit for bit, top-k order, step counts, degree-proportional stationary visits."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from graph_embedding_b200 import _lib  # noqa: E402
+
+
+def _steps_follow_edges(rp, col, walks):
+    """Vectorised binary search of every (a -> b) step in the sorted row of a."""
+    a = walks[:, :-1].ravel().astype(np.int64)
+    b = walks[:, 1:].ravel()
+    lo, hi = rp[a].copy(), rp[a + 1].copy()
+    end = hi.copy()
+    while (lo < hi).any():
+        mid = (lo + hi) >> 1
+        go = (lo < hi) & (col[np.minimum(mid, len(col) - 1)] < b)
+        stay = (lo < hi) & ~go
+        lo = np.where(go, mid + 1, lo)
+        hi = np.where(stay, mid, hi)
+    return bool(((lo < end) & (col[np.minimum(lo, len(col) - 1)] == b)).all())
+
+
+def test_rmat22_node2vec_full_size_properties():
+    h = _lib.GraphHandle.rmat(22, 16 << 22, seed=1)
+    assert h.n == 1 << 22 and h.nnz == 134109214 and h.max_degree == 1678      # 134.1 M directed entries
+    starts = h.nonisolated()
+    assert len(starts) == 4178039                                               # |V+|, 99.6 % of the ids
+    c = h.csr(weights=False, node_ids=False, first_seen=False)
+    rp, col = c["row_ptr"], c["col_idx"]
+    deg = np.diff(rp)
+    assert rp[-1] == h.nnz and deg.max() == 1678 and np.array_equal(np.nonzero(deg)[0], starts)
+    # one full pass through the host API (what bench.py's e2e leg times): 4.18 M walks x 80
+    walks, lens = h.walks(0.25, 4.0, 80, starts, seed=3)
+    assert walks.shape == (len(starts), 80) and (lens == 80).all()             # undirected: no dead ends
+    assert np.array_equal(walks[:, 0], starts) and walks.min() >= 0 and walks.max() < h.n
+    sub = slice(0, len(starts), 211)                                            # 19.8 k walks, 1.56 M steps
+    assert _steps_follow_edges(rp, col, walks[sub])
+    ret = (walks[:, 2:] == walks[:, :-2]).mean()
+    assert 0.10 < ret < 0.25, ret                                               # p = 0.25 favours the return edge (bench: 16 %)
+    # sharding rule: the corpus depends on (seed, global walk id) only, not on the batch split
+    k = 1234567
+    a, _ = h.walks(0.25, 4.0, 80, starts[:k], seed=3, walk_id_base=0)
+    b, _ = h.walks(0.25, 4.0, 80, starts[k:k + 100000], seed=3, walk_id_base=k)
+    assert np.array_equal(a, walks[:k]) and np.array_equal(b, walks[k:k + 100000])
+    other, _ = h.walks(0.25, 4.0, 80, starts[:1000], seed=4)
+    assert not np.array_equal(other, walks[:1000])
+    del walks, a, b
+    # q < 1 (configs[3]'s parameters): Bloom-filtered "others" component, same validity
+    wq, lq = h.walks(4.0, 0.5, 80, starts[sub], seed=5)
+    assert (lq == 80).all() and _steps_follow_edges(rp, col, wq)
+    assert (wq[:, 2:] == wq[:, :-2]).mean() < 0.02                              # p = 4 avoids the return edge
+    # first-order stationary law: visits ~ degree
+    w1, _ = h.walks(1.0, 1.0, 80, starts, seed=6)
+    visits = np.bincount(w1[:, 40:].ravel(), minlength=h.n).astype(np.float64)
+    assert np.corrcoef(visits, deg.astype(np.float64))[0, 1] > 0.995
+
+
+def test_ba10m_topsim_full_size_properties(monkeypatch):
+    n, m = 10_000_000, 8
+    h = _lib.GraphHandle.barabasi_albert(n, m, seed=1)
+    assert h.n == n and h.nnz == 2 * (28 + (n - 8) * 8)                         # 8-clique seed + 8 edges per new vertex
+    q = np.random.RandomState(2).choice(n, 4096, replace=False).astype(np.int64)
+    monkeypatch.delenv("GW_SIMRANK", raising=False)
+    ids, sc = h.simrank_topk(q, 0.6, 5, 10000, 20, seed=1)
+    assert h.simrank_last_steps() == 4096 * 10000 * 10                          # no isolated vertex, no dead end
+    assert (np.diff(sc, axis=1) <= 0).all() and (sc[:, 0] > 0).all() and (sc >= 0).all()
+    assert ids.max() < n and (ids[sc > 0] >= 0).all()
+    assert not (ids == q[:, None]).any()                                        # sim[v][v] = 0
+    tie = (np.diff(sc, axis=1) == 0) & (sc[:, 1:] > 0)
+    assert (np.diff(ids, axis=1)[tie] > 0).all()                                # equal scores: lower id first
+    # sharding rule: results depend on (seed, global query index) only
+    a_ids, a_sc = h.simrank_topk(q[:1500], 0.6, 5, 10000, 20, seed=1, query_id_base=0)
+    b_ids, b_sc = h.simrank_topk(q[1500:], 0.6, 5, 10000, 20, seed=1, query_id_base=1500)
+    assert np.array_equal(np.vstack([a_ids, b_ids]), ids) and np.vstack([a_sc, b_sc]).tobytes() == sc.tobytes()
+    slow = h.simrank_last_slow_queries()
+    assert slow < 64                                                            # the log kernel finishes almost everything
+    # production kernel == exact hash kernel, bit for bit, at full graph size
+    monkeypatch.setenv("GW_SIMRANK", "hash")
+    e_ids, e_sc = h.simrank_topk(q[:192], 0.6, 5, 10000, 20, seed=1)
+    monkeypatch.delenv("GW_SIMRANK", raising=False)
+    assert np.array_equal(e_ids, ids[:192]) and e_sc.tobytes() == sc[:192].tobytes()
+    # the path-tree estimator at full size: same invariants, same sharding rule (scores are x SAMPLE, as the reference)
+    t_ids, t_sc = h.simrank_topk(q[:512], 0.6, 5, 10000, 20, mode=_lib.GW_SIMRANK_HYBRID, seed=1)
+    assert (np.diff(t_sc, axis=1) <= 0).all() and (t_sc[:, 0] > 0).all() and not (t_ids == q[:512, None]).any()
+    u_ids, u_sc = h.simrank_topk(q[200:512], 0.6, 5, 10000, 20, mode=_lib.GW_SIMRANK_HYBRID, seed=1, query_id_base=200)
+    assert np.array_equal(u_ids, t_ids[200:]) and u_sc.tobytes() == t_sc[200:].tobytes()
+    m = np.median(t_sc[:, 0] / 10000.0 / sc[:512, 0])
+    assert 0.5 < m < 1.5, m                                                     # both estimate the same top score
