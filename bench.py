@@ -255,19 +255,21 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     t_all = time.perf_counter()
-    vals = []
-    for _ in range(max(1, min(args.steps, 2))):
+    vals, step_ms = [], []
+    for _ in range(max(1, min(args.steps, 2))):        # each step is one bounded sample of the workload (tier rule 4)
+        t_step = time.perf_counter()
         if args.workload == "node2vec":
             v, sample = cpu_node2vec(args.p, args.q, args.walk_length, args.cpu_seconds, cores)
         else:
             v, sample = cpu_simrank(args.sample, args.sr_step, args.topk, args.cpu_seconds, cores)
         vals.append(v)
+        step_ms.append((time.perf_counter() - t_step) * 1e3)
     v = float(np.mean(vals))
     metric, unit = metric_unit(args)
     line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(step_ms)), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": config_of(args),
+            "config": config_of(args), "steps_run": len(vals),
             "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t_all}
