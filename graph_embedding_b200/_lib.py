@@ -88,6 +88,16 @@ SIGNATURES = {
                                       ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), c_f64p]),
     "gw_topsim_mass_sims": (ctypes.c_int, [c_vp, c_f64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_double, c_i64p,
                                            c_i64p, ctypes.c_int64, ctypes.c_int32, c_f64p]),
+    "gw_comm_unique_id": (ctypes.c_int, [c_vp]),
+    "gw_comm_init": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, c_vp, ctypes.c_int32, ctypes.POINTER(c_vp)]),
+    "gw_comm_info": (ctypes.c_int, [c_vp, c_i32p, c_i32p, c_i32p]),
+    "gw_comm_free": (ctypes.c_int, [c_vp]),
+    "gw_shard_range": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, c_i64p, c_i64p]),
+    "gw_node2vec_walks_sharded": (ctypes.c_int, [c_vp, c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_int32, c_i64p,
+                                                 ctypes.c_int64, ctypes.c_uint64, ctypes.c_int32, c_i32p, c_i32p]),
+    "gw_simrank_topk_sharded": (ctypes.c_int, [c_vp, c_vp, c_i64p, ctypes.c_int64, ctypes.c_double, ctypes.c_int32,
+                                               ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64,
+                                               c_i32p, c_f64p]),
     "gw_simrank_last_steps": (ctypes.c_int, [c_vp, c_i64p]),
     "gw_simrank_last_slow_queries": (ctypes.c_int, [c_vp, c_i64p]),
     "gw_simrank_exact": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_int32, c_i64p, ctypes.c_int64, c_f64p]),
@@ -427,6 +437,62 @@ class GraphHandle:
         check(load().gw_simrank_exact(self.h, float(c), int(iters), ptr(rows, ctypes.c_int64), len(rows),
                                       ptr(out, ctypes.c_double)))
         return out
+
+
+def shard_range(n, rank, nranks):
+    lo, hi = ctypes.c_int64(), ctypes.c_int64()
+    check(load().gw_shard_range(int(n), int(rank), int(nranks), ctypes.byref(lo), ctypes.byref(hi)))
+    return lo.value, hi.value
+
+
+class Comm:
+    """gw_comm: the C-ABI multi-GPU communicator (NCCL loaded at run time).  `unique_id()` on rank 0, ship the 128
+    bytes to the other ranks, then `Comm(rank, nranks, id, device)` everywhere."""
+
+    @staticmethod
+    def unique_id():
+        buf = ctypes.create_string_buffer(128)
+        check(load().gw_comm_unique_id(ctypes.cast(buf, c_vp)))
+        return buf.raw
+
+    def __init__(self, rank, nranks, unique_id, device=0):
+        if len(unique_id) != 128:
+            raise ValueError("a NCCL unique id is 128 bytes")
+        out = c_vp()
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        check(load().gw_comm_init(int(rank), int(nranks), ctypes.cast(buf, c_vp), int(device), ctypes.byref(out)))
+        self._c = c_vp(out.value)
+        self.rank, self.nranks, self.device = int(rank), int(nranks), int(device)
+
+    def close(self):
+        if getattr(self, "_c", None) is not None and self._c.value:
+            load().gw_comm_free(self._c)
+            self._c = c_vp(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def walks(self, handle, p, q, walk_length, starts_all, seed=0, gather=True):
+        """gw_node2vec_walks_sharded: the whole [n, L] corpus on every rank (gather) or this rank's rows only."""
+        starts_all = as_c(starts_all, np.int64)
+        out = np.full((len(starts_all), walk_length), -1, dtype=np.int32)
+        ln = np.zeros(len(starts_all), dtype=np.int32)
+        check(load().gw_node2vec_walks_sharded(handle.h, self._c, float(p), float(q), int(walk_length),
+                                               ptr(starts_all, ctypes.c_int64), len(starts_all), int(seed),
+                                               int(bool(gather)), ptr(out, ctypes.c_int32), ptr(ln, ctypes.c_int32)))
+        return out, ln
+
+    def simrank_topk(self, handle, queries_all, c, step, sample, k, mode=GW_SIMRANK_MC, seed=0):
+        queries_all = as_c(queries_all, np.int64)
+        ids = np.empty((len(queries_all), k), dtype=np.int32)
+        sc = np.empty((len(queries_all), k), dtype=np.float64)
+        check(load().gw_simrank_topk_sharded(handle.h, self._c, ptr(queries_all, ctypes.c_int64), len(queries_all),
+                                             float(c), int(step), int(sample), int(k), int(mode), int(seed),
+                                             ptr(ids, ctypes.c_int32), ptr(sc, ctypes.c_double)))
+        return ids, sc
 
 
 def alias_setup(probs):

@@ -230,6 +230,32 @@ int gw_simrank_last_slow_queries(const gw_graph *g, int64_t *count);
 int gw_simrank_exact(gw_graph *g, double c, int32_t iters, const int64_t *rows, int64_t nrows,
                      double *out_dense);
 
+/* ---- multi-GPU: one process per GPU, graph replicated, units sharded, results gathered over NCCL ----
+ * The path shards into independent units (node2vec.py:53-57: one walk per start node; SingleRandomWalk.java:39-45:
+ * one row per query), so there is no data-path collective: rank r of nranks handles the contiguous slice
+ * gw_shard_range(n, r, nranks) with GLOBAL walk / query ids in the RNG counters, and the only exchange is the
+ * gather of the result blocks.  NCCL is loaded at run time (libnccl.so.2); single-GPU callers never need it.
+ * Bootstrap like any NCCL program: rank 0 calls gw_comm_unique_id and hands the 128 bytes to the other ranks
+ * (file, socket, JVM/Python launcher), then every rank calls gw_comm_init with its device. */
+typedef struct gw_comm gw_comm;
+int gw_comm_unique_id(void *id128);
+int gw_comm_init(int32_t rank, int32_t nranks, const void *id128, int32_t device, gw_comm **out);
+int gw_comm_info(const gw_comm *c, int32_t *rank, int32_t *nranks, int32_t *device);
+int gw_comm_free(gw_comm *c);
+int gw_shard_range(int64_t n, int32_t rank, int32_t nranks, int64_t *lo, int64_t *hi);
+/* Every rank passes the SAME starts[n_starts]; rank r walks its slice with walk ids = global positions.
+ * gather != 0: all ranks receive the whole corpus out_walks[n_starts*walk_length] (+ out_lens) -- identical to one
+ * gw_node2vec_walks call on one GPU; gather == 0 (corpora beyond one GPU / host, e.g. R-MAT-26's 215 GB): only
+ * this rank's rows of out_walks / out_lens are written, at their global offsets. */
+int gw_node2vec_walks_sharded(gw_graph *g, gw_comm *c, double p, double q, int32_t walk_length,
+                              const int64_t *starts, int64_t n_starts, uint64_t seed, int32_t gather,
+                              int32_t *out_walks, int32_t *out_lens);
+/* Every rank passes the SAME queries[nq]; all ranks receive out_ids / out_scores [nq*k], identical to one
+ * gw_simrank_topk call on one GPU. */
+int gw_simrank_topk_sharded(gw_graph *g, gw_comm *c, const int64_t *queries, int64_t nq, double c_decay,
+                            int32_t step, int32_t sample, int32_t k, int32_t mode, uint64_t seed,
+                            int32_t *out_ids, double *out_scores);
+
 #ifdef __cplusplus
 }
 #endif
