@@ -74,3 +74,10 @@ def test_emb_wire_format_round_trips_the_shipped_file(tmp_path):
     out = str(tmp_path / "k.emb")
     cli.save_word2vec_format(out, words, vecs)
     assert open(out, "rb").read() == open(src, "rb").read()
+
+
+def test_shard_range_matches_the_host_rule():
+    from graph_embedding_b200 import dist
+    for n in (0, 1, 7, 100003):
+        for world in (1, 2, 3, 8):
+            assert [_lib.shard_range(n, r, world) for r in range(world)] == [dist.shard_range(n, r, world) for r in range(world)]

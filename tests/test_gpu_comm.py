@@ -38,10 +38,3 @@ def test_two_ranks_gather_equals_one_gpu(tmp_path):
     if _lib.device_count() < 2:
         pytest.skip("needs two GPUs")
     _run(2, tmp_path)
-
-
-def test_shard_range_matches_the_host_rule():
-    from graph_embedding_b200 import dist
-    for n in (0, 1, 7, 100003):
-        for world in (1, 2, 3, 8):
-            assert [_lib.shard_range(n, r, world) for r in range(world)] == [dist.shard_range(n, r, world) for r in range(world)]
