@@ -62,6 +62,13 @@ public final class GraphWalk {
         FunctionDescriptor.of(I, P, P, J, D, I, J, J, J, P, P));
     private static final MethodHandle MASS_SIMS = h("gw_topsim_mass_sims",
         FunctionDescriptor.of(I, P, P, J, I, D, P, P, J, I, P));
+    private static final MethodHandle COMM_ID = h("gw_comm_unique_id", FunctionDescriptor.of(I, P));
+    private static final MethodHandle COMM_INIT = h("gw_comm_init", FunctionDescriptor.of(I, I, I, P, I, P));
+    private static final MethodHandle COMM_FREE = h("gw_comm_free", FunctionDescriptor.of(I, P));
+    private static final MethodHandle TOPK_SHARDED = h("gw_simrank_topk_sharded",
+        FunctionDescriptor.of(I, P, P, P, J, D, I, I, I, I, J, P, P));
+    private static final MethodHandle WALKS_SHARDED = h("gw_node2vec_walks_sharded",
+        FunctionDescriptor.of(I, P, P, D, D, I, P, J, J, I, P, P));
 
     private GraphWalk() {}
 
@@ -249,6 +256,40 @@ public final class GraphWalk {
             MemorySegment out = a.allocate(D, pairA.length);
             check((int) MASS_SIMS.invokeExact(g, m, ns, step, c, pa, pb, (long) pairA.length, exactOrder ? 1 : 0, out));
             return out.toArray(D);
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
+    }
+
+    /** gw_comm_unique_id: 128 bytes created on rank 0 and shipped to the other ranks by the launcher. */
+    public static byte[] commUniqueId() {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment id = a.allocate(128);
+            check((int) COMM_ID.invokeExact(id));
+            return id.toArray(ValueLayout.JAVA_BYTE);
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
+    }
+
+    /** gw_comm_init: one JVM per GPU; returns the communicator handle (free with commFree). */
+    public static MemorySegment commInit(int rank, int nranks, byte[] uniqueId, int device) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment id = a.allocateFrom(ValueLayout.JAVA_BYTE, uniqueId), out = a.allocate(P);
+            check((int) COMM_INIT.invokeExact(rank, nranks, id, device, out));
+            return out.get(P, 0);
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
+    }
+
+    public static void commFree(MemorySegment comm) {
+        try { check((int) COMM_FREE.invokeExact(comm)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
+    }
+
+    /** gw_simrank_topk_sharded: every rank passes the same queries and receives the whole [nq*k] result. */
+    public static void simrankTopkSharded(MemorySegment g, MemorySegment comm, long[] queries, double c, int step, int sample,
+                                          int k, int mode, long seed, int[] outIds, double[] outScores) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment q = a.allocateFrom(J, queries);
+            MemorySegment ids = a.allocate(I, (long) queries.length * k), sc = a.allocate(D, (long) queries.length * k);
+            check((int) TOPK_SHARDED.invokeExact(g, comm, q, (long) queries.length, c, step, sample, k, mode, seed, ids, sc));
+            MemorySegment.copy(ids, I, 0, outIds, 0, outIds.length);
+            MemorySegment.copy(sc, D, 0, outScores, 0, outScores.length);
         } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new AssertionError(t); }
     }
 }
