@@ -99,7 +99,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.004)                                  # the timed region is tens of ms: sample every few ms
 
     def finish(self):
         self._halt.set()
