@@ -247,7 +247,9 @@ __device__ __noinline__ int4 step_by_rejection(const CnParams &P, uint2 m, uint2
             bool take = u < lo;
             if (!take) {                                       // the class of x matters
                 bool common;
-                if (P.rowhash) {                               // exact, 1-2 accesses (both rows are long here)
+                if (c == 0) {                                  // no common neighbour exists: x is in class "a"
+                    common = false;
+                } else if (P.rowhash) {                               // exact, 1-2 accesses (both rows are long here)
                     common = row_contains(P.col, P.rowhash, mprev, e.x);
                     if (acc) (*acc)++;
                 } else {
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                             for (;;) {
                                 int4 e = ld_i4_policy(P.nbr4 + m.x + scale_u32(rk, d), pol_stream);
                                 bool take = e.x != prev;
-                                if (take) {
+                                if (take && c != 0) {                // c == 0: N(cur) & N(prev) is empty, nothing to exclude, no test
                                     // "not adjacent to prev": one 8-byte Bloom word says so for ~99 % of the
                                     // non-neighbours; only positives pay for the exact search over N(prev)
                                     bool maybe = true;
