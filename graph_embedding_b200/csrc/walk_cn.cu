@@ -339,15 +339,20 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                         else if (haveO) comp = 3;
                         else comp = 1;
                         if (COUNT && comp != 0) st_acc++;                  // one random {nbr,cnt,off,deg} access
+                        // A and O both open with the proposal N(cur)[rnd.y]: ONE load instruction for the lanes of either
+                        // component.  Issued inside the two branches, a warp whose lanes split between A and O (q < 1:
+                        // about half and half) waited for two memory latencies per step instead of one.
+                        int4 e = make_int4(0, 0, 0, 0);
+                        if (comp == 1 || comp == 3) e = ld_i4_policy(P.nbr4 + m.x + scale_u32(rnd.y, d), pol_stream);
                         if (comp == 0) {                              // R: return
                             nxt = prev; cn = c; mn = mprev;
                         } else if (comp == 1) {                       // A: uniform over N(cur), prev thinned
-                            uint32_t rk = rnd.y, ra = rnd.z, att = 0;
+                            uint32_t ra = rnd.z, att = 0;
                             for (;;) {
-                                int4 e = ld_i4_policy(P.nbr4 + m.x + scale_u32(rk, d), pol_stream);
                                 if (e.x != prev || unit24(ra) * P.lo < P.r0) { nxt = e.x; cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w); break; }
                                 uint4 r2 = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, ++att), P.key);
-                                rk = r2.x; ra = r2.y;
+                                ra = r2.y;
+                                e = ld_i4_policy(P.nbr4 + m.x + scale_u32(r2.x, d), pol_stream);
                                 if (COUNT) { st_acc++; st_prop++; }
                             }
                         } else if (comp == 2) {                       // C: uniform over N(cur) & N(prev)
@@ -371,10 +376,9 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                                 }
                             }
                         } else {                                      // O: uniform over N(cur) \ N(prev) \ {prev}
-                            uint32_t rk = rnd.y, att = 0;
+                            uint32_t att = 0;
                             const uint32_t ssec = (uint32_t)max(1, (32 - __clz(mprev.y)) - 2);   // S(d_prev) random sectors per search
                             for (;;) {
-                                int4 e = ld_i4_policy(P.nbr4 + m.x + scale_u32(rk, d), pol_stream);
                                 bool take = e.x != prev;
                                 if (take && c != 0) {                // c == 0: N(cur) & N(prev) is empty, nothing to exclude, no test
                                     // "not adjacent to prev": one 8-byte Bloom word says so for ~99 % of the
@@ -395,7 +399,7 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                                 }
                                 if (take) { nxt = e.x; cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w); break; }
                                 uint4 r2 = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, ++att), P.key);
-                                rk = r2.x;
+                                e = ld_i4_policy(P.nbr4 + m.x + scale_u32(r2.x, d), pol_stream);
                                 if (COUNT) { st_acc++; st_prop++; }
                             }
                         }
@@ -579,7 +583,7 @@ int launch_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_
     unsigned grid = (unsigned)((n_starts + 255) / 256);
     bool vec = (L % 8 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 31) == 0);
     const char *occ = getenv("GW_CN_MINB");     // experiment knob: resident blocks per SM the kernel is compiled for
-    int minb = occ ? atoi(occ) : (q < 1.0 ? 6 : 5);   // q < 1 chains two dependent accesses per O step: more walks in flight pay (R-MAT-24: 24.1 -> 25.6 G steps/s); q >= 1 loses 7 % at 6
+    int minb = occ ? atoi(occ) : 5;   // 5 is best for every p, q since O steps of contexts without common neighbours skip the adjacency test (R-MAT-22 p=4 q=0.5: 39.7 / 38.6 / 36.5 G steps/s at 5 / 6 / 8); q >= 1 loses 7 % at 6
     const bool hub = is_hub_graph(g);
     if (!vec) { if (hub) k_walk_cn<false, false, 5, true><<<grid, 256, 0, st>>>(P); else k_walk_cn<false, false, 5, false><<<grid, 256, 0, st>>>(P); }
     else if (hub) {
