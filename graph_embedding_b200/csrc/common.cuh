@@ -110,6 +110,7 @@ struct gw_graph {
     // unweighted, loop-free graphs only)
     int4 *d_nbr4 = nullptr;        // {neighbour, |N(u) & N(v)|, offset(v), degree(v)} per directed entry
     int nbr4_has_counts = 0;
+    int nbr4_packed = 0;          // nbr4[].y = count | reverse index << 16 (every degree < 65536)
     // word-blocked Bloom filter over the undirected edge set (lazy; q < 1 walks): "x not adjacent to prev" in
     // ONE random 8-byte access instead of a binary search over N(prev); positives are verified exactly
     unsigned long long *d_bloom = nullptr;

@@ -120,10 +120,13 @@ __global__ void k_nbr4_nocount(const uint2 *__restrict__ meta, const int32_t *__
     nbr4[e] = make_int4(v, 0, (int)mv.x, (int)mv.y);
 }
 
-// one warp per directed entry e = (u -> v): nbr4[e] = {v, |N(u) & N(v)|, offset(v), degree(v)}
+// one warp per directed entry e = (u -> v): nbr4[e] = {v, |N(u) & N(v)|, offset(v), degree(v)}.
+// pack (every degree < 65536): .y = count | (position of u inside N(v)) << 16 -- the REVERSE index: a walker that
+// moved u -> v knows where its previous vertex sits in the row it is about to sample from and can draw from
+// N(v) \ {u} without rejection.
 __global__ void __launch_bounds__(256) k_common_counts(const uint2 *__restrict__ meta, const int32_t *__restrict__ col,
                                                         const int64_t *__restrict__ row_ptr, int64_t n, int64_t nnz,
-                                                        int4 *__restrict__ nbr4, int *__restrict__ self_loops) {
+                                                        int4 *__restrict__ nbr4, int *__restrict__ self_loops, int pack) {
     const int lane = threadIdx.x & 31;
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -142,7 +145,18 @@ __global__ void __launch_bounds__(256) k_common_counts(const uint2 *__restrict__
         for (uint32_t i = lane; i < ms.y; i += 32)
             cnt += sorted_contains(col + ml.x, ml.y, __ldg(col + ms.x + i)) ? 1 : 0;
         for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (lane == 0) nbr4[e] = make_int4(v, cnt, (int)mv.x, (int)mv.y);
+        if (lane == 0) {
+            int y = cnt;
+            if (pack) {
+                uint32_t lo2 = 0, hi2 = mv.y;                   // lower bound of u in the sorted row of v
+                while (lo2 < hi2) {
+                    const uint32_t mid = (lo2 + hi2) >> 1;
+                    if (__ldg(col + mv.x + mid) < u) lo2 = mid + 1; else hi2 = mid;
+                }
+                y = (int)((uint32_t)cnt | (lo2 << 16));
+            }
+            nbr4[e] = make_int4(v, y, (int)mv.x, (int)mv.y);
+        }
     }
 }
 
@@ -174,7 +188,7 @@ __device__ __forceinline__ float unit24(uint32_t r) { return (float)(r >> 8) * (
 // Returns x's nbr4 entry inside N(cur).
 __device__ __noinline__ int4 common_by_rejection(const CnParams &P, uint2 m, uint2 mprev, bool cur_short, int32_t owner_t,
                                                  uint64_t wid, int32_t pos, uint32_t rk, unsigned long long *acc,
-                                                 unsigned long long *prop) {
+                                                 unsigned long long *prop, uint32_t *kout) {
     const uint32_t s_off = cur_short ? m.x : mprev.x, s_deg = cur_short ? m.y : mprev.y;
     const uint32_t t_off = cur_short ? mprev.x : m.x, t_deg = cur_short ? mprev.y : m.y;
     const uint32_t tsec = (uint32_t)max(1, (32 - __clz(t_deg)) - 2);
@@ -197,6 +211,7 @@ __device__ __noinline__ int4 common_by_rejection(const CnParams &P, uint2 m, uin
                     if (acc) (*acc) += tsec;
                 }
                 if (acc) (*acc)++;
+                *kout = idx;
                 return __ldg(P.nbr4 + m.x + idx);
             }
         } else {
@@ -215,6 +230,7 @@ __device__ __noinline__ int4 common_by_rejection(const CnParams &P, uint2 m, uin
                 if (acc) (*acc) += tsec;
                 if (lo2 < t_deg && __ldg(P.col + t_off + lo2) == x) {
                     if (acc) (*acc)++;
+                    *kout = cur_short ? k : lo2;
                     return __ldg(P.nbr4 + m.x + (cur_short ? k : lo2));      // x's entry inside N(cur)
                 }
             }
@@ -232,7 +248,8 @@ __device__ __noinline__ int4 common_by_rejection(const CnParams &P, uint2 m, uin
 // "u < min(a, b)" accepts without looking; else one Bloom word decides "not common" and only positives are
 // verified by the search over N(prev).  Returns x's nbr4 entry, or .x == -2 for the return step.
 __device__ __noinline__ int4 step_by_rejection(const CnParams &P, uint2 m, uint2 mprev, int32_t prev, int32_t c, uint64_t wid,
-                                               int32_t pos, uint4 rnd, unsigned long long *acc, unsigned long long *prop) {
+                                               int32_t pos, uint4 rnd, unsigned long long *acc, unsigned long long *prop,
+                                               uint32_t *kout) {
     const uint32_t d = m.y;
     const float Wp = P.a * ((float)(d - 1) - (float)c) + P.b * (float)c;
     if (d == 1 || unit24(rnd.x) * (P.r + Wp) < P.r) return make_int4(-2, 0, 0, 0);
@@ -240,8 +257,10 @@ __device__ __noinline__ int4 step_by_rejection(const CnParams &P, uint2 m, uint2
     const uint32_t ssec = (uint32_t)max(1, (32 - __clz(mprev.y)) - 2);
     uint32_t rk = rnd.y, ra = rnd.z, att = 0;
     for (;;) {
-        const int4 e = __ldg(P.nbr4 + m.x + scale_u32(rk, d));
+        const uint32_t k = scale_u32(rk, d);
+        const int4 e = __ldg(P.nbr4 + m.x + k);
         if (acc) (*acc)++;
+        *kout = k;
         if (e.x != prev) {
             const float u = unit24(ra) * hi;
             bool take = u < lo;
@@ -274,7 +293,12 @@ __device__ __noinline__ int4 step_by_rejection(const CnParams &P, uint2 m, uint2
 // COUNT = byte-model mode: same walks, no corpus stores, per-step algorithmic bytes summed.
 // HUB = the graph has rows longer than 2048 entries: common-neighbour draws of long rows go through
 // common_by_rejection (compiled out otherwise: the call costs the common path 8 % on flat-degree graphs).
-template <bool VEC8, bool COUNT, int MINB, bool HUB>
+// RIDX = nbr4[].y carries the reverse index (k_common_counts, pack): the walker tracks where prev sits in N(cur)
+// (rprev) and where cur sits in N(prev) (kcur) and draws from N(cur) \ {prev} directly.  Instantiated only where the
+// rejection of prev would otherwise loop (p thins the return edge below min(1, 1/q), or q < 1 excludes it): there a
+// retry of ONE lane (probability ~ 1/deg) made its whole warp wait for a second memory latency in ~45 % of the
+// warp-steps (ncu source page, R-MAT-22 p=4 q=0.5).
+template <bool VEC8, bool COUNT, int MINB, bool HUB, bool RIDX>
 __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
     const int lane = threadIdx.x & 31;
     const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
@@ -287,6 +311,7 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
     uint2 mprev = make_uint2(0, 0);
     uint2 m = valid ? ld_u2_policy(P.meta + cur, pol_keep) : make_uint2(0, 0);   // the only meta[] load of the walk
     int32_t c = 0;                       // |N(prev) & N(cur)|
+    uint32_t rprev = 0, kcur = 0;        // RIDX: index of prev inside N(cur), index of cur inside N(prev)
     bool alive = valid;
     int32_t len = 1;
     int32_t buf[8];
@@ -304,7 +329,10 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
             if (pos == 0) continue;                   // the start node
             if (pos >= P.L) break;                    // uniform across the grid
             int32_t nxt = -1, cn = 0;
+            uint32_t nk = 0, nr = 0;                     // RIDX: index of nxt inside N(cur), index of cur inside N(nxt)
             uint2 mn = make_uint2(0, 0);                 // row descriptor of nxt
+            auto CNT = [](int y) { return RIDX ? (int32_t)((uint32_t)y & 0xFFFFu) : y; };
+            auto RIX = [](int y) { return (uint32_t)y >> 16; };
             bool want_isect = false;
             uint32_t jsel = 0;
             if (alive) {
@@ -315,14 +343,15 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                     uint4 rnd = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, 0u), P.key);
                     if (COUNT) { st_steps++; if (prev < 0) st_acc++; }
                     if (prev < 0) {                                   // first step: alias_nodes law = uniform
-                        int4 e = ld_i4_policy(P.nbr4 + m.x + scale_u32(rnd.y, d), pol_stream);
-                        nxt = e.x; cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w);
+                        nk = scale_u32(rnd.y, d);
+                        int4 e = ld_i4_policy(P.nbr4 + m.x + nk, pol_stream);
+                        nxt = e.x; cn = CNT(e.y); nr = RIX(e.y); mn = make_uint2((uint32_t)e.z, (uint32_t)e.w);
                     } else if (HUB && P.bloom != nullptr && P.b > P.a && min(d, mprev.y) > 256u) {
                         unsigned long long racc = 0, rprop = 0;
                         const int4 e = step_by_rejection(P, m, mprev, prev, c, wid, pos, rnd, COUNT ? &racc : nullptr,
-                                                         COUNT ? &rprop : nullptr);
-                        if (e.x == -2) { nxt = prev; cn = c; mn = mprev; }
-                        else { nxt = e.x; cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w); }
+                                                         COUNT ? &rprop : nullptr, &nk);
+                        if (e.x == -2) { nxt = prev; cn = c; mn = mprev; nk = rprev; nr = kcur; }
+                        else { nxt = e.x; cn = CNT(e.y); nr = RIX(e.y); mn = make_uint2((uint32_t)e.z, (uint32_t)e.w); }
                         if (COUNT) { st_acc += racc; st_prop += rprop; }
                     } else {
                         const float dm1 = (float)(d - 1);
@@ -338,22 +367,31 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                         else if (haveC && (u < MR + MA + MC || !haveO)) comp = 2;
                         else if (haveO) comp = 3;
                         else comp = 1;
+                        // RIDX: component A's share of prev (mass r0 of MA) is a return step decided up front; everything
+                        // else draws from the d-1 entries that are not prev (index shifted past rprev)
+                        if (RIDX && comp == 1 && unit24(rnd.z) * MA < P.r0) comp = 0;
                         if (COUNT && comp != 0) st_acc++;                  // one random {nbr,cnt,off,deg} access
-                        // A and O both open with the proposal N(cur)[rnd.y]: ONE load instruction for the lanes of either
+                        // A and O both open with one proposal from N(cur): ONE load instruction for the lanes of either
                         // component.  Issued inside the two branches, a warp whose lanes split between A and O (q < 1:
                         // about half and half) waited for two memory latencies per step instead of one.
                         int4 e = make_int4(0, 0, 0, 0);
-                        if (comp == 1 || comp == 3) e = ld_i4_policy(P.nbr4 + m.x + scale_u32(rnd.y, d), pol_stream);
+                        if (RIDX) { nk = scale_u32(rnd.y, d - 1); nk += (nk >= rprev) ? 1u : 0u; }
+                        else nk = scale_u32(rnd.y, d);
+                        if (comp == 1 || comp == 3) e = ld_i4_policy(P.nbr4 + m.x + nk, pol_stream);
                         if (comp == 0) {                              // R: return
-                            nxt = prev; cn = c; mn = mprev;
+                            nxt = prev; cn = c; mn = mprev; nk = rprev; nr = kcur;
                         } else if (comp == 1) {                       // A: uniform over N(cur), prev thinned
-                            uint32_t ra = rnd.z, att = 0;
-                            for (;;) {
-                                if (e.x != prev || unit24(ra) * P.lo < P.r0) { nxt = e.x; cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w); break; }
-                                uint4 r2 = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, ++att), P.key);
-                                ra = r2.y;
-                                e = ld_i4_policy(P.nbr4 + m.x + scale_u32(r2.x, d), pol_stream);
-                                if (COUNT) { st_acc++; st_prop++; }
+                            if (RIDX) {
+                                nxt = e.x; cn = CNT(e.y); nr = RIX(e.y); mn = make_uint2((uint32_t)e.z, (uint32_t)e.w);
+                            } else {
+                                uint32_t ra = rnd.z, att = 0;
+                                for (;;) {
+                                    if (e.x != prev || unit24(ra) * P.lo < P.r0) { nxt = e.x; cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w); break; }
+                                    uint4 r2 = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, ++att), P.key);
+                                    ra = r2.y;
+                                    e = ld_i4_policy(P.nbr4 + m.x + scale_u32(r2.x, d), pol_stream);
+                                    if (COUNT) { st_acc++; st_prop++; }
+                                }
                             }
                         } else if (comp == 2) {                       // C: uniform over N(cur) & N(prev)
                             const bool cur_short = d <= mprev.y;
@@ -364,8 +402,8 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                                 // long rows that share many neighbours (hub pairs of heavy-tailed graphs)
                                 unsigned long long racc = 0, rprop = 0;
                                 const int4 e = common_by_rejection(P, m, mprev, cur_short, cur_short ? prev : cur, wid, pos, rnd.y,
-                                                                   COUNT ? &racc : nullptr, COUNT ? &rprop : nullptr);
-                                nxt = e.x; cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w);
+                                                                   COUNT ? &racc : nullptr, COUNT ? &rprop : nullptr, &nk);
+                                nxt = e.x; cn = CNT(e.y); nr = RIX(e.y); mn = make_uint2((uint32_t)e.z, (uint32_t)e.w);
                                 if (COUNT) { st_acc += racc; st_prop += rprop; }
                             } else {
                                 want_isect = true;
@@ -379,7 +417,7 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                             uint32_t att = 0;
                             const uint32_t ssec = (uint32_t)max(1, (32 - __clz(mprev.y)) - 2);   // S(d_prev) random sectors per search
                             for (;;) {
-                                bool take = e.x != prev;
+                                bool take = RIDX || e.x != prev;     // RIDX: prev was never proposed
                                 if (take && c != 0) {                // c == 0: N(cur) & N(prev) is empty, nothing to exclude, no test
                                     // "not adjacent to prev": one 8-byte Bloom word says so for ~99 % of the
                                     // non-neighbours; only positives pay for the exact search over N(prev)
@@ -397,9 +435,11 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                                         take = !row_contains(P.col, HUB ? P.rowhash : nullptr, mprev, e.x);
                                     }
                                 }
-                                if (take) { nxt = e.x; cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w); break; }
+                                if (take) { nxt = e.x; cn = CNT(e.y); nr = RIX(e.y); mn = make_uint2((uint32_t)e.z, (uint32_t)e.w); break; }
                                 uint4 r2 = Philox::gen(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)pos, ++att), P.key);
-                                e = ld_i4_policy(P.nbr4 + m.x + scale_u32(r2.x, d), pol_stream);
+                                if (RIDX) { nk = scale_u32(r2.x, d - 1); nk += (nk >= rprev) ? 1u : 0u; }
+                                else nk = scale_u32(r2.x, d);
+                                e = ld_i4_policy(P.nbr4 + m.x + nk, pol_stream);
                                 if (COUNT) { st_acc++; st_prop++; }
                             }
                         }
@@ -445,7 +485,7 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                 }
                 if (lane == src) {
                     if (xsel < 0) {                   // counts and rows disagree: cannot happen; stay exact-ish
-                        nxt = prev; cn = c; mn = mprev;
+                        nxt = prev; cn = c; mn = mprev; nk = rprev; nr = kcur;
                     } else {
                         uint32_t idx = isel;          // index of xsel inside N(cur)
                         if (!scan_cur) {
@@ -458,7 +498,7 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                         }
                         nxt = xsel;
                         int4 e = __ldg(P.nbr4 + c_off + idx);
-                        cn = e.y; mn = make_uint2((uint32_t)e.z, (uint32_t)e.w);
+                        cn = CNT(e.y); nk = idx; nr = RIX(e.y); mn = make_uint2((uint32_t)e.z, (uint32_t)e.w);
                     }
                 }
             }
@@ -466,6 +506,7 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                 buf[s] = nxt;
                 if (!VEC8 && !COUNT) o[pos] = nxt;
                 prev = cur; mprev = m; cur = nxt; c = cn; m = mn;
+                if (RIDX) { kcur = nk; rprev = nr; }
                 len = pos + 1;
             }
         }
@@ -517,7 +558,9 @@ int ensure_common_counts(gw_graph *g, cudaStream_t st, bool need_counts) {
     if (g->nnz > 0) {
         int sms = 148;
         device_info(&sms, nullptr);
-        k_common_counts<<<sms * 16, 256, 0, st>>>(g->d_meta, g->d_col, g->d_row_ptr, g->n, g->nnz, g->d_nbr4, flag.p);
+        const char *np = getenv("GW_CN_RIDX");                   // experiment knob: "0" keeps plain counts (rejection of prev)
+        g->nbr4_packed = (g->max_degree < 65536 && !(np && !strcmp(np, "0"))) ? 1 : 0;
+        k_common_counts<<<sms * 16, 256, 0, st>>>(g->d_meta, g->d_col, g->d_row_ptr, g->n, g->nnz, g->d_nbr4, flag.p, g->nbr4_packed);
         GW_LAUNCHED();
     }
     GW_CUDA(cudaEventRecord(e1, st));
@@ -566,6 +609,9 @@ static int ensure_rowhash(gw_graph *g, cudaStream_t st) {
     GW_CUDA(cudaStreamSynchronize(st));
     return GW_OK;
 }
+// A packed nbr4 MUST be read by a RIDX instantiation (the count shares .y with the reverse index); it pays where the
+// return edge is thinned (r0 < lo) or excluded (q < 1), and costs nothing elsewhere (same loads, two more registers).
+static bool use_ridx(const gw_graph *g, const CnParams &) { return g->nbr4_packed != 0; }
 static bool is_hub_graph(const gw_graph *g) { return g->max_degree > 2048 || getenv("GW_CN_HUB") != nullptr; }   // env: test knob for small graphs
 
 int launch_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_starts, int64_t n_starts, uint64_t seed,
@@ -585,14 +631,21 @@ int launch_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_
     const char *occ = getenv("GW_CN_MINB");     // experiment knob: resident blocks per SM the kernel is compiled for
     int minb = occ ? atoi(occ) : 5;   // 5 is best for every p, q since O steps of contexts without common neighbours skip the adjacency test (R-MAT-22 p=4 q=0.5: 39.7 / 38.6 / 36.5 G steps/s at 5 / 6 / 8); q >= 1 loses 7 % at 6
     const bool hub = is_hub_graph(g);
-    if (!vec) { if (hub) k_walk_cn<false, false, 5, true><<<grid, 256, 0, st>>>(P); else k_walk_cn<false, false, 5, false><<<grid, 256, 0, st>>>(P); }
-    else if (hub) {
-        if (minb >= 6) k_walk_cn<true, false, 6, true><<<grid, 256, 0, st>>>(P);
-        else k_walk_cn<true, false, 5, true><<<grid, 256, 0, st>>>(P);
+    const bool ridx = use_ridx(g, P);
+    if (ridx) {                                   // packed nbr4[].y: every reader of this graph's counts must unpack
+        if (!vec) { if (hub) k_walk_cn<false, false, 5, true, true><<<grid, 256, 0, st>>>(P); else k_walk_cn<false, false, 5, false, true><<<grid, 256, 0, st>>>(P); }
+        else if (hub) k_walk_cn<true, false, 5, true, true><<<grid, 256, 0, st>>>(P);
+        else if (minb >= 6) k_walk_cn<true, false, 6, false, true><<<grid, 256, 0, st>>>(P);
+        else k_walk_cn<true, false, 5, false, true><<<grid, 256, 0, st>>>(P);
     }
-    else if (minb >= 8) k_walk_cn<true, false, 8, false><<<grid, 256, 0, st>>>(P);
-    else if (minb >= 6) k_walk_cn<true, false, 6, false><<<grid, 256, 0, st>>>(P);
-    else k_walk_cn<true, false, 5, false><<<grid, 256, 0, st>>>(P);
+    else if (!vec) { if (hub) k_walk_cn<false, false, 5, true, false><<<grid, 256, 0, st>>>(P); else k_walk_cn<false, false, 5, false, false><<<grid, 256, 0, st>>>(P); }
+    else if (hub) {
+        if (minb >= 6) k_walk_cn<true, false, 6, true, false><<<grid, 256, 0, st>>>(P);
+        else k_walk_cn<true, false, 5, true, false><<<grid, 256, 0, st>>>(P);
+    }
+    else if (minb >= 8) k_walk_cn<true, false, 8, false, false><<<grid, 256, 0, st>>>(P);
+    else if (minb >= 6) k_walk_cn<true, false, 6, false, false><<<grid, 256, 0, st>>>(P);
+    else k_walk_cn<true, false, 5, false, false><<<grid, 256, 0, st>>>(P);
     GW_LAUNCHED();
     return GW_OK;
 }
@@ -611,8 +664,12 @@ int count_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_s
     P.walk_id_base = walk_id_base; P.out = nullptr; P.lens = nullptr;
     P.stats = d_stats;
     unsigned grid = (unsigned)((n_starts + 255) / 256);
-    if (is_hub_graph(g)) k_walk_cn<false, true, 5, true><<<grid, 256, 0, st>>>(P);
-    else k_walk_cn<false, true, 5, false><<<grid, 256, 0, st>>>(P);
+    if (use_ridx(g, P)) {
+        if (is_hub_graph(g)) k_walk_cn<false, true, 5, true, true><<<grid, 256, 0, st>>>(P);
+        else k_walk_cn<false, true, 5, false, true><<<grid, 256, 0, st>>>(P);
+    }
+    else if (is_hub_graph(g)) k_walk_cn<false, true, 5, true, false><<<grid, 256, 0, st>>>(P);
+    else k_walk_cn<false, true, 5, false, false><<<grid, 256, 0, st>>>(P);
     GW_LAUNCHED();
     return GW_OK;
 }
