@@ -15,6 +15,8 @@
 // same 16-byte entry as the neighbour id AND the neighbour's row descriptor ({nbr, cnt, offset,
 // degree} quads, `nbr4`), so reading the next vertex also reads the next step's count and the next
 // row's bounds: ONE random 32-byte sector per step in component A, and no dependent meta[] load.
+// The upper half of the count word holds the REVERSE index of the edge (where u sits in N(v)), so the
+// walker always knows the position of prev inside the row it samples and never proposes it (RIDX).
 //
 // This replaces preprocess_transition_probs' sum(deg^2) alias_edges by a sum-over-edges
 // intersection pass (k_common_counts), the only preprocessing that fits HBM at scale.
