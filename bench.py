@@ -415,10 +415,12 @@ def measure(args, rank, world, local):
             kname = "k_walk_free<false,false>"
         roof = {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "traffic": ncu_traffic(kname) if (args.scale == 22 and args.p == 0.25 and args.q == 4.0 and args.rmat_abc == "0.45,0.15,0.15") else None,
-                "kernel": kname, "peak_source": peak_src,
+                "kernel": (("k_walk_cn<VEC8=1,COUNT=0,MINB=5,HUB=%d,RIDX=%d>" % (int(g.max_degree > 2048), int(g.max_degree < 65536 and os.environ.get("GW_CN_RIDX") != "0")))
+                           if mixture else kname), "peak_source": peak_src,
                 "bytes_per_unit": alg_bytes / steps_exec, "units_per_launch": steps_exec, "launch_ms": kernel_ms,
-                "model": ("mixture walker, atom model: 64 B per random access (one {nbr,cnt,offset,degree} entry per "
-                          "non-return step; one Bloom word and, on a positive, S(d_prev) more per adjacency test) + streamed "
+                "model": ("mixture walker, atom model: 64 B per random access (one {nbr,cnt|reverse index,offset,degree} entry per "
+                          "non-return step; one Bloom word and, on a positive, S(d_prev) more per adjacency test of a context "
+                          "that has common neighbours) + streamed "
                           "rows of intersections + 4 B store per step" if mixture else "SURVEY 8(d): 68 + 32*S(d_prev) per step"),
                 "sector_model": {"bytes_per_unit": sector_bytes / steps_exec,
                                  "frac": sector_bytes / (kernel_ms * 1e-3) / 1e9 / peak,
