@@ -64,6 +64,16 @@ def test_rmat22_node2vec_full_size_properties():
     wq, lq = h.walks(4.0, 0.5, 80, starts[sub], seed=5)
     assert (lq == 80).all() and _steps_follow_edges(rp, col, wq)
     assert (wq[:, 2:] == wq[:, :-2]).mean() < 0.02                              # p = 4 avoids the return edge
+    # ... at exactly the law's rate: P(return) = (1/p) / (1/p + c + (deg(cur) - 1 - c)/q), the component the reverse
+    # index serves (prev is never proposed; its share of the mass is decided before the load)
+    ws = wq[::10]
+    prev, cur, nxt = ws[:, :-2].ravel(), ws[:, 1:-1].ravel(), ws[:, 2:].ravel()
+    pred = np.empty(len(prev))
+    for i, (u, v) in enumerate(zip(prev.tolist(), cur.tolist())):
+        cnt = len(np.intersect1d(col[rp[u]:rp[u + 1]], col[rp[v]:rp[v + 1]], assume_unique=True))
+        pred[i] = 0.25 / (0.25 + cnt + (deg[v] - 1 - cnt) * 2.0)
+    obs = (nxt == prev).mean()
+    assert abs(obs - pred.mean()) < 5 * np.sqrt(pred.mean() / len(pred)) + 2e-4, (obs, pred.mean())
     # first-order stationary law: visits ~ degree
     w1, _ = h.walks(1.0, 1.0, 80, starts, seed=6)
     visits = np.bincount(w1[:, 40:].ravel(), minlength=h.n).astype(np.float64)
