@@ -536,3 +536,28 @@ def test_path_mass_estimators_replay_is_bit_exact(g333, o333):
     assert not free[(want == 0) & (cand < sr.MyConfiguration.MIN)].any()          # only candidate pairs are ever scored
     nz = (want != 0) & (free != 0)
     assert nz.sum() >= 0.9 * (want != 0).sum() and np.abs(free[nz] / want[nz] - 1).mean() < 0.25   # values differ by sampling only
+
+
+def test_path_probability_probe_of_the_reference(g333, o333):
+    """simrank/random_test/RandomWalkTest.testPathPro (:54-85), the reference's own hand-run probe, as an assertion on
+    the device walker: the sampled frequency of a given path equals prod 1/deg(path[i]) (getPathPro :87-93), forward
+    and backward, and the single-walk importance identity the estimator rests on (:62, :73) holds:
+    P_forward(path) * deg(mid) / deg(end) == P_double(path) = prod_i 1 / (deg(path[i]) * deg(path[len-1-i]))."""
+    deg = np.diff(o333["row_ptr"])
+    rp, col = o333["row_ptr"], o333["col"]
+    nb = lambda v: col[rp[v]:rp[v + 1]]
+    path = [5, 123, 10]                                          # degrees 52, 12, 30: P = 6.4e-3 forward, 1.1e-2 backward
+    assert 123 in nb(5) and 10 in nb(123)
+    for p in (path, path[::-1]):
+        real = np.prod([1.0 / deg[v] for v in p[:-1]])           # multigraph rows: every neighbour is listed twice (2/deg per distinct one)
+        mult = np.prod([np.count_nonzero(nb(p[i]) == p[i + 1]) for i in range(len(p) - 1)])
+        hits, total = 0, 0
+        for seed in range(8):
+            w = g333.handle.double_walk_paths([p[0]], 40000, len(p) - 1, seed=100 + seed)[0]
+            hits += int(((w[:, 0] == p[1]) & (w[:, 1] == p[2])).sum())
+            total += len(w)
+        want = real * mult
+        assert abs(hits / total - want) < 5 * np.sqrt(want / total), (p, hits / total, want)
+    fwd = np.prod([1.0 / deg[v] for v in path[:-1]])
+    dbl = np.prod([1.0 / (deg[path[i]] * deg[path[len(path) - 1 - i]]) for i in range(len(path) // 2)])
+    assert abs(fwd * deg[path[len(path) // 2]] / deg[path[-1]] - dbl) < 1e-15
