@@ -195,3 +195,57 @@ def test_double_random_walk_converges_to_truncated_exact(g333):
         est = lib.or_double_walk_sim(pp.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), 400, 3, 0.6, v, w)
         errs.append(est - exact[v, w])
     assert np.abs(errs).max() < 6e-3, errs
+
+
+def test_path_mass_tree_hand_traced_known_answer():
+    """TopSim_doubleSample.sample + computePath (TopSim_doubleSample.java:66-178) traced by hand on the path graph
+    0-1-2-3 from vertex 1 with SAMPLE = 8 (every weight >= degree: pure enumeration, no random draw):
+      level 1: queue [0:4, 2:4]                          -> mass[0][1] = 4, mass[2][1] = 4
+      level 2: 0 -> [1:4]; 2 -> [1:2, 3:2]               -> target 1 is the source (skipped), mass[3][2] = 2
+      level 3: 1(w4) -> [0:2, 2:2]; 1(w2) -> [0:1, 2:1]; 3(w2) -> [2:2]
+               queue order [0:2, 2:2, 0:1, 2:1, 2:2], the LAST path on a target wins (an overwrite, :175)
+                                                          -> mass[0][3] = 1, mass[2][3] = 2
+    and getSim (:189-199) of two such trees is the level-wise product sum."""
+    g = S.build_multigraph(np.array([0, 1, 2]), np.array([1, 2, 3]), 4)
+    st0 = S.java_seed(1)
+    m, st = S.mass_tree(g, 1, 8.0, 3, st0)
+    assert st == st0                                             # no draw consumed
+    want = -np.ones((4, 4))
+    want[0, 1] = 4; want[2, 1] = 4; want[3, 2] = 2; want[0, 3] = 1; want[2, 3] = 2
+    assert np.array_equal(m, want)
+    # from vertex 2 (rows keep file order: N(2) = [1, 3]): level 1 [1:4, 3:4]; level 2 1 -> [0:2, 2:2], 3 -> [2:4]
+    # (target 2 is the source) -> mass[0][2] = 2; level 3 0 -> [1:2], 2(w2) -> [1:1, 3:1], 2(w4) -> [1:2, 3:2]
+    # -> queue [1:2, 1:1, 3:1, 1:2, 3:2]: mass[1][3] = 2, mass[3][3] = 2.  NOT the mirror image of the tree from 1:
+    # the queue order follows the adjacency order, and the last writer wins.
+    m2, _ = S.mass_tree(g, 2, 8.0, 3, st0)
+    want2 = -np.ones((4, 4))
+    want2[1, 1] = 4; want2[3, 1] = 4; want2[0, 2] = 2; want2[1, 3] = 2; want2[3, 3] = 2
+    assert np.array_equal(m2, want2)
+    # getSim(1, 2): only targets reached by BOTH trees at the same level count: (0, level 3): 1 * 2, (3, 3)... by hand:
+    # tree 1: {0: l1, 2: l1, 3: l2, 0: l3, 2: l3}; tree 2: {3: l1, 1: l1, 0: l2, 3: l3, 1: l3} -> no common (target, level)
+    assert S.mass_sim(m, m2, 0.6) == 0.0
+    m0, _ = S.mass_tree(g, 3, 8.0, 3, st0)                       # from the pendant vertex: 3 -> [2:8] -> [1:4, 3:4] -> 1 -> [0:2, 2:2], 3 -> [2:4]
+    want0 = -np.ones((4, 4)); want0[2, 1] = 8; want0[1, 2] = 4; want0[0, 3] = 2; want0[2, 3] = 4
+    assert np.array_equal(m0, want0)
+    # getSim(1, 3): common (target, level) pairs: (2, 1): 4 * 8, (0, 3): 1 * 2, (2, 3): 2 * 4
+    assert S.mass_sim(m, m0, 0.6) == 0.6 * 4 * 8 + 0.6 ** 3 * 1 * 2 + 0.6 ** 3 * 2 * 4
+    # the MIN-filtered candidate queue of TopSim_Dev.compute (:72-83): zeros are never offered
+    ids, vals = S.fixedmaxpq_topk_min(np.array([0.0, 0.5, 1e-12, 0.25, 0.5]), 2, S.MIN)
+    assert sorted(ids.tolist()) == [1, 4] and vals.tolist() == [0.5, 0.5]
+    ids, _ = S.fixedmaxpq_topk_min(np.array([0.0, 0.0, 1e-12]), 5, S.MIN)
+    assert len(ids) == 0
+    assert S.topsim_dev_sample_count(10000, 3, 20, 1) == 634 and S.topsim_dev_sample_count(10000, 3, 20, 3) == 0
+
+
+def test_double_random_walk_hand_traced_known_answer():
+    """DoubleRandomWalk.getSim (:77-91) on hand-made path sets: SAMPLE = 2, STEP = 2, C = 0.6.
+    v: paths [5, 7], [6, 8]; w: paths [5, 9], [4, 7].  Pairs (i, j): (0,0) meet at position 0 -> C; (0,1): 5!=4, 7==7
+    -> C^2; (1,0): 6!=5, 8!=9 -> nothing; (1,1): nothing.  Sum = C + C^2, divided by SAMPLE^2 = 4.  A dead end (-1)
+    stops the comparison of that pair."""
+    paths = np.zeros((2, 2, 2), dtype=np.int32)
+    paths[0] = [[5, 7], [6, 8]]
+    paths[1] = [[5, 9], [4, 7]]
+    sim = S.double_walk_matrix(paths, 0.6)
+    assert sim[0, 1] == sim[1, 0] == (0.6 + 0.6 ** 2) / 4 and sim[0, 0] == sim[1, 1] == 0
+    paths[1, 1] = [-1, 0]                                        # w's second walk died at its first step
+    assert S.double_walk_matrix(paths, 0.6)[0, 1] == 0.6 / 4
