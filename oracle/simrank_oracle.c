@@ -24,6 +24,11 @@
  * result is their expectation, and (ii) the independent restatement of the formula in
  * simrank/random_test/RandomWalkTest.java:177-219.
  *
+ * FixedCacheMap, the _M estimators, DoubleRandomWalk, TopSim_doubleSample and TopSim_Dev: UNPINNED at the RNG
+ * boundary for the same reason; anchored on known answers traced by hand from the Java source
+ * (tests/test_oracle_simrank.py: FixedCacheMap.main()'s put sequence, path-mass trees with the last-writer-wins
+ * rule of computePath, getSim products) and on the dense classes they share their walks with.
+ *
  * The adjacency arrives as CSR (row_ptr int64[V+1], col int32[nnz]) built by the Python
  * side in FILE ORDER per vertex (Graph.addEdge appends, duplicates kept).
  */
