@@ -140,24 +140,24 @@ __global__ void __launch_bounds__(256) k_common_counts(const uint2 *__restrict__
         }
         const int32_t u = (int32_t)lo, v = __ldg(col + e);
         if (u == v && lane == 0) atomicExch(self_loops, 1);
-        const uint2 mv = __ldg(meta + v);
-        uint2 ms = __ldg(meta + u), ml = mv;
+        if (u > v) continue;                         // |N(u) & N(v)| is symmetric: the warp of (v -> u) writes both entries
+        const uint2 mv = __ldg(meta + v), mu = __ldg(meta + u);
+        uint2 ms = mu, ml = mv;
         if (ms.y > ml.y) { uint2 t = ms; ms = ml; ml = t; }
         int cnt = 0;
         for (uint32_t i = lane; i < ms.y; i += 32)
             cnt += sorted_contains(col + ml.x, ml.y, __ldg(col + ms.x + i)) ? 1 : 0;
         for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if (lane == 0) {
-            int y = cnt;
-            if (pack) {
-                uint32_t lo2 = 0, hi2 = mv.y;                   // lower bound of u in the sorted row of v
-                while (lo2 < hi2) {
-                    const uint32_t mid = (lo2 + hi2) >> 1;
-                    if (__ldg(col + mv.x + mid) < u) lo2 = mid + 1; else hi2 = mid;
-                }
-                y = (int)((uint32_t)cnt | (lo2 << 16));
+            uint32_t lo2 = 0, hi2 = mv.y;                       // position of u in the sorted row of v = the mirrored entry
+            while (lo2 < hi2) {
+                const uint32_t mid = (lo2 + hi2) >> 1;
+                if (__ldg(col + mv.x + mid) < u) lo2 = mid + 1; else hi2 = mid;
             }
-            nbr4[e] = make_int4(v, y, (int)mv.x, (int)mv.y);
+            const uint32_t k = (uint32_t)(e - (int64_t)mu.x);  // position of v in the row of u
+            nbr4[e] = make_int4(v, (int)((uint32_t)cnt | (pack ? lo2 << 16 : 0u)), (int)mv.x, (int)mv.y);
+            if (u != v && lo2 < mv.y)
+                nbr4[(size_t)mv.x + lo2] = make_int4(u, (int)((uint32_t)cnt | (pack ? k << 16 : 0u)), (int)mu.x, (int)mu.y);
         }
     }
 }
