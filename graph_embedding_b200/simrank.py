@@ -551,18 +551,23 @@ def java_format(x, digits):
 
 
 def _row_topk_exact(row, topk):
-    """FixedMaxPQ fed with every column of a dense row in ascending id (Print.java:31-37).  Zero
-    offers after the heap is full can never replace anything (scores are >= 0), so only the
-    first `topk` columns and the positive ones need to be offered."""
+    """FixedMaxPQ fed with every column of a dense row in ascending id (Print.java:31-37).  Once the heap is full an
+    offer changes it only when it is strictly greater than the current minimum (FixedMaxPQ.java:33-37), so the offers
+    that would be refused are skipped in bulk: the heap goes through exactly the states the reference's does."""
     pq = FixedMaxPQ(topk)
+    row = np.asarray(row)
     n = len(row)
     head = min(topk, n)
     for i in range(head):
         pq.offer(i, float(row[i]))
-    if n > head:
-        rest = np.nonzero(row[head:] > 0)[0] + head
-        for i in rest.tolist():
-            pq.offer(i, float(row[i]))
+    i = head
+    while i < n and topk > 0:
+        ahead = np.nonzero(row[i:] > pq.q[0][1])[0]
+        if len(ahead) == 0:
+            break
+        j = i + int(ahead[0])
+        pq.offer(j, float(row[j]))
+        i = j + 1
     return pq.sortedElement()
 
 
