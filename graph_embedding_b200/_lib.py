@@ -56,7 +56,10 @@ SIGNATURES = {
                                          ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint64, c_i32p, c_i32p]),
     "gw_node2vec_walks_dev": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_int32, c_vp,
                                              ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint64, c_vp, c_vp, c_vp]),
+    "gw_graph_last_handoff": (ctypes.c_int, [c_vp, c_i32p, c_i32p]),
+    "gw_corpus_unpack24": (ctypes.c_int, [c_vp, c_i32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, c_i32p]),
     "gw_graph_prepare_walks": (ctypes.c_int, [c_vp, c_f64p]),
+    "gw_graph_common_counts": (ctypes.c_int, [c_vp, c_i32p, c_i32p]),
     "gw_node2vec_walks_replay": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i64p, ctypes.c_int64, c_f64p,
                                                 ctypes.c_int64, c_i64p, c_i32p, c_i32p]),
     "gw_node2vec_walk_traffic_dev": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_int32, c_vp,
@@ -93,6 +96,7 @@ SIGNATURES = {
     "gw_comm_info": (ctypes.c_int, [c_vp, c_i32p, c_i32p, c_i32p]),
     "gw_comm_free": (ctypes.c_int, [c_vp]),
     "gw_shard_range": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, c_i64p, c_i64p]),
+    "gw_comm_last_times": (ctypes.c_int, [c_vp, c_f64p, c_f64p]),
     "gw_node2vec_walks_sharded": (ctypes.c_int, [c_vp, c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_int32, c_i64p,
                                                  ctypes.c_int64, ctypes.c_uint64, ctypes.c_int32, c_i32p, c_i32p]),
     "gw_simrank_topk_sharded": (ctypes.c_int, [c_vp, c_vp, c_i64p, ctypes.c_int64, ctypes.c_double, ctypes.c_int32,
@@ -100,6 +104,8 @@ SIGNATURES = {
                                                c_i32p, c_f64p]),
     "gw_simrank_last_steps": (ctypes.c_int, [c_vp, c_i64p]),
     "gw_simrank_last_slow_queries": (ctypes.c_int, [c_vp, c_i64p]),
+    "gw_simrank_last_error": (ctypes.c_int, [c_vp, c_i32p]),
+    "gw_simrank_check_args": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
     "gw_simrank_exact": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_int32, c_i64p, ctypes.c_int64, c_f64p]),
 }
 
@@ -271,10 +277,22 @@ class GraphHandle:
                                            int(n_starts), int(seed), int(walk_id_base), c_vp(d_out),
                                            c_vp(d_lens) if d_lens else None, c_vp(stream) if stream else None))
 
+    def last_handoff(self):
+        m, t = ctypes.c_int32(), ctypes.c_int32()
+        check(load().gw_graph_last_handoff(self.h, ctypes.byref(m), ctypes.byref(t)))
+        return {"mode": {0: "none", 1: "direct", 2: "ring", 3: "packed"}[m.value], "copy_threads": t.value}
+
     def prepare_walks(self):
         ms = ctypes.c_double()
         check(load().gw_graph_prepare_walks(self.h, ctypes.byref(ms)))
         return ms.value
+
+    def common_counts(self):
+        """(counts[nnz], reverse_index[nnz]) of the walker's preprocessing, in CSR entry order."""
+        cnt = np.empty(self.nnz, dtype=np.int32)
+        rix = np.empty(self.nnz, dtype=np.int32)
+        check(load().gw_graph_common_counts(self.h, ptr(cnt, ctypes.c_int32), ptr(rix, ctypes.c_int32)))
+        return cnt, rix
 
     def walks_replay(self, walk_length, starts, uniforms, draw_offset=None):
         starts = as_c(starts, np.int64)
@@ -426,6 +444,11 @@ class GraphHandle:
         check(load().gw_simrank_last_steps(self.h, ctypes.byref(s)))
         return s.value
 
+    def simrank_last_error(self):
+        v = ctypes.c_int32()
+        check(load().gw_simrank_last_error(self.h, ctypes.byref(v)))
+        return v.value
+
     def simrank_last_slow_queries(self):
         s = ctypes.c_int64()
         check(load().gw_simrank_last_slow_queries(self.h, ctypes.byref(s)))
@@ -475,15 +498,23 @@ class Comm:
         except Exception:
             pass
 
-    def walks(self, handle, p, q, walk_length, starts_all, seed=0, gather=True):
-        """gw_node2vec_walks_sharded: the whole [n, L] corpus on every rank (gather) or this rank's rows only."""
+    def walks(self, handle, p, q, walk_length, starts_all, seed=0, gather=True, out=None, lens=None):
+        """gw_node2vec_walks_sharded: the whole [n, L] corpus on every rank (gather = True / 1), on rank 0 only
+        (gather = 2) or this rank's rows only, at their global offsets (gather = False / 0)."""
         starts_all = as_c(starts_all, np.int64)
-        out = np.full((len(starts_all), walk_length), -1, dtype=np.int32)
-        ln = np.zeros(len(starts_all), dtype=np.int32)
+        if out is None:
+            out = np.full((len(starts_all), walk_length), -1, dtype=np.int32)
+        ln = np.zeros(len(starts_all), dtype=np.int32) if lens is None else lens
         check(load().gw_node2vec_walks_sharded(handle.h, self._c, float(p), float(q), int(walk_length),
                                                ptr(starts_all, ctypes.c_int64), len(starts_all), int(seed),
-                                               int(bool(gather)), ptr(out, ctypes.c_int32), ptr(ln, ctypes.c_int32)))
+                                               int(gather), ptr(out, ctypes.c_int32), ptr(ln, ctypes.c_int32)))
         return out, ln
+
+    def last_times(self):
+        """(own-slice kernel ms, NCCL exchange ms) of the last sharded call."""
+        a, b = ctypes.c_double(), ctypes.c_double()
+        check(load().gw_comm_last_times(self._c, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
 
     def simrank_topk(self, handle, queries_all, c, step, sample, k, mode=GW_SIMRANK_MC, seed=0):
         queries_all = as_c(queries_all, np.int64)

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/graphwalk.h"
+#include "hostpipe.h"
 
 struct gw_graph;
 namespace gw {
@@ -74,6 +75,11 @@ int device_info(int *sm_count, size_t *free_bytes);
 int ensure_common_counts(gw_graph *g, cudaStream_t st, bool need_counts = true);
 int count_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_starts, int64_t n_starts, uint64_t seed,
                   uint64_t walk_id_base, unsigned long long *d_stats, cudaStream_t st);
+// walk.cu: moves a corpus to host memory through the hand-off pipeline (direct / pinned ring / packed ring); the corpus
+// is produced chunk by chunk by the walker (d_corpus == NULL) or already sits in device memory (d_corpus != NULL).
+int corpus_to_host(gw_graph *g, double p, double q, int32_t walk_length, const int64_t *d_starts, const int32_t *d_corpus,
+                   const int32_t *d_corpus_lens, int64_t n_starts, uint64_t seed, uint64_t walk_id_base, int32_t *out_walks,
+                   int32_t *out_lens);
 int launch_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_starts, int64_t n_starts, uint64_t seed,
                    uint64_t walk_id_base, int32_t *d_out, int32_t *d_lens, cudaStream_t st);
 
@@ -122,10 +128,17 @@ struct gw_graph {
     double common_build_ms = 0;
     // host-API workspace (grow-only): staging buffers and two streams for the chunked pipeline
     void *ws_starts = nullptr; size_t ws_starts_bytes = 0;
-    void *ws_out[2] = {nullptr, nullptr}; size_t ws_out_bytes = 0;
-    void *ws_lens[2] = {nullptr, nullptr}; size_t ws_lens_bytes = 0;
+    void *ws_out[2] = {nullptr, nullptr}; size_t ws_out_bytes[2] = {0, 0};
+    void *ws_lens[2] = {nullptr, nullptr}; size_t ws_lens_bytes[2] = {0, 0};
+    void *ws_pack[2] = {nullptr, nullptr}; size_t ws_pack_bytes[2] = {0, 0};      // 3-byte ids of a chunk (packed hand-off)
     cudaStream_t ws_stream[2] = {nullptr, nullptr};
     cudaEvent_t ws_event = nullptr;
+    // pinned staging ring of the corpus hand-off + the copy threads that drain it into the caller's (pageable) buffer
+    static constexpr int WS_SLOTS = 4;
+    void *ws_pin[WS_SLOTS] = {nullptr, nullptr, nullptr, nullptr}; size_t ws_pin_bytes[WS_SLOTS] = {0, 0, 0, 0};
+    cudaEvent_t ws_pin_event[WS_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    gw::CopyPool *ws_pool = nullptr;
+    int last_handoff = 0;            // how the last gw_node2vec_walks call moved its corpus: 1 direct, 2 ring, 3 packed ring
     // SimRank host-API workspace (grow-only): device queries / ids / scores and a pinned staging block
     void *ws_sr_dev = nullptr; size_t ws_sr_dev_bytes = 0;
     void *ws_sr_pin = nullptr; size_t ws_sr_pin_bytes = 0;

@@ -410,7 +410,9 @@ int gw_graph_free(gw_graph *g) {
     cudaFree(g->d_simrank_scratch); cudaFree(g->d_nbr4); cudaFree(g->d_bloom); cudaFree(g->d_rowhash); cudaFree(g->d_hybrid_scratch);
     cudaFree(g->ws_starts); cudaFree(g->ws_sr_dev);
     if (g->ws_sr_pin) cudaFreeHost(g->ws_sr_pin);
-    for (int i = 0; i < 2; i++) { cudaFree(g->ws_out[i]); cudaFree(g->ws_lens[i]); if (g->ws_stream[i]) cudaStreamDestroy(g->ws_stream[i]); }
+    for (int i = 0; i < 2; i++) { cudaFree(g->ws_out[i]); cudaFree(g->ws_lens[i]); cudaFree(g->ws_pack[i]); if (g->ws_stream[i]) cudaStreamDestroy(g->ws_stream[i]); }
+    for (int i = 0; i < gw_graph::WS_SLOTS; i++) { if (g->ws_pin[i]) cudaFreeHost(g->ws_pin[i]); if (g->ws_pin_event[i]) cudaEventDestroy(g->ws_pin_event[i]); }
+    delete g->ws_pool;
     if (g->ws_event) cudaEventDestroy(g->ws_event);
     delete g;
     return GW_OK;

@@ -819,7 +819,7 @@ struct HybridParams {
     double *cw;           // [grid][cap]             weight of each of the parent's chains = w / ceil(w)
     uint32_t *cnum;       // [grid][cap]             number of chains = ceil(w)
     uint32_t *cofs;       // [grid][cap + 1]         exclusive prefix of cnum
-    uint32_t *ckey;       // [grid][cap]             (index in its level buffer << 4) | level
+    uint32_t *ckey;       // [grid][cap]             (index in its level buffer << 5) | level (levels reach 2*STEP-1 = 19)
     uint32_t *cpar;       // [grid][2*cap]           chain -> parent
     uint32_t cap;
     double cpow[16];      // C^i
@@ -966,7 +966,7 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
                                 for (int pos = 0; pos <= l; pos++) chist[(size_t)pos * cap + k] = vin[(size_t)pos * cap + p];
                                 cw[k] = w / (double)number;
                                 cnum[k] = (uint32_t)number;
-                                ckey[k] = (p << 4) | (uint32_t)l;
+                                ckey[k] = (p << 5) | (uint32_t)l;
                             }
                         }
                     }                                                             // degree 0: randNeighbor == -1, no child
@@ -1034,8 +1034,8 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
                     for (int pos = 0; pos <= LEN; pos++) { path[pos] = -1; dgs[pos] = 0; }
                     if (live) {
                         const uint32_t k = cpar[t], key = ckey[k];
-                        lvl = (int)(key & 15u);
-                        ctr_p = key >> 4;
+                        lvl = (int)(key & 31u);
+                        ctr_p = key >> 5;
                         ctr_lj = ((uint32_t)lvl << 24) | (t - cofs[k]);
                         wq = cw[k];
 #pragma unroll
@@ -1313,6 +1313,18 @@ __global__ void k_gather_rows_zero_diag(const double *__restrict__ A, int64_t n,
     out[r * n + j] = (i == j) ? 0.0 : A[i * n + j];
 }
 
+// A _dev call whose accumulators overflowed (err != 0) may leave entries in the hash tables, and nobody has to read
+// the error before the next call is enqueued: the next call re-initialises the tables ON THE DEVICE when it finds the
+// previous call's error word set (it runs before the header is cleared; costs one empty launch otherwise).
+__global__ void k_sr_clean_if_err(const int *__restrict__ err, unsigned long long *__restrict__ gval, uint32_t *__restrict__ gkeys,
+                                  size_t count) {
+    if (*err == 0) return;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        gval[i] = 0ull;
+        gkeys[i] = 0xFFFFFFFFu;
+    }
+}
+
 }  // namespace gw
 
 using namespace gw;
@@ -1335,16 +1347,21 @@ static int launch_kernels(const SimrankParams &P, int grid, int log_grid, bool u
     return GW_OK;
 }
 
-static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double c, int32_t step, int32_t sample,
-                       int32_t k, int32_t mode, uint64_t seed, uint64_t query_id_base, int32_t *d_out_ids,
-                       double *d_out_scores, double *d_out_dense, cudaStream_t st, bool sync_steps) {
+extern "C" int gw_simrank_check_args(const gw_graph *g, double c, int32_t step, int32_t sample, int32_t k, int32_t mode) {
     if (!g) return fail(GW_E_INVALID, "graph is NULL");
     if (g->flags & GW_F_DIRECTED) return fail(GW_E_INVALID, "SimRank path is defined on undirected graphs (structures/Graph.java)");
     if (step < 1 || step > 10) return fail(GW_E_INVALID, "step must be in 1..10");
     if (sample < 1) return fail(GW_E_INVALID, "sample must be positive");
     if (!(c > 0) || !(c < 1)) return fail(GW_E_INVALID, "decay c must be in (0,1)");
-    if (d_out_ids && (k < 1 || k > SR_LCAND / 2)) return fail(GW_E_INVALID, "k must be in 1..%d", SR_LCAND / 2);
+    if (k < 1 || k > SR_LCAND / 2) return fail(GW_E_INVALID, "k must be in 1..%d", SR_LCAND / 2);
     if (mode != GW_SIMRANK_MC && mode != GW_SIMRANK_HYBRID) return fail(GW_E_INVALID, "unknown estimator mode %d", mode);
+    return GW_OK;
+}
+
+static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double c, int32_t step, int32_t sample,
+                       int32_t k, int32_t mode, uint64_t seed, uint64_t query_id_base, int32_t *d_out_ids,
+                       double *d_out_scores, double *d_out_dense, cudaStream_t st, bool sync_steps) {
+    GW_TRY(gw_simrank_check_args(g, c, step, sample, d_out_ids ? k : 1, mode));
     if (nq == 0) return GW_OK;
     if (nq >= ((int64_t)1 << 31)) return fail(GW_E_TOO_LARGE, "more than 2^31-1 queries in one call");
     GW_CUDA(cudaSetDevice(g->device));
@@ -1391,6 +1408,10 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     P.qlist_out = (int32_t *)(base + off_qlist);
     P.qlist = nullptr;
     P.log_cap = log_cap;
+    if (!fresh && !g->simrank_dirty) {
+        k_sr_clean_if_err<<<sms * 4, 256, 0, st>>>(P.err, P.gval, P.gkeys, (size_t)grid * gs);
+        GW_LAUNCHED();
+    }
     GW_CUDA(cudaMemsetAsync(base, 0, 256, st));
     P.prof = (unsigned long long *)(base + 64);
     if (fresh || g->simrank_dirty) {   // the hash kernel leaves its tables clean; only (re)initialise when the layout changes
@@ -1412,7 +1433,7 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     P.out_ids = d_out_ids; P.out_scores = d_out_scores; P.out_dense = d_out_dense;
     if (hybrid) {
         HybridParams H;
-        H.cap = (uint32_t)std::min<int64_t>((int64_t)2 * step * sample + 1, (int64_t)0x0FFFFFFF);   // index << 4 must fit 32 bits
+        H.cap = (uint32_t)std::min<int64_t>((int64_t)2 * step * sample + 1, (int64_t)0x07FFFFFF);   // index << 5 must fit 32 bits
         const size_t LEN1 = 2 * (size_t)step + 1, capz = H.cap;
         size_t off = 0;
         auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
@@ -1708,6 +1729,19 @@ int gw_simrank_last_steps(const gw_graph *g, int64_t *steps) {
         return GW_OK;
     }
     *steps = g->simrank_last_steps;
+    return GW_OK;
+}
+
+int gw_simrank_last_error(const gw_graph *g, int32_t *code) {
+    if (!g || !code) return fail(GW_E_INVALID, "bad arguments");
+    *code = 0;
+    if (g->d_simrank_scratch) {
+        int h = 0;
+        GW_CUDA(cudaSetDevice(g->device));
+        GW_CUDA(cudaDeviceSynchronize());
+        GW_CUDA(cudaMemcpy(&h, (unsigned char *)g->d_simrank_scratch + 16, sizeof(h), cudaMemcpyDeviceToHost));
+        *code = h;
+    }
     return GW_OK;
 }
 

@@ -283,10 +283,15 @@ int gw_node2vec_walks_dev(gw_graph *g, double p, double q, int32_t walk_length, 
     return GW_OK;
 }
 
-// Host-buffer entry point: chunked, double-buffered pipeline.  The corpus is 4*L bytes per walk
-// (1.3 GB per pass at R-MAT scale-22), so the call is PCIe-bound; chunk c+1 is walked on one
-// stream while chunk c is copied to the caller's buffer on the other.  Staging buffers and streams
-// live in the graph handle (grow-only), so repeated calls do not touch cudaMalloc.
+// Host-buffer entry point: chunked pipeline, three ways to hand the corpus over.  The corpus is
+// 4*L bytes per walk (1.3 GB per pass at R-MAT scale-22), so the call is PCIe-bound; chunk c+1 is walked on one stream
+// while chunk c leaves on the other.
+//   direct  the caller's buffer is page-locked: cudaMemcpyAsync straight into it (no host thread touches the data);
+//   ring    the caller's buffer is pageable (a numpy array, a JVM heap array): chunks land in a library-owned pinned
+//           ring and the copy threads move them on, so the DMA never falls back to the driver's staged pageable path;
+//   packed  graphs of <= 2^24 vertices: ids cross PCIe as 3 bytes (k_pack24) and the copy threads widen them while
+//           draining the ring -- 25 % fewer bytes over the link that bounds the call.
+// Staging buffers, streams, ring and threads live in the graph handle (grow-only): repeated calls allocate nothing.
 static int grow(void **p, size_t *have, size_t need) {
     if (*have >= need) return GW_OK;
     if (*p) cudaFree(*p);
@@ -295,28 +300,145 @@ static int grow(void **p, size_t *have, size_t need) {
     *have = need;
     return GW_OK;
 }
+static int grow_pinned(void **p, size_t *have, size_t need) {
+    if (*have >= need) return GW_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *have = 0;
+    GW_CUDA(cudaMallocHost(p, need));
+    *have = need;
+    return GW_OK;
+}
+
+// 4 ids -> 12 bytes; -1 (padding after a dead end) becomes 0xFFFFFF, the host restores it from the walk's length
+__global__ void k_pack24(const int32_t *__restrict__ in, uint32_t *__restrict__ out, int64_t count) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t i = 4 * t;
+    if (i >= count) return;
+    uint32_t a, b = 0, c = 0, d = 0;
+    if (i + 3 < count) {
+        const int4 v = *reinterpret_cast<const int4 *>(in + i);
+        a = (uint32_t)v.x; b = (uint32_t)v.y; c = (uint32_t)v.z; d = (uint32_t)v.w;
+    } else {
+        a = (uint32_t)in[i];
+        if (i + 1 < count) b = (uint32_t)in[i + 1];
+        if (i + 2 < count) c = (uint32_t)in[i + 2];
+    }
+    a &= 0xFFFFFFu; b &= 0xFFFFFFu; c &= 0xFFFFFFu; d &= 0xFFFFFFu;
+    out[3 * t] = a | (b << 24);
+    out[3 * t + 1] = (b >> 8) | (c << 16);
+    out[3 * t + 2] = (c >> 16) | (d << 8);
+}
+
+enum { GW_HANDOFF_DIRECT = 1, GW_HANDOFF_RING = 2, GW_HANDOFF_PACKED = 3 };
+
+static int pick_handoff(const gw_graph *g, const void *out_walks, int threads) {
+    const bool can_pack = g->n <= ((int64_t)1 << 24);
+    const char *e = getenv("GW_E2E");                         // experiment knob: direct | ring | packed
+    if (e && !strcmp(e, "direct")) return GW_HANDOFF_DIRECT;
+    if (e && !strcmp(e, "ring")) return GW_HANDOFF_RING;
+    if (e && !strcmp(e, "packed")) return can_pack ? GW_HANDOFF_PACKED : GW_HANDOFF_RING;
+    cudaPointerAttributes at;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&at, out_walks) == cudaSuccess) pinned = at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+    else cudaGetLastError();
+    if (can_pack && threads >= 8) return GW_HANDOFF_PACKED;   // the copy threads keep up with the link from ~8 up (profiles/README.md §5)
+    return pinned ? GW_HANDOFF_DIRECT : GW_HANDOFF_RING;
+}
+
+}  // extern "C"
+
+// The hand-off pipeline.  Source of chunk i: the walker (d_corpus == NULL: walks of d_starts[lo, lo+cnt) produced into
+// the handle's chunk buffers) or rows [lo, lo+cnt) of a corpus that already sits in device memory (gathered over NCCL).
+int gw::corpus_to_host(gw_graph *g, double p, double q, int32_t walk_length, const int64_t *d_starts, const int32_t *d_corpus,
+                       const int32_t *d_corpus_lens, int64_t n_starts, uint64_t seed, uint64_t walk_id_base, int32_t *out_walks,
+                       int32_t *out_lens) {
+    if (!g->ws_pool) g->ws_pool = new CopyPool(default_copy_threads());
+    const int mode = pick_handoff(g, out_walks, g->ws_pool->threads());
+    const bool ring = mode != GW_HANDOFF_DIRECT, packed = mode == GW_HANDOFF_PACKED;
+    const bool produce = d_corpus == nullptr;
+    const size_t L = (size_t)walk_length;
+    const int64_t chunk_bytes = ring ? ((int64_t)32 << 20) : ((int64_t)48 << 20);
+    const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(n_starts, chunk_bytes / ((int64_t)L * 4))) & ~(int64_t)7;
+    const bool have_lens = produce || d_corpus_lens != nullptr;
+    const bool want_lens = have_lens && (out_lens != nullptr || packed);
+    for (int i = 0; i < 2; i++)
+        if (!g->ws_stream[i]) GW_CUDA(cudaStreamCreateWithFlags(&g->ws_stream[i], cudaStreamNonBlocking));
+    const size_t chunk_ids = (size_t)chunk * L;
+    const size_t pack_bytes = (chunk_ids + 3) / 4 * 12 + 16;
+    for (int i = 0; i < 2; i++) {
+        if (produce) {
+            GW_TRY(grow(&g->ws_out[i], &g->ws_out_bytes[i], sizeof(int32_t) * chunk_ids));
+            GW_TRY(grow(&g->ws_lens[i], &g->ws_lens_bytes[i], sizeof(int32_t) * (size_t)chunk));
+        }
+        if (packed) GW_TRY(grow(&g->ws_pack[i], &g->ws_pack_bytes[i], pack_bytes));
+    }
+    const size_t payload = packed ? pack_bytes : sizeof(int32_t) * chunk_ids;
+    const size_t lens_off = (payload + 63) & ~(size_t)63;
+    if (ring)
+        for (int i = 0; i < gw_graph::WS_SLOTS; i++) {
+            GW_TRY(grow_pinned(&g->ws_pin[i], &g->ws_pin_bytes[i], lens_off + sizeof(int32_t) * (size_t)chunk + 64));
+            if (!g->ws_pin_event[i]) GW_CUDA(cudaEventCreateWithFlags(&g->ws_pin_event[i], cudaEventDisableTiming));
+        }
+    g->last_handoff = mode;
+    const int64_t nchunks = (n_starts + chunk - 1) / chunk;
+    constexpr int K = gw_graph::WS_SLOTS, LAG = K - 1;
+    for (int64_t i = 0; i < nchunks + (ring ? LAG : 0); i++) {
+        if (i < nchunks) {
+            const int c = (int)(i & 1), r = (int)(i % K);
+            const int64_t lo = i * chunk, cnt = std::min(chunk, n_starts - lo);
+            cudaStream_t st = g->ws_stream[c];
+            const int32_t *src = produce ? (const int32_t *)g->ws_out[c] : d_corpus + (size_t)lo * L;
+            const int32_t *src_lens = produce ? (const int32_t *)g->ws_lens[c] : (d_corpus_lens ? d_corpus_lens + lo : nullptr);
+            if (produce)
+                GW_TRY(gw_node2vec_walks_dev(g, p, q, walk_length, d_starts + lo, cnt, seed, walk_id_base + (uint64_t)lo,
+                                             (int32_t *)g->ws_out[c], want_lens ? (int32_t *)g->ws_lens[c] : nullptr, st));
+            if (!ring) {
+                GW_CUDA(cudaMemcpyAsync(out_walks + (size_t)lo * L, src, sizeof(int32_t) * (size_t)cnt * L, cudaMemcpyDeviceToHost, st));
+                if (out_lens && have_lens)
+                    GW_CUDA(cudaMemcpyAsync(out_lens + lo, src_lens, sizeof(int32_t) * (size_t)cnt, cudaMemcpyDeviceToHost, st));
+            } else {
+                const size_t ids = (size_t)cnt * L;
+                if (packed) {
+                    k_pack24<<<(unsigned)(((ids + 3) / 4 + 255) / 256), 256, 0, st>>>(src, (uint32_t *)g->ws_pack[c], (int64_t)ids);
+                    GW_LAUNCHED();
+                    GW_CUDA(cudaMemcpyAsync(g->ws_pin[r], g->ws_pack[c], (ids + 3) / 4 * 12, cudaMemcpyDeviceToHost, st));
+                } else {
+                    GW_CUDA(cudaMemcpyAsync(g->ws_pin[r], src, sizeof(int32_t) * ids, cudaMemcpyDeviceToHost, st));
+                }
+                if (want_lens)
+                    GW_CUDA(cudaMemcpyAsync((char *)g->ws_pin[r] + lens_off, src_lens, sizeof(int32_t) * (size_t)cnt, cudaMemcpyDeviceToHost, st));
+                GW_CUDA(cudaEventRecord(g->ws_pin_event[r], st));
+            }
+        }
+        const int64_t j = i - LAG;
+        if (ring && j >= 0) {                     // drain chunk j while the device works on j+1 .. j+LAG
+            const int r = (int)(j % K);
+            const int64_t lo = j * chunk, cnt = std::min(chunk, n_starts - lo);
+            GW_CUDA(cudaEventSynchronize(g->ws_pin_event[r]));
+            drain_chunk(g->ws_pool, g->ws_pin[r], packed ? 1 : 0, want_lens ? (const int32_t *)((char *)g->ws_pin[r] + lens_off) : nullptr,
+                        cnt, walk_length, out_walks + (size_t)lo * L, out_lens ? out_lens + lo : nullptr);
+        }
+    }
+    GW_CUDA(cudaStreamSynchronize(g->ws_stream[0]));
+    GW_CUDA(cudaStreamSynchronize(g->ws_stream[1]));
+    return GW_OK;
+}
+
+extern "C" {
 
 int gw_node2vec_walks(gw_graph *g, double p, double q, int32_t walk_length, const int64_t *starts, int64_t n_starts,
                       uint64_t seed, uint64_t walk_id_base, int32_t *out_walks, int32_t *out_lens) {
     if (!g) return fail(GW_E_INVALID, "graph is NULL");
     if (n_starts < 0 || (n_starts > 0 && (!starts || !out_walks))) return fail(GW_E_INVALID, "bad arguments");
     if (walk_length < 1) return fail(GW_E_INVALID, "bad walk_length");
+    if (!(p > 0) || !(q > 0)) return fail(GW_E_INVALID, "p and q must be positive");
+    if (g->flags & GW_F_MULTI) return fail(GW_E_STATE, "node2vec walks need a SIMPLE-mode (sorted) graph");
     if (n_starts == 0) return GW_OK;
     GW_CUDA(cudaSetDevice(g->device));
-    const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(n_starts, ((int64_t)48 << 20) / ((int64_t)walk_length * 4)));
     for (int i = 0; i < 2; i++)
         if (!g->ws_stream[i]) GW_CUDA(cudaStreamCreateWithFlags(&g->ws_stream[i], cudaStreamNonBlocking));
     if (!g->ws_event) GW_CUDA(cudaEventCreateWithFlags(&g->ws_event, cudaEventDisableTiming));
     GW_TRY(grow(&g->ws_starts, &g->ws_starts_bytes, sizeof(int64_t) * (size_t)n_starts + 16));   // + {bad count, bad value}
-    {
-        size_t ob = g->ws_out_bytes, lb = g->ws_lens_bytes;
-        for (int i = 0; i < 2; i++) {
-            size_t o2 = ob, l2 = lb;
-            GW_TRY(grow(&g->ws_out[i], &o2, sizeof(int32_t) * (size_t)chunk * walk_length));
-            GW_TRY(grow(&g->ws_lens[i], &l2, sizeof(int32_t) * (size_t)chunk));
-            if (i == 1) { g->ws_out_bytes = o2; g->ws_lens_bytes = l2; }
-        }
-    }
     // one-off preprocessing (common-neighbour counts) must not race with the two streams
     if (!(g->flags & (GW_F_DIRECTED | GW_F_WEIGHTED))) {
         int rc = ensure_common_counts(g, g->ws_stream[0], !(p == 1.0 && q == 1.0));
@@ -335,19 +457,14 @@ int gw_node2vec_walks(gw_graph *g, double p, double q, int32_t walk_length, cons
     }
     GW_CUDA(cudaEventRecord(g->ws_event, g->ws_stream[0]));
     GW_CUDA(cudaStreamWaitEvent(g->ws_stream[1], g->ws_event, 0));
-    int c = 0;
-    for (int64_t lo = 0; lo < n_starts; lo += chunk, c ^= 1) {
-        const int64_t cnt = std::min(chunk, n_starts - lo);
-        cudaStream_t st = g->ws_stream[c];
-        GW_TRY(gw_node2vec_walks_dev(g, p, q, walk_length, (const int64_t *)g->ws_starts + lo, cnt, seed, walk_id_base + (uint64_t)lo,
-                                     (int32_t *)g->ws_out[c], out_lens ? (int32_t *)g->ws_lens[c] : nullptr, st));
-        GW_CUDA(cudaMemcpyAsync(out_walks + lo * walk_length, g->ws_out[c], sizeof(int32_t) * (size_t)cnt * walk_length,
-                                cudaMemcpyDeviceToHost, st));
-        if (out_lens)
-            GW_CUDA(cudaMemcpyAsync(out_lens + lo, g->ws_lens[c], sizeof(int32_t) * (size_t)cnt, cudaMemcpyDeviceToHost, st));
-    }
-    GW_CUDA(cudaStreamSynchronize(g->ws_stream[0]));
-    GW_CUDA(cudaStreamSynchronize(g->ws_stream[1]));
+    return corpus_to_host(g, p, q, walk_length, (const int64_t *)g->ws_starts, nullptr, nullptr, n_starts, seed, walk_id_base,
+                          out_walks, out_lens);
+}
+
+int gw_graph_last_handoff(const gw_graph *g, int32_t *mode, int32_t *copy_threads) {
+    if (!g) return fail(GW_E_INVALID, "graph is NULL");
+    if (mode) *mode = g->last_handoff;
+    if (copy_threads) *copy_threads = g->ws_pool ? g->ws_pool->threads() : 0;
     return GW_OK;
 }
 
@@ -399,6 +516,32 @@ int gw_graph_prepare_walks(gw_graph *g, double *build_ms) {
         if (rc != GW_OK && rc != GW_E_STATE) return rc;
     }
     if (build_ms) *build_ms = g->common_build_ms;
+    return GW_OK;
+}
+
+__global__ void k_export_counts(const int4 *__restrict__ nbr4, int64_t nnz, int packed, int32_t *__restrict__ cnt, int32_t *__restrict__ ridx) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    const uint32_t y = (uint32_t)nbr4[e].y;
+    cnt[e] = packed ? (int32_t)(y & 0xFFFFu) : (int32_t)y;
+    if (ridx) ridx[e] = packed ? (int32_t)(y >> 16) : -1;
+}
+
+int gw_graph_common_counts(gw_graph *g, int32_t *counts, int32_t *reverse_index) {
+    if (!g || !counts) return fail(GW_E_INVALID, "bad arguments");
+    if (g->flags & (GW_F_DIRECTED | GW_F_WEIGHTED | GW_F_MULTI))
+        return fail(GW_E_STATE, "common-neighbour counts exist for undirected, unweighted SIMPLE graphs only");
+    GW_CUDA(cudaSetDevice(g->device));
+    int rc = ensure_common_counts(g, nullptr);
+    if (rc != GW_OK) return rc == GW_E_STATE ? fail(GW_E_STATE, "graph has self loops: counts are not defined") : rc;
+    if (g->nnz == 0) return GW_OK;
+    DevBuf<int32_t> dc, dr;
+    GW_CUDA(dc.alloc((size_t)g->nnz));
+    if (reverse_index) GW_CUDA(dr.alloc((size_t)g->nnz));
+    k_export_counts<<<(unsigned)((g->nnz + 255) / 256), 256>>>(g->d_nbr4, g->nnz, g->nbr4_packed, dc.p, dr.p);
+    GW_LAUNCHED();
+    GW_CUDA(cudaMemcpy(counts, dc.p, sizeof(int32_t) * (size_t)g->nnz, cudaMemcpyDeviceToHost));
+    if (reverse_index) GW_CUDA(cudaMemcpy(reverse_index, dr.p, sizeof(int32_t) * (size_t)g->nnz, cudaMemcpyDeviceToHost));
     return GW_OK;
 }
 

@@ -122,11 +122,11 @@ __global__ void k_nbr4_nocount(const uint2 *__restrict__ meta, const int32_t *__
     nbr4[e] = make_int4(v, 0, (int)mv.x, (int)mv.y);
 }
 
-// one warp per directed entry e = (u -> v): nbr4[e] = {v, |N(u) & N(v)|, offset(v), degree(v)}.
+// v1 (kept for A/B runs and the bit-identity test, GW_CN_BUILD=v1): one warp per directed entry e = (u -> v): nbr4[e] = {v, |N(u) & N(v)|, offset(v), degree(v)}.
 // pack (every degree < 65536): .y = count | (position of u inside N(v)) << 16 -- the REVERSE index: a walker that
 // moved u -> v knows where its previous vertex sits in the row it is about to sample from and can draw from
 // N(v) \ {u} without rejection.
-__global__ void __launch_bounds__(256) k_common_counts(const uint2 *__restrict__ meta, const int32_t *__restrict__ col,
+__global__ void __launch_bounds__(256) k_common_counts_v1(const uint2 *__restrict__ meta, const int32_t *__restrict__ col,
                                                         const int64_t *__restrict__ row_ptr, int64_t n, int64_t nnz,
                                                         int4 *__restrict__ nbr4, int *__restrict__ self_loops, int pack) {
     const int lane = threadIdx.x & 31;
@@ -159,6 +159,168 @@ __global__ void __launch_bounds__(256) k_common_counts(const uint2 *__restrict__
             if (u != v && lo2 < mv.y)
                 nbr4[(size_t)mv.x + lo2] = make_int4(u, (int)((uint32_t)cnt | (pack ? k << 16 : 0u)), (int)mu.x, (int)mu.y);
         }
+    }
+}
+
+// ---- common-neighbour counts, v2: every undirected edge is intersected ONCE, by its BIGGER endpoint -------------
+// Order the endpoints by (degree, id).  The task of vertex u stages N(u) as an open-addressing hash set in shared
+// memory (2 slots per entry) and, for every neighbour v that is smaller in that order, streams the SHORT row N(v) in
+// coalesced 128-byte lines against it: long rows are only ever probed (in shared memory), never streamed and never
+// binary-searched.  The stream also meets u itself inside N(v) -- that is the reverse index of the edge, for free --
+// and the position of v inside N(u) is the loop index, so both mirrored entries are written without a search.
+// Work = sum over edges of min(deg) probes of ~2 shared-memory words, against sum of min(deg) * log2(max(deg))
+// dependent L2/DRAM loads in v1.  Three task shapes:
+//   small  (deg <= 64):       one warp per u, all smaller rows flattened into one lane-dense index space
+//   block  (64 < deg <= cap): one CTA per (u, chunk of 1024 neighbours), one warp per smaller row
+//   giant  (deg > cap):       same tasks, membership by binary search over N(u) in global memory (L2-resident hubs)
+constexpr uint32_t CC_SMALL = 64;            // rows up to this length: warp tasks
+constexpr uint32_t CC_CHUNK = 1024;          // neighbours per CTA task
+constexpr uint32_t CC_HASH_MAX = 16384;      // shared-memory slots of a CTA task: rows up to 8192 entries
+
+__device__ __forceinline__ uint32_t cc_slot(int32_t x, uint32_t mask) {
+    uint32_t h = (uint32_t)x * 0x9E3779B1u;
+    h ^= h >> 15;
+    return h & mask;
+}
+__device__ __forceinline__ void cc_insert(int32_t *tab, uint32_t mask, int32_t x) {
+    uint32_t s = cc_slot(x, mask);
+    while (atomicCAS(tab + s, -1, x) != -1) s = (s + 1) & mask;       // SIMPLE rows hold no duplicates
+}
+__device__ __forceinline__ bool cc_contains(const int32_t *tab, uint32_t mask, int32_t x) {
+    uint32_t s = cc_slot(x, mask);
+    for (;;) {
+        const int32_t v = tab[s];
+        if (v == x) return true;
+        if (v < 0) return false;
+        s = (s + 1) & mask;
+    }
+}
+__device__ __forceinline__ bool cc_smaller(uint32_t dv, int32_t v, uint32_t du, int32_t u) {   // (dv, v) < (du, u)
+    return dv < du || (dv == du && v < u);
+}
+__device__ __forceinline__ void cc_write_pair(int4 *__restrict__ nbr4, int pack, int32_t u, uint2 mu, uint32_t k, int32_t v, uint2 mv,
+                                              uint32_t pos_u_in_v, uint32_t cnt) {
+    nbr4[(size_t)mu.x + k] = make_int4(v, (int)(cnt | (pack ? pos_u_in_v << 16 : 0u)), (int)mv.x, (int)mv.y);
+    nbr4[(size_t)mv.x + pos_u_in_v] = make_int4(u, (int)(cnt | (pack ? k << 16 : 0u)), (int)mu.x, (int)mu.y);
+}
+
+// block / giant tasks are listed by this pass: tasks[i] = {u, first neighbour index}
+__global__ void k_cc_list_tasks(const uint2 *__restrict__ meta, int64_t n, uint2 *__restrict__ tasks, unsigned int *__restrict__ ntasks,
+                                unsigned int cap) {
+    const int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    const uint32_t d = __ldg(meta + u).y;
+    if (d <= CC_SMALL) return;
+    const uint32_t nt = (d + CC_CHUNK - 1) / CC_CHUNK;
+    const unsigned int at = atomicAdd(ntasks, nt);
+    for (uint32_t t = 0; t < nt && at + t < cap; t++) tasks[at + t] = make_uint2((uint32_t)u, t * CC_CHUNK);
+}
+
+// one warp per small vertex; per-warp shared memory: hash[128] | pre[65] | offv[64] | acc[64]
+__global__ void __launch_bounds__(256) k_cc_small(const uint2 *__restrict__ meta, const int32_t *__restrict__ col, int64_t n,
+                                                   int4 *__restrict__ nbr4, int *__restrict__ self_loops, int pack) {
+    __shared__ int32_t s_hash[8][128];
+    __shared__ uint32_t s_pre[8][CC_SMALL + 1];
+    __shared__ uint32_t s_off[8][CC_SMALL];
+    __shared__ uint32_t s_acc[8][CC_SMALL];          // count | (position of u inside N(v)) << 16
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int32_t *hash = s_hash[wib];
+    uint32_t *pre = s_pre[wib], *offv = s_off[wib], *acc = s_acc[wib];
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t uu = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; uu < n; uu += nwarps) {
+        const int32_t u = (int32_t)uu;
+        const uint2 mu = __ldg(meta + u);
+        if (mu.y == 0 || mu.y > CC_SMALL) continue;
+        uint32_t mask = 63;
+        while (mask + 1 < 2 * mu.y) mask = 2 * mask + 1;             // 64 or 128 slots
+        for (uint32_t i = lane; i <= mask; i += 32) hash[i] = -1;
+        __syncwarp();
+        // the row of u (two entries per lane), descriptors of its neighbours, eligibility = smaller endpoint
+        uint32_t run = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t k = h * 32 + lane;
+            uint32_t dv = 0;
+            if (k < mu.y) {
+                const int32_t v = __ldg(col + mu.x + k);
+                cc_insert(hash, mask, v);
+                const uint2 mv = __ldg(meta + v);
+                offv[k] = mv.x;
+                acc[k] = 0;
+                if (v == u) { atomicExch(self_loops, 1); nbr4[(size_t)mu.x + k] = make_int4(u, 0, (int)mu.x, (int)mu.y); }
+                else if (cc_smaller(mv.y, v, mu.y, u)) dv = mv.y;
+            }
+            uint32_t inc = dv;                                        // inclusive warp scan of the eligible lengths
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            if (k < CC_SMALL) pre[k] = run + inc - dv;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) pre[CC_SMALL] = run;
+        __syncwarp();
+        const uint32_t total = run;
+        for (uint32_t t = lane; t < total; t += 32) {
+            uint32_t lo = 0, hi = CC_SMALL;                           // largest k with pre[k] <= t (empty rows repeat their prefix)
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (pre[mid] <= t) lo = mid; else hi = mid; }
+            const uint32_t i = t - pre[lo];
+            const int32_t x = __ldg(col + offv[lo] + i);
+            if (x == u) atomicAdd(acc + lo, i << 16);
+            else if (cc_contains(hash, mask, x)) atomicAdd(acc + lo, 1u);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t k = h * 32 + lane;
+            if (k < mu.y && pre[k + 1] > pre[k]) {                    // eligible (an eligible row holds u: never empty)
+                const int32_t v = __ldg(col + mu.x + k);
+                const uint32_t a = acc[k];
+                cc_write_pair(nbr4, pack, u, mu, k, v, make_uint2(offv[k], pre[k + 1] - pre[k]), a >> 16, a & 0xFFFFu);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// one CTA per task {u, k0}: neighbours k0 .. k0+CC_CHUNK of u, one warp per smaller row
+__global__ void __launch_bounds__(256) k_cc_block(const uint2 *__restrict__ meta, const int32_t *__restrict__ col,
+                                                   const uint2 *__restrict__ tasks, unsigned int ntasks, int4 *__restrict__ nbr4,
+                                                   int *__restrict__ self_loops, int pack) {
+    extern __shared__ int32_t s_tab[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    for (unsigned int ti = blockIdx.x; ti < ntasks; ti += gridDim.x) {
+        const uint2 tk = tasks[ti];
+        const int32_t u = (int32_t)tk.x;
+        const uint2 mu = __ldg(meta + u);
+        const bool in_smem = 2 * mu.y <= CC_HASH_MAX;
+        uint32_t mask = 127;
+        if (in_smem) {
+            while (mask + 1 < 2 * mu.y) mask = 2 * mask + 1;
+            for (uint32_t i = threadIdx.x; i <= mask; i += blockDim.x) s_tab[i] = -1;
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < mu.y; i += blockDim.x) cc_insert(s_tab, mask, __ldg(col + mu.x + i));
+            __syncthreads();
+        }
+        const uint32_t kend = min(mu.y, tk.y + CC_CHUNK);
+        for (uint32_t k = tk.y + wib; k < kend; k += 8) {
+            const int32_t v = __ldg(col + mu.x + k);
+            if (v == u) {
+                if (lane == 0) { atomicExch(self_loops, 1); nbr4[(size_t)mu.x + k] = make_int4(u, 0, (int)mu.x, (int)mu.y); }
+                continue;
+            }
+            const uint2 mv = __ldg(meta + v);
+            if (!cc_smaller(mv.y, v, mu.y, u)) continue;
+            uint32_t cnt = 0, pos = 0;
+            for (uint32_t b0 = 0; b0 < mv.y; b0 += 32) {
+                const uint32_t i = b0 + lane;
+                if (i < mv.y) {
+                    const int32_t x = __ldg(col + mv.x + i);
+                    if (x == u) pos = i;
+                    else if (in_smem ? cc_contains(s_tab, mask, x) : sorted_contains(col + mu.x, mu.y, x)) cnt++;
+                }
+            }
+            for (int o = 16; o; o >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); pos += __shfl_xor_sync(0xffffffffu, pos, o); }
+            if (lane == 0) cc_write_pair(nbr4, pack, u, mu, k, v, mv, pos, cnt);
+        }
+        __syncthreads();                                             // the table is rebuilt by the next task
     }
 }
 
@@ -562,8 +724,40 @@ int ensure_common_counts(gw_graph *g, cudaStream_t st, bool need_counts) {
         device_info(&sms, nullptr);
         const char *np = getenv("GW_CN_RIDX");                   // experiment knob: "0" keeps plain counts (rejection of prev)
         g->nbr4_packed = (g->max_degree < 65536 && !(np && !strcmp(np, "0"))) ? 1 : 0;
-        k_common_counts<<<sms * 16, 256, 0, st>>>(g->d_meta, g->d_col, g->d_row_ptr, g->n, g->nnz, g->d_nbr4, flag.p, g->nbr4_packed);
-        GW_LAUNCHED();
+        const char *bv = getenv("GW_CN_BUILD");                  // experiment knob: "v1" = one warp per directed entry
+        if (bv && !strcmp(bv, "v1")) {
+            k_common_counts_v1<<<sms * 16, 256, 0, st>>>(g->d_meta, g->d_col, g->d_row_ptr, g->n, g->nnz, g->d_nbr4, flag.p, g->nbr4_packed);
+            GW_LAUNCHED();
+        } else {
+            const bool have_tasks = (uint32_t)g->max_degree > CC_SMALL;
+            if (!have_tasks) {
+                k_cc_small<<<sms * 16, 256, 0, st>>>(g->d_meta, g->d_col, g->n, g->d_nbr4, flag.p, g->nbr4_packed);
+                GW_LAUNCHED();
+            } else {
+                const unsigned int cap = (unsigned int)std::min<int64_t>(g->nnz / 64 + g->nnz / CC_CHUNK + 16, 0x7FFFFFFF);
+                DevBuf<uint2> tasks;
+                DevBuf<unsigned int> nt;
+                GW_CUDA(tasks.alloc(cap)); GW_CUDA(nt.alloc(1));
+                GW_CUDA(cudaMemsetAsync(nt.p, 0, sizeof(unsigned int), st));
+                k_cc_list_tasks<<<(unsigned)((g->n + 255) / 256), 256, 0, st>>>(g->d_meta, g->n, tasks.p, nt.p, cap);
+                GW_LAUNCHED();
+                unsigned int hn = 0;
+                GW_CUDA(cudaMemcpyAsync(&hn, nt.p, sizeof(hn), cudaMemcpyDeviceToHost, st));
+                k_cc_small<<<sms * 16, 256, 0, st>>>(g->d_meta, g->d_col, g->n, g->d_nbr4, flag.p, g->nbr4_packed);   // runs while the host waits for the task count
+                GW_LAUNCHED();
+                GW_CUDA(cudaStreamSynchronize(st));
+                if (hn > cap) return fail(GW_E_STATE, "common-neighbour task list overflow (%u > %u)", hn, cap);
+                uint32_t slots = 128;
+                while (slots < 2u * (uint32_t)g->max_degree && slots < CC_HASH_MAX) slots <<= 1;
+                const size_t smem = sizeof(int32_t) * slots;
+                GW_CUDA(cudaFuncSetAttribute(k_cc_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                if (hn > 0) {
+                    k_cc_block<<<hn, 256, smem, st>>>(g->d_meta, g->d_col, tasks.p, hn, g->d_nbr4, flag.p, g->nbr4_packed);
+                    GW_LAUNCHED();
+                }
+                GW_CUDA(cudaStreamSynchronize(st));              // tasks / nt are released on return
+            }
+        }
     }
     GW_CUDA(cudaEventRecord(e1, st));
     int h = 0;

@@ -125,10 +125,25 @@ int gw_node2vec_walks_dev(gw_graph *g, double p, double q, int32_t walk_length,
                           const int64_t *d_starts, int64_t n_starts, uint64_t seed,
                           uint64_t walk_id_base, int32_t *d_out_walks, int32_t *d_out_lens,
                           void *stream);
+/* How the last gw_node2vec_walks call on this graph moved its corpus to the host: mode 1 = direct DMA
+ * into the caller's page-locked buffer, 2 = pinned ring drained by the library's copy threads (pageable buffers),
+ * 3 = the same ring with ids crossing PCIe as 3 bytes (graphs of <= 2^24 vertices); copy_threads = size of the pool.
+ * Either pointer may be NULL. */
+int gw_graph_last_handoff(const gw_graph *g, int32_t *mode, int32_t *copy_threads);
+/* Host half of the packed hand-off, usable on its own (no device involved): widens a corpus of n_walks rows of
+ * walk_length little-endian 3-byte ids into int32; positions >= lens[w] become -1 (lens may be NULL: every row is
+ * full).  threads <= 0 = the library's default copy-thread count. */
+int gw_corpus_unpack24(const void *packed, const int32_t *lens, int64_t n_walks, int32_t walk_length, int32_t threads,
+                       int32_t *out_walks);
 /* Optional: runs the walker's one-off preprocessing now (per-edge common-neighbour counts, the
  * scalable stand-in for preprocess_transition_probs' alias_edges, node2vec.py:99-108) instead of
  * lazily inside the first walk call; build_ms (may be NULL) receives its device time. */
 int gw_graph_prepare_walks(gw_graph *g, double *build_ms);
+/* The preprocessing's result, for inspection and tests: counts[nnz] = |N(u) & N(v)| of every directed CSR entry
+ * (u -> v) -- what decides the masses of get_alias_edge's three weight classes (node2vec.py:69-76) -- and, when
+ * reverse_index != NULL, the position of u inside the sorted row of v (-1 when the graph has rows >= 65536 entries
+ * and the walker keeps no reverse index).  Undirected, unweighted, loop-free SIMPLE graphs only (GW_E_STATE otherwise). */
+int gw_graph_common_counts(gw_graph *g, int32_t *counts, int32_t *reverse_index);
 /* Replay: consumes the reference's own np.random.rand() stream (two fp64 draws per executed
  * step, node2vec.py:156-160) and start order; needs gw_alias_nodes + gw_alias_edges built with
  * the same p,q.  draw_offset[n_starts+1] may be NULL when no walk can hit a dead end
@@ -225,6 +240,14 @@ int gw_simrank_last_steps(const gw_graph *g, int64_t *steps);
 /* Queries of the last gw_simrank_topk* call that were finished by the exact hash-table kernel
  * instead of the log-structured fast path (threshold at the single-hit level; results identical). */
 int gw_simrank_last_slow_queries(const gw_graph *g, int64_t *count);
+/* The argument checks every gw_simrank_topk* / gw_simrank_rows call starts with (graph kind, decay in (0,1), step in
+ * 1..10, sample >= 1, k in 1..128, known mode), without touching the device: GW_OK or GW_E_INVALID + message. */
+int gw_simrank_check_args(const gw_graph *g, double c, int32_t step, int32_t sample, int32_t k, int32_t mode);
+/* Device-side status of the last gw_simrank_topk* call on this graph (synchronises the device): 0, or the code of an
+ * accumulator / path-buffer overflow, in which case the results of that call are truncated.  The host-buffer entry
+ * points report this themselves (GW_E_STATE); callers of the _dev entry point check here after their stream has
+ * finished.  The next call restores the accumulators on the device either way. */
+int gw_simrank_last_error(const gw_graph *g, int32_t *code);
 /* Exact SimRank (simrank/SimRank.java:36-77): iters Jacobi sweeps of S <- c P S P^T, diag = 1,
  * diag zeroed at the end; returns the requested rows out[nrows*n].  O(n^2) device memory. */
 int gw_simrank_exact(gw_graph *g, double c, int32_t iters, const int64_t *rows, int64_t nrows,
@@ -243,10 +266,16 @@ int gw_comm_init(int32_t rank, int32_t nranks, const void *id128, int32_t device
 int gw_comm_info(const gw_comm *c, int32_t *rank, int32_t *nranks, int32_t *device);
 int gw_comm_free(gw_comm *c);
 int gw_shard_range(int64_t n, int32_t rank, int32_t nranks, int64_t *lo, int64_t *hi);
+/* Device time of the last gw_*_sharded call on this communicator, split into this rank's own slice (kernels) and the
+ * NCCL exchange of the result blocks (0 for gather = 0: nothing is exchanged).  Either pointer may be NULL. */
+int gw_comm_last_times(const gw_comm *c, double *compute_ms, double *gather_ms);
 /* Every rank passes the SAME starts[n_starts]; rank r walks its slice with walk ids = global positions.
- * gather != 0: all ranks receive the whole corpus out_walks[n_starts*walk_length] (+ out_lens) -- identical to one
- * gw_node2vec_walks call on one GPU; gather == 0 (corpora beyond one GPU / host, e.g. R-MAT-26's 215 GB): only
- * this rank's rows of out_walks / out_lens are written, at their global offsets. */
+ * gather == 1: all ranks receive the whole corpus out_walks[n_starts*walk_length] (+ out_lens) -- identical to one
+ * gw_node2vec_walks call on one GPU; gather == 2: only rank 0 receives it (grouped ncclSend/ncclRecv; out_walks may be
+ * NULL elsewhere); gather == 0 (corpora beyond one GPU / host, e.g. R-MAT-26's 215 GB): nothing is exchanged, only this
+ * rank's rows of out_walks / out_lens are written, at their global offsets, through the same chunked hand-off pipeline
+ * as gw_node2vec_walks.  A collective call: per-rank failures (a start node outside the graph in one slice, an
+ * allocation) are agreed on over NCCL and returned by every rank. */
 int gw_node2vec_walks_sharded(gw_graph *g, gw_comm *c, double p, double q, int32_t walk_length,
                               const int64_t *starts, int64_t n_starts, uint64_t seed, int32_t gather,
                               int32_t *out_walks, int32_t *out_lens);

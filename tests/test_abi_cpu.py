@@ -81,3 +81,29 @@ def test_shard_range_matches_the_host_rule():
     for n in (0, 1, 7, 100003):
         for world in (1, 2, 3, 8):
             assert [_lib.shard_range(n, r, world) for r in range(world)] == [dist.shard_range(n, r, world) for r in range(world)]
+
+
+def test_corpus_unpack24_host_half_of_the_packed_handoff():
+    """gw_corpus_unpack24 (copy-thread pool + AVX2 / scalar widening) against numpy, ragged rows included: the host
+    half of gw_node2vec_walks' packed hand-off runs without a device."""
+    L_ = _lib.load()
+    rs = np.random.RandomState(5)
+    for n_walks, L, threads in [(1, 1, 1), (7, 5, 3), (8, 80, 2), (1000, 80, 4), (4099, 37, 16), (333, 80, 0)]:
+        ids = rs.randint(0, 1 << 24, size=(n_walks, L)).astype(np.int32)
+        ids[rs.randint(n_walks), :] = (1 << 24) - 1                          # the largest id is not a pad
+        lens = np.full(n_walks, L, dtype=np.int32)
+        short = rs.rand(n_walks) < 0.2
+        lens[short] = rs.randint(0, L + 1, size=int(short.sum()))
+        want = ids.copy()
+        want[np.arange(L)[None, :] >= lens[:, None]] = -1
+        b = np.where(want < 0, 0xFFFFFF, want).astype("<u4").view(np.uint8).reshape(-1, 4)[:, :3].copy().reshape(-1)
+        out = np.full((n_walks, L), 12345, dtype=np.int32)
+        rc = L_.gw_corpus_unpack24(b.ctypes.data_as(ctypes.c_void_p), lens.ctypes.data_as(_lib.c_i32p), n_walks, L, threads,
+                                   out.ctypes.data_as(_lib.c_i32p))
+        assert rc == 0 and np.array_equal(out, want), (n_walks, L, threads)
+        out2 = np.empty((n_walks, L), dtype=np.int32)                         # lens == NULL: every row is full
+        b2 = ids.astype("<u4").view(np.uint8).reshape(-1, 4)[:, :3].copy().reshape(-1)
+        assert L_.gw_corpus_unpack24(b2.ctypes.data_as(ctypes.c_void_p), None, n_walks, L, threads,
+                                     out2.ctypes.data_as(_lib.c_i32p)) == 0
+        assert np.array_equal(out2, ids)
+    assert L_.gw_corpus_unpack24(None, None, 4, 80, 1, None) == _lib.GW_E_INVALID
