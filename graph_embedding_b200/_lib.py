@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libgraphwalk.so")
 GW_OK, GW_E_INVALID, GW_E_CUDA, GW_E_IO, GW_E_TOO_LARGE, GW_E_STATE, GW_E_KEY = 0, -1, -2, -3, -4, -5, -6
 GW_MODE_SIMPLE, GW_MODE_MULTI = 0, 1
 GW_F_DIRECTED, GW_F_WEIGHTED, GW_F_MULTI = 1, 2, 4
-GW_SIMRANK_MC, GW_SIMRANK_HYBRID = 0, 1
+GW_SIMRANK_MC, GW_SIMRANK_HYBRID, GW_SIMRANK_MC_F64 = 0, 1, 2
 
 
 class GraphWalkError(RuntimeError):

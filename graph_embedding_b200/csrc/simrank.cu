@@ -48,6 +48,7 @@ struct SimrankParams {
     int32_t sample;
     int32_t k;
     float coef[16];                  // C^i / SAMPLE (i = 1..STEP)
+    double cpow64[16];               // C^i in fp64 (arithmetic-reference kernel only)
     uint2 key;
     uint64_t query_id_base;
     // per-CTA global scratch
@@ -186,7 +187,7 @@ __device__ __forceinline__ int4 ld_nbr4(const int4 *ptr) {
 // called STEP*ILP times by every lane (lock-step), x = C^i * deg(path[i]) / deg(path[2i]) / SAMPLE.
 // Sample s draws word (t & 3) of Philox(qid, s, t >> 2) at step t: paths do not depend on ILP,
 // block size or grid.
-template <int STEP, int ILP, typename Emit>
+template <int STEP, int ILP, bool F64 = false, typename Emit>
 __device__ __forceinline__ int walk_group(const SimrankParams &P, int32_t v, uint2 mv, uint64_t qid, int32_t g,
                                           Emit &&emit) {
     constexpr int LEN = 2 * STEP;
@@ -209,8 +210,13 @@ __device__ __forceinline__ int walk_group(const SimrankParams &P, int32_t v, uin
 #pragma unroll
         for (int j = 0; j < i; j++) ok &= (path[k][j] != path[k][2 * i - j]);   // isFirstMeet :100-106
         // m[k] still describes path[2i]: its degree is the divisor
-        const float x = __fdividef(P.coef[i] * (float)dmid[k][i], (float)max(m[k].y, 1u));
-        emit(ok, (uint32_t)target, x);
+        if constexpr (F64) {
+            // SingleRandomWalk.java:89 in its own type and operation order: cache[i] * deg(inter) / deg(target) / SAMPLE
+            emit(ok, (uint32_t)target, P.cpow64[i] * (double)dmid[k][i] / (double)max(m[k].y, 1u) / (double)P.sample);
+        } else {
+            const float x = __fdividef(P.coef[i] * (float)dmid[k][i], (float)max(m[k].y, 1u));
+            emit(ok, (uint32_t)target, x);
+        }
     };
 #pragma unroll
     for (int t = 0; t < LEN; t++) {
@@ -425,6 +431,28 @@ __global__ void __launch_bounds__(SR_BLOCK, 2) k_simrank_mc(SimrankParams P) {
     }
     for (int o = 16; o; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
     if ((tid & 31) == 0 && my_steps && !P.qlist) atomicAdd(P.steps, my_steps);   // handed-over queries were counted by the log kernel
+}
+
+// ---------------------------------------------------------------------------------------------
+// arithmetic reference (GW_SIMRANK_MC_F64): the SAME Philox walks as the two production kernels, every
+// increment evaluated and added in fp64 as SingleRandomWalk.java:89 does, straight into the dense row.
+// Exists to bound what fp32 increments + 32.32 fixed-point accumulation cost (tests: <= 1e-6 absolute).
+// ---------------------------------------------------------------------------------------------
+template <int STEP>
+__global__ void __launch_bounds__(256) k_simrank_f64(SimrankParams P) {
+    unsigned long long my_steps = 0;
+    for (int64_t qi = blockIdx.x; qi < P.nq; qi += gridDim.x) {
+        const int32_t v = (int32_t)P.queries[qi];
+        const uint64_t qid = P.query_id_base + (uint64_t)qi;
+        const uint2 mv = __ldg(P.meta + v);
+        double *row = P.out_dense + (size_t)qi * (size_t)P.n;
+        for (int32_t g = threadIdx.x; g < P.sample; g += blockDim.x)
+            my_steps += (unsigned long long)walk_group<STEP, 1, true>(P, v, mv, qid, g, [&](bool ok, uint32_t target, double x) {
+                if (ok) atomicAdd(row + target, x);
+            });
+    }
+    for (int o = 16; o; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
+    if ((threadIdx.x & 31) == 0 && my_steps) atomicAdd(P.steps, my_steps);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1354,7 +1382,7 @@ extern "C" int gw_simrank_check_args(const gw_graph *g, double c, int32_t step, 
     if (sample < 1) return fail(GW_E_INVALID, "sample must be positive");
     if (!(c > 0) || !(c < 1)) return fail(GW_E_INVALID, "decay c must be in (0,1)");
     if (k < 1 || k > SR_LCAND / 2) return fail(GW_E_INVALID, "k must be in 1..%d", SR_LCAND / 2);
-    if (mode != GW_SIMRANK_MC && mode != GW_SIMRANK_HYBRID) return fail(GW_E_INVALID, "unknown estimator mode %d", mode);
+    if (mode != GW_SIMRANK_MC && mode != GW_SIMRANK_HYBRID && mode != GW_SIMRANK_MC_F64) return fail(GW_E_INVALID, "unknown estimator mode %d", mode);
     return GW_OK;
 }
 
@@ -1368,6 +1396,7 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     int sms = 0;
     GW_TRY(device_info(&sms, nullptr));
     const bool hybrid = mode == GW_SIMRANK_HYBRID;
+    if (mode == GW_SIMRANK_MC_F64 && !d_out_dense) return fail(GW_E_INVALID, "GW_SIMRANK_MC_F64 produces dense rows only (gw_simrank_rows)");
     const int grid = (int)std::min<int64_t>(nq, (int64_t)sms * (hybrid ? 1 : 2));
     const int log_grid = (int)std::min<int64_t>(nq, (int64_t)sms);      // log kernel: one 1024-thread CTA per SM
     const char *force = getenv("GW_SIMRANK");
@@ -1427,6 +1456,7 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     P.inv_sample = 1.0 / (double)sample;
     for (int i = 0; i < 16; i++) P.coef[i] = 0;
     for (int i = 1; i <= step; i++) P.coef[i] = (float)(pow(c, i) / (double)sample);   // cache[i] = Math.pow(C, i) (:34-36), / SAMPLE (:89)
+    for (int i = 0; i < 16; i++) P.cpow64[i] = (i >= 1 && i <= step) ? pow(c, i) : 0.0;
     P.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     P.query_id_base = query_id_base;
     P.gs_mask = gs - 1; P.olist_cap = ocap;
@@ -1475,6 +1505,12 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
             k_topsim_hybrid<N, false><<<grid, SR_BLOCK, sizeof(HyShared<false>), st>>>(Q, H); break;
         switch (step) { GW_HY(1) GW_HY(2) GW_HY(3) GW_HY(4) GW_HY(5) GW_HY(6) GW_HY(7) GW_HY(8) GW_HY(9) default: GW_HY(10) }
 #undef GW_HY
+        GW_LAUNCHED();
+    } else if (mode == GW_SIMRANK_MC_F64) {
+        const int fgrid = (int)std::min<int64_t>(nq, (int64_t)sms * 8);
+#define GW_F64(N) case N: k_simrank_f64<N><<<fgrid, 256, 0, st>>>(P); break;
+        switch (step) { GW_F64(1) GW_F64(2) GW_F64(3) GW_F64(4) GW_F64(5) GW_F64(6) GW_F64(7) GW_F64(8) GW_F64(9) default: GW_F64(10) }
+#undef GW_F64
         GW_LAUNCHED();
     } else
     switch (step) {

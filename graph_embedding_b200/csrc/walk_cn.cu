@@ -344,6 +344,26 @@ struct CnParams {
 };
 
 __device__ __forceinline__ float unit24(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ double unit32(uint32_t r) { return ((double)r + 0.5) * (1.0 / 4294967296.0); }
+
+// Component choice of the mixture for rows longer than WIDE_MIN_DEG entries (HUB instantiations only): the same
+// decision tree as the fp32 code in k_walk_cn, evaluated in fp64 with 32-bit uniforms.
+constexpr uint32_t WIDE_MIN_DEG = 4096;
+__device__ __noinline__ int pick_component_wide(const CnParams &P, uint32_t d, int32_t c, uint32_t r0bits, uint32_t r2bits, bool ridx) {
+    const double a = (double)P.a, b = (double)P.b, r = (double)P.r, lo = (double)P.lo, r0 = (double)P.r0;
+    const double dm1 = (double)(d - 1);
+    const double MR = r - r0, MA = lo * dm1 + r0, MC = (b - lo) * (double)c, MO = (a - lo) * (dm1 - (double)c);
+    const double u = unit32(r0bits) * (MR + MA + MC + MO);
+    const bool haveC = MC > 0.0, haveO = MO > 0.0;
+    int comp;
+    if (d == 1 || u < MR) comp = 0;
+    else if (u < MR + MA) comp = 1;
+    else if (haveC && (u < MR + MA + MC || !haveO)) comp = 2;
+    else if (haveO) comp = 3;
+    else comp = 1;
+    if (ridx && comp == 1 && unit32(r2bits) * MA < r0) comp = 0;
+    return comp;
+}
 
 // Uniform draw from N(cur) & N(prev) by rejection: x uniform over the SHORTER row S, accepted iff it is in
 // the other row T (uniform over S, conditioned on membership, is uniform over S & T).  The membership test
@@ -415,8 +435,8 @@ __device__ __noinline__ int4 step_by_rejection(const CnParams &P, uint2 m, uint2
                                                int32_t pos, uint4 rnd, unsigned long long *acc, unsigned long long *prop,
                                                uint32_t *kout) {
     const uint32_t d = m.y;
-    const float Wp = P.a * ((float)(d - 1) - (float)c) + P.b * (float)c;
-    if (d == 1 || unit24(rnd.x) * (P.r + Wp) < P.r) return make_int4(-2, 0, 0, 0);
+    const double Wp = (double)P.a * ((double)(d - 1) - (double)c) + (double)P.b * (double)c;      // both rows are long: fp64 + 32-bit uniform
+    if (d == 1 || unit32(rnd.x) * ((double)P.r + Wp) < (double)P.r) return make_int4(-2, 0, 0, 0);
     const float hi = fmaxf(P.a, P.b), lo = fminf(P.a, P.b);
     const uint32_t ssec = (uint32_t)max(1, (32 - __clz(mprev.y)) - 2);
     uint32_t rk = rnd.y, ra = rnd.z, att = 0;
@@ -518,6 +538,13 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                         else { nxt = e.x; cn = CNT(e.y); nr = RIX(e.y); mn = make_uint2((uint32_t)e.z, (uint32_t)e.w); }
                         if (COUNT) { st_acc += racc; st_prop += rprop; }
                     } else {
+                        int comp;                                     // 0 = R, 1 = A, 2 = C, 3 = O
+                        if (HUB && d > WIDE_MIN_DEG) {
+                            // long rows: masses in fp64 against a 32-bit uniform.  fp32 masses and 24-bit uniforms resolve
+                            // a component's probability to ~6e-8 of the total; the return mass of a 163 k-entry row is
+                            // ~1e-4 of it, i.e. a 6e-4 relative error no test could see.  Pure ALU, off the memory path.
+                            comp = pick_component_wide(P, d, c, rnd.x, rnd.z, RIDX);
+                        } else {
                         const float dm1 = (float)(d - 1);
                         const float MR = P.r - P.r0;
                         const float MA = P.lo * dm1 + P.r0;
@@ -525,7 +552,6 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                         const float MO = (P.a - P.lo) * (dm1 - (float)c);
                         float u = unit24(rnd.x) * (MR + MA + MC + MO);
                         const bool haveC = MC > 0.0f, haveO = MO > 0.0f;
-                        int comp;                                     // 0 = R, 1 = A, 2 = C, 3 = O
                         if (d == 1 || u < MR) comp = 0;               // d == 1: prev is the only neighbour
                         else if (u < MR + MA) comp = 1;
                         else if (haveC && (u < MR + MA + MC || !haveO)) comp = 2;
@@ -534,6 +560,7 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                         // RIDX: component A's share of prev (mass r0 of MA) is a return step decided up front; everything
                         // else draws from the d-1 entries that are not prev (index shifted past rprev)
                         if (RIDX && comp == 1 && unit24(rnd.z) * MA < P.r0) comp = 0;
+                        }
                         if (COUNT && comp != 0) st_acc++;                  // one random {nbr,cnt,off,deg} access
                         // A and O both open with one proposal from N(cur): ONE load instruction for the lanes of either
                         // component.  Issued inside the two branches, a warp whose lanes split between A and O (q < 1:

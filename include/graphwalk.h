@@ -52,6 +52,9 @@ extern "C" {
 /* SimRank estimator modes */
 #define GW_SIMRANK_MC 0     /* simrank/SingleRandomWalk.java:53-106 (scores / SAMPLE) */
 #define GW_SIMRANK_HYBRID 1 /* simrank/TopSim_singleSample.java:62-203 (scores x SAMPLE, as the reference) */
+#define GW_SIMRANK_MC_F64 2 /* gw_simrank_rows only: the walks of GW_SIMRANK_MC (same seed => same paths) with every
+                               increment evaluated and added in fp64 as SingleRandomWalk.java:89 -- the arithmetic
+                               reference that bounds the production kernels' fp32 / 32.32 fixed-point accumulation */
 
 typedef struct gw_graph gw_graph;
 

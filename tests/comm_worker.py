@@ -34,6 +34,13 @@ starts = np.tile(h.nonisolated(), 2)[:100003]                    # odd count: ra
 whole, wl = h.walks(0.25, 4.0, 40, starts, seed=9)
 got, gl = comm.walks(h, 0.25, 4.0, 40, starts, seed=9)
 assert np.array_equal(got, whole) and np.array_equal(gl, wl), "gathered corpus differs from the single-GPU corpus"
+ct, gt = comm.last_times()
+assert ct > 0 and (gt > 0 or nranks == 1), (ct, gt)               # own slice | NCCL exchange, device-timed
+root, rl = comm.walks(h, 0.25, 4.0, 40, starts, seed=9, gather=2)  # gather to rank 0 only (grouped ncclSend / ncclRecv)
+if rank == 0:
+    assert np.array_equal(root, whole) and np.array_equal(rl, wl)
+else:
+    assert (root == -1).all()                                      # nothing is written on the other ranks
 mine, ml = comm.walks(h, 4.0, 0.5, 40, starts, seed=9, gather=False)
 lo, hi = _lib.shard_range(len(starts), rank, nranks)
 ref, _ = h.walks(4.0, 0.5, 40, starts[lo:hi], seed=9, walk_id_base=lo)
@@ -50,6 +57,26 @@ try:
     raise SystemExit("an out-of-range start node was accepted")
 except KeyError:
     pass                                                         # every rank refuses together, nobody waits inside NCCL
+# fewer units than ranks + an argument every rank must refuse: ranks with an empty slice return too, nobody hangs
+for bad in (dict(p=-1.0), dict(L=0)):
+    try:
+        comm.walks(h, bad.get("p", 1.0), 1.0, bad.get("L", 10), np.array([0], dtype=np.int64))
+        raise SystemExit("an invalid argument was accepted")
+    except ValueError:
+        pass
+try:
+    comm.simrank_topk(b, q[:1], 0.6, 11, 100, 20)                  # step out of range, one query for nranks ranks
+    raise SystemExit("step = 11 was accepted")
+except ValueError:
+    pass
+try:
+    comm.simrank_topk(b, np.array([b.n + 3], dtype=np.int64), 0.6, 5, 100, 20)
+    raise SystemExit("an out-of-range query was accepted")
+except KeyError:
+    pass
+one, _ = comm.walks(h, 1.0, 1.0, 10, np.array([5], dtype=np.int64), seed=1)   # one unit: all but one slice are empty
+ref1, _ = h.walks(1.0, 1.0, 10, np.array([5], dtype=np.int64), seed=1)
+assert np.array_equal(one, ref1)
 comm.close()
 with open("%s.%d" % (out, rank), "w") as f:
     f.write("ok")
