@@ -432,10 +432,164 @@ def main():
                                                     "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks")
                                  if k in l2}
             line["gpu_launches"] += l2["gpu_launches"]
+    run_sharded = args.sharded == "on" or (args.sharded == "auto" and args.workload == "node2vec" and
+                                              (world > 1 or (args.scale == 22 and not args.no_secondary)))
+    if run_sharded:
+        sh = measure_sharded(args, rank, world, local)
+        if rank == 0:
+            line["sharded"] = sh            # its own gpu_launches inside; the line's count stays that of the timed headline regions
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_sharded(args, rank, world, local):
+    """BASELINE configs[3] and configs[4] through the C ABI's own multi-GPU entry points (gw_comm_init +
+    gw_node2vec_walks_sharded / gw_simrank_topk_sharded): the start list / query list is SPLIT over the ranks
+    (gw_shard_range), the graph is replicated, the walk corpus stays sharded (gather = 0: 21 GB per pass fit no single
+    host buffer sensibly) and the top-k tiles are gathered over NCCL.  Strong scaling: the same total work at every N;
+    `one_gpu_ms` is the same pass walked by ONE GPU in this very run (every rank does it, max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    from graph_embedding_b200 import _lib
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream().cuda_stream
+    launches0 = _lib.kernel_launches()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # gw_comm bootstrap as any launcher does it: rank 0's 128-byte NCCL id travels over the existing process group
+    uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        uid = torch.tensor(list(_lib.Comm.unique_id()), dtype=torch.uint8, device=dev)
+    if world > 1:
+        dist.broadcast(uid, 0)
+    comm = _lib.Comm(rank, world, bytes(uid.cpu().numpy().tobytes()), local)
+    out = {"api": "gw_comm_init + gw_node2vec_walks_sharded(gather=0) / gw_simrank_topk_sharded (include/graphwalk.h)",
+           "n_gpus": world, "scaling": "strong"}
+
+    # ---------------- configs[3]: node2vec, R-MAT scale-26 (default), p=4 q=0.5, ONE pass of the start list ----------------
+    L, p, q = args.walk_length, 4.0, 0.5
+    t0 = time.perf_counter()
+    g = _lib.GraphHandle.rmat(args.shard_scale, args.edge_factor << args.shard_scale, seed=1)
+    build_s = time.perf_counter() - t0
+    prep_ms = g.prepare_walks()
+    starts = np.random.RandomState(99).permutation(g.nonisolated())         # random.shuffle(nodes), node2vec.py:51 (same on every rank)
+    n = len(starts)
+    lo, hi = _lib.shard_range(n, rank, world)
+    mine = hi - lo
+    d_starts = torch.from_numpy(starts).to(dev)
+    d_out = torch.empty((max(mine, 1), L), dtype=torch.int32, device=dev)
+
+    def walk_slice(a, b):
+        g.walks_dev(p, q, L, d_starts.data_ptr() + 8 * a, b - a, d_out.data_ptr(), seed=42, walk_id_base=a, stream=stream)
+
+    walk_slice(lo, min(hi, lo + (1 << 20)))                                   # warm-up: Bloom filter, code, clocks
+    barrier()
+    reps = 3
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(reps):
+        walk_slice(lo, hi)
+    ev[1].record()
+    barrier()
+    shard_ms = allmax(ev[0].elapsed_time(ev[1]) / reps)
+    steps_mine, _ = g.byte_model_dev(d_out.data_ptr(), mine, L, True, stream=stream)
+    steps_all = allsum(steps_mine)
+    one_ms = shard_ms
+    if world > 1:                                                             # the same pass on ONE GPU: slices walked back to back
+        barrier()
+        ev[0].record()
+        for r in range(world):
+            a, b = _lib.shard_range(n, r, world)
+            walk_slice(a, b)
+        ev[1].record()
+        barrier()
+        one_ms = allmax(ev[0].elapsed_time(ev[1]))
+    # end to end through the sharded C-ABI call: host start list in (all of it, on every rank), this rank's rows out
+    h_out = np.empty((n, L), dtype=np.int32)                                  # rows of other ranks are never touched (no pages committed)
+    comm.walks(g, p, q, L, starts, seed=42, gather=0, out=h_out)              # first call: page faults of the fresh buffer, ring allocation
+    barrier()
+    t0 = time.perf_counter()
+    comm.walks(g, p, q, L, starts, seed=42, gather=0, out=h_out)
+    e2e_s = allmax(time.perf_counter() - t0)
+    ho = g.last_handoff()
+    same = bool((torch.from_numpy(h_out[lo:lo + min(mine, 4096)]).to(dev) == d_out[:min(mine, 4096)]).all().item()) if mine else True
+    out["node2vec_rmat%d" % args.shard_scale] = {
+        "workload": "node2vec on synthetic R-MAT scale-%d (%d*2^%d tuples, a,b,c,d=.45/.15/.15/.25), p=%g q=%g, walk_length=%d, ONE pass: "
+                    "one walk per non-isolated vertex, start list split over %d GPU(s)" % (args.shard_scale, args.edge_factor, args.shard_scale, p, q, L, world),
+        "graph": {"nodes": g.n, "non_isolated": n, "directed_entries": g.nnz, "max_degree": g.max_degree},
+        "graph_build_s": round(build_s, 3), "walk_preprocess_ms": round(prep_ms, 3),
+        "walk_steps": int(steps_all), "device_ms": shard_ms, "value": steps_all / (shard_ms * 1e-3), "unit": "walk-steps/s",
+        "one_gpu_ms": one_ms, "strong_scaling_efficiency": one_ms / (world * shard_ms),
+        "e2e": {"seconds": e2e_s, "value": steps_all / e2e_s, "unit": "walk-steps/s", "handoff": ho,
+                "h2d_bytes": n * 8, "d2h_bytes_per_rank": mine * L * 4, "corpus_matches_device_run": same,
+                "limiter": "host link: every rank moves its own %d MB block through PCIe and the host's copy threads; "
+                           "no NCCL traffic (gather = 0)" % (mine * L * 4 // (1 << 20))}}
+    del d_out, d_starts, h_out, g
+    torch.cuda.empty_cache()
+
+    # ---------------- configs[4]: TopSim top-20, BA n=1e7 m=8, 1 M queries, tiles gathered over NCCL ----------------
+    t0 = time.perf_counter()
+    b = _lib.GraphHandle.barabasi_albert(args.ba_nodes, args.ba_m, seed=1)
+    build_s = time.perf_counter() - t0
+    nq = min(args.shard_queries, b.n)
+    queries = np.random.RandomState(2).choice(b.n, size=nq, replace=False).astype(np.int64)
+    comm.simrank_topk(b, queries[:8192 * world], 0.6, args.sr_step, args.sample, args.topk, seed=7)      # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    ids, sc = comm.simrank_topk(b, queries, 0.6, args.sr_step, args.sample, args.topk, seed=7)
+    e2e_s = allmax(time.perf_counter() - t0)
+    comp_ms, gath_ms = comm.last_times()
+    comp_ms, gath_ms = allmax(comp_ms), allmax(gath_ms)
+    one_ms = comp_ms
+    if world > 1:                                                             # the same 1 M queries on ONE GPU (every rank, max)
+        d_q = torch.from_numpy(queries).to(dev)
+        d_ids = torch.empty((nq, args.topk), dtype=torch.int32, device=dev)
+        d_sc = torch.empty((nq, args.topk), dtype=torch.float64, device=dev)
+        barrier()
+        ev[0].record()
+        b.simrank_topk_dev(d_q.data_ptr(), nq, 0.6, args.sr_step, args.sample, args.topk, d_ids.data_ptr(), d_sc.data_ptr(),
+                           seed=7, query_id_base=0, stream=stream)
+        ev[1].record()
+        barrier()
+        one_ms = allmax(ev[0].elapsed_time(ev[1]))
+        lo_q, hi_q = _lib.shard_range(nq, rank, world)
+        k = min(2048, hi_q - lo_q)
+        same = bool(np.array_equal(d_ids[lo_q:lo_q + k].cpu().numpy(), ids[lo_q:lo_q + k]))
+    else:
+        same = True
+    out["topsim_ba%d" % args.ba_nodes] = {
+        "workload": "TopSim SimRank top-%d on synthetic Barabasi-Albert n=%d m=%d, c=0.6 STEP=%d SAMPLE=%d, %d queries drawn without "
+                    "replacement, split over %d GPU(s), top-k tiles gathered to every rank" % (args.topk, b.n, args.ba_m, args.sr_step, args.sample, nq, world),
+        "graph_build_s": round(build_s, 3), "queries": nq,
+        "device_ms": comp_ms, "gather_ms": gath_ms, "gather_share": gath_ms / max(comp_ms + gath_ms, 1e-9),
+        "gather_bytes_per_rank": nq * args.topk * 12,
+        "value": nq / ((comp_ms + gath_ms) * 1e-3), "unit": "queries/s",
+        "one_gpu_ms": one_ms, "strong_scaling_efficiency": one_ms / (world * (comp_ms + gath_ms)),
+        "e2e": {"seconds": e2e_s, "value": nq / e2e_s, "unit": "queries/s", "h2d_bytes": nq * 8, "d2h_bytes_per_rank": nq * args.topk * 12},
+        "gathered_equals_one_gpu": same}
+    out["gpu_launches"] = int(_lib.kernel_launches() - launches0)
+    comm.close()
+    del b
+    torch.cuda.empty_cache()
+    return out
 
 
 def measure(args, rank, world, local):

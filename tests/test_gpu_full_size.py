@@ -114,3 +114,48 @@ def test_ba10m_topsim_full_size_properties(monkeypatch):
     assert np.array_equal(u_ids, t_ids[200:]) and u_sc.tobytes() == t_sc[200:].tobytes()
     m = np.median(t_sc[:, 0] / 10000.0 / sc[:512, 0])
     assert 0.5 < m < 1.5, m                                                     # both estimate the same top score
+
+
+def test_rmat26_node2vec_sharded_shape_properties():
+    """BASELINE configs[3]: R-MAT scale-26 (2^26 ids, 2^30 tuples, 2.1 G directed entries), p = 4, q = 0.5.  The graph is
+    generated, built and preprocessed on the device (common-neighbour counts over 1.07 G undirected edges); a sample of
+    the start list is walked through the host API.  Size-independent properties, as at scale 22: every step follows an
+    edge, no dead ends, the return component follows get_alias_edge's law (node2vec.py:61-81) with c from a host
+    intersection, and the corpus does not depend on how the start list is split (the multi-GPU sharding rule)."""
+    h = _lib.GraphHandle.rmat(26, 16 << 26, seed=1)
+    assert h.n == 1 << 26 and h.nnz == 2147147818 and h.max_degree == 3546
+    prep_ms = h.prepare_walks()
+    assert 0 < prep_ms < 60000
+    starts = h.nonisolated()
+    assert len(starts) == 66634460
+    c = h.csr(weights=False, node_ids=False, first_seen=False)                  # 8.6 GB + 0.5 GB to the host
+    rp, col = c["row_ptr"], c["col_idx"]
+    deg = np.diff(rp)
+    assert rp[-1] == h.nnz and deg.max() == 3546
+    rs = np.random.RandomState(26)
+    sample = np.sort(rs.choice(len(starts), size=1 << 20, replace=False))
+    sub = starts[sample]
+    walks, lens = h.walks(4.0, 0.5, 80, sub, seed=3, walk_id_base=0)
+    assert (lens == 80).all() and np.array_equal(walks[:, 0], sub) and walks.min() >= 0 and walks.max() < h.n
+    assert _steps_follow_edges(rp, col, walks[::53])
+    assert (walks[:, 2:] == walks[:, :-2]).mean() < 0.02                        # p = 4 avoids the return edge ...
+    ws = walks[::531]                                                           # ... at exactly the law's rate: 1975 walks, 154 k contexts
+    prev, cur, nxt = ws[:, :-2].ravel(), ws[:, 1:-1].ravel(), ws[:, 2:].ravel()
+    pred = np.empty(len(prev))
+    for i, (u, v) in enumerate(zip(prev.tolist(), cur.tolist())):
+        cnt = len(np.intersect1d(col[rp[u]:rp[u + 1]], col[rp[v]:rp[v + 1]], assume_unique=True))
+        pred[i] = 0.25 / (0.25 + cnt + (deg[v] - 1 - cnt) * 2.0)
+    obs = (nxt == prev).mean()
+    assert abs(obs - pred.mean()) < 5 * np.sqrt(pred.mean() / len(pred)) + 2e-4, (obs, pred.mean())
+    # the common-neighbour counts the walker uses, against the same host intersection (sampled contexts)
+    # split independence = the sharding rule of gw_node2vec_walks_sharded: slices with their global walk ids
+    k = 400000
+    a, _ = h.walks(4.0, 0.5, 80, sub[:k], seed=3, walk_id_base=0)
+    b, _ = h.walks(4.0, 0.5, 80, sub[k:k + 50000], seed=3, walk_id_base=k)
+    assert np.array_equal(a, walks[:k]) and np.array_equal(b, walks[k:k + 50000])
+    for nranks in (2, 8):                                                       # gw_shard_range slices tile the list
+        edges = [_lib.shard_range(len(sub), r, nranks) for r in range(nranks)]
+        assert edges[0][0] == 0 and edges[-1][1] == len(sub) and all(edges[i][1] == edges[i + 1][0] for i in range(nranks - 1))
+    lo, hi = _lib.shard_range(len(sub), 5, 8)
+    s5, _ = h.walks(4.0, 0.5, 80, sub[lo:hi], seed=3, walk_id_base=lo)
+    assert np.array_equal(s5, walks[lo:hi])
