@@ -113,6 +113,14 @@ void unpack24(const uint8_t *src, int32_t *dst, size_t count) {
     unpack24_scalar(src, dst, count);
 }
 
+void copy_stream(const void *src, void *dst, size_t bytes) {
+#if defined(__x86_64__)
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) { copy_stream_avx2(src, dst, bytes); return; }
+#endif
+    memcpy(dst, src, bytes);
+}
+
 namespace {
 struct DrainJob {
     const uint8_t *src;
@@ -132,7 +140,7 @@ void drain_part(int part, int nparts, void *arg) {
     if (w0 >= w1) return;
     const size_t first = (size_t)w0 * (size_t)J.L, count = (size_t)(w1 - w0) * (size_t)J.L;
     if (J.packed) unpack24(J.src + 3 * first, J.dst + first, count);
-    else memcpy(J.dst + first, J.src + 4 * first, 4 * count);
+    else copy_stream(J.src + 4 * first, J.dst + first, 4 * count);
     if (J.lens) {
         if (J.packed)
             for (int64_t w = w0; w < w1; w++) {

@@ -37,7 +37,10 @@ void unpack24(const uint8_t *src, int32_t *dst, size_t count);
 void unpack24_scalar(const uint8_t *src, int32_t *dst, size_t count);
 #if defined(__x86_64__)
 void unpack24_avx2(const uint8_t *src, int32_t *dst, size_t count);     // unpack_avx2.cpp, built with -mavx2
+void copy_stream_avx2(const void *src, void *dst, size_t bytes);        // memcpy with non-temporal stores (no read-for-ownership)
 #endif
+// plain chunk copy of the ring (ids stay 4 bytes): non-temporal stores when the CPU has AVX2, memcpy otherwise
+void copy_stream(const void *src, void *dst, size_t bytes);
 
 // One chunk of walks, staged in pinned memory, into rows [0, n_walks) of dst (row length L ids).
 //   packed != 0: src holds 3-byte ids; else 4-byte ids (plain copy).

@@ -41,5 +41,20 @@ void unpack24_avx2(const uint8_t *src, int32_t *dst, size_t count) {
     unpack24_scalar(src + 3 * i, dst + i, count - i);
 }
 
+void copy_stream_avx2(const void *src, void *dst, size_t bytes) {
+    const uint8_t *s = (const uint8_t *)src;
+    uint8_t *d = (uint8_t *)dst;
+    size_t i = 0;
+    while (i < bytes && ((uintptr_t)(d + i) & 31)) { d[i] = s[i]; i++; }
+    for (; i + 128 <= bytes; i += 128) {
+        const __m256i a = _mm256_loadu_si256((const __m256i *)(s + i)), b = _mm256_loadu_si256((const __m256i *)(s + i + 32));
+        const __m256i c = _mm256_loadu_si256((const __m256i *)(s + i + 64)), e = _mm256_loadu_si256((const __m256i *)(s + i + 96));
+        _mm256_stream_si256((__m256i *)(d + i), a); _mm256_stream_si256((__m256i *)(d + i + 32), b);
+        _mm256_stream_si256((__m256i *)(d + i + 64), c); _mm256_stream_si256((__m256i *)(d + i + 96), e);
+    }
+    _mm_sfence();
+    for (; i < bytes; i++) d[i] = s[i];
+}
+
 }  // namespace gw
 #endif

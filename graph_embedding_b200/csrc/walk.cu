@@ -341,8 +341,11 @@ static int pick_handoff(const gw_graph *g, const void *out_walks, int threads) {
     bool pinned = false;
     if (cudaPointerGetAttributes(&at, out_walks) == cudaSuccess) pinned = at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
     else cudaGetLastError();
-    if (can_pack && threads >= 8) return GW_HANDOFF_PACKED;   // the copy threads keep up with the link from ~8 up (profiles/README.md §5)
-    return pinned ? GW_HANDOFF_DIRECT : GW_HANDOFF_RING;
+    // measured (profiles/README.md section 5, 16 host threads): direct DMA into page-locked memory runs at the link's
+    // rate and costs no core; into pageable memory the packed ring reaches 0.97 of that, the plain ring 0.69 (host
+    // copy bandwidth), so packing is what makes a pageable caller whole -- and buys a pinned one nothing
+    if (pinned) return GW_HANDOFF_DIRECT;
+    return can_pack ? GW_HANDOFF_PACKED : GW_HANDOFF_RING;
 }
 
 }  // extern "C"
