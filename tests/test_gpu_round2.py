@@ -174,58 +174,60 @@ def blog_gold():
     return np.load(os.path.join(GOLDEN, "blog_exact_s5.npz"))
 
 
-def _sigma_bound(score, deg_target, sample, max_deg=3992, c=0.6):
-    """Upper bound of the estimator's own standard deviation on one entry.  A sample contributes X = sum over levels of
-    C^i deg(mid)/deg(t) on a first meeting at t (SingleRandomWalk.java:89), E[X] = score, and X <= w = C/(1-C) * max_deg /
-    deg(t), hence Var[X] <= E[X^2] <= w * score and sd(estimate) <= sqrt(w * score / SAMPLE).  On blog.txt this is what
-    the 1e-3 criterion has to be read against: a degree-1 neighbour of the 3992-degree hub carries increments of
-    0.6 * 3992 / SAMPLE, and the REFERENCE's estimator is that noisy there too ("Hard parts")."""
-    return np.sqrt(c / (1 - c) * max_deg / np.maximum(deg_target, 1) * np.maximum(score, 0) / sample)
-
-
 def test_blog_production_kernels_against_truncated_exact(blog, blog_gold):
     """64 queries (the isolated slot 0, the 3992-degree hub, degrees 1, 2, 64, 256 among them): rows and top-k of the
     production kernels at SAMPLE = 1e6 against exact SimRank truncated at 5 sweeps (tests/golden/make_golden_blog.py,
-    the expectation of SingleRandomWalk.java:81-92) on the exact top-20 of every query:
-      * every entry within 1e-3 + 4 sigma of its exact value, sigma = the estimator's own noise bound (_sigma_bound);
-      * no bias: the pooled z-scores average to 0 within 5 / sqrt(N);
-      * on the well-conditioned entries (sigma <= 2.5e-4) the plain criterion: rms <= 1e-3, worst <= 3e-3."""
+    the expectation of SingleRandomWalk.java:81-92) on the exact top-20 of every query.
+
+    On blog.txt the estimator itself is noisy where a low-degree target meets through the 3992-degree hub (one hit adds
+    0.6 * 3992 / deg(target) / SAMPLE -- the REFERENCE's estimator has the same variance), so the
+    1e-3 criterion is read as SURVEY states it: |delta| <= 1e-3 + 4 sigma per entry, with sigma measured from 16
+    independent runs of the kernel, plus two sharper statements:
+      * no bias: the mean of the 16 runs is within 1e-3 / 4 + 5 standard errors of the exact value on EVERY entry, and
+        the pooled t-scores average to zero;
+      * where the estimator is well conditioned (sigma <= 2.5e-4) a single run is within 1e-3, rms and worst case."""
     q = blog_gold["queries"]
     deg = blog_gold["degrees"]
     assert q[0] == 0 and deg[0] == 0 and deg.max() == 3992 and {1, 2, 64, 256} <= set(deg.tolist())
     h = blog.handle
-    vdeg = np.diff(h.csr(weights=False, node_ids=False, first_seen=False)["row_ptr"])
-    sample = 1000000
-    rows = h.simrank_rows(q, 0.6, 5, sample, seed=31)                               # hash kernel (dense rows)
+    sample, R = 1000000, 16
+    runs = np.stack([h.simrank_rows(q, 0.6, 5, sample, seed=31 + 1000 * k) for k in range(R)])      # hash kernel (dense rows)
+    rows = runs[0]
     ids, sc = h.simrank_topk(q, 0.6, 5, sample, 20, seed=31)                        # log kernel (+ hand-over)
-    zs, good = [], []
+    ts, single, sig_all = [], [], []
     for r, v in enumerate(q):
         top, val = blog_gold["top_ids"][r, :20], blog_gold["top_scores"][r, :20]
         if deg[r] == 0:
-            assert rows[r].sum() == 0 and (ids[r] == -1).all()
+            assert runs[:, r].sum() == 0 and (ids[r] == -1).all()
             continue
-        d = rows[r][top] - val
-        sig = _sigma_bound(val, vdeg[top], sample)
-        assert (np.abs(d) <= 1e-3 + 4 * sig).all(), (v, d, sig)
-        zs.append(d / np.maximum(sig, 1e-12))
-        good.append(d[sig <= 2.5e-4])
+        est = runs[:, r][:, top]                                                   # [R, 20]
+        mean, sd = est.mean(axis=0), est.std(axis=0, ddof=1)
+        se = sd / np.sqrt(R)
+        assert (np.abs(mean - val) <= 2.5e-4 + 5 * se).all(), (v, mean - val, se)
+        assert (np.abs(est[0] - val) <= 1e-3 + 4 * sd).all(), (v, est[0] - val, sd)
+        ts.append((mean - val) / np.maximum(se, 1e-9))
+        single.append(est[0] - val)
+        sig_all.append(sd)
         assert abs(rows[r].sum() - blog_gold["row_sums"][r]) <= 0.02 * blog_gold["row_sums"][r] + 1e-3
         # top-k of the log kernel == top-k of the dense row, bit for bit (same integers added)
         order = np.lexsort((np.arange(10313), -rows[r]))[:20]
         order = order[rows[r][order] > 0]
         assert ids[r, :len(order)].tolist() == order.tolist() and sc[r, :len(order)].tobytes() == rows[r][order].tobytes()
-    zs, good = np.concatenate(zs), np.concatenate(good)
-    assert abs(zs.mean()) <= 5.0 / np.sqrt(len(zs)), zs.mean()                      # unbiased (the z's have variance <= 1)
-    assert np.abs(zs).max() <= 5.0 and zs.std() > 0.02                              # within its noise -- and it IS an estimate
-    assert len(good) >= 200 and np.sqrt(np.mean(good ** 2)) <= 1e-3 and np.abs(good).max() <= 3e-3, (len(good), np.abs(good).max())
+    ts, single, sig_all = np.concatenate(ts), np.concatenate(single), np.concatenate(sig_all)
+    assert abs(ts.mean()) <= 5.0 * 1.1 / np.sqrt(len(ts)), ts.mean()                # t(15) scores: sd ~ 1.07
+    assert (np.abs(ts) > 3.5).mean() <= 0.02 and sig_all.min() > 0                  # ... and it IS an estimate
+    good = single[sig_all <= 2.5e-4]
+    assert len(good) >= 100 and np.sqrt(np.mean(good ** 2)) <= 1e-3 and np.abs(good).max() <= 1e-3 + 1e-4, (len(good), np.abs(good).max())
     # path-tree estimator (x SAMPLE, TopSim_singleSample.java:189) on the same fixture: lower variance, same expectation
-    hs = 100000
-    hy = h.simrank_rows(q[:24], 0.6, 5, hs, mode=_lib.GW_SIMRANK_HYBRID, seed=5) / float(hs)
+    hs, RH = 100000, 8
+    hy = np.stack([h.simrank_rows(q[:24], 0.6, 5, hs, mode=_lib.GW_SIMRANK_HYBRID, seed=5 + 77 * k) for k in range(RH)]) / float(hs)
     for r in range(24):
         if deg[r] == 0:
             continue
         top, val = blog_gold["top_ids"][r, :20], blog_gold["top_scores"][r, :20]
-        assert (np.abs(hy[r][top] - val) <= 1e-3 + 4 * _sigma_bound(val, vdeg[top], hs)).all(), q[r]
+        est = hy[:, r][:, top]
+        se = est.std(axis=0, ddof=1) / np.sqrt(RH)
+        assert (np.abs(est.mean(axis=0) - val) <= 2.5e-4 + 6 * se).all(), (q[r], est.mean(axis=0) - val, se)
 
 
 def test_blog_precision_sweep_device_equals_cpu_port_within_noise(blog, blog_gold, tmp_path):
