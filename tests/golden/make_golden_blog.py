@@ -3,8 +3,9 @@ of 64 query vertices -- the EXPECTATION of SingleRandomWalk / TopSim_singleSampl
 
 Computed by the oracle's pinned exact routine (oracle/simrank_oracle.py simrank_exact_matrix: the array form of
 SimRank.java:36-77, itself pinned to 5e-9 on the repository's shipped golden vector), ~100 s on one core for the
-10313 x 10313 matrix; only the 64 largest entries of each query row are kept (ids + fp64 scores), which is all the
-parity test reads (the exact top-20 and the near-ties just below it).
+10313 x 10313 matrix; kept per query row: the 64 largest entries (the exact top-20 and the near-ties just below it)
+and the 20 largest entries among targets of degree >= 16 (the well-conditioned part of the row), ids + fp64 scores +
+target degrees -- all the parity tests read.
 
     python tests/golden/make_golden_blog.py
 """
@@ -35,9 +36,17 @@ queries = np.array(sorted(special + rest[:64 - len(special)]), dtype=np.int64)
 exact = S.simrank_exact_matrix(g, 0.6, 5)
 ids = np.zeros((64, 64), dtype=np.int32)
 sc = np.zeros((64, 64), dtype=np.float64)
+# The exact top-20 of a blog vertex are degree-1 / degree-2 targets (leaves of the hubs) whose scores are near-ties and
+# whose Monte-Carlo increments are huge (C * deg(mid) / deg(target)): the estimator is heavy-tailed exactly there.  A
+# second list keeps the 20 best targets of degree >= 16 per query, where a 1e-3 absolute criterion is meaningful.
+wid = np.zeros((64, 20), dtype=np.int32)
+wsc = np.zeros((64, 20), dtype=np.float64)
 for r, v in enumerate(queries):
-    order = np.lexsort((np.arange(V), -exact[v]))[:64]                # score desc, id asc
-    ids[r], sc[r] = order, exact[v][order]
+    order = np.lexsort((np.arange(V), -exact[v]))                     # score desc, id asc
+    ids[r], sc[r] = order[:64], exact[v][order[:64]]
+    wc = order[(deg[order] >= 16) & (order != v)][:20]
+    wid[r], wsc[r] = wc, exact[v][wc]
 np.savez_compressed(os.path.join(HERE, "blog_exact_s5.npz"), queries=queries, degrees=deg[queries].astype(np.int32),
-                    top_ids=ids, top_scores=sc, row_sums=exact[queries].sum(axis=1), c=0.6, sweeps=5)
+                    top_ids=ids, top_scores=sc, top_degrees=deg[ids].astype(np.int32), wc_ids=wid, wc_scores=wsc,
+                    wc_degrees=deg[wid].astype(np.int32), row_sums=exact[queries].sum(axis=1), c=0.6, sweeps=5)
 print("wrote blog_exact_s5.npz; degrees of the queries:", sorted(deg[queries].tolist())[-5:], "sum of row sums", exact[queries].sum())

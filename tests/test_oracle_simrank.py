@@ -249,3 +249,36 @@ def test_double_random_walk_hand_traced_known_answer():
     assert sim[0, 1] == sim[1, 0] == (0.6 + 0.6 ** 2) / 4 and sim[0, 0] == sim[1, 1] == 0
     paths[1, 1] = [-1, 0]                                        # w's second walk died at its first step
     assert S.double_walk_matrix(paths, 0.6)[0, 1] == 0.6 / 4
+
+
+def test_blog_exact_fixture_is_the_expectation_of_the_restated_estimator(tmp_path):
+    """tests/golden/blog_exact_s5.npz (exact SimRank, 5 sweeps, by the pinned exact routine) against the C restatement of
+    SingleRandomWalk.walk (SingleRandomWalk.java:53-92) on blog.txt, for three mid-degree queries, on the
+    well-conditioned entries of their rows (the 20 best targets of degree >= 16): the mean of 6 runs of SAMPLE = 1e5
+    sits within 3e-4 + 6 standard errors of the fixture, and the row sums agree.  (The exact top-20 themselves are
+    leaves of the hubs; one hit there adds 0.6 * 3992 / deg / SAMPLE and six CPU runs say nothing about the standard
+    error -- the GPU test resolves them at SAMPLE = 1e7.)  The same fixture is what the GPU kernels are held against."""
+    import gzip
+    from conftest import DATA, GOLDEN
+    gold = np.load(os.path.join(GOLDEN, "blog_exact_s5.npz"))
+    f = tmp_path / "blog.txt"
+    f.write_bytes(gzip.open(os.path.join(DATA, "blog.txt.gz"), "rb").read())
+    g = S.load_multigraph(str(f), 10313, ",")
+    deg = gold["degrees"]
+    picks = np.nonzero((deg > 20) & (deg < 300))[0][:3]
+    used = 0
+    for r in picks:
+        v = int(gold["queries"][r])
+        top, val = gold["wc_ids"][r], gold["wc_scores"][r]
+        st = S.java_seed(1000 + v)
+        est, sums = [], []
+        for _ in range(6):
+            row, _, st = S.single_random_walk_row(g, v, 100000, 5, 0.6, st)
+            est.append(row[top]); sums.append(row.sum())
+        est = np.array(est)
+        ok = (est > 0).all(axis=0)
+        se = est.std(axis=0, ddof=1) / np.sqrt(len(est))
+        assert (np.abs(est.mean(axis=0) - val)[ok] <= 3e-4 + 6 * se[ok]).all(), (v, (est.mean(axis=0) - val)[ok], se[ok])
+        assert abs(np.mean(sums) - gold["row_sums"][r]) <= 0.03 * gold["row_sums"][r]
+        used += int(ok.sum())
+    assert used >= 40
