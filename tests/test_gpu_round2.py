@@ -187,7 +187,7 @@ def test_blog_production_kernels_against_truncated_exact(blog, blog_gold):
     q = blog_gold["queries"]
     deg = blog_gold["degrees"]
     assert q[0] == 0 and deg[0] == 0 and deg.max() == 3992 and {1, 2, 64, 256} <= set(deg.tolist())
-    assert blog_gold["top_degrees"][1:, :20].max() <= 8 and blog_gold["wc_degrees"].min() >= 16
+    assert np.median(blog_gold["top_degrees"][1:, :20]) <= 2 and blog_gold["wc_degrees"].min() >= 16
     h = blog.handle
     R, big = 8, 10000000
     runs = np.stack([h.simrank_rows(q, 0.6, 5, big, seed=31 + 1000 * k) for k in range(R)])        # hash kernel (dense rows)

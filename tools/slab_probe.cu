@@ -14,6 +14,7 @@
 //      against T steps of the plain dependent chain, same number of accesses.
 // Net verdict = E_binned vs E_chain.   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/slab_probe tools/slab_probe.cu
 #include <cuda_runtime.h>
+#include <cassert>
 
 #include <algorithm>
 #include <cstdint>
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(1024) k_step_gather(const int4 *__restrict__ a
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
         uint32_t i = (blockIdx.x * ITEMS + k) * 1024 + threadIdx.x;
-        if (i < n) { r[k] = rec[i]; v[k] = ld64(a + r[k].y); }
+        if (i < n) { r[k] = rec[i]; assert(r[k].y <= mask && r[k].x < n); v[k] = ld64(a + r[k].y); }
     }
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(1024) k_step_gather(const int4 *__restrict__ a
             uint32_t nxt = mix((uint32_t)v[k].x + s) & mask;
             outT[r[k].x] = (uint32_t)v[k].y;                    // corpus column of this step (transposed layout), scattered 4-byte store
             rec[i] = make_uint2(r[k].x, nxt);
+            assert((nxt >> shift) < (uint32_t)nbins);
             atomicAdd(&sh[nxt >> shift], 1u);
         }
     }
@@ -125,7 +127,9 @@ __global__ void __launch_bounds__(1024) k_scatter(const uint2 *__restrict__ rec,
         uint32_t i = (blockIdx.x * ITEMS + k) * 1024 + threadIdx.x;
         if (i < n) {
             uint2 r = rec[i];
+            assert((r.y >> shift) < (uint32_t)nbins);
             uint32_t pos = atomicAdd(&cur[r.y >> shift], 1u);
+            assert(pos < n);
             dst[pos] = r;
         }
     }
@@ -212,6 +216,15 @@ int main(int argc, char **argv) {
         CK(cudaMemcpy(rec[0], hr.data(), (size_t)W * 8, cudaMemcpyHostToDevice));
         cudaStream_t st;
         CK(cudaStreamCreate(&st));
+        {   // one step outside the graph first: a failing assert then names its line
+            k_step_gather<<<grid, 1024, 0, st>>>(a, rec[0], W, E - 1, 0, shift, nbins, d_hist, d_outT);
+            CK(cudaStreamSynchronize(st));
+            k_scan<<<1, 1024, 0, st>>>(d_hist, grid, nbins);
+            CK(cudaStreamSynchronize(st));
+            k_scatter<<<grid, 1024, 0, st>>>(rec[0], rec[1], W, shift, nbins, d_hist);
+            CK(cudaStreamSynchronize(st));
+            printf("  (one un-captured step ran, %d bins)\n", nbins);
+        }
         cudaGraph_t graph;
         cudaGraphExec_t exec;
         CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeGlobal));
