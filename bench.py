@@ -530,7 +530,11 @@ def measure_sharded(args, rank, world, local):
     comm.walks(g, p, q, L, starts, seed=42, gather=0, out=h_out)
     e2e_s = allmax(time.perf_counter() - t0)
     ho = g.last_handoff()
-    same = bool((torch.from_numpy(h_out[lo:lo + min(mine, 4096)]).to(dev) == d_out[:min(mine, 4096)]).all().item()) if mine else True
+    k = min(mine, 4096)
+    if k:                                                                     # the rows that arrived == the rows a device-resident run produces
+        walk_slice(lo, lo + k)
+        torch.cuda.synchronize()
+    same = bool((torch.from_numpy(h_out[lo:lo + k]).to(dev) == d_out[:k]).all().item()) if k else True
     out["node2vec_rmat%d" % args.shard_scale] = {
         "workload": "node2vec on synthetic R-MAT scale-%d (%d*2^%d tuples, a,b,c,d=.45/.15/.15/.25), p=%g q=%g, walk_length=%d, ONE pass: "
                     "one walk per non-isolated vertex, start list split over %d GPU(s)" % (args.shard_scale, args.edge_factor, args.shard_scale, p, q, L, world),
@@ -552,9 +556,11 @@ def measure_sharded(args, rank, world, local):
     nq = min(args.shard_queries, b.n)
     queries = np.random.RandomState(2).choice(b.n, size=nq, replace=False).astype(np.int64)
     comm.simrank_topk(b, queries[:8192 * world], 0.6, args.sr_step, args.sample, args.topk, seed=7)      # warm-up
+    ids = np.zeros((nq, args.topk), dtype=np.int32)                            # result buffers committed before the clock starts
+    sc = np.zeros((nq, args.topk), dtype=np.float64)
     barrier()
     t0 = time.perf_counter()
-    ids, sc = comm.simrank_topk(b, queries, 0.6, args.sr_step, args.sample, args.topk, seed=7)
+    comm.simrank_topk(b, queries, 0.6, args.sr_step, args.sample, args.topk, seed=7, out=(ids, sc))
     e2e_s = allmax(time.perf_counter() - t0)
     comp_ms, gath_ms = comm.last_times()
     comp_ms, gath_ms = allmax(comp_ms), allmax(gath_ms)
@@ -563,13 +569,16 @@ def measure_sharded(args, rank, world, local):
         d_q = torch.from_numpy(queries).to(dev)
         d_ids = torch.empty((nq, args.topk), dtype=torch.int32, device=dev)
         d_sc = torch.empty((nq, args.topk), dtype=torch.float64, device=dev)
-        barrier()
-        ev[0].record()
-        b.simrank_topk_dev(d_q.data_ptr(), nq, 0.6, args.sr_step, args.sample, args.topk, d_ids.data_ptr(), d_sc.data_ptr(),
-                           seed=7, query_id_base=0, stream=stream)
-        ev[1].record()
-        barrier()
-        one_ms = allmax(ev[0].elapsed_time(ev[1]))
+        one_ms = None
+        for _ in range(2):                                                    # first run sizes the scratch for 1 M queries
+            barrier()
+            ev[0].record()
+            b.simrank_topk_dev(d_q.data_ptr(), nq, 0.6, args.sr_step, args.sample, args.topk, d_ids.data_ptr(), d_sc.data_ptr(),
+                               seed=7, query_id_base=0, stream=stream)
+            ev[1].record()
+            barrier()
+            t = allmax(ev[0].elapsed_time(ev[1]))
+            one_ms = t if one_ms is None else min(one_ms, t)
         lo_q, hi_q = _lib.shard_range(nq, rank, world)
         k = min(2048, hi_q - lo_q)
         same = bool(np.array_equal(d_ids[lo_q:lo_q + k].cpu().numpy(), ids[lo_q:lo_q + k]))

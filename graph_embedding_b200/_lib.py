@@ -91,6 +91,20 @@ SIGNATURES = {
                                       ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), c_f64p]),
     "gw_topsim_mass_sims": (ctypes.c_int, [c_vp, c_f64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_double, c_i64p,
                                            c_i64p, ctypes.c_int64, ctypes.c_int32, c_f64p]),
+    "gw_sgns_create": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_uint64, ctypes.c_int32, ctypes.POINTER(c_vp)]),
+    "gw_sgns_free": (ctypes.c_int, [c_vp]),
+    "gw_sgns_count_dev": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, ctypes.c_int32, c_vp]),
+    "gw_sgns_finalize_vocab": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_int32]),
+    "gw_sgns_train_dev": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_double,
+                                         ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_uint64, ctypes.c_int32,
+                                         ctypes.c_int32, c_vp]),
+    "gw_sgns_info": (ctypes.c_int, [c_vp, c_i64p, c_i32p, c_f64p, c_i64p]),
+    "gw_sgns_vectors": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), c_i64p]),
+    "gw_sgns_set_vectors": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
+    "gw_node2vec_embeddings": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_int32, ctypes.c_int32, c_i64p,
+                                              ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                              ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_uint64,
+                                              ctypes.POINTER(ctypes.c_float), c_i64p, c_f64p]),
     "gw_comm_unique_id": (ctypes.c_int, [c_vp]),
     "gw_comm_init": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, c_vp, ctypes.c_int32, ctypes.POINTER(c_vp)]),
     "gw_comm_info": (ctypes.c_int, [c_vp, c_i32p, c_i32p, c_i32p]),
@@ -462,6 +476,75 @@ class GraphHandle:
         return out
 
 
+class SkipGram:
+    """gw_sgns: skip-gram with negative sampling over walks that sit in device memory (node2vec/src/main.py:92-101)."""
+
+    def __init__(self, n_words, dimensions=128, seed=1, device=None):
+        """n_words: the vocabulary size, or a GraphHandle (its vertices, on its device)."""
+        if isinstance(n_words, GraphHandle):
+            n_words, device = n_words.n, n_words.device if device is None else device
+        out = c_vp()
+        check(load().gw_sgns_create(int(n_words), int(dimensions), int(seed), int(device or 0), ctypes.byref(out)))
+        self._m = c_vp(out.value)
+        self.n, self.dimensions = int(n_words), int(dimensions)
+
+    def close(self):
+        if getattr(self, "_m", None) is not None and self._m.value:
+            load().gw_sgns_free(self._m)
+            self._m = c_vp(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def count_dev(self, d_walks, n_walks, walk_length, stream=0):
+        check(load().gw_sgns_count_dev(self._m, c_vp(d_walks), int(n_walks), int(walk_length), c_vp(stream) if stream else None))
+
+    def finalize_vocab(self, sample=1e-3, negative=5):
+        check(load().gw_sgns_finalize_vocab(self._m, float(sample), int(negative)))
+
+    def train_dev(self, d_walks, n_walks, walk_length, window=10, alpha=0.025, min_alpha=0.0001, words_before=0.0,
+                  total_words=None, sentence_id_base=0, subsample=True, sequential=False, stream=0):
+        tw = float(total_words if total_words is not None else self.info()["total_words"])
+        check(load().gw_sgns_train_dev(self._m, c_vp(d_walks), int(n_walks), int(walk_length), int(window), float(alpha),
+                                       float(min_alpha), float(words_before), tw, int(sentence_id_base), int(bool(subsample)),
+                                       int(bool(sequential)), c_vp(stream) if stream else None))
+
+    def info(self):
+        n, d, tw, tp = ctypes.c_int64(), ctypes.c_int32(), ctypes.c_double(), ctypes.c_int64()
+        check(load().gw_sgns_info(self._m, ctypes.byref(n), ctypes.byref(d), ctypes.byref(tw), ctypes.byref(tp)))
+        return {"n": n.value, "dimensions": d.value, "total_words": tw.value, "trained_pairs": tp.value}
+
+    def vectors(self, syn1neg=False, counts=False):
+        v = np.empty((self.n, self.dimensions), dtype=np.float32)
+        w = np.empty((self.n, self.dimensions), dtype=np.float32) if syn1neg else None
+        c = np.empty(self.n, dtype=np.int64) if counts else None
+        check(load().gw_sgns_vectors(self._m, ptr(v, ctypes.c_float), ptr(w, ctypes.c_float), ptr(c, ctypes.c_int64)))
+        return (v,) + ((w,) if syn1neg else ()) + ((c,) if counts else ()) if (syn1neg or counts) else v
+
+    def set_vectors(self, syn0=None, syn1neg=None):
+        a = None if syn0 is None else as_c(syn0, np.float32)
+        b = None if syn1neg is None else as_c(syn1neg, np.float32)
+        check(load().gw_sgns_set_vectors(self._m, ptr(a, ctypes.c_float), ptr(b, ctypes.c_float)))
+
+
+def node2vec_embeddings(handle, p, q, walk_length, num_walks, starts, dimensions=128, window=10, iter=1, negative=5,
+                        sample=1e-3, alpha=0.025, min_alpha=0.0001, seed=1):
+    """gw_node2vec_embeddings: walks -> vocabulary -> skip-gram, all on the device.  starts: [num_walks, n_starts] dense
+    indices (the shuffled node list of every pass).  -> (vectors [n, dim] float32, counts [n] int64, seconds dict)."""
+    starts = as_c(starts, np.int64).reshape(int(num_walks), -1)
+    vec = np.empty((handle.n, int(dimensions)), dtype=np.float32)
+    cnt = np.empty(handle.n, dtype=np.int64)
+    sec = np.zeros(3, dtype=np.float64)
+    check(load().gw_node2vec_embeddings(handle.h, float(p), float(q), int(walk_length), int(num_walks),
+                                        ptr(starts, ctypes.c_int64), starts.shape[1], int(dimensions), int(window), int(iter),
+                                        int(negative), float(sample), float(alpha), float(min_alpha), int(seed),
+                                        ptr(vec, ctypes.c_float), ptr(cnt, ctypes.c_int64), ptr(sec, ctypes.c_double)))
+    return vec, cnt, {"walks": sec[0], "vocabulary_scan": sec[1], "training": sec[2]}
+
+
 def shard_range(n, rank, nranks):
     lo, hi = ctypes.c_int64(), ctypes.c_int64()
     check(load().gw_shard_range(int(n), int(rank), int(nranks), ctypes.byref(lo), ctypes.byref(hi)))
@@ -516,10 +599,13 @@ class Comm:
         check(load().gw_comm_last_times(self._c, ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
 
-    def simrank_topk(self, handle, queries_all, c, step, sample, k, mode=GW_SIMRANK_MC, seed=0):
+    def simrank_topk(self, handle, queries_all, c, step, sample, k, mode=GW_SIMRANK_MC, seed=0, out=None):
         queries_all = as_c(queries_all, np.int64)
-        ids = np.empty((len(queries_all), k), dtype=np.int32)
-        sc = np.empty((len(queries_all), k), dtype=np.float64)
+        if out is not None:
+            ids, sc = out
+        else:
+            ids = np.empty((len(queries_all), k), dtype=np.int32)
+            sc = np.empty((len(queries_all), k), dtype=np.float64)
         check(load().gw_simrank_topk_sharded(handle.h, self._c, ptr(queries_all, ctypes.c_int64), len(queries_all),
                                              float(c), int(step), int(sample), int(k), int(mode), int(seed),
                                              ptr(ids, ctypes.c_int32), ptr(sc, ctypes.c_double)))

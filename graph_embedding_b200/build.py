@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["graph.cu", "alias.cu", "walk.cu", "walk_cn.cu", "simrank.cu", "doublewalk.cu", "comm.cu"]
+SOURCES = ["graph.cu", "alias.cu", "walk.cu", "walk_cn.cu", "simrank.cu", "doublewalk.cu", "comm.cu", "skipgram.cu"]
 # host-only sources (copy-thread pool, id unpacking); the AVX2 routine is its own file, picked at run time
 HOST_SOURCES = {"hostpipe.cpp": [], "unpack_avx2.cpp": ["-mavx2"]}
 HOST_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-fvisibility=default", "-pthread"]

@@ -256,6 +256,41 @@ int gw_simrank_last_error(const gw_graph *g, int32_t *code);
 int gw_simrank_exact(gw_graph *g, double c, int32_t iters, const int64_t *rows, int64_t nrows,
                      double *out_dense);
 
+/* ---- skip-gram on the walk corpus  (node2vec/src/main.py:92-101 learn_embeddings = gensim 0.13.3 Word2Vec(sg=1, hs=0,
+ * negative=5, sample=1e-3, alpha=0.025, min_alpha=0.0001)) ----
+ * The consumer of the corpus, on the device: the 13-215 GB hand-off that bounds the walk API end to end never happens.
+ * A model holds syn0 (the embeddings, initialised to (uniform - 0.5) / dimensions) and syn1neg (zeros) for n_words
+ * words (the n vertices of a graph), the word counts of the vocabulary scan, gensim's subsampling thresholds and the negative-sampling table.
+ * dimensions: 32, 64, 128 or 256.  Words are dense vertex indices; -1 pads a walk.  Training runs one warp per walk,
+ * walks concurrently, rows updated without locks (Hogwild, as gensim's worker threads); the random streams are Philox
+ * keyed by (seed, sentence id), so a run is reproducible in its draws though not in the order of racing updates. */
+typedef struct gw_sgns gw_sgns;
+int gw_sgns_create(int64_t n_words, int32_t dimensions, uint64_t seed, int32_t device, gw_sgns **out);
+int gw_sgns_free(gw_sgns *m);
+/* build_vocab's scan: adds the words of d_walks[n_walks*walk_length] (device) to the model's counts. */
+int gw_sgns_count_dev(gw_sgns *m, const int32_t *d_walks, int64_t n_walks, int32_t walk_length, void *stream);
+/* scale_vocab + make_cum_table from the counts scanned so far: subsampling thresholds for `sample` (0 = keep all) and
+ * the table negatives are drawn from (proportional to count^0.75).  negative: draws per pair, 1..64. */
+int gw_sgns_finalize_vocab(gw_sgns *m, double sample, int32_t negative);
+/* train_batch_sg over d_walks: learning rate of walk s = alpha - (alpha - min_alpha) * (words_before + s*walk_length) /
+ * total_words; sentence ids sentence_id_base + s key the random streams; subsample = 0 switches the draw off;
+ * sequential != 0 runs ONE warp over the walks in order (deterministic: the mode the tests compare with the oracle). */
+int gw_sgns_train_dev(gw_sgns *m, const int32_t *d_walks, int64_t n_walks, int32_t walk_length, int32_t window, double alpha,
+                      double min_alpha, double words_before, double total_words, uint64_t sentence_id_base,
+                      int32_t subsample, int32_t sequential, void *stream);
+int gw_sgns_info(const gw_sgns *m, int64_t *n, int32_t *dimensions, double *total_words, int64_t *trained_pairs);
+/* Copies to host (any pointer may be NULL): syn0[n*dimensions] (the embeddings), syn1neg[n*dimensions], counts[n]. */
+int gw_sgns_vectors(const gw_sgns *m, float *out_syn0, float *out_syn1neg, int64_t *out_counts);
+int gw_sgns_set_vectors(gw_sgns *m, const float *syn0, const float *syn1neg);
+/* main.py:104-114 from simulate_walks to the embeddings in one call, the corpus never materialised: starts holds
+ * num_walks shuffled start orders of n_starts vertices each (node2vec.py:51), pass w is regenerated from the seed
+ * (walk ids w*n_starts + i) for the vocabulary scan and for each of the `iter` epochs.  out_vectors[n*dimensions],
+ * out_counts[n] (may be NULL), out_seconds3 (may be NULL) = device seconds spent in {walks, vocabulary scan, training}. */
+int gw_node2vec_embeddings(gw_graph *g, double p, double q, int32_t walk_length, int32_t num_walks, const int64_t *starts,
+                           int64_t n_starts, int32_t dimensions, int32_t window, int32_t iter, int32_t negative, double sample,
+                           double alpha, double min_alpha, uint64_t seed, float *out_vectors, int64_t *out_counts,
+                           double *out_seconds3);
+
 /* ---- multi-GPU: one process per GPU, graph replicated, units sharded, results gathered over NCCL ----
  * The path shards into independent units (node2vec.py:53-57: one walk per start node; SingleRandomWalk.java:39-45:
  * one row per query), so there is no data-path collective: rank r of nranks handles the contiguous slice

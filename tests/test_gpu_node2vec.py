@@ -300,7 +300,7 @@ def test_drop_in_module_and_cli(tmp_path):
     import random
     from graph_embedding_b200 import main as cli
     out = str(tmp_path / "walks.txt")
-    args = cli.parse_args(["--input", os.path.join(DATA, "karate.edgelist"), "--delimiter", " ", "--output", out,
+    args = cli.parse_args(["--input", os.path.join(DATA, "karate.edgelist"), "--delimiter", " ", "--output", out, "--emit", "walks",
                            "--p", "1", "--q", "1", "--walk-length", "80", "--num-walks", "10"])
     random.seed(0); np.random.seed(0)
     walks = cli.main(args)
