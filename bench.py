@@ -64,6 +64,11 @@ def parse():
     ap.add_argument("--shard-scale", type=int, default=26, help="R-MAT scale of the sharded node2vec pass (configs[3]: 26)")
     ap.add_argument("--shard-queries", type=int, default=1_000_000, help="queries of the sharded TopSim run (configs[4]: 1 M)")
     ap.add_argument("--no-e2e-variants", action="store_true", help="skip the pageable / forced hand-off e2e variants")
+    ap.add_argument("--embeddings", default="auto", choices=["auto", "on", "off"],
+                    help="the device consumer of the corpus (SURVEY 8(f)4): walks -> vocabulary -> skip-gram on the headline graph "
+                         "(auto: on for the default N = 1 run)")
+    ap.add_argument("--dimensions", type=int, default=128)
+    ap.add_argument("--window-size", type=int, default=10)
     return ap.parse_args()
 
 
@@ -438,10 +443,65 @@ def main():
         sh = measure_sharded(args, rank, world, local)
         if rank == 0:
             line["sharded"] = sh            # its own gpu_launches inside; the line's count stays that of the timed headline regions
+    if args.embeddings == "on" or (args.embeddings == "auto" and args.workload == "node2vec" and world == 1 and
+                                   args.scale == 22 and not args.no_secondary):
+        line["embeddings"] = measure_embeddings(args, local)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_embeddings(args, local):
+    """The consumer of the corpus on the device (node2vec/src/main.py:92-101, gensim Word2Vec sg=1 negative=5): ONE
+    pass of walks from every non-isolated vertex, vocabulary scan, one epoch of skip-gram -- gw_node2vec_embeddings, the
+    corpus regenerated from its seed and never moved.  Reported beside what the same pass costs when the corpus has to
+    be handed to a host trainer first (the e2e of the headline)."""
+    import torch
+    from graph_embedding_b200 import _lib
+    peak, peak_src = measured_peak()
+    ra, rb, rc = [float(x) for x in args.rmat_abc.split(",")]
+    g = _lib.GraphHandle.rmat(args.scale, args.edge_factor << args.scale, a=ra, b=rb, c=rc, seed=1)
+    g.prepare_walks()
+    starts = np.random.RandomState(7).permutation(g.nonisolated())[None, :]
+    L, dim, neg = args.walk_length, args.dimensions, 5
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    vec, cnt, sec = _lib.node2vec_embeddings(g, args.p, args.q, L, 1, starts, dimensions=dim, window=args.window_size, iter=1,
+                                             negative=neg, sample=1e-3, seed=11)
+    wall = time.perf_counter() - t0
+    words = int(cnt.sum())
+    # pairs of the epoch: counted by the kernel (gw_sgns_info) -- re-run the training leg on a held model to read it
+    m = _lib.SkipGram(g, dim, seed=11)
+    d_starts = torch.from_numpy(starts[0]).cuda()
+    d_w = torch.empty((starts.shape[1], L), dtype=torch.int32, device="cuda")
+    g.walks_dev(args.p, args.q, L, d_starts.data_ptr(), starts.shape[1], d_w.data_ptr(), seed=11, walk_id_base=0)
+    m.count_dev(d_w.data_ptr(), starts.shape[1], L)
+    m.finalize_vocab(sample=1e-3, negative=neg)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    m.train_dev(d_w.data_ptr(), starts.shape[1], L, window=args.window_size, total_words=float(words))
+    ev[1].record()
+    torch.cuda.synchronize()
+    train_ms = ev[0].elapsed_time(ev[1])
+    pairs = m.info()["trained_pairs"]
+    row = 4.0 * dim
+    # per pair: syn0[word2] read + written and `negative` syn1neg rows read + written; per centre word: its own syn1neg row
+    # once (it stays in registers across the window)
+    alg = pairs * (2.0 * row + neg * 2.0 * row) + words * 2.0 * row
+    finite = bool(np.isfinite(vec).all())
+    del m, d_w, g
+    torch.cuda.empty_cache()
+    return {"api": "gw_node2vec_embeddings (walks -> vocabulary scan -> skip-gram with negative sampling, corpus never leaves the device)",
+            "workload": "R-MAT scale-%d, p=%g q=%g, ONE pass of walks (L=%d), dimensions=%d window=%d negative=%d sample=1e-3, one epoch"
+                        % (args.scale, args.p, args.q, L, dim, args.window_size, neg),
+            "words": words, "trained_pairs": int(pairs), "seconds": {"wall": wall, **{k: float(v) for k, v in sec.items()}},
+            "words_per_s": words / sec["training"], "pairs_per_s": pairs / (train_ms * 1e-3),
+            "roofline": {"bound": "hbm", "kernel": "k_sgns<%d>" % (dim // 32), "bytes_per_unit": alg / max(pairs, 1), "units_per_launch": int(pairs),
+                         "launch_ms": train_ms, "achieved": alg / (train_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (train_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                         "model": "rows touched per (word, word2) pair x %d B, read and written (L2 hits of hot rows not discounted)" % int(row)},
+            "vectors_finite": finite}
 
 
 def measure_sharded(args, rank, world, local):

@@ -145,6 +145,13 @@ __global__ void __launch_bounds__(256) k_sgns(SgParams P) {
             const int32_t center = sent[i];
             const int b = (int)(sg_next(rs) % (uint32_t)P.window);               // reduced_windows[i]
             const int j0 = max(0, i - P.window + b), j1 = min(m, i + P.window + 1 - b);
+            // the positive row syn1neg[center] is target 0 of EVERY pair of this center: it stays in registers across the
+            // window (same operations in the same order as reading and writing it per pair; a negative draw equal to
+            // the center is skipped by the algorithm, so nothing else touches the row in between)
+            float *rc = P.syn1 + (size_t)center * dim + lane * PER;
+            float yc[PER];
+#pragma unroll
+            for (int k = 0; k < PER; k++) yc[k] = rc[k];
             for (int j = j0; j < j1; j++) {
                 if (j == i) continue;
                 float *r1 = P.syn0 + (size_t)sent[j] * dim + lane * PER;
@@ -162,18 +169,24 @@ __global__ void __launch_bounds__(256) k_sgns(SgParams P) {
                     float *r2 = P.syn1 + (size_t)target * dim + lane * PER;
                     float y[PER], f = 0.0f;
 #pragma unroll
-                    for (int k = 0; k < PER; k++) { y[k] = r2[k]; f = fmaf(x[k], y[k], f); }
+                    for (int k = 0; k < PER; k++) { y[k] = d == 0 ? yc[k] : r2[k]; f = fmaf(x[k], y[k], f); }
                     for (int o = 16; o; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
                     if (f <= -SG_MAX_EXP || f >= SG_MAX_EXP) continue;
                     const float sig = c_exp_table[(int)((f + SG_MAX_EXP) * (SG_EXP_TABLE / SG_MAX_EXP / 2.0f))];
                     const float g = (label - sig) * alpha;
 #pragma unroll
-                    for (int k = 0; k < PER; k++) { work[k] = fmaf(g, y[k], work[k]); r2[k] = fmaf(g, x[k], y[k]); }
+                    for (int k = 0; k < PER; k++) {
+                        work[k] = fmaf(g, y[k], work[k]);
+                        const float upd = fmaf(g, x[k], y[k]);
+                        if (d == 0) yc[k] = upd; else r2[k] = upd;
+                    }
                 }
 #pragma unroll
                 for (int k = 0; k < PER; k++) r1[k] = x[k] + work[k];
                 my_pairs++;
             }
+#pragma unroll
+            for (int k = 0; k < PER; k++) rc[k] = yc[k];
         }
         __syncwarp();
     }
