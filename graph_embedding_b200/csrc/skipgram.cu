@@ -335,8 +335,11 @@ int gw_sgns_train_dev(gw_sgns *m, const int32_t *d_walks, int64_t n_walks, int32
     P.key = make_uint2((uint32_t)m->seed, (uint32_t)(m->seed >> 32)); P.sentence_id_base = sentence_id_base; P.pairs = m->pairs;
     int sms = 148;
     device_info(&sms, nullptr);
-    const int threads = sequential ? 32 : 256;
-    const unsigned grid = sequential ? 1u : (unsigned)std::min<int64_t>((n_walks + 7) / 8, (int64_t)sms * 8);
+    // Hogwild needs far more rows than writers: at most one concurrent warp per 4 words, but never fewer than the 8
+    // workers gensim starts by default (a 34-word vocabulary hammered by 9 000 warps loses most of its updates)
+    const int64_t max_warps = std::max<int64_t>(8, m->n / 4);
+    const int threads = sequential ? 32 : (max_warps < 8 ? 32 : 256);
+    const unsigned grid = sequential ? 1u : (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((n_walks + 7) / 8, (int64_t)sms * 8), max_warps / 8));
     const size_t smem = sizeof(int32_t) * (size_t)(threads / 32) * walk_length;
     cudaStream_t st = (cudaStream_t)stream;
     switch (m->dim) {
