@@ -58,6 +58,7 @@ SIGNATURES = {
                                              ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint64, c_vp, c_vp, c_vp]),
     "gw_graph_last_handoff": (ctypes.c_int, [c_vp, c_i32p, c_i32p]),
     "gw_corpus_unpack24": (ctypes.c_int, [c_vp, c_i32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, c_i32p]),
+    "gw_py_random_shuffle": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint32), c_i32p, c_i64p, ctypes.c_int64]),
     "gw_graph_prepare_walks": (ctypes.c_int, [c_vp, c_f64p]),
     "gw_graph_common_counts": (ctypes.c_int, [c_vp, c_i32p, c_i32p]),
     "gw_node2vec_walks_replay": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i64p, ctypes.c_int64, c_f64p,
@@ -543,6 +544,27 @@ def node2vec_embeddings(handle, p, q, walk_length, num_walks, starts, dimensions
                                         int(negative), float(sample), float(alpha), float(min_alpha), int(seed),
                                         ptr(vec, ctypes.c_float), ptr(cnt, ctypes.c_int64), ptr(sec, ctypes.c_double)))
     return vec, cnt, {"walks": sec[0], "vocabulary_scan": sec[1], "training": sec[2]}
+
+
+def py_random_shuffle(items):
+    """random.shuffle(items) for a contiguous int64 numpy array: same permutation, same state of Python's global `random`
+    afterwards, 100x faster than the interpreter's loop (gw_py_random_shuffle)."""
+    import random
+    assert items.dtype == np.int64 and items.flags.c_contiguous
+    ver, st, gauss = random.getstate()
+    if ver != 3 or len(st) != 625:                       # an interpreter with another generator: keep the contract, lose the speed
+        lst = items.tolist()
+        random.shuffle(lst)
+        items[:] = lst
+        return items
+    mt = np.array(st[:624], dtype=np.uint32)
+    idx = ctypes.c_int32(st[624])
+    rc = load().gw_py_random_shuffle(mt.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), ctypes.byref(idx), ptr(items, ctypes.c_int64),
+                                     len(items))
+    if rc != 0:
+        raise ValueError("gw_py_random_shuffle rejected its arguments")
+    random.setstate((3, tuple(int(x) for x in mt) + (idx.value,), gauss))
+    return items
 
 
 def shard_range(n, rank, nranks):

@@ -137,14 +137,13 @@ def main(args):
         return walks
     # walks -> vocabulary -> skip-gram without the corpus leaving the device; the start orders keep the reference's
     # contract (cumulative random.shuffle of list(G.nodes()), node2vec.py:47-51; np.random seeds the device streams)
-    import random
     import numpy as np
-    nodes = nx_G.nodes()
+    order = G._dense_many(nx_G.nodes())
     seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 31)
     starts = []
     for _ in range(args.num_walks):
-        random.shuffle(nodes)
-        starts.append(G._dense_many(nodes))
+        _lib.py_random_shuffle(order)                     # random.shuffle(nodes), on Python's own generator
+        starts.append(order.copy())
     vec, cnt, _ = _lib.node2vec_embeddings(G._h, args.p, args.q, args.walk_length, args.num_walks, np.stack(starts),
                                            dimensions=args.dimensions, window=args.window_size, iter=args.iter, seed=seed)
     order = _by_count(cnt, G._dense_many(nx_G.nodes()).tolist())

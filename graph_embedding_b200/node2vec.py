@@ -183,18 +183,22 @@ class Graph():
 
     def simulate_walks(self, num_walks, walk_length, as_array=False):
         """node2vec.py:41-59: num_walks passes over the cumulatively shuffled node list."""
-        nodes = self._g.nodes()
+        # the cumulatively shuffled node list, as dense indices: shuffling indices instead of ids is the same permutation,
+        # and gw_py_random_shuffle is random.shuffle itself (same draws from Python's global generator, same state left)
+        order = self._dense_many(self._g.nodes())
         print('Walk iteration:')
         seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 31)
         starts = []
         for walk_iter in range(num_walks):
             print(str(walk_iter + 1), '/', str(num_walks))
-            random.shuffle(nodes)
-            starts.append(self._dense_many(nodes))
+            _lib.py_random_shuffle(order)
+            starts.append(order.copy())
         starts = np.concatenate(starts) if starts else np.zeros(0, dtype=np.int64)
         w, l = self._h.walks(self.p, self.q, walk_length, starts, seed=seed)
         if as_array:
             ids = self._g.node_ids
+            if len(ids) and ids[0] == 0 and ids[-1] == len(ids) - 1:        # ids are the dense indices (generated graphs): nothing to map
+                return w, l
             return np.where(w >= 0, ids[np.maximum(w, 0)], -1), l
         return self._to_lists(w, l)
 

@@ -138,6 +138,12 @@ int gw_graph_last_handoff(const gw_graph *g, int32_t *mode, int32_t *copy_thread
  * full).  threads <= 0 = the library's default copy-thread count. */
 int gw_corpus_unpack24(const void *packed, const int32_t *lens, int64_t n_walks, int32_t walk_length, int32_t threads,
                        int32_t *out_walks);
+/* simulate_walks' `random.shuffle(nodes)` (node2vec.py:51) at native speed ON THE INTERPRETER'S OWN GENERATOR: mt624 /
+ * mt_index are the 624 state words and the position of CPython's `random.getstate()` (MT19937), updated in place; items[n]
+ * is permuted exactly as `random.shuffle` (CPython 3.2+: j = _randbelow(i + 1) by getrandbits with rejection, i = n-1 .. 1)
+ * would, and the state left behind is the one the Python loop would leave, so the reference's global-RNG "seed interface"
+ * keeps its meaning.  Host only. */
+int gw_py_random_shuffle(uint32_t *mt624, int32_t *mt_index, int64_t *items, int64_t n);
 /* Optional: runs the walker's one-off preprocessing now (per-edge common-neighbour counts, the
  * scalable stand-in for preprocess_transition_probs' alias_edges, node2vec.py:99-108) instead of
  * lazily inside the first walk call; build_ms (may be NULL) receives its device time. */

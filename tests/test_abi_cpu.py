@@ -107,3 +107,22 @@ def test_corpus_unpack24_host_half_of_the_packed_handoff():
                                      out2.ctypes.data_as(_lib.c_i32p)) == 0
         assert np.array_equal(out2, ids)
     assert L_.gw_corpus_unpack24(None, None, 4, 80, 1, None) == _lib.GW_E_INVALID
+
+
+def test_native_shuffle_is_random_shuffle():
+    """gw_py_random_shuffle: the permutation and the state of Python's global generator afterwards are those of
+    random.shuffle (node2vec.py:51 shuffles ONE list cumulatively; the drop-in must consume the same draws)."""
+    import random
+    for seed, n in [(0, 34), (1, 1), (2, 2), (3, 1000), (4, 4097), (5, 65536), (6, 100003), (7, 0)]:
+        random.seed(seed)
+        for _ in range(3):                                          # position inside the 624-word block varies
+            random.random()
+        ref = list(range(100, 100 + n))
+        st0 = random.getstate()
+        random.shuffle(ref); random.shuffle(ref)                    # cumulative, as simulate_walks does
+        tail_ref = [random.random() for _ in range(5)]
+        random.setstate(st0)
+        a = np.arange(100, 100 + n, dtype=np.int64)
+        _lib.py_random_shuffle(a); _lib.py_random_shuffle(a)
+        assert a.tolist() == ref, (seed, n)
+        assert [random.random() for _ in range(5)] == tail_ref      # the generator was left where random.shuffle leaves it
