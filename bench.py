@@ -679,6 +679,8 @@ def measure(args, rank, world, local):
     extra = {}
     if args.workload == "node2vec":
         L = args.walk_length
+        _lib.GraphHandle.rmat(8, 16 << 8, seed=1)              # CUDA context, module load: not part of the graph build
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         ra, rb, rc = [float(x) for x in args.rmat_abc.split(",")]
         g = _lib.GraphHandle.rmat(args.scale, args.edge_factor << args.scale, a=ra, b=rb, c=rc, seed=1)

@@ -94,7 +94,7 @@ int default_copy_threads() {
     const int ranks = (lw && atoi(lw) > 0) ? atoi(lw) : 1;
     int t = hw / ranks;
     if (t < 1) t = 1;
-    if (t > 16) t = 16;
+    if (t > 12) t = 12;                 // profiles/r2_handoff_sweep.txt: the ring saturates the host memory system at 12
     return t;
 }
 

@@ -27,7 +27,7 @@ class CopyPool {
 };
 
 // Number of copy threads for this process: GW_HOST_THREADS, else hardware threads / LOCAL_WORLD_SIZE (torchrun
-// exports it: one rank per GPU shares the box), clamped to [1, 16].
+// exports it: one rank per GPU shares the box), clamped to [1, 12].
 int default_copy_threads();
 
 // dst[i] = little-endian 24-bit src[3i .. 3i+2], zero-extended, for i in [0, count).  src must be readable up to

@@ -895,8 +895,16 @@ __device__ __forceinline__ uint32_t block_scan(HY &Y, uint32_t val, int tid, uin
 // per-CTA log + sketch, no global atomics); a query it cannot finish exactly is handed to the LOGACC = false
 // instantiation (exact two-tier hash, also the dense-rows path).  Both add the same integers
 // round(val / SAMPLE * 2^32), so results do not depend on which one ran; scores leave x SAMPLE (P.out_scale).
+#ifdef HY_PROFILE
+#define HY_TICK(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long t_ = clock64(); atomicAdd(P.prof + (slot), (unsigned long long)(t_ - hy_last)); hy_last = t_; } } while (0)
+#else
+#define HY_TICK(slot) do { } while (0)
+#endif
 template <int STEP, bool LOGACC>
 __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, HybridParams H) {
+#ifdef HY_PROFILE
+    long long hy_last = clock64();
+#endif
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HyShared<LOGACC> &Y = *reinterpret_cast<HyShared<LOGACC> *>(smem_raw);
     auto &S = Y.acc;
@@ -946,6 +954,7 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
         const uint64_t qid = P.query_id_base + (uint64_t)qi;
         if (tid == 0) { vb[0] = v; wb[0] = (double)P.sample; Y.n_in = 1; Y.n_cp = 0; }
         __syncthreads();
+        HY_TICK(3);                                                // (previous query's top-k / reset ends here)
         // ======================= phase 1: the enumerated prefix, level by level =======================
         for (int l = 0; l <= LEN; l++) {
             const int b = l & 1;
@@ -1031,6 +1040,7 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
             __syncthreads();
         }
         __syncthreads();
+        HY_TICK(0);                                                // prefix
         // ======================= phase 2: the chains =======================
         const uint32_t n_cp = Y.n_cp;
         if (n_cp > cap) { if (tid == 0) atomicExch(P.err, 3); }
@@ -1056,6 +1066,7 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
                     for (uint32_t j = 0; j < c; j++) cpar[o + j] = k;
                 }
                 __syncthreads();
+                HY_TICK(1);                                        // chain set-up (scan, chain -> parent map)
                 for (uint32_t t0 = (uint32_t)(tid - lane); t0 < n_chain; t0 += SR_BLOCK) {
                     const uint32_t t = t0 + lane;
                     const bool live = t < n_chain;
@@ -1116,6 +1127,8 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
                 }
             }
         }
+        __syncthreads();
+        HY_TICK(2);                                                // chains
         if constexpr (LOGACC) {
             __syncthreads();
             log_finish_query(S, P, log, qi, tid, [] { __syncthreads(); });
@@ -1797,6 +1810,14 @@ int gw_simrank_last_slow_queries(const gw_graph *g, int64_t *count) {
         GW_CUDA(cudaDeviceSynchronize());
         GW_CUDA(cudaMemcpy(&h, (unsigned char *)g->d_simrank_scratch + 32, sizeof(h), cudaMemcpyDeviceToHost));
         *count = (int64_t)h;
+#ifdef HY_PROFILE
+        {
+            unsigned long long pr[16];
+            GW_CUDA(cudaMemcpy(pr, (unsigned char *)g->d_simrank_scratch + 64, sizeof(pr), cudaMemcpyDeviceToHost));
+            const char *nm[4] = {"prefix (phase 1)", "chain set-up", "chains", "top-k + reset + query switch"};
+            for (int i = 0; i < 4; i++) fprintf(stderr, "HY_PROFILE %-30s %12llu cycles\n", nm[i], pr[i]);
+        }
+#endif
 #ifdef SR_PROFILE
         unsigned long long pr[16];
         GW_CUDA(cudaMemcpy(pr, (unsigned char *)g->d_simrank_scratch + 64, sizeof(pr), cudaMemcpyDeviceToHost));

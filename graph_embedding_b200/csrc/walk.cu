@@ -341,9 +341,10 @@ static int pick_handoff(const gw_graph *g, const void *out_walks, int threads) {
     bool pinned = false;
     if (cudaPointerGetAttributes(&at, out_walks) == cudaSuccess) pinned = at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
     else cudaGetLastError();
-    // measured (profiles/README.md section 5, 16 host threads): direct DMA into page-locked memory runs at the link's
-    // rate and costs no core; into pageable memory the packed ring reaches 0.97 of that, the plain ring 0.69 (host
-    // copy bandwidth), so packing is what makes a pageable caller whole -- and buys a pinned one nothing
+    // measured (profiles/r2_handoff_sweep.txt, README R2-3): 3-byte ids + copy threads beat plain DMA from ~6 threads up
+    // (12 threads: 14.4-15.7 G steps/s into pinned OR pageable memory against 12.9-13.5 G for direct DMA: the link carries
+    // 25 % less); with few threads (N ranks sharing a box) direct DMA into page-locked memory wins and costs no core
+    if (can_pack && threads >= 6) return GW_HANDOFF_PACKED;
     if (pinned) return GW_HANDOFF_DIRECT;
     return can_pack ? GW_HANDOFF_PACKED : GW_HANDOFF_RING;
 }
