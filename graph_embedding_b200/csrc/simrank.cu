@@ -856,6 +856,7 @@ struct HybridParams {
     uint32_t *cofs;       // [grid][cap + 1]         exclusive prefix of cnum
     uint32_t *ckey;       // [grid][cap]             (index in its level buffer << 5) | level (levels reach 2*STEP-1 = 19)
     uint32_t *cpar;       // [grid][2*cap]           chain -> parent
+    uint2 *cmeta;         // [grid][cap]             row descriptor of the parent's last vertex (the chain's first load needs it)
     uint32_t cap;
     double cpow[16];      // C^i
 };
@@ -924,6 +925,7 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
     uint32_t *cofs = H.cofs + (size_t)blockIdx.x * (cap + 1);
     uint32_t *ckey = H.ckey + (size_t)blockIdx.x * cap;
     uint32_t *cpar = H.cpar + (size_t)blockIdx.x * 2 * cap;
+    uint2 *cmeta = H.cmeta + (size_t)blockIdx.x * cap;
 
     if constexpr (LOGACC) {
         for (int i = tid; i < SR_HS; i += SR_BLOCK) { S.keys[i] = SR_EMPTY; S.lo[i] = 0; }
@@ -1007,7 +1009,9 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
                         if (number > 0) {
                             const uint32_t k = atomicAdd(&Y.n_cp, 1u);
                             if (k < cap) {
-                                for (int pos = 0; pos <= l; pos++) chist[(size_t)pos * cap + k] = vin[(size_t)pos * cap + p];
+                                // parent-major history: a chain reads its parent's 2*STEP+1 slots as one contiguous piece
+                                for (int pos = 0; pos <= l; pos++) chist[(size_t)k * (LEN + 1) + pos] = vin[(size_t)pos * cap + p];
+                                cmeta[k] = m;
                                 cw[k] = w / (double)number;
                                 cnum[k] = (uint32_t)number;
                                 ckey[k] = (p << 5) | (uint32_t)l;
@@ -1079,14 +1083,20 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
 #pragma unroll
                     for (int pos = 0; pos <= LEN; pos++) { path[pos] = -1; dgs[pos] = 0; }
                     if (live) {
-                        const uint32_t k = cpar[t], key = ckey[k];
+                        // ONE dependent step after cpar[t]: key, offset, weight, row descriptor and the whole history slot of
+                        // the parent are independent loads (the history is read unconditionally and masked by the level;
+                        // before, cpar -> key -> history -> meta were four latencies in a row in front of six walk loads)
+                        const uint32_t k = cpar[t], key = ckey[k], co = cofs[k];
+                        const int32_t *hrow = chist + (size_t)k * (LEN + 1);
+                        wq = cw[k];
+                        m = cmeta[k];
+#pragma unroll
+                        for (int pos = 0; pos <= LEN; pos++) path[pos] = hrow[pos];
                         lvl = (int)(key & 31u);
                         ctr_p = key >> 5;
-                        ctr_lj = ((uint32_t)lvl << 24) | (t - cofs[k]);
-                        wq = cw[k];
+                        ctr_lj = ((uint32_t)lvl << 24) | (t - co);
 #pragma unroll
-                        for (int pos = 0; pos <= LEN; pos++) if (pos <= lvl) path[pos] = chist[(size_t)pos * cap + k];
-                        m = __ldg(P.meta + path[lvl]);
+                        for (int pos = 0; pos <= LEN; pos++) if (pos > lvl) path[pos] = -1;
                         len = lvl;
                     }
                     bool alive = live;
@@ -1495,6 +1505,7 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
         const size_t o_co = take((size_t)grid * (capz + 1) * sizeof(uint32_t));
         const size_t o_ck = take((size_t)grid * capz * sizeof(uint32_t));
         const size_t o_cp = take((size_t)grid * 2 * capz * sizeof(uint32_t));
+        const size_t o_cm = take((size_t)grid * capz * sizeof(uint2));
         if (g->hybrid_scratch_bytes < off + 16) {
             cudaFree(g->d_hybrid_scratch);
             g->d_hybrid_scratch = nullptr; g->hybrid_scratch_bytes = 0;
@@ -1508,7 +1519,7 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
         H.wbuf = (double *)(hb + o_w); H.cw = (double *)(hb + o_cw);
         H.vbuf = (int32_t *)(hb + o_v); H.chist = (int32_t *)(hb + o_ch);
         H.cnum = (uint32_t *)(hb + o_cn); H.cofs = (uint32_t *)(hb + o_co);
-        H.ckey = (uint32_t *)(hb + o_ck); H.cpar = (uint32_t *)(hb + o_cp);
+        H.ckey = (uint32_t *)(hb + o_ck); H.cpar = (uint32_t *)(hb + o_cp); H.cmeta = (uint2 *)(hb + o_cm);
         for (int i = 0; i < 16; i++) H.cpow[i] = i <= step ? pow(c, i) : 0.0;
         // top-k: log-structured instantiation first, then the exact one over the queries it handed over;
         // dense rows: the exact instantiation alone

@@ -32,6 +32,7 @@ namespace gw {
 
 constexpr int SG_EXP_TABLE = 1000;
 constexpr float SG_MAX_EXP = 6.0f;
+constexpr int SG_NB = 6;                     // targets (positive + negatives) whose rows are requested together
 __constant__ float c_exp_table[SG_EXP_TABLE];
 
 struct SgParams {
@@ -104,7 +105,7 @@ __global__ void k_sg_init(float *__restrict__ syn0, float *__restrict__ syn1, in
 // PER floats of a row per lane (dim = 32 * PER); one warp per sentence; `seq` != 0: ONE warp walks all sentences in
 // order (the test mode that is compared with the sequential restatement)
 template <int PER>
-__global__ void __launch_bounds__(256) k_sgns(SgParams P) {
+__global__ void __launch_bounds__(256, PER <= 4 ? 3 : 2) k_sgns(SgParams P) {
     extern __shared__ int32_t s_sent[];                              // [warps per CTA][L]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     int32_t *sent = s_sent + (size_t)wib * P.L;
@@ -158,27 +159,52 @@ __global__ void __launch_bounds__(256) k_sgns(SgParams P) {
                 float x[PER], work[PER];
 #pragma unroll
                 for (int k = 0; k < PER; k++) { x[k] = r1[k]; work[k] = 0.0f; }
-                for (int d = 0; d <= P.negative; d++) {
-                    int32_t target = center;
-                    float label = 1.0f;
-                    if (d > 0) {
-                        target = P.negtab[sg_next(rs) & P.negtab_mask];
-                        if (target == center) continue;
-                        label = 0.0f;
+                // targets in groups of SG_NB: the draws of a group are made first (they depend on the random stream only),
+                // then ALL its syn1neg rows are requested at once, then the group is processed in gensim's order -- six
+                // 512-byte rows in flight per warp instead of one (the kernel is bound by memory latency x occupancy
+                // otherwise).  A negative drawn twice inside a group is re-read after the first update, so the
+                // arithmetic is that of the one-row-at-a-time loop, operation for operation.
+                for (int d0 = 0; d0 <= P.negative; d0 += SG_NB) {
+                    int32_t tg[SG_NB];
+                    float yv[SG_NB][PER];
+#pragma unroll
+                    for (int u = 0; u < SG_NB; u++) {
+                        const int d = d0 + u;
+                        tg[u] = -1;
+                        if (d == 0) tg[u] = center;
+                        else if (d <= P.negative) {
+                            const int32_t t = P.negtab[sg_next(rs) & P.negtab_mask];
+                            tg[u] = t == center ? -1 : t;                       // a draw equal to the centre word is skipped
+                        }
                     }
-                    float *r2 = P.syn1 + (size_t)target * dim + lane * PER;
-                    float y[PER], f = 0.0f;
 #pragma unroll
-                    for (int k = 0; k < PER; k++) { y[k] = d == 0 ? yc[k] : r2[k]; f = fmaf(x[k], y[k], f); }
-                    for (int o = 16; o; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
-                    if (f <= -SG_MAX_EXP || f >= SG_MAX_EXP) continue;
-                    const float sig = c_exp_table[(int)((f + SG_MAX_EXP) * (SG_EXP_TABLE / SG_MAX_EXP / 2.0f))];
-                    const float g = (label - sig) * alpha;
+                    for (int u = 0; u < SG_NB; u++)
+                        if (tg[u] >= 0 && d0 + u != 0) {
+                            const float *r2 = P.syn1 + (size_t)tg[u] * dim + lane * PER;
 #pragma unroll
-                    for (int k = 0; k < PER; k++) {
-                        work[k] = fmaf(g, y[k], work[k]);
-                        const float upd = fmaf(g, x[k], y[k]);
-                        if (d == 0) yc[k] = upd; else r2[k] = upd;
+                            for (int k = 0; k < PER; k++) yv[u][k] = r2[k];
+                        }
+#pragma unroll
+                    for (int u = 0; u < SG_NB; u++) {
+                        if (tg[u] < 0) continue;
+                        const bool pos = d0 + u == 0;
+                        float *r2 = P.syn1 + (size_t)tg[u] * dim + lane * PER;
+                        bool dup = false;
+#pragma unroll
+                        for (int e = 0; e < u; e++) dup |= (e + d0 != 0) && tg[e] == tg[u];
+                        float y[PER], f = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < PER; k++) { y[k] = pos ? yc[k] : (dup ? r2[k] : yv[u][k]); f = fmaf(x[k], y[k], f); }
+                        for (int o = 16; o; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
+                        if (f <= -SG_MAX_EXP || f >= SG_MAX_EXP) continue;
+                        const float sig = c_exp_table[(int)((f + SG_MAX_EXP) * (SG_EXP_TABLE / SG_MAX_EXP / 2.0f))];
+                        const float g = ((pos ? 1.0f : 0.0f) - sig) * alpha;
+#pragma unroll
+                        for (int k = 0; k < PER; k++) {
+                            work[k] = fmaf(g, y[k], work[k]);
+                            const float upd = fmaf(g, x[k], y[k]);
+                            if (pos) yc[k] = upd; else r2[k] = upd;
+                        }
                     }
                 }
 #pragma unroll
