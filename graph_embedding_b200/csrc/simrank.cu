@@ -896,6 +896,106 @@ __device__ __forceinline__ uint32_t block_scan(HY &Y, uint32_t val, int tid, uin
 // per-CTA log + sketch, no global atomics); a query it cannot finish exactly is handed to the LOGACC = false
 // instantiation (exact two-tier hash, also the dense-rows path).  Both add the same integers
 // round(val / SAMPLE * 2^32), so results do not depend on which one ran; scores leave x SAMPLE (P.out_scale).
+// CILP chains per thread walked in lock step (chain ids t_first + k * t_stride), then computePathSim for the levels each
+// chain added (TopSim_singleSample.java:167-203).  emit(k, i, ok, target, fx) is called for every k < CILP and i = 1..STEP by
+// every lane (dead lanes emit ok = false), fx = round(weight * C^i * deg(path[i]) / deg(path[2i]) / SAMPLE * 2^32).
+// Set-up is ONE dependent step after cpar[t]: key, offset, weight, row descriptor and the whole history slot of the
+// parent are independent loads (the history is read unconditionally and masked by the level).
+template <int STEP, int CILP, typename Emit>
+__device__ __forceinline__ int hy_walk_chains(const SimrankParams &P, const HybridParams &H, const uint32_t *cpar, const uint32_t *ckey,
+                                              const uint32_t *cofs, const double *cw, const uint2 *cmeta, const int32_t *chist,
+                                              uint64_t qid, int32_t v, uint32_t t_first, uint32_t t_stride, uint32_t n_chain, Emit &&emit) {
+    constexpr int LEN = 2 * STEP;
+    int32_t path[CILP][LEN + 1];
+    uint32_t dgs[CILP][LEN + 1];
+    int lvl[CILP], len[CILP];
+    double wq[CILP];
+    uint32_t ctr_p[CILP], ctr_lj[CILP];
+    uint2 m[CILP];
+    bool live[CILP], alive[CILP];
+    uint4 r[CILP];
+    int steps = 0;
+#pragma unroll
+    for (int k = 0; k < CILP; k++) {
+        const uint32_t t = t_first + (uint32_t)k * t_stride;
+        live[k] = t < n_chain;
+        lvl[k] = LEN; len[k] = 0; wq[k] = 0.0; ctr_p[k] = 0; ctr_lj[k] = 0; m[k] = make_uint2(0, 0); r[k] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int pos = 0; pos <= LEN; pos++) { path[k][pos] = -1; dgs[k][pos] = 0; }
+        if (live[k]) {
+            const uint32_t kp = cpar[t], key = ckey[kp], co = cofs[kp];
+            const int32_t *hrow = chist + (size_t)kp * (LEN + 1);
+            wq[k] = cw[kp];
+            m[k] = cmeta[kp];
+#pragma unroll
+            for (int pos = 0; pos <= LEN; pos++) path[k][pos] = hrow[pos];
+            lvl[k] = (int)(key & 31u);
+            ctr_p[k] = key >> 5;
+            ctr_lj[k] = ((uint32_t)lvl[k] << 24) | (t - co);
+#pragma unroll
+            for (int pos = 0; pos <= LEN; pos++) if (pos > lvl[k]) path[k][pos] = -1;
+            len[k] = lvl[k];
+        }
+        alive[k] = live[k];
+    }
+#pragma unroll
+    for (int sidx = 0; sidx < LEN; sidx++) {
+        int4 e[CILP];
+        bool go[CILP];
+#pragma unroll
+        for (int k = 0; k < CILP; k++) {
+            go[k] = false;
+            if (alive[k] && sidx >= lvl[k]) {
+                const int off = sidx - lvl[k];
+                if ((off & 3) == 0)
+                    r[k] = Philox::gen(make_uint4((uint32_t)qid ^ (0x9E3779B9u * (uint32_t)(off >> 2)), (uint32_t)(qid >> 32), ctr_p[k], ctr_lj[k]), P.key);
+                const uint32_t rw = (off & 3) == 0 ? r[k].x : (off & 3) == 1 ? r[k].y : (off & 3) == 2 ? r[k].z : r[k].w;
+                if (m[k].y == 0) alive[k] = false;                        // randNeighbor == -1: the chain ends
+                else { e[k] = ld_nbr4(P.nbr4 + m[k].x + scale_u32(rw, m[k].y)); go[k] = true; }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CILP; k++)
+            if (go[k]) {
+                path[k][sidx + 1] = e[k].x;
+                dgs[k][sidx + 1] = (uint32_t)e[k].w;
+                m[k] = make_uint2((uint32_t)e[k].z, (uint32_t)e[k].w);
+                len[k] = sidx + 1;
+                steps++;
+            }
+    }
+#pragma unroll
+    for (int i = 1; i <= STEP; i++) {
+#pragma unroll
+        for (int k = 0; k < CILP; k++) {
+            const int32_t target = path[k][2 * i];
+            bool ok = live[k] && 2 * i > lvl[k] && 2 * i <= len[k] && target != v;
+#pragma unroll
+            for (int j = 0; j < i; j++) ok &= (path[k][j] != path[k][2 * i - j]);
+            unsigned long long fx = 0;
+            if (ok) {
+                const uint32_t dmid = i > lvl[k] ? dgs[k][i] : __ldg(P.meta + path[k][i]).y;
+                const double val = wq[k] * H.cpow[i] * (double)dmid / (double)dgs[k][2 * i];
+                fx = __double2ull_rn(val * P.inv_sample * SR_FIX);
+            }
+            emit(k, i, ok, (uint32_t)target, fx);
+        }
+    }
+    return steps;
+}
+
+// walker -> accumulator rings of the chain phase (log-structured instantiation): warps [0, 8) walk chains, warps [8, 16)
+// insert their contributions -- the split k_simrank_log uses, for the same reason (profiles/README.md R2-6: 81 % of the
+// kernel is the chain phase, and inside it every warp alternated between ~7 memory latencies and five insertions)
+template <int STEP>
+struct HyRing {
+    static constexpr int CILP = STEP <= 5 ? 2 : 1;
+    static constexpr int PAIRS = SR_BLOCK / 64, STAGES = 2;
+    uint2 slot[PAIRS][STAGES][CILP * STEP * 32];
+    unsigned long long full[PAIRS][STAGES];
+    unsigned long long empty[PAIRS][STAGES];
+};
+
 #ifdef HY_PROFILE
 #define HY_TICK(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long t_ = clock64(); atomicAdd(P.prof + (slot), (unsigned long long)(t_ - hy_last)); hy_last = t_; } } while (0)
 #else
@@ -909,6 +1009,15 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HyShared<LOGACC> &Y = *reinterpret_cast<HyShared<LOGACC> *>(smem_raw);
     auto &S = Y.acc;
+    HyRing<STEP> &R = *reinterpret_cast<HyRing<STEP> *>(smem_raw + ((sizeof(HyShared<LOGACC>) + 15) & ~(size_t)15));   // LOGACC only
+    uint32_t stage_no = 0;                                     // ring stages produced / consumed by this warp so far
+    if constexpr (LOGACC) {
+        if (threadIdx.x < HyRing<STEP>::PAIRS * HyRing<STEP>::STAGES) {
+            mbar_init(&R.full[threadIdx.x / HyRing<STEP>::STAGES][threadIdx.x % HyRing<STEP>::STAGES], 32);
+            mbar_init(&R.empty[threadIdx.x / HyRing<STEP>::STAGES][threadIdx.x % HyRing<STEP>::STAGES], 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     uint2 *log = P.log + (size_t)blockIdx.x * P.log_cap;
     constexpr int LEN = 2 * STEP;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -1071,69 +1180,47 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
                 }
                 __syncthreads();
                 HY_TICK(1);                                        // chain set-up (scan, chain -> parent map)
-                for (uint32_t t0 = (uint32_t)(tid - lane); t0 < n_chain; t0 += SR_BLOCK) {
-                    const uint32_t t = t0 + lane;
-                    const bool live = t < n_chain;
-                    int32_t path[LEN + 1];
-                    uint32_t dgs[LEN + 1];
-                    int lvl = LEN, len = 0;
-                    double wq = 0.0;
-                    uint32_t ctr_p = 0, ctr_lj = 0;
-                    uint2 m = make_uint2(0, 0);
+                if constexpr (LOGACC) {
+                    using Ring = HyRing<STEP>;
+                    constexpr int CILP = Ring::CILP;
+                    const int wrp = tid >> 5;
+                    if (wrp < Ring::PAIRS) {                   // ---- walkers ----
+                        bool overflow = false;
+                        for (uint32_t g0 = (uint32_t)wrp * 32 * CILP; g0 < n_chain; g0 += Ring::PAIRS * 32 * CILP, stage_no++) {
+                            const uint32_t st = stage_no % Ring::STAGES, ph = (stage_no / Ring::STAGES) & 1;
+                            mbar_wait(&R.empty[wrp][st], ph ^ 1);
+                            uint2 *slot = R.slot[wrp][st];
+                            my_steps += (unsigned long long)hy_walk_chains<STEP, CILP>(P, H, cpar, ckey, cofs, cw, cmeta, chist, qid, v,
+                                g0 + lane, 32u, n_chain, [&](int k, int i, bool ok, uint32_t key, unsigned long long fx) {
+                                    if (ok && fx > 0xFFFFFFFFull) { overflow = true; fx = 0xFFFFFFFFull; }     // the exact instantiation redoes the query
+                                    slot[((i - 1) * CILP + k) * 32 + lane] = make_uint2(ok ? key : SR_EMPTY, (uint32_t)fx);
+                                });
+                            mbar_arrive(&R.full[wrp][st]);
+                        }
+                        if (overflow) S.slow = 1;
+                    } else {                                   // ---- accumulators ----
+                        const int pw = wrp - Ring::PAIRS;
+                        for (uint32_t g0 = (uint32_t)pw * 32 * CILP; g0 < n_chain; g0 += Ring::PAIRS * 32 * CILP, stage_no++) {
+                            const uint32_t st = stage_no % Ring::STAGES, ph = (stage_no / Ring::STAGES) & 1;
+                            mbar_wait(&R.full[pw][st], ph);
 #pragma unroll
-                    for (int pos = 0; pos <= LEN; pos++) { path[pos] = -1; dgs[pos] = 0; }
-                    if (live) {
-                        // ONE dependent step after cpar[t]: key, offset, weight, row descriptor and the whole history slot of
-                        // the parent are independent loads (the history is read unconditionally and masked by the level;
-                        // before, cpar -> key -> history -> meta were four latencies in a row in front of six walk loads)
-                        const uint32_t k = cpar[t], key = ckey[k], co = cofs[k];
-                        const int32_t *hrow = chist + (size_t)k * (LEN + 1);
-                        wq = cw[k];
-                        m = cmeta[k];
+                            for (int k = 0; k < CILP; k++) {
+                                uint32_t ek[STEP];
+                                unsigned long long ex[STEP];
 #pragma unroll
-                        for (int pos = 0; pos <= LEN; pos++) path[pos] = hrow[pos];
-                        lvl = (int)(key & 31u);
-                        ctr_p = key >> 5;
-                        ctr_lj = ((uint32_t)lvl << 24) | (t - co);
-#pragma unroll
-                        for (int pos = 0; pos <= LEN; pos++) if (pos > lvl) path[pos] = -1;
-                        len = lvl;
-                    }
-                    bool alive = live;
-                    uint4 r = make_uint4(0, 0, 0, 0);
-#pragma unroll
-                    for (int sidx = 0; sidx < LEN; sidx++) {
-                        if (alive && sidx >= lvl) {
-                            const int off = sidx - lvl;
-                            if ((off & 3) == 0)
-                                r = Philox::gen(make_uint4((uint32_t)qid ^ (0x9E3779B9u * (uint32_t)(off >> 2)), (uint32_t)(qid >> 32), ctr_p, ctr_lj), P.key);
-                            const uint32_t rw = (off & 3) == 0 ? r.x : (off & 3) == 1 ? r.y : (off & 3) == 2 ? r.z : r.w;
-                            if (m.y == 0) alive = false;                          // randNeighbor == -1: the chain ends
-                            else {
-                                const int4 e = ld_nbr4(P.nbr4 + m.x + scale_u32(rw, m.y));
-                                path[sidx + 1] = e.x;
-                                dgs[sidx + 1] = (uint32_t)e.w;
-                                m = make_uint2((uint32_t)e.z, (uint32_t)e.w);
-                                len = sidx + 1;
-                                my_steps++;
+                                for (int i = 0; i < STEP; i++) {
+                                    const uint2 en = R.slot[pw][st][(i * CILP + k) * 32 + lane];
+                                    ek[i] = en.x; ex[i] = (unsigned long long)en.y;
+                                }
+                                if (k == CILP - 1) mbar_arrive(&R.empty[pw][st]);          // stage is in registers: give it back
+                                log_insert_batch<STEP>(S, P, log, lane, ek, ex);
                             }
                         }
                     }
-                    // computePathSim for the levels this chain added (:167-203)
-#pragma unroll
-                    for (int i = 1; i <= STEP; i++) {
-                        const int32_t target = path[2 * i];
-                        bool ok = live && 2 * i > lvl && 2 * i <= len && target != v;
-#pragma unroll
-                        for (int j = 0; j < i; j++) ok &= (path[j] != path[2 * i - j]);
-                        unsigned long long fx = 0;
-                        if (ok) {
-                            const uint32_t dmid = i > lvl ? dgs[i] : __ldg(P.meta + path[i]).y;
-                            const double val = wq * H.cpow[i] * (double)dmid / (double)dgs[2 * i];
-                            fx = __double2ull_rn(val * P.inv_sample * SR_FIX);
-                        }
-                        add(ok, (uint32_t)target, fx);
-                    }
+                } else {
+                    for (uint32_t t0 = (uint32_t)(tid - lane); t0 < n_chain; t0 += SR_BLOCK)
+                        my_steps += (unsigned long long)hy_walk_chains<STEP, 1>(P, H, cpar, ckey, cofs, cw, cmeta, chist, qid, v, t0 + lane, 0u,
+                            n_chain, [&](int, int, bool ok, uint32_t key, unsigned long long fx) { add(ok, key, fx); });
                 }
             }
         }
@@ -1528,8 +1615,9 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
         if (hy_log) Q.qlist = P.qlist_out;
 #define GW_HY(N) case N: \
             if (hy_log) { \
-                GW_CUDA(cudaFuncSetAttribute(k_topsim_hybrid<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HyShared<true>))); \
-                k_topsim_hybrid<N, true><<<grid, SR_BLOCK, sizeof(HyShared<true>), st>>>(P, H); \
+                const size_t hsm = ((sizeof(HyShared<true>) + 15) & ~(size_t)15) + sizeof(HyRing<N>); \
+                GW_CUDA(cudaFuncSetAttribute(k_topsim_hybrid<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm)); \
+                k_topsim_hybrid<N, true><<<grid, SR_BLOCK, hsm, st>>>(P, H); \
                 GW_LAUNCHED(); \
             } \
             GW_CUDA(cudaFuncSetAttribute(k_topsim_hybrid<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HyShared<false>))); \
