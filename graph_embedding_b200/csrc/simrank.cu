@@ -1203,18 +1203,16 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
                         for (uint32_t g0 = (uint32_t)pw * 32 * CILP; g0 < n_chain; g0 += Ring::PAIRS * 32 * CILP, stage_no++) {
                             const uint32_t st = stage_no % Ring::STAGES, ph = (stage_no / Ring::STAGES) & 1;
                             mbar_wait(&R.full[pw][st], ph);
+                            // all CILP * STEP contributions of the lane in ONE batch: the insert is a chain of dependent
+                            // shared-memory round trips per warp, so its throughput is the number of entries in flight
+                            uint32_t ek[CILP * STEP], ev[CILP * STEP];
 #pragma unroll
-                            for (int k = 0; k < CILP; k++) {
-                                uint32_t ek[STEP];
-                                unsigned long long ex[STEP];
-#pragma unroll
-                                for (int i = 0; i < STEP; i++) {
-                                    const uint2 en = R.slot[pw][st][(i * CILP + k) * 32 + lane];
-                                    ek[i] = en.x; ex[i] = (unsigned long long)en.y;
-                                }
-                                if (k == CILP - 1) mbar_arrive(&R.empty[pw][st]);          // stage is in registers: give it back
-                                log_insert_batch<STEP>(S, P, log, lane, ek, ex);
+                            for (int i = 0; i < CILP * STEP; i++) {
+                                const uint2 en = R.slot[pw][st][i * 32 + lane];
+                                ek[i] = en.x; ev[i] = en.y;
                             }
+                            mbar_arrive(&R.empty[pw][st]);                                 // stage is in registers: give it back
+                            log_insert_chunk<CILP * STEP>(S, P, log, lane, ek, ev);
                         }
                     }
                 } else {
