@@ -855,8 +855,9 @@ struct HybridParams {
     uint32_t *cnum;       // [grid][cap]             number of chains = ceil(w)
     uint32_t *cofs;       // [grid][cap + 1]         exclusive prefix of cnum
     uint32_t *ckey;       // [grid][cap]             (index in its level buffer << 5) | level (levels reach 2*STEP-1 = 19)
-    uint32_t *cpar;       // [grid][2*cap]           chain -> parent
-    uint2 *cmeta;         // [grid][cap]             row descriptor of the parent's last vertex (the chain's first load needs it)
+    uint2 *cpar;          // [grid][2*cap]           chain -> {parent, child number}
+    uint4 *crec;          // [grid][cap]             parent record {key, offset, degree of its last vertex, -}: ONE 16-byte load
+    uint32_t hrow;        // ints per history slot (2*STEP+1 rounded up to a multiple of 4: read as 16-byte pieces)
     uint32_t cap;
     double cpow[16];      // C^i
 };
@@ -902,10 +903,10 @@ __device__ __forceinline__ uint32_t block_scan(HY &Y, uint32_t val, int tid, uin
 // Set-up is ONE dependent step after cpar[t]: key, offset, weight, row descriptor and the whole history slot of the
 // parent are independent loads (the history is read unconditionally and masked by the level).
 template <int STEP, int CILP, typename Emit>
-__device__ __forceinline__ int hy_walk_chains(const SimrankParams &P, const HybridParams &H, const uint32_t *cpar, const uint32_t *ckey,
-                                              const uint32_t *cofs, const double *cw, const uint2 *cmeta, const int32_t *chist,
+__device__ __forceinline__ int hy_walk_chains(const SimrankParams &P, const HybridParams &H, const uint2 *cpar, const uint4 *crec,
+                                              const double *cw, const int32_t *chist,
                                               uint64_t qid, int32_t v, uint32_t t_first, uint32_t t_stride, uint32_t n_chain, Emit &&emit) {
-    constexpr int LEN = 2 * STEP;
+    constexpr int LEN = 2 * STEP, HROW = (LEN + 1 + 3) & ~3;
     int32_t path[CILP][LEN + 1];
     uint32_t dgs[CILP][LEN + 1];
     int lvl[CILP], len[CILP];
@@ -923,15 +924,19 @@ __device__ __forceinline__ int hy_walk_chains(const SimrankParams &P, const Hybr
 #pragma unroll
         for (int pos = 0; pos <= LEN; pos++) { path[k][pos] = -1; dgs[k][pos] = 0; }
         if (live[k]) {
-            const uint32_t kp = cpar[t], key = ckey[kp], co = cofs[kp];
-            const int32_t *hrow = chist + (size_t)kp * (LEN + 1);
-            wq[k] = cw[kp];
-            m[k] = cmeta[kp];
+            const uint2 cp = cpar[t];                                   // {parent, child number}: 8 bytes, coalesced over t
+            const uint4 rec = crec[cp.x];
+            const int4 *hrow = reinterpret_cast<const int4 *>(chist + (size_t)cp.x * HROW);
+            wq[k] = cw[cp.x];
+            m[k] = make_uint2(rec.y, rec.z);
+            int32_t hv[HROW];
 #pragma unroll
-            for (int pos = 0; pos <= LEN; pos++) path[k][pos] = hrow[pos];
-            lvl[k] = (int)(key & 31u);
-            ctr_p[k] = key >> 5;
-            ctr_lj[k] = ((uint32_t)lvl[k] << 24) | (t - co);
+            for (int c4 = 0; c4 < HROW / 4; c4++) { const int4 q4 = hrow[c4]; hv[4 * c4] = q4.x; hv[4 * c4 + 1] = q4.y; hv[4 * c4 + 2] = q4.z; hv[4 * c4 + 3] = q4.w; }
+#pragma unroll
+            for (int pos = 0; pos <= LEN; pos++) path[k][pos] = hv[pos];
+            lvl[k] = (int)(rec.x & 31u);
+            ctr_p[k] = rec.x >> 5;
+            ctr_lj[k] = ((uint32_t)lvl[k] << 24) | cp.y;
 #pragma unroll
             for (int pos = 0; pos <= LEN; pos++) if (pos > lvl[k]) path[k][pos] = -1;
             len[k] = lvl[k];
@@ -1001,17 +1006,22 @@ struct HyRing {
 #else
 #define HY_TICK(slot) do { } while (0)
 #endif
-template <int STEP, bool LOGACC>
+#ifdef HY_PROFILE
+#define HY_WTICK(slot) do { if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == SR_BLOCK / 2)) { long long t_ = clock64(); atomicAdd(P.prof + (slot), (unsigned long long)(t_ - hy_wlast)); hy_wlast = t_; } } while (0)
+#else
+#define HY_WTICK(slot) do { } while (0)
+#endif
+template <int STEP, bool LOGACC, bool SPLIT = false>
 __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, HybridParams H) {
 #ifdef HY_PROFILE
-    long long hy_last = clock64();
+    long long hy_last = clock64(), hy_wlast = clock64();
 #endif
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HyShared<LOGACC> &Y = *reinterpret_cast<HyShared<LOGACC> *>(smem_raw);
     auto &S = Y.acc;
     HyRing<STEP> &R = *reinterpret_cast<HyRing<STEP> *>(smem_raw + ((sizeof(HyShared<LOGACC>) + 15) & ~(size_t)15));   // LOGACC only
     uint32_t stage_no = 0;                                     // ring stages produced / consumed by this warp so far
-    if constexpr (LOGACC) {
+    if constexpr (LOGACC && SPLIT) {
         if (threadIdx.x < HyRing<STEP>::PAIRS * HyRing<STEP>::STAGES) {
             mbar_init(&R.full[threadIdx.x / HyRing<STEP>::STAGES][threadIdx.x % HyRing<STEP>::STAGES], 32);
             mbar_init(&R.empty[threadIdx.x / HyRing<STEP>::STAGES][threadIdx.x % HyRing<STEP>::STAGES], 32);
@@ -1033,8 +1043,9 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
     uint32_t *cnum = H.cnum + (size_t)blockIdx.x * cap;
     uint32_t *cofs = H.cofs + (size_t)blockIdx.x * (cap + 1);
     uint32_t *ckey = H.ckey + (size_t)blockIdx.x * cap;
-    uint32_t *cpar = H.cpar + (size_t)blockIdx.x * 2 * cap;
-    uint2 *cmeta = H.cmeta + (size_t)blockIdx.x * cap;
+    uint2 *cpar = H.cpar + (size_t)blockIdx.x * 2 * cap;
+    uint4 *crec = H.crec + (size_t)blockIdx.x * cap;
+    constexpr int HROW = (LEN + 1 + 3) & ~3;
 
     if constexpr (LOGACC) {
         for (int i = tid; i < SR_HS; i += SR_BLOCK) { S.keys[i] = SR_EMPTY; S.lo[i] = 0; }
@@ -1119,11 +1130,10 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
                             const uint32_t k = atomicAdd(&Y.n_cp, 1u);
                             if (k < cap) {
                                 // parent-major history: a chain reads its parent's 2*STEP+1 slots as one contiguous piece
-                                for (int pos = 0; pos <= l; pos++) chist[(size_t)k * (LEN + 1) + pos] = vin[(size_t)pos * cap + p];
-                                cmeta[k] = m;
+                                for (int pos = 0; pos <= l; pos++) chist[(size_t)k * HROW + pos] = vin[(size_t)pos * cap + p];
+                                crec[k] = make_uint4((p << 5) | (uint32_t)l, m.x, m.y, (uint32_t)number);
                                 cw[k] = w / (double)number;
                                 cnum[k] = (uint32_t)number;
-                                ckey[k] = (p << 5) | (uint32_t)l;
                             }
                         }
                     }                                                             // degree 0: randNeighbor == -1, no child
@@ -1176,11 +1186,11 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
             else {
                 for (uint32_t k = tid; k < n_cp; k += SR_BLOCK) {
                     const uint32_t o = cofs[k], c = cnum[k];
-                    for (uint32_t j = 0; j < c; j++) cpar[o + j] = k;
+                    for (uint32_t j = 0; j < c; j++) cpar[o + j] = make_uint2(k, j);
                 }
                 __syncthreads();
                 HY_TICK(1);                                        // chain set-up (scan, chain -> parent map)
-                if constexpr (LOGACC) {
+                if constexpr (LOGACC && SPLIT) {
                     using Ring = HyRing<STEP>;
                     constexpr int CILP = Ring::CILP;
                     const int wrp = tid >> 5;
@@ -1188,9 +1198,11 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
                         bool overflow = false;
                         for (uint32_t g0 = (uint32_t)wrp * 32 * CILP; g0 < n_chain; g0 += Ring::PAIRS * 32 * CILP, stage_no++) {
                             const uint32_t st = stage_no % Ring::STAGES, ph = (stage_no / Ring::STAGES) & 1;
+                            HY_WTICK(5);                                        // walker: walking
                             mbar_wait(&R.empty[wrp][st], ph ^ 1);
+                            HY_WTICK(4);                                        // walker: waiting for a free stage
                             uint2 *slot = R.slot[wrp][st];
-                            my_steps += (unsigned long long)hy_walk_chains<STEP, CILP>(P, H, cpar, ckey, cofs, cw, cmeta, chist, qid, v,
+                            my_steps += (unsigned long long)hy_walk_chains<STEP, CILP>(P, H, cpar, crec, cw, chist, qid, v,
                                 g0 + lane, 32u, n_chain, [&](int k, int i, bool ok, uint32_t key, unsigned long long fx) {
                                     if (ok && fx > 0xFFFFFFFFull) { overflow = true; fx = 0xFFFFFFFFull; }     // the exact instantiation redoes the query
                                     slot[((i - 1) * CILP + k) * 32 + lane] = make_uint2(ok ? key : SR_EMPTY, (uint32_t)fx);
@@ -1202,7 +1214,9 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
                         const int pw = wrp - Ring::PAIRS;
                         for (uint32_t g0 = (uint32_t)pw * 32 * CILP; g0 < n_chain; g0 += Ring::PAIRS * 32 * CILP, stage_no++) {
                             const uint32_t st = stage_no % Ring::STAGES, ph = (stage_no / Ring::STAGES) & 1;
+                            HY_WTICK(7);                                        // accumulator: inserting
                             mbar_wait(&R.full[pw][st], ph);
+                            HY_WTICK(6);                                        // accumulator: waiting for its walker
                             // all CILP * STEP contributions of the lane in ONE batch: the insert is a chain of dependent
                             // shared-memory round trips per warp, so its throughput is the number of entries in flight
                             uint32_t ek[CILP * STEP], ev[CILP * STEP];
@@ -1217,7 +1231,7 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
                     }
                 } else {
                     for (uint32_t t0 = (uint32_t)(tid - lane); t0 < n_chain; t0 += SR_BLOCK)
-                        my_steps += (unsigned long long)hy_walk_chains<STEP, 1>(P, H, cpar, ckey, cofs, cw, cmeta, chist, qid, v, t0 + lane, 0u,
+                        my_steps += (unsigned long long)hy_walk_chains<STEP, 1>(P, H, cpar, crec, cw, chist, qid, v, t0 + lane, 0u,
                             n_chain, [&](int, int, bool ok, uint32_t key, unsigned long long fx) { add(ok, key, fx); });
                 }
             }
@@ -1585,12 +1599,13 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
         const size_t o_w = take((size_t)grid * 2 * capz * sizeof(double));
         const size_t o_cw = take((size_t)grid * capz * sizeof(double));
         const size_t o_v = take((size_t)grid * 2 * LEN1 * capz * sizeof(int32_t));
-        const size_t o_ch = take((size_t)grid * LEN1 * capz * sizeof(int32_t));
+        const size_t HR = (LEN1 + 3) & ~(size_t)3;
+        const size_t o_ch = take((size_t)grid * HR * capz * sizeof(int32_t));
         const size_t o_cn = take((size_t)grid * capz * sizeof(uint32_t));
         const size_t o_co = take((size_t)grid * (capz + 1) * sizeof(uint32_t));
         const size_t o_ck = take((size_t)grid * capz * sizeof(uint32_t));
-        const size_t o_cp = take((size_t)grid * 2 * capz * sizeof(uint32_t));
-        const size_t o_cm = take((size_t)grid * capz * sizeof(uint2));
+        const size_t o_cp = take((size_t)grid * 2 * capz * sizeof(uint2));
+        const size_t o_cm = take((size_t)grid * capz * sizeof(uint4));
         if (g->hybrid_scratch_bytes < off + 16) {
             cudaFree(g->d_hybrid_scratch);
             g->d_hybrid_scratch = nullptr; g->hybrid_scratch_bytes = 0;
@@ -1604,18 +1619,24 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
         H.wbuf = (double *)(hb + o_w); H.cw = (double *)(hb + o_cw);
         H.vbuf = (int32_t *)(hb + o_v); H.chist = (int32_t *)(hb + o_ch);
         H.cnum = (uint32_t *)(hb + o_cn); H.cofs = (uint32_t *)(hb + o_co);
-        H.ckey = (uint32_t *)(hb + o_ck); H.cpar = (uint32_t *)(hb + o_cp); H.cmeta = (uint2 *)(hb + o_cm);
+        H.ckey = (uint32_t *)(hb + o_ck); H.cpar = (uint2 *)(hb + o_cp); H.crec = (uint4 *)(hb + o_cm); H.hrow = (uint32_t)HR;
         for (int i = 0; i < 16; i++) H.cpow[i] = i <= step ? pow(c, i) : 0.0;
         // top-k: log-structured instantiation first, then the exact one over the queries it handed over;
         // dense rows: the exact instantiation alone
         const bool hy_log = d_out_ids && !d_out_dense && !(force && !strcmp(force, "hash"));
         SimrankParams Q = P;
         if (hy_log) Q.qlist = P.qlist_out;
+        const char *hsp = getenv("GW_HY_SPLIT");               // experiment knob: "1" = walker / accumulator warps in the chain phase
+        const bool hy_split = hsp && !strcmp(hsp, "1");
 #define GW_HY(N) case N: \
-            if (hy_log) { \
+            if (hy_log && hy_split) { \
                 const size_t hsm = ((sizeof(HyShared<true>) + 15) & ~(size_t)15) + sizeof(HyRing<N>); \
-                GW_CUDA(cudaFuncSetAttribute(k_topsim_hybrid<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm)); \
-                k_topsim_hybrid<N, true><<<grid, SR_BLOCK, hsm, st>>>(P, H); \
+                GW_CUDA(cudaFuncSetAttribute(k_topsim_hybrid<N, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm)); \
+                k_topsim_hybrid<N, true, true><<<grid, SR_BLOCK, hsm, st>>>(P, H); \
+                GW_LAUNCHED(); \
+            } else if (hy_log) { \
+                GW_CUDA(cudaFuncSetAttribute(k_topsim_hybrid<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HyShared<true>))); \
+                k_topsim_hybrid<N, true><<<grid, SR_BLOCK, sizeof(HyShared<true>), st>>>(P, H); \
                 GW_LAUNCHED(); \
             } \
             GW_CUDA(cudaFuncSetAttribute(k_topsim_hybrid<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HyShared<false>))); \
@@ -1911,8 +1932,9 @@ int gw_simrank_last_slow_queries(const gw_graph *g, int64_t *count) {
         {
             unsigned long long pr[16];
             GW_CUDA(cudaMemcpy(pr, (unsigned char *)g->d_simrank_scratch + 64, sizeof(pr), cudaMemcpyDeviceToHost));
-            const char *nm[4] = {"prefix (phase 1)", "chain set-up", "chains", "top-k + reset + query switch"};
-            for (int i = 0; i < 4; i++) fprintf(stderr, "HY_PROFILE %-30s %12llu cycles\n", nm[i], pr[i]);
+            const char *nm[8] = {"prefix (phase 1)", "chain set-up", "chains", "top-k + reset + query switch", "walker 0: waits for a stage",
+                                 "walker 0: walks (+ other phases)", "accumulator 0: waits for walker", "accumulator 0: inserts (+ other phases)"};
+            for (int i = 0; i < 8; i++) fprintf(stderr, "HY_PROFILE %-40s %12llu cycles\n", nm[i], pr[i]);
         }
 #endif
 #ifdef SR_PROFILE
