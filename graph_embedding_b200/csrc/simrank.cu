@@ -1038,7 +1038,7 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
     const size_t cap = H.cap;
     int32_t *vb = H.vbuf + (size_t)blockIdx.x * 2 * (LEN + 1) * cap;
     double *wb = H.wbuf + (size_t)blockIdx.x * 2 * cap;
-    int32_t *chist = H.chist + (size_t)blockIdx.x * (LEN + 1) * cap;
+    int32_t *chist = H.chist + (size_t)blockIdx.x * (size_t)((LEN + 1 + 3) & ~3) * cap;     // history slots of (2*STEP+1 rounded up to 4) ints
     double *cw = H.cw + (size_t)blockIdx.x * cap;
     uint32_t *cnum = H.cnum + (size_t)blockIdx.x * cap;
     uint32_t *cofs = H.cofs + (size_t)blockIdx.x * (cap + 1);
