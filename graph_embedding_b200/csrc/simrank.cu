@@ -69,6 +69,7 @@ struct SimrankParams {
     const int32_t *qlist;            // read by the hash kernel (NULL = all queries)
     uint32_t *qcount;
     unsigned long long *prof;        // SR_PROFILE builds: per-phase clock64 totals of CTA 0
+    uint32_t *work;                  // path-tree kernel: [0] / [1] = next unclaimed query of the log / exact launch
     double out_scale;                // fixed point -> score: 2^-32 (Monte Carlo), SAMPLE * 2^-32 (path tree, x SAMPLE as the reference)
     double inv_sample;               // path tree: contributions are accumulated / SAMPLE so that they fit the 0.32 fixed-point table
 };
@@ -870,6 +871,7 @@ struct HyShared {
     double cw[SR_BLOCK];
     uint32_t warp_tot[SR_BLOCK / 32];
     uint32_t n_in, n_out, n_cp, scan_base;
+    uint32_t next_q;                     // the query this CTA fetched from the work counter
 };
 
 // block exclusive scan of one value per thread; returns the exclusive prefix, *total = block sum
@@ -1070,7 +1072,14 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
 
     // exact instantiation as the slow path: only the queries the log instantiation handed over (P.qlist / P.qcount)
     const int64_t n_work = P.qlist ? (int64_t)*P.qcount : P.nq;
-    for (int64_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+    // Queries are CLAIMED from a global counter, not dealt out by stride: a path tree costs between a few thousand and a
+    // few hundred thousand steps depending on the hubs near its root, and with a static deal the kernel ends when the
+    // unluckiest of 148 CTAs does (measured: +10 % on BA-10M).  Results are keyed by the query index, not by the CTA.
+    for (;;) {
+        if (tid == 0) Y.next_q = atomicAdd(P.work + (LOGACC ? 0 : 1), 1u);
+        __syncthreads();
+        const int64_t wi = (int64_t)Y.next_q;
+        if (wi >= n_work) break;
         const int64_t qi = P.qlist ? (int64_t)P.qlist[wi] : wi;
         const int32_t v = (int32_t)P.queries[qi];
         const uint64_t qid = P.query_id_base + (uint64_t)qi;
@@ -1572,6 +1581,7 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     }
     GW_CUDA(cudaMemsetAsync(base, 0, 256, st));
     P.prof = (unsigned long long *)(base + 64);
+    P.work = (uint32_t *)(base + 48);
     if (fresh || g->simrank_dirty) {   // the hash kernel leaves its tables clean; only (re)initialise when the layout changes
         GW_CUDA(cudaMemsetAsync(P.gval, 0, (size_t)grid * gs * 8, st));
         GW_CUDA(cudaMemsetAsync(P.gkeys, 0xFF, (size_t)grid * gs * 4, st));
