@@ -73,3 +73,24 @@ def test_sharded_results_equal_single_process(tmp_path, world, n_units):
         z = np.load(os.path.join(str(tmp_path), "r%d.npz" % r))
         assert np.array_equal(z["corpus"], want_w)
         assert np.array_equal(z["ids"], want_i) and np.array_equal(z["sc"], want_s)
+
+
+def test_reference_arm_line_says_what_it_ran():
+    """bench.py --impl reference (the CPU arm the driver runs beside ours): the JSON line must carry the samples really
+    taken as `steps`, a timed region that fits the run, and the graph really walked in config.workload."""
+    import json
+    import subprocess
+    import sys
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    t0 = time.time()
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                          "--cpu-seconds", "1", "--no-secondary"], capture_output=True, text=True, timeout=300)
+    wall = time.time() - t0
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["steps"] == 2 and line["warmup"] == 1 and line["value"] > 1e4
+    assert line["steps"] * line["ms_per_step"] * 1e-3 <= wall                       # the timed region fits the run
+    assert "R-MAT scale-10" in line["config"]["workload"] and line["cpu_baseline"]["kind"] == "port"
+    assert line["preprocess"]["entries_per_s"] > 1e4 and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["unit"] == "walk-steps/s" and line["higher_is_better"] is True
