@@ -769,6 +769,9 @@ int ensure_common_counts(gw_graph *g, cudaStream_t st, bool need_counts) {
                 k_cc_list_tasks<<<(unsigned)((g->n + 255) / 256), 256, 0, st>>>(g->d_meta, g->n, tasks.p, nt.p, cap);
                 GW_LAUNCHED();
                 unsigned int hn = 0;
+                cudaEvent_t t1, t2;
+                const bool timing = getenv("GW_TIMING") != nullptr;
+                if (timing) { cudaEventCreate(&t1); cudaEventCreate(&t2); }
                 GW_CUDA(cudaMemcpyAsync(&hn, nt.p, sizeof(hn), cudaMemcpyDeviceToHost, st));
                 k_cc_small<<<sms * 16, 256, 0, st>>>(g->d_meta, g->d_col, g->n, g->d_nbr4, flag.p, g->nbr4_packed);   // runs while the host waits for the task count
                 GW_LAUNCHED();
@@ -778,11 +781,19 @@ int ensure_common_counts(gw_graph *g, cudaStream_t st, bool need_counts) {
                 while (slots < 2u * (uint32_t)g->max_degree && slots < CC_HASH_MAX) slots <<= 1;
                 const size_t smem = sizeof(int32_t) * slots;
                 GW_CUDA(cudaFuncSetAttribute(k_cc_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                if (timing) cudaEventRecord(t1, st);
                 if (hn > 0) {
                     k_cc_block<<<hn, 256, smem, st>>>(g->d_meta, g->d_col, tasks.p, hn, g->d_nbr4, flag.p, g->nbr4_packed);
                     GW_LAUNCHED();
                 }
+                if (timing) cudaEventRecord(t2, st);
                 GW_CUDA(cudaStreamSynchronize(st));              // tasks / nt are released on return
+                if (timing) {
+                    float a = 0, b = 0;
+                    cudaEventElapsedTime(&a, e0, t1); cudaEventElapsedTime(&b, t1, t2);
+                    fprintf(stderr, "common counts: task list + warp tasks %.1f ms (%u CTA tasks, %zu B of shared memory each), CTA tasks %.1f ms\n", a, hn, smem, b);
+                    cudaEventDestroy(t1); cudaEventDestroy(t2);
+                }
             }
         }
     }
