@@ -173,7 +173,10 @@ __global__ void __launch_bounds__(256) k_common_counts_v1(const uint2 *__restric
 //   small  (deg <= 64):       one warp per u, all smaller rows flattened into one lane-dense index space
 //   block  (64 < deg <= cap): one CTA per (u, chunk of 1024 neighbours), one warp per smaller row
 //   giant  (deg > cap):       same tasks, membership by binary search over N(u) in global memory (L2-resident hubs)
-constexpr uint32_t CC_SMALL = 64;            // rows up to this length: warp tasks
+#ifndef GW_CC_SMALL
+#define GW_CC_SMALL 64
+#endif
+constexpr uint32_t CC_SMALL = GW_CC_SMALL;   // rows up to this length: warp tasks (a multiple of 32)
 constexpr uint32_t CC_CHUNK = 1024;          // neighbours per CTA task
 constexpr uint32_t CC_HASH_MAX = 16384;      // shared-memory slots of a CTA task: rows up to 8192 entries
 
@@ -219,7 +222,7 @@ __global__ void k_cc_list_tasks(const uint2 *__restrict__ meta, int64_t n, uint2
 // one warp per small vertex; per-warp shared memory: hash[128] | pre[65] | offv[64] | acc[64]
 __global__ void __launch_bounds__(256) k_cc_small(const uint2 *__restrict__ meta, const int32_t *__restrict__ col, int64_t n,
                                                    int4 *__restrict__ nbr4, int *__restrict__ self_loops, int pack) {
-    __shared__ int32_t s_hash[8][128];
+    __shared__ int32_t s_hash[8][2 * CC_SMALL];
     __shared__ uint32_t s_pre[8][CC_SMALL + 1];
     __shared__ uint32_t s_off[8][CC_SMALL];
     __shared__ uint32_t s_acc[8][CC_SMALL];          // count | (position of u inside N(v)) << 16
@@ -232,13 +235,13 @@ __global__ void __launch_bounds__(256) k_cc_small(const uint2 *__restrict__ meta
         const uint2 mu = __ldg(meta + u);
         if (mu.y == 0 || mu.y > CC_SMALL) continue;
         uint32_t mask = 63;
-        while (mask + 1 < 2 * mu.y) mask = 2 * mask + 1;             // 64 or 128 slots
+        while (mask + 1 < 2 * mu.y) mask = 2 * mask + 1;             // 64 .. 2 * CC_SMALL slots
         for (uint32_t i = lane; i <= mask; i += 32) hash[i] = -1;
         __syncwarp();
         // the row of u (two entries per lane), descriptors of its neighbours, eligibility = smaller endpoint
         uint32_t run = 0;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
+        for (int h = 0; h < (int)(CC_SMALL / 32); h++) {
             const uint32_t k = h * 32 + lane;
             uint32_t dv = 0;
             if (k < mu.y) {
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(256) k_cc_small(const uint2 *__restrict__ meta
         }
         __syncwarp();
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
+        for (int h = 0; h < (int)(CC_SMALL / 32); h++) {
             const uint32_t k = h * 32 + lane;
             if (k < mu.y && pre[k + 1] > pre[k]) {                    // eligible (an eligible row holds u: never empty)
                 const int32_t v = __ldg(col + mu.x + k);

@@ -50,9 +50,12 @@ def allgather(x):
     return [float(o.item()) for o in out]
 
 
-def d2h(reps=4):
+def d2h(reps=4, together=True):
     h.copy_(d, non_blocking=True)
-    barrier()
+    if together:
+        barrier()
+    else:
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(reps):
         h.copy_(d, non_blocking=True)
@@ -106,7 +109,7 @@ if world > 1:                                           # one rank at a time: th
     alone = []
     for r in range(world):
         barrier()
-        x = d2h() if r == rank else 0.0
+        x = d2h(together=False) if r == rank else 0.0
         barrier()
         alone.append(max(allgather(x)))
     res["d2h_one_rank_at_a_time_GBs"] = [round(x, 1) for x in alone]
