@@ -344,7 +344,12 @@ static int pick_handoff(const gw_graph *g, const void *out_walks, int threads) {
     // measured (profiles/r2_handoff_sweep.txt, README R2-3): 3-byte ids + copy threads beat plain DMA from ~6 threads up
     // (12 threads: 14.4-15.7 G steps/s into pinned OR pageable memory against 12.9-13.5 G for direct DMA: the link carries
     // 25 % less); with few threads (N ranks sharing a box) direct DMA into page-locked memory wins and costs no core
-    if (can_pack && threads >= 6) return GW_HANDOFF_PACKED;
+    // ... but the packed ring costs 2.5 bytes of HOST memory traffic per corpus byte against 1 for direct DMA, and the host is
+    // what N ranks share: at N = 4 packed gave 16.0 G steps/s for the whole box (profiles/r2_bench_n4.json), direct DMA 31.7 G
+    // (round 1).  A pinned caller therefore gets the packed ring only when it has the box to itself.
+    const char *lw = getenv("LOCAL_WORLD_SIZE");
+    const bool alone = !(lw && atoi(lw) > 1);
+    if (can_pack && threads >= 6 && (alone || !pinned)) return GW_HANDOFF_PACKED;
     if (pinned) return GW_HANDOFF_DIRECT;
     return can_pack ? GW_HANDOFF_PACKED : GW_HANDOFF_RING;
 }
