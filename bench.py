@@ -490,7 +490,21 @@ def measure_embeddings(args, local):
     # once (it stays in registers across the window)
     alg = pairs * (2.0 * row + neg * 2.0 * row) + words * 2.0 * row
     finite = bool(np.isfinite(vec).all())
-    del m, d_w, g
+    # what the embedding learnt: P(cosine of an edge's endpoints > cosine of a random vertex pair), 50 k of each (0.5 = nothing)
+    c = g.csr(weights=False, node_ids=False, first_seen=False)
+    rs = np.random.RandomState(0)
+    e = rs.randint(0, g.nnz, size=50000)
+    eu = np.searchsorted(c["row_ptr"], e, side="right") - 1
+    ev = c["col_idx"][e]
+    ru, rv = rs.choice(starts[0], 50000), rs.choice(starts[0], 50000)
+
+    def cos(a, b):
+        x, y = vec[a], vec[b]
+        return (x * y).sum(1) / np.maximum(np.linalg.norm(x, axis=1) * np.linalg.norm(y, axis=1), 1e-20)
+    pos, neg = np.sort(cos(eu, ev)), cos(ru, rv)
+    auc = float(np.searchsorted(pos, neg, side="left").sum())           # pairs (edge, random) with edge cosine < random cosine
+    auc = 1.0 - auc / (len(pos) * len(neg))
+    del c, m, d_w, g
     torch.cuda.empty_cache()
     return {"api": "gw_node2vec_embeddings (walks -> vocabulary scan -> skip-gram with negative sampling, corpus never leaves the device)",
             "workload": "R-MAT scale-%d, p=%g q=%g, ONE pass of walks (L=%d), dimensions=%d window=%d negative=%d sample=1e-3, one epoch"
@@ -503,7 +517,7 @@ def measure_embeddings(args, local):
                          "traffic": ncu_traffic("k_sgns<%d>" % (dim // 32), "rmat%d/ef%d/abc=%s/p=%g/q=%g/L=%d/dim=%d/window=%d/negative=%d/sample=0.001"
                                                 % (args.scale, args.edge_factor, args.rmat_abc, args.p, args.q, L, dim, args.window_size, neg), pairs),
                          "model": "rows touched per (word, word2) pair x %d B, read and written (L2 hits of hot rows not discounted)" % int(row)},
-            "vectors_finite": finite}
+            "vectors_finite": finite, "edge_auc_after_one_epoch": auc}
 
 
 def measure_sharded(args, rank, world, local):

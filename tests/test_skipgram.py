@@ -170,3 +170,22 @@ def test_cli_writes_the_reference_output_and_learn_embeddings_takes_walk_lists(t
     assert w4 == words3 and v4.shape == (34, 32) and sorted(int(w) for w in words3) == list(range(1, 35))
     cnt = np.bincount(np.array([t for w in walks for t in w]), minlength=35)
     assert [cnt[int(w)] for w in words3] == sorted((cnt[int(w)] for w in words3), reverse=True)      # descending count
+
+
+@pytest.mark.gpu
+def test_pipeline_at_scale_learns_the_graph():
+    """R-MAT scale-16 (65 k vertices, 1 M undirected edges), 10 passes of walks, one epoch, 9 472 warps racing on the rows
+    (Hogwild): the endpoints of an edge end up closer than random vertex pairs (AUC 0.93 measured; 0.50 untrained)."""
+    from graph_embedding_b200 import _lib
+    h = _lib.GraphHandle.rmat(16, 16 << 16, seed=1)
+    c = h.csr(weights=False, node_ids=False, first_seen=False)
+    rs = np.random.RandomState(1)
+    nodes = h.nonisolated()
+    starts = np.stack([rs.permutation(nodes) for _ in range(10)])
+    vec, cnt, sec = _lib.node2vec_embeddings(h, 1.0, 1.0, 80, 10, starts, dimensions=128, window=10, iter=1, seed=3)
+    assert cnt.sum() == 10 * len(nodes) * 80 and np.isfinite(vec).all()
+    deg = np.diff(c["row_ptr"])
+    assert np.corrcoef(cnt[deg > 0], deg[deg > 0])[0, 1] > 0.95                      # first-order walks visit ~ degree
+    assert G.edge_auc(vec, c["row_ptr"], c["col_idx"], np.random.RandomState(0)) > 0.85
+    m = _lib.SkipGram(h, 128, seed=3)
+    assert abs(G.edge_auc(m.vectors(), c["row_ptr"], c["col_idx"], np.random.RandomState(0)) - 0.5) < 0.05
