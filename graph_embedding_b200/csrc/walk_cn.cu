@@ -303,25 +303,34 @@ __global__ void __launch_bounds__(256) k_cc_block(const uint2 *__restrict__ meta
             __syncthreads();
         }
         const uint32_t kend = min(mu.y, tk.y + CC_CHUNK);
-        for (uint32_t k = tk.y + wib; k < kend; k += 8) {
-            const int32_t v = __ldg(col + mu.x + k);
-            if (v == u) {
+        // neighbour -> its row descriptor -> its row are three dependent loads (47 % of the stall samples, ncu source page):
+        // the neighbour of iteration k + 16 and the descriptor of iteration k + 8 are requested while iteration k streams
+        uint32_t k = tk.y + wib;
+        int32_t v = k < kend ? __ldg(col + mu.x + k) : -1;
+        int32_t v_next = k + 8 < kend ? __ldg(col + mu.x + k + 8) : -1;
+        uint2 mv = v >= 0 ? __ldg(meta + v) : make_uint2(0, 0);
+        for (; k < kend; k += 8) {
+            const int32_t v_next2 = k + 16 < kend ? __ldg(col + mu.x + k + 16) : -1;
+            const uint2 mv_next = v_next >= 0 ? __ldg(meta + v_next) : make_uint2(0, 0);
+            const int32_t v_cur = v;
+            const uint2 mv_cur = mv;
+            v = v_next; mv = mv_next; v_next = v_next2;
+            if (v_cur == u) {
                 if (lane == 0) { atomicExch(self_loops, 1); nbr4[(size_t)mu.x + k] = make_int4(u, 0, (int)mu.x, (int)mu.y); }
                 continue;
             }
-            const uint2 mv = __ldg(meta + v);
-            if (!cc_smaller(mv.y, v, mu.y, u)) continue;
+            if (!cc_smaller(mv_cur.y, v_cur, mu.y, u)) continue;
             uint32_t cnt = 0, pos = 0;
-            for (uint32_t b0 = 0; b0 < mv.y; b0 += 32) {
+            for (uint32_t b0 = 0; b0 < mv_cur.y; b0 += 32) {
                 const uint32_t i = b0 + lane;
-                if (i < mv.y) {
-                    const int32_t x = __ldg(col + mv.x + i);
+                if (i < mv_cur.y) {
+                    const int32_t x = __ldg(col + mv_cur.x + i);
                     if (x == u) pos = i;
                     else if (in_smem ? cc_contains(s_tab, mask, x) : sorted_contains(col + mu.x, mu.y, x)) cnt++;
                 }
             }
             for (int o = 16; o; o >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); pos += __shfl_xor_sync(0xffffffffu, pos, o); }
-            if (lane == 0) cc_write_pair(nbr4, pack, u, mu, k, v, mv, pos, cnt);
+            if (lane == 0) cc_write_pair(nbr4, pack, u, mu, k, v_cur, mv_cur, pos, cnt);
         }
         __syncthreads();                                             // the table is rebuilt by the next task
     }
