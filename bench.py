@@ -556,7 +556,16 @@ def measure_sharded(args, rank, world, local):
         uid = torch.tensor(list(_lib.Comm.unique_id()), dtype=torch.uint8, device=dev)
     if world > 1:
         dist.broadcast(uid, 0)
-    comm = _lib.Comm(rank, world, bytes(uid.cpu().numpy().tobytes()), local)
+    # NCCL announces itself on stdout when NCCL_DEBUG is set (the image sets VERSION): keep stdout for the one JSON line
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        comm = _lib.Comm(rank, world, bytes(uid.cpu().numpy().tobytes()), local)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
     out = {"api": "gw_comm_init + gw_node2vec_walks_sharded(gather=0) / gw_simrank_topk_sharded (include/graphwalk.h)",
            "n_gpus": world, "scaling": "strong"}
 
