@@ -360,7 +360,10 @@ __device__ __forceinline__ double unit32(uint32_t r) { return ((double)r + 0.5) 
 
 // Component choice of the mixture for rows longer than WIDE_MIN_DEG entries (HUB instantiations only): the same
 // decision tree as the fp32 code in k_walk_cn, evaluated in fp64 with 32-bit uniforms.
-constexpr uint32_t WIDE_MIN_DEG = 4096;
+#ifndef GW_WIDE_MIN_DEG
+#define GW_WIDE_MIN_DEG 4096
+#endif
+constexpr uint32_t WIDE_MIN_DEG = GW_WIDE_MIN_DEG;
 __device__ __noinline__ int pick_component_wide(const CnParams &P, uint32_t d, int32_t c, uint32_t r0bits, uint32_t r2bits, bool ridx) {
     const double a = (double)P.a, b = (double)P.b, r = (double)P.r, lo = (double)P.lo, r0 = (double)P.r0;
     const double dm1 = (double)(d - 1);
@@ -552,10 +555,30 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                     } else {
                         int comp;                                     // 0 = R, 1 = A, 2 = C, 3 = O
                         if (HUB && d > WIDE_MIN_DEG) {
-                            // long rows: masses in fp64 against a 32-bit uniform.  fp32 masses and 24-bit uniforms resolve
-                            // a component's probability to ~6e-8 of the total; the return mass of a 163 k-entry row is
-                            // ~1e-4 of it, i.e. a 6e-4 relative error no test could see.  Pure ALU, off the memory path.
-                            comp = pick_component_wide(P, d, c, rnd.x, rnd.z, RIDX);
+                            // long rows: the component is the one fp64 masses and a 32-bit uniform select.  fp32 masses and
+                            // 24-bit uniforms resolve a component's probability to ~6e-8 of the total; the return mass of a
+                            // 163 k-entry row is ~1e-4 of it, i.e. a 6e-4 relative error no test could see.  The fp32
+                            // evaluation of the SAME 32-bit draw differs from the fp64 one by < 2^-21 of the total mass, so
+                            // it decides whenever the draw is further than 2^-20 of the total from every boundary (all but
+                            // ~6e-6 of the steps); the fp64 routine -- a call, 27 % of the step time when it ran for every
+                            // hub step (Graph500 shape, p=4 q=0.5) -- settles the rest.  Pure ALU, off the memory path.
+                            const float dm1 = (float)(d - 1);
+                            const float MR = P.r - P.r0, MA = P.lo * dm1 + P.r0, MC = (P.b - P.lo) * (float)c, MO = (P.a - P.lo) * (dm1 - (float)c);
+                            const float tot = MR + MA + MC + MO, eps = tot * (1.0f / 1048576.0f);
+                            const float u = (float)rnd.x * (1.0f / 4294967296.0f) * tot;
+                            const bool haveC = MC > 0.0f, haveO = MO > 0.0f;
+                            bool near = fabsf(u - MR) < eps || fabsf(u - (MR + MA)) < eps || fabsf(u - (MR + MA + MC)) < eps;
+                            if (d == 1 || u < MR) comp = 0;
+                            else if (u < MR + MA) comp = 1;
+                            else if (haveC && (u < MR + MA + MC || !haveO)) comp = 2;
+                            else if (haveO) comp = 3;
+                            else comp = 1;
+                            if (RIDX && comp == 1) {
+                                const float u2 = (float)rnd.z * (1.0f / 4294967296.0f) * MA;
+                                near = near || fabsf(u2 - P.r0) < MA * (1.0f / 1048576.0f);
+                                if (u2 < P.r0) comp = 0;
+                            }
+                            if (near) comp = pick_component_wide(P, d, c, rnd.x, rnd.z, RIDX);
                         } else {
                         const float dm1 = (float)(d - 1);
                         const float MR = P.r - P.r0;
