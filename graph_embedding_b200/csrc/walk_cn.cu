@@ -914,7 +914,11 @@ int launch_walk_cn(gw_graph *g, double p, double q, int32_t L, const int64_t *d_
     }
     else if (!vec) { if (hub) k_walk_cn<false, false, 5, true, false><<<grid, 256, 0, st>>>(P); else k_walk_cn<false, false, 5, false, false><<<grid, 256, 0, st>>>(P); }
     else if (hub) {
+        // (the heavy-tailed instantiation carries the rejection paths and spills at 48 registers: GW_CN_MINB=3/4 trade
+        // resident CTAs for registers)
         if (minb >= 6) k_walk_cn<true, false, 6, true, false><<<grid, 256, 0, st>>>(P);
+        else if (occ && minb == 4) k_walk_cn<true, false, 4, true, false><<<grid, 256, 0, st>>>(P);
+        else if (occ && minb == 3) k_walk_cn<true, false, 3, true, false><<<grid, 256, 0, st>>>(P);
         else k_walk_cn<true, false, 5, true, false><<<grid, 256, 0, st>>>(P);
     }
     else if (minb >= 8) k_walk_cn<true, false, 8, false, false><<<grid, 256, 0, st>>>(P);
