@@ -554,38 +554,21 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                         if (COUNT) { st_acc += racc; st_prop += rprop; }
                     } else {
                         int comp;                                     // 0 = R, 1 = A, 2 = C, 3 = O
-                        if (HUB && d > WIDE_MIN_DEG) {
-                            // long rows: the component is the one fp64 masses and a 32-bit uniform select.  fp32 masses and
-                            // 24-bit uniforms resolve a component's probability to ~6e-8 of the total; the return mass of a
-                            // 163 k-entry row is ~1e-4 of it, i.e. a 6e-4 relative error no test could see.  The fp32
-                            // evaluation of the SAME 32-bit draw differs from the fp64 one by < 2^-21 of the total mass, so
-                            // it decides whenever the draw is further than 2^-20 of the total from every boundary (all but
-                            // ~6e-6 of the steps); the fp64 routine -- a call, 27 % of the step time when it ran for every
-                            // hub step (Graph500 shape, p=4 q=0.5) -- settles the rest.  Pure ALU, off the memory path.
-                            const float dm1 = (float)(d - 1);
-                            const float MR = P.r - P.r0, MA = P.lo * dm1 + P.r0, MC = (P.b - P.lo) * (float)c, MO = (P.a - P.lo) * (dm1 - (float)c);
-                            const float tot = MR + MA + MC + MO, eps = tot * (1.0f / 1048576.0f);
-                            const float u = (float)rnd.x * (1.0f / 4294967296.0f) * tot;
-                            const bool haveC = MC > 0.0f, haveO = MO > 0.0f;
-                            bool near = fabsf(u - MR) < eps || fabsf(u - (MR + MA)) < eps || fabsf(u - (MR + MA + MC)) < eps;
-                            if (d == 1 || u < MR) comp = 0;
-                            else if (u < MR + MA) comp = 1;
-                            else if (haveC && (u < MR + MA + MC || !haveO)) comp = 2;
-                            else if (haveO) comp = 3;
-                            else comp = 1;
-                            if (RIDX && comp == 1) {
-                                const float u2 = (float)rnd.z * (1.0f / 4294967296.0f) * MA;
-                                near = near || fabsf(u2 - P.r0) < MA * (1.0f / 1048576.0f);
-                                if (u2 < P.r0) comp = 0;
-                            }
-                            if (near) comp = pick_component_wide(P, d, c, rnd.x, rnd.z, RIDX);
-                        } else {
+                        // Component choice in fp32.  Rows longer than WIDE_MIN_DEG entries (HUB instantiations only) must get
+                        // the component that fp64 masses and a 32-bit uniform select: fp32 masses and 24-bit uniforms resolve
+                        // a probability to ~6e-8 of the total, and the return mass of a 163 k-entry row is ~1e-4 of it (a
+                        // 6e-4 relative error no test could see).  For them the SAME decision tree runs on the 32-bit draw;
+                        // its fp32 evaluation differs from the fp64 one by < 2^-21 of the total mass, so it stands
+                        // whenever the draw is further than 2^-20 of the total from every boundary (all but ~6e-6 of the
+                        // steps) and the fp64 routine settles the rest.  Pure ALU, off the memory path.
+                        const bool widep = HUB && d > WIDE_MIN_DEG;
                         const float dm1 = (float)(d - 1);
                         const float MR = P.r - P.r0;
                         const float MA = P.lo * dm1 + P.r0;
                         const float MC = (P.b - P.lo) * (float)c;
                         const float MO = (P.a - P.lo) * (dm1 - (float)c);
-                        float u = unit24(rnd.x) * (MR + MA + MC + MO);
+                        const float tot = MR + MA + MC + MO;
+                        const float u = (widep ? (float)rnd.x * (1.0f / 4294967296.0f) : unit24(rnd.x)) * tot;
                         const bool haveC = MC > 0.0f, haveO = MO > 0.0f;
                         if (d == 1 || u < MR) comp = 0;               // d == 1: prev is the only neighbour
                         else if (u < MR + MA) comp = 1;
@@ -594,7 +577,16 @@ __global__ void __launch_bounds__(256, MINB) k_walk_cn(CnParams P) {
                         else comp = 1;
                         // RIDX: component A's share of prev (mass r0 of MA) is a return step decided up front; everything
                         // else draws from the d-1 entries that are not prev (index shifted past rprev)
-                        if (RIDX && comp == 1 && unit24(rnd.z) * MA < P.r0) comp = 0;
+                        float u2 = 0.0f;
+                        if (RIDX && comp == 1) {
+                            u2 = (widep ? (float)rnd.z * (1.0f / 4294967296.0f) : unit24(rnd.z)) * MA;
+                            if (u2 < P.r0) comp = 0;
+                        }
+                        if (widep) {
+                            const float eps = tot * (1.0f / 1048576.0f);
+                            const bool near = fabsf(u - MR) < eps || fabsf(u - (MR + MA)) < eps || fabsf(u - (MR + MA + MC)) < eps ||
+                                              (RIDX && u >= MR && u < MR + MA && fabsf(u2 - P.r0) < MA * (1.0f / 1048576.0f));
+                            if (near) comp = pick_component_wide(P, d, c, rnd.x, rnd.z, RIDX);
                         }
                         if (COUNT && comp != 0) st_acc++;                  // one random {nbr,cnt,off,deg} access
                         // A and O both open with one proposal from N(cur): ONE load instruction for the lanes of either
