@@ -337,3 +337,35 @@ def test_long_row_component_choice_in_fp64():
         law = r / (r + a * (n_leaf - 1))                                            # no common neighbour, nothing adjacent to prev
         sigma = np.sqrt(law * (1 - law) / n_ctx)
         assert n_ctx > 1e7 and abs(ret / n_ctx - law) <= 5 * sigma + 1e-7, (p, q, ret / n_ctx, law, sigma)
+
+
+@pytest.mark.parametrize("n_walks,L", [(1, 1), (5, 2), (7, 3), (1025, 5), (33, 81)])
+def test_handoff_edge_shapes(n_walks, L, monkeypatch):
+    """tiny corpora, odd row lengths, fewer walks than a chunk, a single position per walk: every path returns what the
+    direct path returns (packed rows are 3*L bytes: not a multiple of 4 for most of these)."""
+    h = _lib.GraphHandle.from_file(os.path.join(DATA, "karate.edgelist"), delimiter=" ")
+    starts = (np.arange(n_walks, dtype=np.int64) * 7) % h.n
+    monkeypatch.setenv("GW_E2E", "direct")
+    ref, ref_l = h.walks(0.5, 2.0, L, starts, seed=3)
+    assert ref.shape == (n_walks, L) and (ref[:, 0] == starts).all() and (ref_l == L).all()
+    for mode in ("ring", "packed"):
+        monkeypatch.setenv("GW_E2E", mode)
+        w, l = h.walks(0.5, 2.0, L, starts, seed=3)
+        assert np.array_equal(w, ref) and np.array_equal(l, ref_l), (mode, n_walks, L)
+
+
+def test_handoff_threads_knob_and_many_calls(monkeypatch):
+    """GW_HOST_THREADS sizes the pool of a fresh handle; repeated calls on one handle reuse ring and pool."""
+    monkeypatch.setenv("GW_HOST_THREADS", "3")
+    monkeypatch.setenv("GW_E2E", "packed")
+    h = _lib.GraphHandle.rmat(12, 16 << 12, seed=2)
+    starts = np.tile(h.nonisolated(), 40)
+    a, _ = h.walks(0.25, 4.0, 80, starts, seed=1)
+    assert h.last_handoff() == {"mode": "packed", "copy_threads": 3}
+    for _ in range(5):
+        b, _ = h.walks(0.25, 4.0, 80, starts, seed=1)
+        assert np.array_equal(a, b)
+    c, _ = h.walks(0.25, 4.0, 40, starts[:1000], seed=1)                              # smaller request after a larger one
+    monkeypatch.setenv("GW_E2E", "direct")
+    d, _ = h.walks(0.25, 4.0, 40, starts[:1000], seed=1)
+    assert np.array_equal(c, d)

@@ -189,3 +189,31 @@ def test_pipeline_at_scale_learns_the_graph():
     assert G.edge_auc(vec, c["row_ptr"], c["col_idx"], np.random.RandomState(0)) > 0.85
     m = _lib.SkipGram(h, 128, seed=3)
     assert abs(G.edge_auc(m.vectors(), c["row_ptr"], c["col_idx"], np.random.RandomState(0)) - 0.5) < 0.05
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,negative", [(64, 1), (256, 8)])
+def test_other_dimensions_and_negative_counts_match_the_restatement(dim, negative):
+    """64 and 256 dimensions (2 and 8 floats per lane), 1 and 8 negatives (less than one group of rows, more than one)."""
+    import torch
+    from graph_embedding_b200 import _lib
+    h = _lib.GraphHandle.from_file(os.path.join(DATA, "karate.edgelist"), delimiter=" ")
+    g = O.load_graph(os.path.join(DATA, "karate.edgelist"), " ")
+    walks = _corpus(g, 1, 16, 9)
+    n = h.n
+    counts = np.bincount(walks[walks >= 0], minlength=n)
+    d_w = torch.from_numpy(walks).cuda()
+    m = _lib.SkipGram(h, dim, seed=21)
+    m.count_dev(d_w.data_ptr(), len(walks), walks.shape[1])
+    m.finalize_vocab(sample=0.0, negative=negative)
+    syn0, syn1 = G.init_vectors(n, dim, 21)
+    keep, tab = G.scale_vocab(counts, 0.0), G.negative_table(counts, G.table_size(n))
+    total = float(counts.sum())
+    m.train_dev(d_w.data_ptr(), len(walks), walks.shape[1], window=4, alpha=0.05, min_alpha=0.001, total_words=total,
+                sentence_id_base=7, subsample=False, sequential=True)
+    pairs = G.train(walks, syn0, syn1, keep, tab, 4, negative, 0.05, 0.001, 0.0, total, 21, sentence_id_base=7, subsample=False)
+    v1, w1 = m.vectors(syn1neg=True)
+    assert m.info()["trained_pairs"] == pairs
+    assert np.abs(v1 - syn0).max() <= 2e-6 and np.abs(w1 - syn1).max() <= 2e-6
+    with pytest.raises(ValueError):
+        m.finalize_vocab(sample=0.0, negative=0)
