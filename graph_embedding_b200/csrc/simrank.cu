@@ -1238,6 +1238,23 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
                             log_insert_chunk<CILP * STEP>(S, P, log, lane, ek, ev);
                         }
                     }
+                } else if constexpr (LOGACC) {
+                    // every warp walks TWO chains per lane in lock step (1024 loads in flight per SM: the chain phase is a
+                    // stream of true DRAM misses and 512 in flight do not reach the access ceiling), then inserts the
+                    // 2 * STEP contributions of the lane as one batch
+                    constexpr int CILP = HyRing<STEP>::CILP;
+                    bool overflow = false;
+                    for (uint32_t g0 = (uint32_t)(tid >> 5) * 32 * CILP; g0 < n_chain; g0 += SR_BLOCK * CILP) {
+                        uint32_t ek[CILP * STEP], ev[CILP * STEP];
+                        my_steps += (unsigned long long)hy_walk_chains<STEP, CILP>(P, H, cpar, crec, cw, chist, qid, v, g0 + lane, 32u,
+                            n_chain, [&](int k, int i, bool ok, uint32_t key, unsigned long long fx) {
+                                if (ok && fx > 0xFFFFFFFFull) { overflow = true; fx = 0xFFFFFFFFull; }
+                                ek[(i - 1) * CILP + k] = ok ? key : SR_EMPTY;
+                                ev[(i - 1) * CILP + k] = (uint32_t)fx;
+                            });
+                        log_insert_chunk<CILP * STEP>(S, P, log, lane, ek, ev);
+                    }
+                    if (overflow) S.slow = 1;
                 } else {
                     for (uint32_t t0 = (uint32_t)(tid - lane); t0 < n_chain; t0 += SR_BLOCK)
                         my_steps += (unsigned long long)hy_walk_chains<STEP, 1>(P, H, cpar, crec, cw, chist, qid, v, t0 + lane, 0u,
