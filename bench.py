@@ -445,7 +445,12 @@ def main():
             line["sharded"] = sh            # its own gpu_launches inside; the line's count stays that of the timed headline regions
     if args.embeddings == "on" or (args.embeddings == "auto" and args.workload == "node2vec" and world == 1 and
                                    args.scale == 22 and not args.no_secondary):
-        line["embeddings"] = measure_embeddings(args, local)
+        try:                                 # an add-on block (one rank, no collective): its failure must not take the headline line with it
+            line["embeddings"] = measure_embeddings(args, local)
+        except Exception as ex:              # noqa: BLE001 -- reported in the line, and on stderr
+            import traceback
+            traceback.print_exc()
+            line["embeddings"] = {"error": repr(ex)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -495,15 +500,15 @@ def measure_embeddings(args, local):
     rs = np.random.RandomState(0)
     e = rs.randint(0, g.nnz, size=50000)
     eu = np.searchsorted(c["row_ptr"], e, side="right") - 1
-    ev = c["col_idx"][e]
+    ecol = c["col_idx"][e]
     ru, rv = rs.choice(starts[0], 50000), rs.choice(starts[0], 50000)
 
     def cos(a, b):
         x, y = vec[a], vec[b]
         return (x * y).sum(1) / np.maximum(np.linalg.norm(x, axis=1) * np.linalg.norm(y, axis=1), 1e-20)
-    pos, neg = np.sort(cos(eu, ev)), cos(ru, rv)
-    auc = float(np.searchsorted(pos, neg, side="left").sum())           # pairs (edge, random) with edge cosine < random cosine
-    auc = 1.0 - auc / (len(pos) * len(neg))
+    cpos, cneg = np.sort(cos(eu, ecol)), cos(ru, rv)
+    auc = float(np.searchsorted(cpos, cneg, side="left").sum())        # pairs (edge, random) with edge cosine < random cosine
+    auc = 1.0 - auc / (len(cpos) * len(cneg))
     del c, m, d_w, g
     torch.cuda.empty_cache()
     return {"api": "gw_node2vec_embeddings (walks -> vocabulary scan -> skip-gram with negative sampling, corpus never leaves the device)",
