@@ -377,7 +377,7 @@ def run_reference(args):
             "wall_s": None}
     line.update(extra)
     line["wall_s"] = time.perf_counter() - t_all
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def metric_unit(args):
@@ -405,8 +405,27 @@ def config_of(args):
 
 
 # ---------------------------------------------------------------------------------------------
+_JSON_OUT = None                    # the process's real stdout once main() has pointed fd 1 at stderr
+
+
+def emit(line):
+    """The ONE JSON line of this run, on the real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_OUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_OUT, data)
+
+
 def main():
+    global _JSON_OUT
     args = parse()
+    # stdout carries the JSON line and nothing else: NCCL (torch's and gw_comm's) announces its version on fd 1 whenever
+    # NCCL_DEBUG is set (the image sets VERSION), native libraries may print too -- all of that goes to stderr
+    sys.stdout.flush()
+    _JSON_OUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
         return
@@ -452,7 +471,7 @@ def main():
             traceback.print_exc()
             line["embeddings"] = {"error": repr(ex)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -564,16 +583,7 @@ def measure_sharded(args, rank, world, local):
         uid = torch.tensor(list(_lib.Comm.unique_id()), dtype=torch.uint8, device=dev)
     if world > 1:
         dist.broadcast(uid, 0)
-    # NCCL announces itself on stdout when NCCL_DEBUG is set (the image sets VERSION): keep stdout for the one JSON line
-    sys.stdout.flush()
-    saved = os.dup(1)
-    os.dup2(2, 1)
-    try:
-        comm = _lib.Comm(rank, world, bytes(uid.cpu().numpy().tobytes()), local)
-    finally:
-        sys.stdout.flush()
-        os.dup2(saved, 1)
-        os.close(saved)
+    comm = _lib.Comm(rank, world, bytes(uid.cpu().numpy().tobytes()), local)
     out = {"api": "gw_comm_init + gw_node2vec_walks_sharded(gather=0) / gw_simrank_topk_sharded (include/graphwalk.h)",
            "n_gpus": world, "scaling": "strong"}
 
@@ -651,12 +661,15 @@ def measure_sharded(args, rank, world, local):
     comm.simrank_topk(b, queries[:8192 * world], 0.6, args.sr_step, args.sample, args.topk, seed=7)      # warm-up
     ids = np.zeros((nq, args.topk), dtype=np.int32)                            # result buffers committed before the clock starts
     sc = np.zeros((nq, args.topk), dtype=np.float64)
-    barrier()
-    t0 = time.perf_counter()
-    comm.simrank_topk(b, queries, 0.6, args.sr_step, args.sample, args.topk, seed=7, out=(ids, sc))
-    e2e_s = allmax(time.perf_counter() - t0)
-    comp_ms, gath_ms = comm.last_times()
-    comp_ms, gath_ms = allmax(comp_ms), allmax(gath_ms)
+    runs = []
+    for _ in range(2):                                                        # as for one_gpu_ms below: two runs, the faster one counts
+        barrier()
+        t0 = time.perf_counter()
+        comm.simrank_topk(b, queries, 0.6, args.sr_step, args.sample, args.topk, seed=7, out=(ids, sc))
+        e2e_r = allmax(time.perf_counter() - t0)
+        c_ms, g_ms = comm.last_times()
+        runs.append((allmax(c_ms), allmax(g_ms), e2e_r))
+    comp_ms, gath_ms, e2e_s = min(runs, key=lambda r: r[0] + r[1])
     one_ms = comp_ms
     if world > 1:                                                             # the same 1 M queries on ONE GPU (every rank, max)
         d_q = torch.from_numpy(queries).to(dev)
@@ -681,7 +694,7 @@ def measure_sharded(args, rank, world, local):
         "workload": "TopSim SimRank top-%d on synthetic Barabasi-Albert n=%d m=%d, c=0.6 STEP=%d SAMPLE=%d, %d queries drawn without "
                     "replacement, split over %d GPU(s), top-k tiles gathered to every rank" % (args.topk, b.n, args.ba_m, args.sr_step, args.sample, nq, world),
         "graph_build_s": round(build_s, 3), "queries": nq,
-        "device_ms": comp_ms, "gather_ms": gath_ms, "gather_share": gath_ms / max(comp_ms + gath_ms, 1e-9),
+        "device_ms": comp_ms, "device_ms_runs": [r[0] + r[1] for r in runs], "gather_ms": gath_ms, "gather_share": gath_ms / max(comp_ms + gath_ms, 1e-9),
         "gather_bytes_per_rank": nq * args.topk * 12,
         "value": nq / ((comp_ms + gath_ms) * 1e-3), "unit": "queries/s",
         "one_gpu_ms": one_ms, "strong_scaling_efficiency": one_ms / (world * (comp_ms + gath_ms)),
