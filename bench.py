@@ -537,10 +537,10 @@ def measure_embeddings(args, local):
                         % (args.scale, args.p, args.q, L, dim, args.window_size, neg),
             "words": words, "trained_pairs": int(pairs), "seconds": {"wall": wall, **{k: float(v) for k, v in sec.items()}},
             "words_per_s": words / sec["training"], "pairs_per_s": pairs / (train_ms * 1e-3),
-            "roofline": {"bound": "hbm", "kernel": "k_sgns<%d>" % (dim // 32), "bytes_per_unit": alg / max(pairs, 1), "units_per_launch": int(pairs),
+            "roofline": {"bound": "hbm", "kernel": "k_sgns_pipe<%d>" % (dim // 32), "bytes_per_unit": alg / max(pairs, 1), "units_per_launch": int(pairs),
                          "launch_ms": train_ms, "achieved": alg / (train_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg / (train_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
-                         "traffic": ncu_traffic("k_sgns<%d>" % (dim // 32), "rmat%d/ef%d/abc=%s/p=%g/q=%g/L=%d/dim=%d/window=%d/negative=%d/sample=0.001"
+                         "traffic": ncu_traffic("k_sgns_pipe<%d>" % (dim // 32), "rmat%d/ef%d/abc=%s/p=%g/q=%g/L=%d/dim=%d/window=%d/negative=%d/sample=0.001"
                                                 % (args.scale, args.edge_factor, args.rmat_abc, args.p, args.q, L, dim, args.window_size, neg), pairs),
                          "model": "rows touched per (word, word2) pair x %d B, read and written (L2 hits of hot rows not discounted)" % int(row)},
             "vectors_finite": finite, "edge_auc_after_one_pass": auc,

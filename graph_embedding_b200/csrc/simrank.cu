@@ -205,6 +205,7 @@ __device__ __forceinline__ int walk_group(const SimrankParams &P, int32_t v, uin
         dmid[k][0] = 0;
         m[k] = mv;
         alive[k] = g * ILP + k < P.sample;
+        dith[k] = 0;
     }
     auto emit_level = [&](int i, int k) {
         const int32_t target = path[k][2 * i];          // -1 when the walk ended before 2i steps (:66)

@@ -102,46 +102,130 @@ __global__ void k_sg_init(float *__restrict__ syn0, float *__restrict__ syn1, in
     }
 }
 
-// PER floats of a row per lane (dim = 32 * PER); one warp per sentence; `seq` != 0: ONE warp walks all sentences in
-// order (the test mode that is compared with the sequential restatement)
+// PER consecutive floats of a row, as the widest aligned vector the lane's piece allows (rows start 4 * dim bytes apart from a
+// 256-byte aligned base: a lane's piece of 4 / 8 floats is 16-byte aligned, of 2 floats 8-byte aligned)
+template <int PER>
+__device__ __forceinline__ void ld_row(float (&x)[PER], const float *p) {
+    if constexpr (PER % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < PER / 4; q++) {
+            const float4 v = *reinterpret_cast<const float4 *>(p + 4 * q);
+            x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+        }
+    } else if constexpr (PER == 2) {
+        const float2 v = *reinterpret_cast<const float2 *>(p);
+        x[0] = v.x; x[1] = v.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < PER; k++) x[k] = p[k];
+    }
+}
+template <int PER>
+__device__ __forceinline__ void st_row(float *p, const float (&x)[PER]) {
+    if constexpr (PER % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < PER / 4; q++) *reinterpret_cast<float4 *>(p + 4 * q) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+    } else if constexpr (PER == 2) {
+        *reinterpret_cast<float2 *>(p) = make_float2(x[0], x[1]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < PER; k++) p[k] = x[k];
+    }
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// One group of up to SG_NB targets of a (word, word2) pair, in gensim's order: tg[u] < 0 = no target in this slot; slot 0
+// of the group that starts at d0 == 0 is the positive target (its row lives in yc).  ALL syn1neg rows of the group are
+// requested at once, then the group is processed target by target -- six 512-byte rows in flight per warp instead of
+// one.  A negative drawn twice inside a group is re-read after the first update, so the arithmetic is that of the
+// one-row-at-a-time loop, operation for operation.
+template <int PER>
+__device__ __forceinline__ void sg_group(const SgParams &P, const int32_t (&tg)[SG_NB], int d0, int lane, float alpha,
+                                         const float (&x)[PER], float (&work)[PER], float (&yc)[PER]) {
+    constexpr int dim = 32 * PER;
+    float yv[SG_NB][PER];
+#pragma unroll
+    for (int u = 0; u < SG_NB; u++)
+        if (tg[u] >= 0 && d0 + u != 0) ld_row<PER>(yv[u], P.syn1 + (size_t)tg[u] * dim + lane * PER);
+#pragma unroll
+    for (int u = 0; u < SG_NB; u++) {
+        if (tg[u] < 0) continue;
+        const bool pos = d0 + u == 0;
+        float *r2 = P.syn1 + (size_t)tg[u] * dim + lane * PER;
+        bool dup = false;
+#pragma unroll
+        for (int e = 0; e < u; e++) dup |= (e + d0 != 0) && tg[e] == tg[u];
+        float y[PER], f = 0.0f;
+        if (dup) ld_row<PER>(yv[u], r2);
+#pragma unroll
+        for (int k = 0; k < PER; k++) { y[k] = pos ? yc[k] : yv[u][k]; f = fmaf(x[k], y[k], f); }
+        for (int o = 16; o; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
+        if (f <= -SG_MAX_EXP || f >= SG_MAX_EXP) continue;
+        const float sig = c_exp_table[(int)((f + SG_MAX_EXP) * (SG_EXP_TABLE / SG_MAX_EXP / 2.0f))];
+        const float g = ((pos ? 1.0f : 0.0f) - sig) * alpha;
+        float upd[PER];
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            work[k] = fmaf(g, y[k], work[k]);
+            upd[k] = fmaf(g, x[k], y[k]);
+        }
+        if (pos) {
+#pragma unroll
+            for (int k = 0; k < PER; k++) yc[k] = upd[k];
+        } else {
+            st_row<PER>(r2, upd);
+        }
+    }
+}
+
+// subsampling + compaction of one sentence into shared memory (train_batch_sg: words that fail the draw vanish); returns
+// its length.  Called by all 32 lanes.
+__device__ __forceinline__ int sg_compact(const SgParams &P, const int32_t *row, uint64_t sid, int lane, int32_t *sent) {
+    int m = 0;
+    for (int base = 0; base < P.L; base += 32) {
+        const int pos = base + lane;
+        int32_t w = pos < P.L ? row[pos] : -1;
+        bool keep = w >= 0;
+        if (keep && P.keep) {
+            const uint4 r = Philox::gen(make_uint4((uint32_t)sid, (uint32_t)(sid >> 32), (uint32_t)(pos >> 2), 0x5342u), P.key);
+            const uint32_t rw = (pos & 3) == 0 ? r.x : (pos & 3) == 1 ? r.y : (pos & 3) == 2 ? r.z : r.w;
+            keep = !(P.keep[w] < rw);
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) sent[m + __popc(bal & ((1u << lane) - 1))] = w;
+        m += __popc(bal);
+    }
+    __syncwarp();
+    return m;
+}
+
+__device__ __forceinline__ float sg_alpha(const SgParams &P, int64_t s) {   // linear in the raw words seen before this sentence
+    double prog = (P.words_before + (double)s * (double)P.L) / P.total_words;
+    if (prog > 1.0) prog = 1.0;
+    return (float)fmax(P.alpha_min, P.alpha0 - (P.alpha0 - P.alpha_min) * prog);
+}
+
+__device__ __forceinline__ uint64_t sg_stream(const SgParams &P, uint64_t sid) {   // one scalar random stream per sentence, replicated in every lane
+    const uint4 r = Philox::gen(make_uint4((uint32_t)sid, (uint32_t)(sid >> 32), 0u, 0x5353u), P.key);
+    return ((uint64_t)r.x << 32) | r.y;
+}
+
+// PER floats of a row per lane (dim = 32 * PER); one warp per sentence.  General kernel: any number of negatives, the
+// targets of a pair in groups of SG_NB.
 template <int PER>
 __global__ void __launch_bounds__(256, PER <= 4 ? 3 : 2) k_sgns(SgParams P) {
     extern __shared__ int32_t s_sent[];                              // [warps per CTA][L]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     int32_t *sent = s_sent + (size_t)wib * P.L;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int dim = 32 * PER;
+    constexpr int dim = 32 * PER;
     unsigned long long my_pairs = 0;
     for (int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; s < P.n_walks; s += nwarps) {
         const uint64_t sid = P.sentence_id_base + (uint64_t)s;
-        const int32_t *row = P.walks + s * P.L;
-        // ---- subsampling + compaction of the sentence (train_batch_sg: words that fail the draw vanish) ----
-        int m = 0;
-        for (int base = 0; base < P.L; base += 32) {
-            const int pos = base + lane;
-            int32_t w = pos < P.L ? row[pos] : -1;
-            bool keep = w >= 0;
-            if (keep && P.keep) {
-                const uint4 r = Philox::gen(make_uint4((uint32_t)sid, (uint32_t)(sid >> 32), (uint32_t)(pos >> 2), 0x5342u), P.key);
-                const uint32_t rw = (pos & 3) == 0 ? r.x : (pos & 3) == 1 ? r.y : (pos & 3) == 2 ? r.z : r.w;
-                keep = !(P.keep[w] < rw);
-            }
-            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-            if (keep) sent[m + __popc(bal & ((1u << lane) - 1))] = w;
-            m += __popc(bal);
-        }
-        __syncwarp();
+        const int m = sg_compact(P, P.walks + s * P.L, sid, lane, sent);
         if (m < 2) continue;
-        // learning rate of this sentence: linear in the raw words seen before it
-        double prog = (P.words_before + (double)s * (double)P.L) / P.total_words;
-        if (prog > 1.0) prog = 1.0;
-        const float alpha = (float)fmax(P.alpha_min, P.alpha0 - (P.alpha0 - P.alpha_min) * prog);
-        // one scalar random stream per sentence, replicated in every lane (uniform control flow)
-        uint64_t rs;
-        {
-            const uint4 r = Philox::gen(make_uint4((uint32_t)sid, (uint32_t)(sid >> 32), 0u, 0x5353u), P.key);
-            rs = ((uint64_t)r.x << 32) | r.y;
-        }
+        const float alpha = sg_alpha(P, s);
+        uint64_t rs = sg_stream(P, sid);
         for (int i = 0; i < m; i++) {
             const int32_t center = sent[i];
             const int b = (int)(sg_next(rs) % (uint32_t)P.window);               // reduced_windows[i]
@@ -151,22 +235,16 @@ __global__ void __launch_bounds__(256, PER <= 4 ? 3 : 2) k_sgns(SgParams P) {
             // the center is skipped by the algorithm, so nothing else touches the row in between)
             float *rc = P.syn1 + (size_t)center * dim + lane * PER;
             float yc[PER];
-#pragma unroll
-            for (int k = 0; k < PER; k++) yc[k] = rc[k];
+            ld_row<PER>(yc, rc);
             for (int j = j0; j < j1; j++) {
                 if (j == i) continue;
                 float *r1 = P.syn0 + (size_t)sent[j] * dim + lane * PER;
                 float x[PER], work[PER];
+                ld_row<PER>(x, r1);
 #pragma unroll
-                for (int k = 0; k < PER; k++) { x[k] = r1[k]; work[k] = 0.0f; }
-                // targets in groups of SG_NB: the draws of a group are made first (they depend on the random stream only),
-                // then ALL its syn1neg rows are requested at once, then the group is processed in gensim's order -- six
-                // 512-byte rows in flight per warp instead of one (the kernel is bound by memory latency x occupancy
-                // otherwise).  A negative drawn twice inside a group is re-read after the first update, so the
-                // arithmetic is that of the one-row-at-a-time loop, operation for operation.
+                for (int k = 0; k < PER; k++) work[k] = 0.0f;
                 for (int d0 = 0; d0 <= P.negative; d0 += SG_NB) {
-                    int32_t tg[SG_NB];
-                    float yv[SG_NB][PER];
+                    int32_t tg[SG_NB];                                           // the draws depend on the random stream only: made first
 #pragma unroll
                     for (int u = 0; u < SG_NB; u++) {
                         const int d = d0 + u;
@@ -177,43 +255,99 @@ __global__ void __launch_bounds__(256, PER <= 4 ? 3 : 2) k_sgns(SgParams P) {
                             tg[u] = t == center ? -1 : t;                       // a draw equal to the centre word is skipped
                         }
                     }
-#pragma unroll
-                    for (int u = 0; u < SG_NB; u++)
-                        if (tg[u] >= 0 && d0 + u != 0) {
-                            const float *r2 = P.syn1 + (size_t)tg[u] * dim + lane * PER;
-#pragma unroll
-                            for (int k = 0; k < PER; k++) yv[u][k] = r2[k];
-                        }
-#pragma unroll
-                    for (int u = 0; u < SG_NB; u++) {
-                        if (tg[u] < 0) continue;
-                        const bool pos = d0 + u == 0;
-                        float *r2 = P.syn1 + (size_t)tg[u] * dim + lane * PER;
-                        bool dup = false;
-#pragma unroll
-                        for (int e = 0; e < u; e++) dup |= (e + d0 != 0) && tg[e] == tg[u];
-                        float y[PER], f = 0.0f;
-#pragma unroll
-                        for (int k = 0; k < PER; k++) { y[k] = pos ? yc[k] : (dup ? r2[k] : yv[u][k]); f = fmaf(x[k], y[k], f); }
-                        for (int o = 16; o; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
-                        if (f <= -SG_MAX_EXP || f >= SG_MAX_EXP) continue;
-                        const float sig = c_exp_table[(int)((f + SG_MAX_EXP) * (SG_EXP_TABLE / SG_MAX_EXP / 2.0f))];
-                        const float g = ((pos ? 1.0f : 0.0f) - sig) * alpha;
-#pragma unroll
-                        for (int k = 0; k < PER; k++) {
-                            work[k] = fmaf(g, y[k], work[k]);
-                            const float upd = fmaf(g, x[k], y[k]);
-                            if (pos) yc[k] = upd; else r2[k] = upd;
-                        }
-                    }
+                    sg_group<PER>(P, tg, d0, lane, alpha, x, work, yc);
                 }
 #pragma unroll
-                for (int k = 0; k < PER; k++) r1[k] = x[k] + work[k];
+                for (int k = 0; k < PER; k++) x[k] += work[k];
+                st_row<PER>(r1, x);
                 my_pairs++;
             }
-#pragma unroll
-            for (int k = 0; k < PER; k++) rc[k] = yc[k];
+            st_row<PER>(rc, yc);
         }
+        __syncwarp();
+    }
+    if (lane == 0 && my_pairs && P.pairs) atomicAdd(P.pairs, my_pairs);
+}
+
+// Production kernel for negative < SG_NB (gensim's default 5): the same loops, software-pipelined over the PAIRS of a
+// sentence.  The random stream of a sentence does not depend on the data (one draw per centre, `negative` draws per pair),
+// so a generator runs two pairs ahead of the arithmetic: the negative-table lookups of pair s + 2 are issued, the rows of
+// pair s + 1 (context, negatives, a new centre) are prefetched into L2, then pair s is trained.  A pair no longer waits
+// for two dependent DRAM latencies (table, then rows) but for L2 hits; values are still LOADED after the previous pair's
+// stores, so the arithmetic is unchanged (one warp in order reproduces the restatement exactly as before).
+constexpr int SG_PN = SG_NB - 1;
+struct SgPair {
+    int i, j;
+    int32_t t[SG_PN];            // raw draws of the negative table (compared with the centre when used)
+};
+
+template <int PER>
+__global__ void __launch_bounds__(256, PER <= 4 ? 3 : 2) k_sgns_pipe(SgParams P) {
+    extern __shared__ int32_t s_sent[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int32_t *sent = s_sent + (size_t)wib * P.L;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    constexpr int dim = 32 * PER;
+    unsigned long long my_pairs = 0;
+    for (int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; s < P.n_walks; s += nwarps) {
+        const uint64_t sid = P.sentence_id_base + (uint64_t)s;
+        const int m = sg_compact(P, P.walks + s * P.L, sid, lane, sent);
+        if (m < 2) continue;
+        const float alpha = sg_alpha(P, s);
+        uint64_t rs = sg_stream(P, sid);
+        int gi = -1, gj = 0, gj1 = 0;                                  // generator: centre, next context position, end of the window
+        auto gen = [&](SgPair &d) -> bool {
+            for (;;) {
+                if (gj < gj1) {
+                    if (gj == gi) { gj++; continue; }
+                    d.i = gi; d.j = gj++;
+#pragma unroll
+                    for (int u = 0; u < SG_PN; u++) d.t[u] = u < P.negative ? P.negtab[sg_next(rs) & P.negtab_mask] : -1;
+                    return true;
+                }
+                if (++gi >= m) return false;
+                const int b = (int)(sg_next(rs) % (uint32_t)P.window);           // reduced_windows[i]
+                gj = max(0, gi - P.window + b); gj1 = min(m, gi + P.window + 1 - b);
+            }
+        };
+        SgPair d0, d1, d2;
+        bool h0 = gen(d0), h1 = h0 && gen(d1);
+        int ci = -1;                                                   // centre whose syn1neg row is in yc
+        float *rc = nullptr;
+        float yc[PER];
+        while (h0) {
+            const bool h2 = h1 && gen(d2);                             // table lookups of pair s + 2 leave now
+            if (h1) {                                                  // rows of pair s + 1 -> L2
+                prefetch_l2(P.syn0 + (size_t)sent[d1.j] * dim + lane * PER);
+#pragma unroll
+                for (int u = 0; u < SG_PN; u++)
+                    if (d1.t[u] >= 0) prefetch_l2(P.syn1 + (size_t)d1.t[u] * dim + lane * PER);
+                if (d1.i != d0.i) prefetch_l2(P.syn1 + (size_t)sent[d1.i] * dim + lane * PER);
+            }
+            if (d0.i != ci) {                                          // new centre: its row stays in registers across the window
+                if (ci >= 0) st_row<PER>(rc, yc);
+                ci = d0.i;
+                rc = P.syn1 + (size_t)sent[ci] * dim + lane * PER;
+                ld_row<PER>(yc, rc);
+            }
+            const int32_t center = sent[ci];
+            float *r1 = P.syn0 + (size_t)sent[d0.j] * dim + lane * PER;
+            float x[PER], work[PER];
+            ld_row<PER>(x, r1);
+#pragma unroll
+            for (int k = 0; k < PER; k++) work[k] = 0.0f;
+            int32_t tg[SG_NB];
+            tg[0] = center;
+#pragma unroll
+            for (int u = 0; u < SG_PN; u++) tg[u + 1] = d0.t[u] == center ? -1 : d0.t[u];   // a draw equal to the centre word is skipped
+            sg_group<PER>(P, tg, 0, lane, alpha, x, work, yc);
+#pragma unroll
+            for (int k = 0; k < PER; k++) x[k] += work[k];
+            st_row<PER>(r1, x);
+            my_pairs++;
+            d0 = d1; d1 = d2; h0 = h1; h1 = h2;
+        }
+        if (ci >= 0) st_row<PER>(rc, yc);
         __syncwarp();
     }
     if (lane == 0 && my_pairs && P.pairs) atomicAdd(P.pairs, my_pairs);
@@ -361,19 +495,26 @@ int gw_sgns_train_dev(gw_sgns *m, const int32_t *d_walks, int64_t n_walks, int32
     P.key = make_uint2((uint32_t)m->seed, (uint32_t)(m->seed >> 32)); P.sentence_id_base = sentence_id_base; P.pairs = m->pairs;
     int sms = 148;
     device_info(&sms, nullptr);
-    // Hogwild needs far more rows than writers: at most one concurrent warp per 4 words, but never fewer than the 8
-    // workers gensim starts by default (a 34-word vocabulary hammered by 9 000 warps loses most of its updates)
-    const int64_t max_warps = std::max<int64_t>(8, m->n / 4);
-    const int threads = sequential ? 32 : (max_warps < 8 ? 32 : 256);
-    const unsigned grid = sequential ? 1u : (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((n_walks + 7) / 8, (int64_t)sms * 8), max_warps / 8));
+    // Hogwild needs far more rows than writers: every warp holds ~7 rows between their load and their store, and an update
+    // another warp makes to one of them in between is lost.  At most one concurrent warp per 16 words (karate: 2 warps,
+    // R-MAT-22: no limit below the grid): tools/sg_hogwild_probe.py -- on 34 words 8 warps of the pipelined kernel lose
+    // 0.05 of edge AUC against the sequential order, 2 warps 0.01; at 4 M words the cap is never reached
+    int64_t max_warps = std::max<int64_t>(1, m->n / 16);
+    if (const char *mw = getenv("GW_SG_WARPS")) max_warps = std::max<int64_t>(1, atoll(mw));     // experiment knob
+    const int threads = sequential ? 32 : 32 * (int)std::min<int64_t>(8, max_warps);
+    const unsigned grid = sequential ? 1u : (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((n_walks + 7) / 8, (int64_t)sms * 8), max_warps / (threads / 32)));
     const size_t smem = sizeof(int32_t) * (size_t)(threads / 32) * walk_length;
     cudaStream_t st = (cudaStream_t)stream;
+    const char *pe = getenv("GW_SG_PIPE");                  // "0": the unpipelined kernel (A/B measurements)
+    const bool pipe = m->negative < SG_NB && !(pe && !strcmp(pe, "0"));
+#define GW_SG(PER_) do { if (pipe) k_sgns_pipe<PER_><<<grid, threads, smem, st>>>(P); else k_sgns<PER_><<<grid, threads, smem, st>>>(P); } while (0)
     switch (m->dim) {
-        case 32: k_sgns<1><<<grid, threads, smem, st>>>(P); break;
-        case 64: k_sgns<2><<<grid, threads, smem, st>>>(P); break;
-        case 128: k_sgns<4><<<grid, threads, smem, st>>>(P); break;
-        default: k_sgns<8><<<grid, threads, smem, st>>>(P); break;
+        case 32: GW_SG(1); break;
+        case 64: GW_SG(2); break;
+        case 128: GW_SG(4); break;
+        default: GW_SG(8); break;
     }
+#undef GW_SG
     GW_LAUNCHED();
     return GW_OK;
 }

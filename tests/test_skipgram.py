@@ -122,7 +122,7 @@ def test_parallel_training_reaches_the_restatements_quality_and_the_pipeline_cal
     for e in range(2):
         G.train(walks, syn0, syn1, keep, tab, 5, 5, 0.025, 0.0001, e * counts.sum(), total, 3, sentence_id_base=e * len(walks), subsample=False)
     auc_ref = G.edge_auc(syn0, g["row_ptr"], g["col_idx"], np.random.RandomState(0))
-    # device, sentences concurrently (Hogwild; the launcher keeps at most one warp per 4 words, 8 at least: gensim's workers)
+    # device, sentences concurrently (Hogwild; the launcher keeps at most one concurrent warp per 16 words)
     d_w = torch.from_numpy(walks).cuda()
     m = _lib.SkipGram(h, 32, seed=3)
     m.count_dev(d_w.data_ptr(), len(walks), walks.shape[1])
