@@ -70,6 +70,12 @@ struct SimrankParams {
     uint32_t *qcount;
     unsigned long long *prof;        // SR_PROFILE builds: per-phase clock64 totals of CTA 0
     uint32_t *work;                  // path-tree kernel: [0] / [1] = next unclaimed query of the log / exact launch
+    // Scratch SLOTS: the log and path-tree kernels are launched with many more CTAs than fit the machine (one 512/1024-thread
+    // CTA per SM is resident); a CTA takes one of `nslots` per-CTA scratch areas when it starts and gives it back when it
+    // ends.  nslots >= the CTAs that can be resident, so a starting CTA always finds one.
+    uint32_t *slots;                 // [nslots] 0 = free
+    uint32_t nslots;
+    uint32_t quota;                  // path-tree kernel: queries a CTA claims before it ends (0 = until none is left)
     double out_scale;                // fixed point -> score: 2^-32 (Monte Carlo), SAMPLE * 2^-32 (path tree, x SAMPLE as the reference)
     double inv_sample;               // path tree: contributions are accumulated / SAMPLE so that they fit the 0.32 fixed-point table
 };
@@ -519,6 +525,21 @@ struct SrRing {
     unsigned long long full[SR_PAIRS][STAGES];
     unsigned long long empty[SR_PAIRS][STAGES];
 };
+// Called by ONE thread of a starting CTA.  Why CTAs are launched in many waves instead of one persistent wave: dependent random
+// 16-byte loads run at 39.6 G/s in a kernel whose CTAs all start together and stay (any occupancy, any chain length), and at
+// 49-51 G/s from the third wave of CTAs of a launch on (tools/gather_bench.cu mode -5, profiles/r2_gather_waves.txt);
+// k_simrank_log: 464 k -> 548 k queries/s with 16 CTAs per SM slot, results bit-identical.
+__device__ __forceinline__ uint32_t take_slot(const SimrankParams &P) {
+    uint32_t sl = blockIdx.x % P.nslots;
+    while (atomicCAS(P.slots + sl, 0u, 1u) != 0u) sl = sl + 1 == P.nslots ? 0 : sl + 1;
+    __threadfence();
+    return sl;
+}
+__device__ __forceinline__ void give_slot(const SimrankParams &P, uint32_t sl) {   // after the CTA's last access to the slot's scratch
+    __threadfence();
+    atomicExch(P.slots + sl, 0u);
+}
+
 __device__ __forceinline__ void acc_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(SR_ABLOCK) : "memory"); }
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
@@ -754,7 +775,8 @@ __global__ void __launch_bounds__(2 * SR_ABLOCK, 1) k_simrank_log(SimrankParams 
     constexpr int WILP = Ring::WILP;
     Ring &R = *reinterpret_cast<Ring *>(smem_raw + ((sizeof(SrLogShared) + 15) & ~(size_t)15));
     const int tid = threadIdx.x, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    uint2 *log = P.log + (size_t)blockIdx.x * P.log_cap;
+    __shared__ uint32_t s_slot;
+    if (tid == 0) s_slot = take_slot(P);
     uint32_t *t3keys = S.hist;
 
     if (tid < SR_PAIRS * Ring::STAGES) {
@@ -801,6 +823,8 @@ __global__ void __launch_bounds__(2 * SR_ABLOCK, 1) k_simrank_log(SimrankParams 
 
     // =============================== accumulators ===============================
     const int pw = wrp - SR_PAIRS, atid = tid - SR_ABLOCK;
+    const uint32_t my_slot = s_slot;                           // only the accumulator warps touch the log
+    uint2 *log = P.log + (size_t)my_slot * P.log_cap;
     for (int64_t qi = blockIdx.x; qi < P.nq; qi += gridDim.x) {
         // ---------------- phase A: drain my walker's ring ----------------
         for (int32_t g0 = pw * 32; g0 < ngroups; g0 += SR_PAIRS * 32, stage_no++) {
@@ -827,6 +851,8 @@ __global__ void __launch_bounds__(2 * SR_ABLOCK, 1) k_simrank_log(SimrankParams 
         log_finish_query(S, P, log, qi, atid, [] { acc_barrier(); });
         SR_TICK(10);                                           // reset
     }
+    acc_barrier();                                             // only the accumulator warps touch the log
+    if (atid == 0) give_slot(P, my_slot);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -852,11 +878,14 @@ __global__ void __launch_bounds__(2 * SR_ABLOCK, 1) k_simrank_log(SimrankParams 
 struct HybridParams {
     int32_t *vbuf;        // [grid][2][LEN+1][cap]   level buffers of the enumerated prefix
     double *wbuf;         // [grid][2][cap]
+    uint2 *dbuf;          // [grid][2][cap]          row descriptor {offset, degree} of each path's last vertex (it arrives with the nbr4 entry)
     int32_t *chist;       // [grid][LEN+1][cap]      chain parents: history up to their level
     double *cw;           // [grid][cap]             weight of each of the parent's chains = w / ceil(w)
     uint32_t *cnum;       // [grid][cap]             number of chains = ceil(w)
     uint32_t *cofs;       // [grid][cap + 1]         exclusive prefix of cnum
-    uint32_t *ckey;       // [grid][cap]             (index in its level buffer << 5) | level (levels reach 2*STEP-1 = 19)
+    uint32_t *eofs;       // [grid][cap]             expansion of a level: children per path, then their exclusive prefix
+    uint32_t *eoff;       // [grid][cap]             expansion of a level: row offset of an enumerating path's last vertex
+    double *ecw;          // [grid][cap]             expansion of a level: weight each child of an enumerating path receives
     uint2 *cpar;          // [grid][2*cap]           chain -> {parent, child number}
     uint4 *crec;          // [grid][cap]             parent record {key, offset, degree of its last vertex, -}: ONE 16-byte load
     uint32_t hrow;        // ints per history slot (2*STEP+1 rounded up to a multiple of 4: read as 16-byte pieces)
@@ -867,11 +896,10 @@ struct HybridParams {
 template <bool LOGACC>
 struct HyShared {
     typename std::conditional<LOGACC, SrLogShared, SrShared>::type acc;
-    uint32_t ofs[SR_BLOCK + 1];
-    uint32_t roff[SR_BLOCK];
-    double cw[SR_BLOCK];
+    uint32_t ofs[SR_BLOCK + 1];          // children before each thread's run of paths (expansion), + total
     uint32_t warp_tot[SR_BLOCK / 32];
-    uint32_t n_in, n_out, n_cp, scan_base;
+    uint32_t n_in, n_cp, n_chain;
+    uint32_t slot;                       // scratch slot of this CTA (take_slot)
     uint32_t next_q;                     // the query this CTA fetched from the work counter
 };
 
@@ -1031,23 +1059,29 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    uint2 *log = P.log + (size_t)blockIdx.x * P.log_cap;
+    if (threadIdx.x == 0) Y.slot = take_slot(P);
+    __syncthreads();
+    const size_t sl = Y.slot;
+    uint2 *log = P.log + (size_t)sl * P.log_cap;
     constexpr int LEN = 2 * STEP;
     const int tid = threadIdx.x, lane = tid & 31;
     const size_t gs = (size_t)P.gs_mask + 1;
-    uint32_t *gkeys = P.gkeys + blockIdx.x * gs;
-    unsigned long long *gval = P.gval + blockIdx.x * gs;
-    uint32_t *olist = P.olist + (size_t)blockIdx.x * P.olist_cap;
+    uint32_t *gkeys = P.gkeys + sl * gs;
+    unsigned long long *gval = P.gval + sl * gs;
+    uint32_t *olist = P.olist + (size_t)sl * P.olist_cap;
     const size_t cap = H.cap;
-    int32_t *vb = H.vbuf + (size_t)blockIdx.x * 2 * (LEN + 1) * cap;
-    double *wb = H.wbuf + (size_t)blockIdx.x * 2 * cap;
-    int32_t *chist = H.chist + (size_t)blockIdx.x * (size_t)((LEN + 1 + 3) & ~3) * cap;     // history slots of (2*STEP+1 rounded up to 4) ints
-    double *cw = H.cw + (size_t)blockIdx.x * cap;
-    uint32_t *cnum = H.cnum + (size_t)blockIdx.x * cap;
-    uint32_t *cofs = H.cofs + (size_t)blockIdx.x * (cap + 1);
-    uint32_t *ckey = H.ckey + (size_t)blockIdx.x * cap;
-    uint2 *cpar = H.cpar + (size_t)blockIdx.x * 2 * cap;
-    uint4 *crec = H.crec + (size_t)blockIdx.x * cap;
+    int32_t *vb = H.vbuf + (size_t)sl * 2 * (LEN + 1) * cap;
+    double *wb = H.wbuf + (size_t)sl * 2 * cap;
+    uint2 *db = H.dbuf + (size_t)sl * 2 * cap;
+    int32_t *chist = H.chist + (size_t)sl * (size_t)((LEN + 1 + 3) & ~3) * cap;     // history slots of (2*STEP+1 rounded up to 4) ints
+    double *cw = H.cw + (size_t)sl * cap;
+    uint32_t *cnum = H.cnum + (size_t)sl * cap;
+    uint32_t *cofs = H.cofs + (size_t)sl * (cap + 1);
+    uint32_t *eofs = H.eofs + (size_t)sl * cap;
+    uint32_t *eoff = H.eoff + (size_t)sl * cap;
+    double *ecw = H.ecw + (size_t)sl * cap;
+    uint2 *cpar = H.cpar + (size_t)sl * 2 * cap;
+    uint4 *crec = H.crec + (size_t)sl * cap;
     constexpr int HROW = (LEN + 1 + 3) & ~3;
 
     if constexpr (LOGACC) {
@@ -1076,7 +1110,7 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
     // Queries are CLAIMED from a global counter, not dealt out by stride: a path tree costs between a few thousand and a
     // few hundred thousand steps depending on the hubs near its root, and with a static deal the kernel ends when the
     // unluckiest of 148 CTAs does (measured: +10 % on BA-10M).  Results are keyed by the query index, not by the CTA.
-    for (;;) {
+    for (uint32_t done = 0; P.quota == 0 || done < P.quota; done++) {
         if (tid == 0) Y.next_q = atomicAdd(P.work + (LOGACC ? 0 : 1), 1u);
         __syncthreads();
         const int64_t wi = (int64_t)Y.next_q;
@@ -1084,7 +1118,7 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
         const int64_t qi = P.qlist ? (int64_t)P.qlist[wi] : wi;
         const int32_t v = (int32_t)P.queries[qi];
         const uint64_t qid = P.query_id_base + (uint64_t)qi;
-        if (tid == 0) { vb[0] = v; wb[0] = (double)P.sample; Y.n_in = 1; Y.n_cp = 0; }
+        if (tid == 0) { vb[0] = v; wb[0] = (double)P.sample; db[0] = __ldg(P.meta + v); Y.n_in = 1; Y.n_cp = 0; Y.n_chain = 0; }
         __syncthreads();
         HY_TICK(3);                                                // (previous query's top-k / reset ends here)
         // ======================= phase 1: the enumerated prefix, level by level =======================
@@ -1094,6 +1128,8 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
             const double *win = wb + (size_t)b * cap;
             int32_t *vout = vb + (size_t)(b ^ 1) * (LEN + 1) * cap;
             double *wout = wb + (size_t)(b ^ 1) * cap;
+            const uint2 *din = db + (size_t)b * cap;
+            uint2 *dout = db + (size_t)(b ^ 1) * cap;
             const uint32_t n_in = Y.n_in;
             if (n_in == 0) break;                                  // every path has been handed to the chains (uniform)
             // ---- computePathSim at even levels (i = l/2), :80-83 and :157 ----
@@ -1119,57 +1155,81 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
                     add(ok, (uint32_t)target, fx);
                 }
             }
+            HY_TICK(8);                                            // prefix: contributions of an even level
             if (l == LEN) break;
             // ---- expand level l -> l+1: enumerating paths stay in the level buffers, sampling paths become chain parents ----
-            if (tid == 0) Y.n_out = 0;
-            __syncthreads();
-            for (uint32_t base = 0; base < n_in; base += SR_BLOCK) {
-                const uint32_t p = base + tid;
-                uint32_t nchild = 0;
-                if (p < n_in) {
-                    const int32_t cur = vin[(size_t)l * cap + p];
-                    const double w = win[p];
-                    const uint2 m = __ldg(P.meta + cur);
-                    if (m.y != 0 && w >= (double)m.y) {                           // :99-125 enumerate
-                        nchild = m.y;
-                        Y.roff[tid] = m.x;
-                        Y.cw[tid] = w / (double)m.y;
-                    } else if (m.y != 0) {                                        // :126-149 sample ceil(w): a chain parent
-                        const int number = ((double)(int)w == w) ? (int)w : (int)w + 1;
+            // Three passes over the WHOLE level with three barriers, whatever its size (a level of 4 000 paths used to take
+            // eight rounds of 512 with two dependent DRAM latencies and seven barriers each).
+            // pass 1: classify every path
+            for (uint32_t base = 0; base < n_in; base += SR_BLOCK * 4) {
+                double w[4];
+                uint2 m[4];                                                       // no DRAM access here: the descriptors came with the entries
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t p = base + (uint32_t)u * SR_BLOCK + tid;
+                    w[u] = p < n_in ? win[p] : 0.0;
+                    m[u] = p < n_in ? din[p] : make_uint2(0u, 0u);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t p = base + (uint32_t)u * SR_BLOCK + tid;
+                    if (p >= n_in) continue;
+                    uint32_t nchild = 0;
+                    if (m[u].y != 0 && w[u] >= (double)m[u].y) {                  // :99-125 enumerate
+                        nchild = m[u].y;
+                        eoff[p] = m[u].x;
+                        ecw[p] = w[u] / (double)m[u].y;
+                    } else if (m[u].y != 0) {                                     // :126-149 sample ceil(w): a chain parent
+                        const int number = ((double)(int)w[u] == w[u]) ? (int)w[u] : (int)w[u] + 1;
                         if (number > 0) {
                             const uint32_t k = atomicAdd(&Y.n_cp, 1u);
+                            const uint32_t o = atomicAdd(&Y.n_chain, (uint32_t)number);   // its chains' ids (any order: draws are keyed by path, not by id)
                             if (k < cap) {
                                 // parent-major history: a chain reads its parent's 2*STEP+1 slots as one contiguous piece
                                 for (int pos = 0; pos <= l; pos++) chist[(size_t)k * HROW + pos] = vin[(size_t)pos * cap + p];
-                                crec[k] = make_uint4((p << 5) | (uint32_t)l, m.x, m.y, (uint32_t)number);
-                                cw[k] = w / (double)number;
+                                crec[k] = make_uint4((p << 5) | (uint32_t)l, m[u].x, m[u].y, (uint32_t)number);
+                                cw[k] = w[u] / (double)number;
                                 cnum[k] = (uint32_t)number;
+                                cofs[k] = o;
                             }
                         }
                     }                                                             // degree 0: randNeighbor == -1, no child
+                    eofs[p] = nchild;
                 }
-                uint32_t T;
-                const uint32_t excl = block_scan(Y, nchild, tid, &T);
-                Y.ofs[tid] = excl;
-                __syncthreads();
-                const uint32_t out_base = Y.n_out;
-                if (out_base + (uint64_t)T > cap) { if (tid == 0) atomicExch(P.err, 3); break; }
-                // one thread per child
-                for (uint32_t c = tid; c < T; c += SR_BLOCK) {
-                    uint32_t lo2 = 0, hi2 = SR_BLOCK;                  // last slot t with ofs[t] <= c
-                    while (hi2 - lo2 > 1) { uint32_t mid = (lo2 + hi2) >> 1; if (Y.ofs[mid] <= c) lo2 = mid; else hi2 = mid; }
-                    const uint32_t t = lo2, j = c - Y.ofs[t], parent = base + t, oi = out_base + c;
-                    for (int pos = 0; pos <= l; pos++) vout[(size_t)pos * cap + oi] = vin[(size_t)pos * cap + parent];
-                    vout[(size_t)(l + 1) * cap + oi] = __ldg(P.col + Y.roff[t] + j);
-                    wout[oi] = Y.cw[t];
-                    my_steps++;
-                }
-                __syncthreads();
-                if (tid == 0) Y.n_out = out_base + T;
-                __syncthreads();
             }
             __syncthreads();
-            if (tid == 0) Y.n_in = Y.n_out;
+            HY_TICK(9);                                            // prefix: pass 1
+            // pass 2: exclusive prefix of the child counts in path order -- every thread owns a contiguous run of paths, ONE block scan
+            const uint32_t run_len = (n_in + SR_BLOCK - 1) / SR_BLOCK;
+            const uint32_t p0 = min(n_in, (uint32_t)tid * run_len), p1 = min(n_in, p0 + run_len);
+            uint32_t mine = 0;
+            for (uint32_t p = p0; p < p1; p++) mine += eofs[p];
+            uint32_t T;
+            uint32_t run = block_scan(Y, mine, tid, &T);
+            Y.ofs[tid] = run;
+            for (uint32_t p = p0; p < p1; p++) { const uint32_t c = eofs[p]; eofs[p] = run; run += c; }
+            __syncthreads();
+            if ((uint64_t)T > cap) { if (tid == 0) { atomicExch(P.err, 3); Y.n_in = 0; } __syncthreads(); break; }
+            HY_TICK(10);                                           // prefix: pass 2
+            // pass 3: one thread per child; its path = the last one whose prefix is <= the child's index (threads' runs by
+            // bisection in shared memory, then along the run)
+            for (uint32_t c = tid; c < T; c += SR_BLOCK) {
+                uint32_t lo2 = 0, hi2 = SR_BLOCK;                      // last thread t with ofs[t] <= c
+                while (hi2 - lo2 > 1) { const uint32_t mid = (lo2 + hi2) >> 1; if (Y.ofs[mid] <= c) lo2 = mid; else hi2 = mid; }
+                uint32_t parent = lo2 * run_len;
+                const uint32_t pend = min(n_in, parent + run_len);
+                while (parent + 1 < pend && eofs[parent + 1] <= c) parent++;
+                const uint32_t j = c - eofs[parent];
+                for (int pos = 0; pos <= l; pos++) vout[(size_t)pos * cap + c] = vin[(size_t)pos * cap + parent];
+                const int4 e = ld_nbr4(P.nbr4 + eoff[parent] + j);                  // the level's ONE round trip to DRAM
+                vout[(size_t)(l + 1) * cap + c] = e.x;
+                dout[c] = make_uint2((uint32_t)e.z, (uint32_t)e.w);
+                wout[c] = ecw[parent];
+                my_steps++;
+            }
+            __syncthreads();
+            HY_TICK(11);                                           // prefix: pass 3
+            if (tid == 0) Y.n_in = T;
             __syncthreads();
         }
         __syncthreads();
@@ -1178,20 +1238,8 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
         const uint32_t n_cp = Y.n_cp;
         if (n_cp > cap) { if (tid == 0) atomicExch(P.err, 3); }
         else if (n_cp > 0) {
-            // exclusive prefix of the chain counts, chain -> parent map
-            if (tid == 0) Y.scan_base = 0;
-            __syncthreads();
-            for (uint32_t base = 0; base < n_cp; base += SR_BLOCK) {
-                const uint32_t k = base + tid;
-                const uint32_t val = k < n_cp ? cnum[k] : 0u;
-                uint32_t T;
-                const uint32_t excl = block_scan(Y, val, tid, &T);
-                if (k < n_cp) cofs[k] = Y.scan_base + excl;
-                __syncthreads();
-                if (tid == 0) Y.scan_base += T;
-                __syncthreads();
-            }
-            const uint32_t n_chain = Y.scan_base;
+            // chain -> parent map (the chains' ids were handed out when their parents were created)
+            const uint32_t n_chain = Y.n_chain;
             if (n_chain > 2 * cap) { if (tid == 0) atomicExch(P.err, 3); }
             else {
                 for (uint32_t k = tid; k < n_cp; k += SR_BLOCK) {
@@ -1274,6 +1322,8 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
     }
     for (int o = 16; o; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
     if (lane == 0 && my_steps && !P.qlist) atomicAdd(P.steps, my_steps);   // handed-over queries were counted by the log instantiation
+    __syncthreads();
+    if (tid == 0) give_slot(P, (uint32_t)sl);
 }
 
 // ---------------- replay mode: java.util.Random on the device ----------------
@@ -1554,7 +1604,12 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     const bool hybrid = mode == GW_SIMRANK_HYBRID;
     if (mode == GW_SIMRANK_MC_F64 && !d_out_dense) return fail(GW_E_INVALID, "GW_SIMRANK_MC_F64 produces dense rows only (gw_simrank_rows)");
     const int grid = (int)std::min<int64_t>(nq, (int64_t)sms * (hybrid ? 1 : 2));
-    const int log_grid = (int)std::min<int64_t>(nq, (int64_t)sms);      // log kernel: one 1024-thread CTA per SM
+    // log and path-tree kernels: one 1024- / 512-thread CTA is resident per SM, but the launch holds SR_WAVES CTAs per SM
+    // (each with 1/SR_WAVES of the queries) -- see take_slot for the measurement behind it.  GW_SR_WAVES overrides (1 = persistent).
+    int sr_waves = 16;
+    if (const char *wv = getenv("GW_SR_WAVES")) sr_waves = std::max(1, atoi(wv));
+    const int nslots = (int)std::min<int64_t>(nq, (int64_t)sms);                    // scratch areas = CTAs that can be resident
+    const int log_grid = (int)std::min<int64_t>(nq, (int64_t)sms * sr_waves);
     const char *force = getenv("GW_SIMRANK");
     const bool use_log = !hybrid && d_out_ids && !d_out_dense && !(force && !strcmp(force, "hash"));
     // hash-kernel tier-2 table: >= 2x the distinct targets one query can produce
@@ -1566,12 +1621,12 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     // log capacity = the most contributions one query can make (path tree: every path of every even level)
     const uint32_t log_cap = (uint32_t)std::min<int64_t>(hybrid ? (int64_t)sample * step * (step + 1) + step : (int64_t)sample * step,
                                                          (int64_t)0x7FFFFFFF);
-    // layout: [64 B header][gval u64 grid*gs][gkeys u32 grid*gs][olist u32 grid*ocap][log uint2 grid*log_cap][qlist i32 nq]
-    size_t off_gval = 256;
+    // layout: [4 KB header: counters at 0..255, scratch-slot flags from 1024][gval u64 grid*gs][gkeys u32 grid*gs][olist u32 grid*ocap][log uint2 grid*log_cap][qlist i32 nq]
+    size_t off_gval = 4096;
     size_t off_gkeys = off_gval + (size_t)grid * gs * 8;
     size_t off_olist = off_gkeys + (size_t)grid * gs * 4;
     size_t off_log = (off_olist + (size_t)grid * ocap * 4 + 15) & ~(size_t)15;
-    size_t off_qlist = off_log + (size_t)grid * log_cap * 8;
+    size_t off_qlist = off_log + (size_t)std::max(grid, nslots) * log_cap * 8;
     size_t need = off_qlist + (size_t)nq * 4 + 16;
     const bool fresh = g->simrank_scratch_bytes < need || g->simrank_layout != (uint64_t)gs * 1000003u + (uint64_t)grid;
     if (g->simrank_scratch_bytes < need) {
@@ -1597,7 +1652,9 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
         k_sr_clean_if_err<<<sms * 4, 256, 0, st>>>(P.err, P.gval, P.gkeys, (size_t)grid * gs);
         GW_LAUNCHED();
     }
-    GW_CUDA(cudaMemsetAsync(base, 0, 256, st));
+    GW_CUDA(cudaMemsetAsync(base, 0, 4096, st));
+    if (nslots > 768) return fail(GW_E_STATE, "%d scratch slots do not fit the header", nslots);
+    P.slots = (uint32_t *)(base + 1024); P.nslots = (uint32_t)nslots; P.quota = 0;
     P.prof = (unsigned long long *)(base + 64);
     P.work = (uint32_t *)(base + 48);
     if (fresh || g->simrank_dirty) {   // the hash kernel leaves its tables clean; only (re)initialise when the layout changes
@@ -1625,6 +1682,7 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
         size_t off = 0;
         auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
         const size_t o_w = take((size_t)grid * 2 * capz * sizeof(double));
+        const size_t o_d = take((size_t)grid * 2 * capz * sizeof(uint2));
         const size_t o_cw = take((size_t)grid * capz * sizeof(double));
         const size_t o_v = take((size_t)grid * 2 * LEN1 * capz * sizeof(int32_t));
         const size_t HR = (LEN1 + 3) & ~(size_t)3;
@@ -1632,6 +1690,8 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
         const size_t o_cn = take((size_t)grid * capz * sizeof(uint32_t));
         const size_t o_co = take((size_t)grid * (capz + 1) * sizeof(uint32_t));
         const size_t o_ck = take((size_t)grid * capz * sizeof(uint32_t));
+        const size_t o_eo = take((size_t)grid * capz * sizeof(uint32_t));
+        const size_t o_ew = take((size_t)grid * capz * sizeof(double));
         const size_t o_cp = take((size_t)grid * 2 * capz * sizeof(uint2));
         const size_t o_cm = take((size_t)grid * capz * sizeof(uint4));
         if (g->hybrid_scratch_bytes < off + 16) {
@@ -1644,10 +1704,10 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
             g->hybrid_scratch_bytes = off + 16;
         }
         unsigned char *hb = (unsigned char *)g->d_hybrid_scratch;
-        H.wbuf = (double *)(hb + o_w); H.cw = (double *)(hb + o_cw);
+        H.wbuf = (double *)(hb + o_w); H.dbuf = (uint2 *)(hb + o_d); H.cw = (double *)(hb + o_cw);
         H.vbuf = (int32_t *)(hb + o_v); H.chist = (int32_t *)(hb + o_ch);
         H.cnum = (uint32_t *)(hb + o_cn); H.cofs = (uint32_t *)(hb + o_co);
-        H.ckey = (uint32_t *)(hb + o_ck); H.cpar = (uint2 *)(hb + o_cp); H.crec = (uint4 *)(hb + o_cm); H.hrow = (uint32_t)HR;
+        H.eofs = (uint32_t *)(hb + o_ck); H.eoff = (uint32_t *)(hb + o_eo); H.ecw = (double *)(hb + o_ew); H.cpar = (uint2 *)(hb + o_cp); H.crec = (uint4 *)(hb + o_cm); H.hrow = (uint32_t)HR;
         for (int i = 0; i < 16; i++) H.cpow[i] = i <= step ? pow(c, i) : 0.0;
         // top-k: log-structured instantiation first, then the exact one over the queries it handed over;
         // dense rows: the exact instantiation alone
@@ -1656,15 +1716,19 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
         if (hy_log) Q.qlist = P.qlist_out;
         const char *hsp = getenv("GW_HY_SPLIT");               // experiment knob: "1" = walker / accumulator warps in the chain phase
         const bool hy_split = hsp && !strcmp(hsp, "1");
+        // log instantiation: sr_waves CTAs per SM in the launch, each ends after its share of the queries (claimed dynamically)
+        const int hy_grid = (int)std::min<int64_t>(nq, (int64_t)sms * sr_waves);
+        SimrankParams PL = P;
+        PL.quota = (uint32_t)((nq + hy_grid - 1) / hy_grid);
 #define GW_HY(N) case N: \
             if (hy_log && hy_split) { \
                 const size_t hsm = ((sizeof(HyShared<true>) + 15) & ~(size_t)15) + sizeof(HyRing<N>); \
                 GW_CUDA(cudaFuncSetAttribute(k_topsim_hybrid<N, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm)); \
-                k_topsim_hybrid<N, true, true><<<grid, SR_BLOCK, hsm, st>>>(P, H); \
+                k_topsim_hybrid<N, true, true><<<hy_grid, SR_BLOCK, hsm, st>>>(PL, H); \
                 GW_LAUNCHED(); \
             } else if (hy_log) { \
                 GW_CUDA(cudaFuncSetAttribute(k_topsim_hybrid<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HyShared<true>))); \
-                k_topsim_hybrid<N, true><<<grid, SR_BLOCK, sizeof(HyShared<true>), st>>>(P, H); \
+                k_topsim_hybrid<N, true><<<hy_grid, SR_BLOCK, sizeof(HyShared<true>), st>>>(PL, H); \
                 GW_LAUNCHED(); \
             } \
             GW_CUDA(cudaFuncSetAttribute(k_topsim_hybrid<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HyShared<false>))); \
@@ -1960,9 +2024,10 @@ int gw_simrank_last_slow_queries(const gw_graph *g, int64_t *count) {
         {
             unsigned long long pr[16];
             GW_CUDA(cudaMemcpy(pr, (unsigned char *)g->d_simrank_scratch + 64, sizeof(pr), cudaMemcpyDeviceToHost));
-            const char *nm[8] = {"prefix (phase 1)", "chain set-up", "chains", "top-k + reset + query switch", "walker 0: waits for a stage",
-                                 "walker 0: walks (+ other phases)", "accumulator 0: waits for walker", "accumulator 0: inserts (+ other phases)"};
-            for (int i = 0; i < 8; i++) fprintf(stderr, "HY_PROFILE %-40s %12llu cycles\n", nm[i], pr[i]);
+            const char *nm[12] = {"prefix: rest (level switches)", "chain set-up", "chains", "top-k + reset + query switch", "walker 0: waits for a stage",
+                                  "walker 0: walks (+ other phases)", "accumulator 0: waits for walker", "accumulator 0: inserts (+ other phases)",
+                                  "prefix: contributions of even levels", "prefix: pass 1 (classify)", "prefix: pass 2 (scan)", "prefix: pass 3 (children)"};
+            for (int i = 0; i < 12; i++) fprintf(stderr, "HY_PROFILE %-40s %12llu cycles\n", nm[i], pr[i]);
         }
 #endif
 #ifdef SR_PROFILE

@@ -41,6 +41,37 @@ __global__ void k_chain(const int4 *__restrict__ a, uint32_t mask, int steps, ui
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
+// dependent chain whose trajectory is the thread's own: two threads that meet on an entry part again (k_chain's merge for good,
+// which turns long runs into same-address hot spots)
+__global__ void k_chain_own(const int4 *__restrict__ a, uint32_t mask, int steps, uint32_t salt, uint32_t *out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t i = mix(t * 2654435761u + salt) & mask;
+    uint32_t acc = 0;
+    for (int s = 0; s < steps; s++) {
+        const int4 v = __ldg(a + i);
+        acc += v.y;
+        i = mix((uint32_t)v.x + s + t * 0x9E3779B9u) & mask;
+    }
+    out[t] = acc;
+}
+
+// single-wave experiments: thread-id offset (is it the ids?) and a per-block start delay (is it the lock step?)
+__global__ void k_chain_var(const int4 *__restrict__ a, uint32_t mask, int steps, uint32_t salt, uint32_t toff, int delay_us, uint32_t *out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x + toff;
+    if (delay_us) {
+        const long long until = clock64() + (long long)(mix(blockIdx.x * 7919u + salt) % (uint32_t)delay_us) * 1900;
+        while (clock64() < until) { }
+    }
+    uint32_t i = mix(t * 2654435761u + salt) & mask;
+    uint32_t acc = 0;
+    for (int s = 0; s < steps; s++) {
+        const int4 v = __ldg(a + i);
+        acc += v.y;
+        i = mix((uint32_t)v.x + s + t * 0x9E3779B9u) & mask;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 // pair mode: every step loads the random entry AND its partner at byte distance `dist` (same naturally
 // aligned 2*dist block).  If pairs run at the single-load rate the ceiling is a DRAM activate / L2-miss
 // REQUEST rate that locality can amortise, not bytes.
@@ -192,6 +223,66 @@ int main(int argc, char **argv) {
             float ms; cudaEventElapsedTime(&ms, e0, e1);
             printf("64 MiB footprint over %6.0f MiB (stride %4u lines): %7.3f ms  %6.1f G loads/s\n", n * 16.0 / (1 << 20), stride, ms, (double)nthreads * steps / ms / 1e6);
             cudaFree(a);
+        }
+        printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
+        return 0;
+    }
+    if (argc > 1 && atoi(argv[1]) == -5) {   // mode 7: chain length x occupancy, chains that cannot merge (the thread id enters every index)
+        size_t n = (size_t)1 << 27; int4 *a; uint32_t *out;
+        cudaMalloc(&a, n * sizeof(int4)); cudaMalloc(&out, 148 * 2048 * 4);
+        uint32_t *out2; cudaMalloc(&out2, (size_t)4 << 24);
+        k_fill<<<(unsigned)((n + 255) / 256), 256>>>(a, n);
+        const int lens[] = {10, 80, 400, 2000};
+        for (int tpsm = 512; tpsm <= 2048; tpsm *= 2)
+            for (int li = 0; li < 4; li++) {
+                const int steps = lens[li], reps = 4000 / steps > 0 ? 4000 / steps : 1;
+                const int grid = 148 * (tpsm / 256);
+                cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+                k_chain_own<<<grid, 256>>>(a, (uint32_t)(n - 1), steps, 0, out);
+                cudaEventRecord(e0);
+                for (int r = 0; r < reps; r++) k_chain_own<<<grid, 256>>>(a, (uint32_t)(n - 1), steps, 1 + r, out);
+                cudaEventRecord(e1); cudaEventSynchronize(e1);
+                float ms; cudaEventElapsedTime(&ms, e0, e1);
+                printf("%4d threads/SM, %4d loads per chain, %3d launches: %6.1f G loads/s\n", tpsm, steps, reps, (double)grid * 256 * steps * reps / ms / 1e6);
+            }
+        // the same chains as MANY waves of blocks in one launch (blocks retire and start all the time: the warps of an SM
+        // are at different steps), and with 2.5 GiB (the BA n = 1e7 m = 8 nbr4 array)
+        for (int li = 0; li < 3; li++) {
+            const int steps = lens[li + 1];
+            const int grid = (1 << 22) / 256 * (li == 0 ? 4 : 1);
+            cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+            k_chain_own<<<grid, 256>>>(a, (uint32_t)(n - 1), steps, 0, out2);
+            cudaEventRecord(e0);
+            k_chain_own<<<grid, 256>>>(a, (uint32_t)(n - 1), steps, 1, out2);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            printf("%d blocks of 256 in one launch, %4d loads per chain: %6.1f G loads/s\n", grid, steps, (double)grid * 256 * steps / ms / 1e6);
+        }
+        {
+            struct { uint32_t toff; int delay; int steps; const char *what; } v[] = {
+                {0, 0, 2000, "one wave, ids from 0"}, {10000000u, 0, 2000, "one wave, ids from 1e7"},
+                {0, 200, 2000, "one wave, blocks start 0-200 us apart"}, {0, 2000, 2000, "one wave, blocks start 0-2 ms apart"}};
+            for (int vi = 0; vi < 4; vi++) {
+                cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+                k_chain_var<<<1184, 256>>>(a, (uint32_t)(n - 1), v[vi].steps, 0, v[vi].toff, v[vi].delay, out2);
+                cudaEventRecord(e0);
+                k_chain_var<<<1184, 256>>>(a, (uint32_t)(n - 1), v[vi].steps, 1, v[vi].toff, v[vi].delay, out2);
+                cudaEventRecord(e1); cudaEventSynchronize(e1);
+                float ms; cudaEventElapsedTime(&ms, e0, e1);
+                printf("%-40s %4d loads per chain: %7.3f ms %6.1f G loads/s (delays included)\n", v[vi].what, v[vi].steps, ms, 1184.0 * 256 * v[vi].steps / ms / 1e6);
+            }
+        }
+        // how many blocks does it take?  (1184 = one resident wave of 8 per SM)
+        const int grids[] = {1184, 1332, 2368, 4736, 9472, 18944, 1184};
+        for (int gi = 0; gi < 7; gi++) {
+            const int steps = 400, grid = grids[gi];
+            cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+            k_chain_own<<<grid, 256>>>(a, (uint32_t)(n - 1), steps, 0, out2);
+            cudaEventRecord(e0);
+            k_chain_own<<<grid, 256>>>(a, (uint32_t)(n - 1), steps, 1, out2);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            printf("%5d blocks of 256, %4d loads per chain: %7.3f ms %6.1f G loads/s\n", grid, steps, ms, (double)grid * 256 * steps / ms / 1e6);
         }
         printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
         return 0;

@@ -11,3 +11,4 @@ for i in range(3):
     ids, sc = g.simrank_topk(q, 0.6, 5, 10000, 20, mode=_lib.GW_SIMRANK_HYBRID, seed=1 + i)
     dt = time.perf_counter() - t0
     print("hybrid: %d queries in %.1f ms = %.0f queries/s, %d tree steps per query" % (len(q), dt * 1e3, len(q) / dt, g.simrank_last_steps() / len(q)), flush=True)
+print("slow queries (HY_PROFILE builds print their phase totals here):", g.simrank_last_slow_queries(), flush=True)
