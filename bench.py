@@ -931,8 +931,11 @@ def measure(args, rank, world, local):
                 "model": "SURVEY 8(d): 64 B per walk step (here ONE random 16-byte entry = one 64-byte HBM atom) + 12 B per result slot",
                 "walk_steps_per_s": walk_steps / (kernel_ms * 1e-3),
                 "access_rate": {"achieved_G_per_s": rate, "ceiling_G_per_s": ceil, "frac": (rate / ceil) if ceil else None,
-                                "note": "one dependent random load per walk step; ceiling measured by tools/gather_bench.cu for an array "
-                                        "of nbr4's size (profiles/gather_ceiling.json)"}}
+                                "note": "one dependent random load per walk step; ceiling = DRAM-missing dependent loads/s measured by "
+                                        "tools/gather_bench.cu for an array of nbr4's size in a many-wave launch (profiles/gather_ceiling.json; "
+                                        "a single resident wave of CTAs is held at 39.6 G/s, profiles/r2_gather_waves.txt).  The Monte-Carlo "
+                                        "kernel's first two steps of every walk start at the query vertex and hit L1/L2 (~20 % of its loads), "
+                                        "so its rate can exceed the ceiling of misses"}}
         roof["frac"] = roof["achieved"] / peak
         e2e = None
         if not args.no_e2e:
