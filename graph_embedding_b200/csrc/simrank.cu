@@ -1023,9 +1023,12 @@ __device__ __forceinline__ int hy_walk_chains(const SimrankParams &P, const Hybr
 // walker -> accumulator rings of the chain phase (log-structured instantiation): warps [0, 8) walk chains, warps [8, 16)
 // insert their contributions -- the split k_simrank_log uses, for the same reason (profiles/README.md R2-6: 81 % of the
 // kernel is the chain phase, and inside it every warp alternated between ~7 memory latencies and five insertions)
+#ifndef HY_CILP
+#define HY_CILP 2                    // chains walked in lock step per thread of the path-tree kernel's chain phase
+#endif
 template <int STEP>
 struct HyRing {
-    static constexpr int CILP = STEP <= 5 ? 2 : 1;
+    static constexpr int CILP = STEP <= 5 ? HY_CILP : 1;
     static constexpr int PAIRS = SR_BLOCK / 64, STAGES = 2;
     uint2 slot[PAIRS][STAGES][CILP * STEP * 32];
     unsigned long long full[PAIRS][STAGES];
@@ -1294,14 +1297,19 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
                     constexpr int CILP = HyRing<STEP>::CILP;
                     bool overflow = false;
                     for (uint32_t g0 = (uint32_t)(tid >> 5) * 32 * CILP; g0 < n_chain; g0 += SR_BLOCK * CILP) {
-                        uint32_t ek[CILP * STEP], ev[CILP * STEP];
+                        uint32_t ek[CILP][STEP], ev[CILP][STEP];
                         my_steps += (unsigned long long)hy_walk_chains<STEP, CILP>(P, H, cpar, crec, cw, chist, qid, v, g0 + lane, 32u,
                             n_chain, [&](int k, int i, bool ok, uint32_t key, unsigned long long fx) {
                                 if (ok && fx > 0xFFFFFFFFull) { overflow = true; fx = 0xFFFFFFFFull; }
-                                ek[(i - 1) * CILP + k] = ok ? key : SR_EMPTY;
-                                ev[(i - 1) * CILP + k] = (uint32_t)fx;
+                                ek[k][i - 1] = ok ? key : SR_EMPTY;
+                                ev[k][i - 1] = (uint32_t)fx;
                             });
-                        log_insert_chunk<CILP * STEP>(S, P, log, lane, ek, ev);
+                        if constexpr (CILP <= 2) {
+                            log_insert_chunk<CILP * STEP>(S, P, log, lane, &ek[0][0], &ev[0][0]);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < CILP; k++) log_insert_chunk<STEP>(S, P, log, lane, ek[k], ev[k]);
+                        }
                     }
                     if (overflow) S.slow = 1;
                 } else {

@@ -369,3 +369,33 @@ def test_handoff_threads_knob_and_many_calls(monkeypatch):
     monkeypatch.setenv("GW_E2E", "direct")
     d, _ = h.walks(0.25, 4.0, 40, starts[:1000], seed=1)
     assert np.array_equal(c, d)
+
+
+# ---------------------------------------------------------------------------------------------
+# launch geometry of the SimRank kernels: many waves of CTAs over scratch slots (simrank.cu take_slot)
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode_name", ["mc", "hybrid"])
+def test_simrank_results_do_not_depend_on_the_number_of_cta_waves(mode_name, monkeypatch):
+    """One persistent CTA per SM (GW_SR_WAVES=1), 3 or 16 CTAs per SM slot, more queries than slots and fewer: the top-k
+    tiles are the same bits (32.32 fixed-point sums; draws keyed by query and sample / path, never by CTA)."""
+    mode = _lib.GW_SIMRANK_MC if mode_name == "mc" else _lib.GW_SIMRANK_HYBRID
+    g = _lib.GraphHandle.barabasi_albert(20000, 6, seed=4)
+    rs = np.random.RandomState(8)
+    for nq in (1, 5, 700):
+        q = rs.choice(g.n, nq, replace=False).astype(np.int64)
+        ref = None
+        for waves in ("1", "3", "16"):
+            monkeypatch.setenv("GW_SR_WAVES", waves)
+            ids, sc = g.simrank_topk(q, 0.6, 4, 2000, 10, mode=mode, seed=21)
+            assert g.simrank_last_error() == 0
+            if ref is None:
+                ref = (ids.copy(), sc.copy())
+                assert (sc[:, 0] > 0).all()
+            else:
+                assert np.array_equal(ids, ref[0]) and np.array_equal(sc, ref[1]), (mode_name, nq, waves)
+    # a second graph handle on the same device while the first one is alive: slots live in each graph's own scratch
+    g2 = _lib.GraphHandle.barabasi_albert(3000, 4, seed=5)
+    monkeypatch.delenv("GW_SR_WAVES")
+    a = g2.simrank_topk(np.arange(200, dtype=np.int64), 0.6, 3, 500, 5, mode=mode, seed=2)
+    b = g2.simrank_topk(np.arange(200, dtype=np.int64), 0.6, 3, 500, 5, mode=mode, seed=2)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
