@@ -787,6 +787,10 @@ int ensure_common_counts(gw_graph *g, cudaStream_t st, bool need_counts) {
         device_info(&sms, nullptr);
         const char *np = getenv("GW_CN_RIDX");                   // experiment knob: "0" keeps plain counts (rejection of prev)
         g->nbr4_packed = (g->max_degree < 65536 && !(np && !strcmp(np, "0"))) ? 1 : 0;
+        // CTAs of k_cc_small in the launch per SM (8 of 256 threads are resident): 8 / 16 / 32 / 64 / 128 / 256 -> R-MAT-22 22.1 /
+        // 21.6 / 20.8 / 20.6 / 20.3 / 20.3 ms, R-MAT-26 443 / 437 / 432 / 426 / 424 / 422 ms (tools/prep_waves_probe.py)
+        int cc_ctas = 128;
+        if (const char *cs = getenv("GW_CC_CTAS_PER_SM")) cc_ctas = std::max(1, atoi(cs));   // experiment knob
         const char *bv = getenv("GW_CN_BUILD");                  // experiment knob: "v1" = one warp per directed entry
         if (bv && !strcmp(bv, "v1")) {
             k_common_counts_v1<<<sms * 16, 256, 0, st>>>(g->d_meta, g->d_col, g->d_row_ptr, g->n, g->nnz, g->d_nbr4, flag.p, g->nbr4_packed);
@@ -794,7 +798,7 @@ int ensure_common_counts(gw_graph *g, cudaStream_t st, bool need_counts) {
         } else {
             const bool have_tasks = (uint32_t)g->max_degree > CC_SMALL;
             if (!have_tasks) {
-                k_cc_small<<<sms * 16, 256, 0, st>>>(g->d_meta, g->d_col, g->n, g->d_nbr4, flag.p, g->nbr4_packed);
+                k_cc_small<<<sms * cc_ctas, 256, 0, st>>>(g->d_meta, g->d_col, g->n, g->d_nbr4, flag.p, g->nbr4_packed);
                 GW_LAUNCHED();
             } else {
                 GW_CUDA(cudaMemsetAsync(nt.p, 0, sizeof(unsigned int), st));
@@ -805,7 +809,7 @@ int ensure_common_counts(gw_graph *g, cudaStream_t st, bool need_counts) {
                 const bool timing = getenv("GW_TIMING") != nullptr;
                 if (timing) { cudaEventCreate(&t1); cudaEventCreate(&t2); }
                 GW_CUDA(cudaMemcpyAsync(&hn, nt.p, sizeof(hn), cudaMemcpyDeviceToHost, st));
-                k_cc_small<<<sms * 16, 256, 0, st>>>(g->d_meta, g->d_col, g->n, g->d_nbr4, flag.p, g->nbr4_packed);   // runs while the host waits for the task count
+                k_cc_small<<<sms * cc_ctas, 256, 0, st>>>(g->d_meta, g->d_col, g->n, g->d_nbr4, flag.p, g->nbr4_packed);   // runs while the host waits for the task count
                 GW_LAUNCHED();
                 GW_CUDA(cudaStreamSynchronize(st));
                 if (hn > cap) return fail(GW_E_STATE, "common-neighbour task list overflow (%u > %u)", hn, cap);
