@@ -1,4 +1,4 @@
-"""Short profiling target (ncu --set full): BA n=1e7 m=8, two batches of 2048 TopSim queries (C=0.6 STEP=5 SAMPLE=1e4, k=20)."""
+"""Short profiling target (ncu --set full): BA n=1e7 m=8, two batches of NQ (default 8192) TopSim queries (C=0.6 STEP=5 SAMPLE=1e4, k=20)."""
 import os
 import sys
 
@@ -9,7 +9,7 @@ import torch
 from graph_embedding_b200 import _lib
 
 g = _lib.GraphHandle.barabasi_albert(10_000_000, 8, seed=1)
-nq = 2048
+nq = int(os.environ.get("NQ", 8192))
 q = torch.from_numpy(np.random.RandomState(2).choice(g.n, size=2 * nq, replace=False).astype(np.int64)).cuda()
 ids = torch.empty((nq, 20), dtype=torch.int32, device="cuda")
 sc = torch.empty((nq, 20), dtype=torch.float64, device="cuda")
