@@ -955,19 +955,20 @@ __device__ __forceinline__ int hy_walk_chains(const SimrankParams &P, const Hybr
 #pragma unroll
         for (int pos = 0; pos <= LEN; pos++) { path[k][pos] = -1; dgs[k][pos] = 0; }
         if (live[k]) {
-            const uint2 cp = cpar[t];                                   // {parent, child number}: 8 bytes, coalesced over t
+            const uint2 cp = cpar[t];                                   // {parent, level << 24 | child number}: 8 bytes, coalesced over t
+            const int lv = (int)(cp.y >> 24);
             const uint4 rec = crec[cp.x];
             const int4 *hrow = reinterpret_cast<const int4 *>(chist + (size_t)cp.x * HROW);
             wq[k] = cw[cp.x];
             m[k] = make_uint2(rec.y, rec.z);
             int32_t hv[HROW];
 #pragma unroll
-            for (int c4 = 0; c4 < HROW / 4; c4++) { const int4 q4 = hrow[c4]; hv[4 * c4] = q4.x; hv[4 * c4 + 1] = q4.y; hv[4 * c4 + 2] = q4.z; hv[4 * c4 + 3] = q4.w; }
+            for (int c4 = 0; c4 < HROW / 4; c4++) { const int4 q4 = 4 * c4 <= lv ? hrow[c4] : make_int4(-1, -1, -1, -1); hv[4 * c4] = q4.x; hv[4 * c4 + 1] = q4.y; hv[4 * c4 + 2] = q4.z; hv[4 * c4 + 3] = q4.w; }
 #pragma unroll
             for (int pos = 0; pos <= LEN; pos++) path[k][pos] = hv[pos];
-            lvl[k] = (int)(rec.x & 31u);
+            lvl[k] = lv;
             ctr_p[k] = rec.x >> 5;
-            ctr_lj[k] = ((uint32_t)lvl[k] << 24) | cp.y;
+            ctr_lj[k] = cp.y;                                          // (level << 24) | child number
 #pragma unroll
             for (int pos = 0; pos <= LEN; pos++) if (pos > lvl[k]) path[k][pos] = -1;
             len[k] = lvl[k];
@@ -1247,7 +1248,8 @@ __global__ void __launch_bounds__(SR_BLOCK, 1) k_topsim_hybrid(SimrankParams P, 
             else {
                 for (uint32_t k = tid; k < n_cp; k += SR_BLOCK) {
                     const uint32_t o = cofs[k], c = cnum[k];
-                    for (uint32_t j = 0; j < c; j++) cpar[o + j] = make_uint2(k, j);
+                    const uint32_t lv24 = (crec[k].x & 31u) << 24;            // the level rides in the chain map: a chain then knows which
+                    for (uint32_t j = 0; j < c; j++) cpar[o + j] = make_uint2(k, lv24 | j);   // pieces of its parent's history exist
                 }
                 __syncthreads();
                 HY_TICK(1);                                        // chain set-up (scan, chain -> parent map)

@@ -72,6 +72,20 @@ __global__ void k_chain_var(const int4 *__restrict__ a, uint32_t mask, int steps
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
+// do CTAs that retire at once count as "turnover"?  The first `ndummy` blocks of the launch return immediately
+__global__ void k_chain_dummy(const int4 *__restrict__ a, uint32_t mask, int steps, uint32_t salt, uint32_t ndummy, uint32_t *out) {
+    if (blockIdx.x < ndummy) return;
+    const uint32_t t = (blockIdx.x - ndummy) * blockDim.x + threadIdx.x;
+    uint32_t i = mix(t * 2654435761u + salt) & mask;
+    uint32_t acc = 0;
+    for (int s = 0; s < steps; s++) {
+        const int4 v = __ldg(a + i);
+        acc += v.y;
+        i = mix((uint32_t)v.x + s + t * 0x9E3779B9u) & mask;
+    }
+    out[t] = acc;
+}
+
 // pair mode: every step loads the random entry AND its partner at byte distance `dist` (same naturally
 // aligned 2*dist block).  If pairs run at the single-load rate the ceiling is a DRAM activate / L2-miss
 // REQUEST rate that locality can amortise, not bytes.
@@ -270,6 +284,18 @@ int main(int argc, char **argv) {
                 cudaEventRecord(e1); cudaEventSynchronize(e1);
                 float ms; cudaEventElapsedTime(&ms, e0, e1);
                 printf("%-40s %4d loads per chain: %7.3f ms %6.1f G loads/s (delays included)\n", v[vi].what, v[vi].steps, ms, 1184.0 * 256 * v[vi].steps / ms / 1e6);
+            }
+        }
+        {
+            const uint32_t nd[] = {0, 1184, 2368, 4736, 18944, 148000};
+            for (int vi = 0; vi < 6; vi++) {
+                cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+                k_chain_dummy<<<1184 + nd[vi], 256>>>(a, (uint32_t)(n - 1), 2000, 0, nd[vi], out2);
+                cudaEventRecord(e0);
+                k_chain_dummy<<<1184 + nd[vi], 256>>>(a, (uint32_t)(n - 1), 2000, 1, nd[vi], out2);
+                cudaEventRecord(e1); cudaEventSynchronize(e1);
+                float ms; cudaEventElapsedTime(&ms, e0, e1);
+                printf("one working wave after %6u blocks that return at once: %7.3f ms %6.1f G loads/s\n", nd[vi], ms, 1184.0 * 256 * 2000 / ms / 1e6);
             }
         }
         // how many blocks does it take?  (1184 = one resident wave of 8 per SM)
