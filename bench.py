@@ -933,7 +933,7 @@ def measure(args, rank, world, local):
                 "access_rate": {"achieved_G_per_s": rate, "ceiling_G_per_s": ceil, "frac": (rate / ceil) if ceil else None,
                                 "note": "one dependent random load per walk step; ceiling = DRAM-missing dependent loads/s measured by "
                                         "tools/gather_bench.cu for an array of nbr4's size in a many-wave launch (profiles/gather_ceiling.json; "
-                                        "a single resident wave of CTAs is held at 39.6 G/s, profiles/r2_gather_waves.txt).  The Monte-Carlo "
+                                        "equal work per SM ends at 39.6 G/s because the SMs come in three throughput classes, profiles/r2_gather_waves.txt).  The Monte-Carlo "
                                         "kernel's first two steps of every walk start at the query vertex and hit L1/L2 (~20 % of its loads), "
                                         "so its rate can exceed the ceiling of misses"}}
         roof["frac"] = roof["achieved"] / peak

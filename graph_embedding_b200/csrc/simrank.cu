@@ -525,10 +525,11 @@ struct SrRing {
     unsigned long long full[SR_PAIRS][STAGES];
     unsigned long long empty[SR_PAIRS][STAGES];
 };
-// Called by ONE thread of a starting CTA.  Why CTAs are launched in many waves instead of one persistent wave: dependent random
-// 16-byte loads run at 39.6 G/s in a kernel whose CTAs all start together and stay (any occupancy, any chain length), and at
-// 49-51 G/s from the third wave of CTAs of a launch on (tools/gather_bench.cu mode -5, profiles/r2_gather_waves.txt);
-// k_simrank_log: 464 k -> 548 k queries/s with 16 CTAs per SM slot, results bit-identical.
+// Called by ONE thread of a starting CTA.  Why many CTAs per SM slot instead of one persistent CTA with a static share of the
+// queries: the SMs are not equal for random access -- equal chains of dependent random loads take 1.54 ms on 12 SMs, 2.29 ms on 96
+// and 3.06 ms on 40 (tools/gather_bench.cu mode -5, profiles/r2_gather_waves.txt) -- so equal shares end with the slowest class
+// (39.6 G loads/s) while small CTAs handed out by the hardware keep every SM busy (51 G/s).  k_simrank_log: 464 k -> 548 k
+// queries/s with 16 CTAs per SM slot, results bit-identical.
 __device__ __forceinline__ uint32_t take_slot(const SimrankParams &P) {
     uint32_t sl = blockIdx.x % P.nslots;
     while (atomicCAS(P.slots + sl, 0u, 1u) != 0u) sl = sl + 1 == P.nslots ? 0 : sl + 1;

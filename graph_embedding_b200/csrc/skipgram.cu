@@ -503,7 +503,7 @@ int gw_sgns_train_dev(gw_sgns *m, const int32_t *d_walks, int64_t n_walks, int32
     if (const char *mw = getenv("GW_SG_WARPS")) max_warps = std::max<int64_t>(1, atoll(mw));     // experiment knob
     const int threads = sequential ? 32 : 32 * (int)std::min<int64_t>(8, max_warps);
     // CTAs in the launch per SM (3 of 256 threads are resident at dimensions <= 128): 8 -> 836 M pairs/s, 3 -> 870, 32 -> 873,
-    // 128 -> 882 (2^20 walks of the R-MAT-22 corpus): many short CTAs leave no tail and keep the SMs at different phases
+    // 128 -> 882 (2^20 walks of the R-MAT-22 corpus): many short CTAs leave no tail (the SMs do not all run at the same rate: profiles/r2_gather_waves.txt)
     int ctas_per_sm = 128;
     if (const char *cs = getenv("GW_SG_CTAS_PER_SM")) ctas_per_sm = std::max(1, atoi(cs));      // experiment knob
     const unsigned grid = sequential ? 1u : (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((n_walks + 7) / 8, (int64_t)sms * ctas_per_sm), max_warps / (threads / 32)));

@@ -86,6 +86,53 @@ __global__ void k_chain_dummy(const int4 *__restrict__ a, uint32_t mask, int ste
     out[t] = acc;
 }
 
+// do SHORT working waves count?  The first `nprime` blocks walk `psteps` loads, the others `steps`
+__global__ void k_chain_prime(const int4 *__restrict__ a, uint32_t mask, int steps, int psteps, uint32_t salt, uint32_t nprime, uint32_t *out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int my = blockIdx.x < nprime ? psteps : steps;
+    uint32_t i = mix(t * 2654435761u + salt) & mask;
+    uint32_t acc = 0;
+    for (int s = 0; s < my; s++) {
+        const int4 v = __ldg(a + i);
+        acc += v.y;
+        i = mix((uint32_t)v.x + s + t * 0x9E3779B9u) & mask;
+    }
+    out[t] = acc;
+}
+
+// ... or is it PENDING CTAs that matter?  The LAST `ntail` blocks of the launch return at once: they stay undispatched while the
+// working wave holds every CTA slot
+__global__ void k_chain_tail(const int4 *__restrict__ a, uint32_t mask, int steps, uint32_t salt, uint32_t nwork, uint32_t *out) {
+    if (blockIdx.x >= nwork) return;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t i = mix(t * 2654435761u + salt) & mask;
+    uint32_t acc = 0;
+    for (int s = 0; s < steps; s++) {
+        const int4 v = __ldg(a + i);
+        acc += v.y;
+        i = mix((uint32_t)v.x + s + t * 0x9E3779B9u) & mask;
+    }
+    out[t] = acc;
+}
+
+// when, inside a many-wave launch, is the rate high?  Every block records its start and end on the global timer
+__global__ void k_chain_times(const int4 *__restrict__ a, uint32_t mask, int steps, uint32_t salt, uint32_t *out, unsigned long long *t0, unsigned long long *t1,
+                              uint32_t *sm) {
+    unsigned long long now;
+    if (threadIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); t0[blockIdx.x] = now; uint32_t id; asm volatile("mov.u32 %0, %%smid;" : "=r"(id)); sm[blockIdx.x] = id; }
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t i = mix(t * 2654435761u + salt) & mask;
+    uint32_t acc = 0;
+    for (int s = 0; s < steps; s++) {
+        const int4 v = __ldg(a + i);
+        acc += v.y;
+        i = mix((uint32_t)v.x + s + t * 0x9E3779B9u) & mask;
+    }
+    out[t] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); t1[blockIdx.x] = now; }
+}
+
 // pair mode: every step loads the random entry AND its partner at byte distance `dist` (same naturally
 // aligned 2*dist block).  If pairs run at the single-load rate the ceiling is a DRAM activate / L2-miss
 // REQUEST rate that locality can amortise, not bytes.
@@ -296,6 +343,71 @@ int main(int argc, char **argv) {
                 cudaEventRecord(e1); cudaEventSynchronize(e1);
                 float ms; cudaEventElapsedTime(&ms, e0, e1);
                 printf("one working wave after %6u blocks that return at once: %7.3f ms %6.1f G loads/s\n", nd[vi], ms, 1184.0 * 256 * 2000 / ms / 1e6);
+            }
+        }
+        {
+            const int ps[] = {1, 10, 50, 200};
+            for (int vi = 0; vi < 4; vi++)
+                for (uint32_t np = 2368; np <= 4736; np += 2368) {
+                    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+                    k_chain_prime<<<1184 + np, 256>>>(a, (uint32_t)(n - 1), 2000, ps[vi], 0, np, out2);
+                    cudaEventRecord(e0);
+                    k_chain_prime<<<1184 + np, 256>>>(a, (uint32_t)(n - 1), 2000, ps[vi], 1, np, out2);
+                    cudaEventRecord(e1); cudaEventSynchronize(e1);
+                    float ms; cudaEventElapsedTime(&ms, e0, e1);
+                    const double loads = 1184.0 * 256 * 2000 + (double)np * 256 * ps[vi];
+                    printf("one working wave after %u blocks of %3d loads per chain: %7.3f ms %6.1f G loads/s overall\n", np, ps[vi], ms, loads / ms / 1e6);
+                }
+        }
+        {
+            const uint32_t nt[] = {0, 148, 1184, 2368, 4736, 18944};
+            for (int vi = 0; vi < 6; vi++) {
+                cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+                k_chain_tail<<<1184 + nt[vi], 256>>>(a, (uint32_t)(n - 1), 2000, 0, 1184, out2);
+                cudaEventRecord(e0);
+                k_chain_tail<<<1184 + nt[vi], 256>>>(a, (uint32_t)(n - 1), 2000, 1, 1184, out2);
+                cudaEventRecord(e1); cudaEventSynchronize(e1);
+                float ms; cudaEventElapsedTime(&ms, e0, e1);
+                printf("one working wave with %6u blocks that return at once PENDING behind it: %7.3f ms %6.1f G loads/s\n", nt[vi], ms, 1184.0 * 256 * 2000 / ms / 1e6);
+            }
+        }
+        const int tgrids[] = {1184, 2368, 4736, 18944};
+        for (int tg = 0; tg < 4; tg++) {   // per-block lifetimes: loads/s by millisecond (a block's loads spread evenly over its lifetime)
+            const int grid = tgrids[tg], steps = 400;
+            unsigned long long *t0, *t1, *h0 = new unsigned long long[grid], *h1 = new unsigned long long[grid];
+            uint32_t *dsm, *hsm = new uint32_t[grid];
+            cudaMalloc(&t0, grid * 8); cudaMalloc(&t1, grid * 8); cudaMalloc(&dsm, grid * 4);
+            k_chain_times<<<grid, 256>>>(a, (uint32_t)(n - 1), steps, 0, out2, t0, t1, dsm);
+            k_chain_times<<<grid, 256>>>(a, (uint32_t)(n - 1), steps, 1, out2, t0, t1, dsm);
+            cudaDeviceSynchronize();
+            cudaMemcpy(hsm, dsm, grid * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(h0, t0, grid * 8, cudaMemcpyDeviceToHost); cudaMemcpy(h1, t1, grid * 8, cudaMemcpyDeviceToHost);
+            unsigned long long lo = ~0ull, hi = 0;
+            for (int b = 0; b < grid; b++) { if (h0[b] < lo) lo = h0[b]; if (h1[b] > hi) hi = h1[b]; }
+            const int nb = (int)((hi - lo) / 1000000) + 1;
+            double *bins = new double[nb]();
+            double life_first = 0, life_mid = 0, life_last = 0;
+            for (int b = 0; b < grid; b++) {
+                const double s0 = (double)(h0[b] - lo) / 1e6, s1 = (double)(h1[b] - lo) / 1e6, per = 256.0 * steps / (s1 - s0);
+                for (int k = (int)s0; k <= (int)s1 && k < nb; k++) { const double a0 = s0 > k ? s0 : k, a1 = s1 < k + 1 ? s1 : k + 1; if (a1 > a0) bins[k] += per * (a1 - a0); }
+                if (b < 1184) life_first += s1 - s0; else if (b >= grid - 1184) life_last += s1 - s0; else if (b >= 8 * 1184 && b < 9 * 1184) life_mid += s1 - s0;
+            }
+            printf("%d-block launch, %d loads per chain: total %.2f ms; mean block lifetime: first 1184 blocks %.3f ms, blocks 9472..10655 %.3f ms, last 1184 blocks %.3f ms\n",
+                   grid, steps, (double)(hi - lo) / 1e6, life_first / 1184, life_mid / 1184, life_last / 1184);
+            printf("G loads/s by millisecond:");
+            for (int k = 0; k < nb; k++) printf(" %.1f", bins[k] / 1e6);
+            printf("\n");
+            if (grid == 1184) {   // which SMs are slow?  mean lifetime of the 8 blocks of every SM, sorted
+                double sum[256] = {0}; int cnt[256] = {0}; double v[256]; int nv = 0, maxid = 0;
+                for (int b = 0; b < grid; b++) { const int id = hsm[b] & 255; sum[id] += (double)(h1[b] - h0[b]) / 1e6; cnt[id]++; if (id > maxid) maxid = id; }
+                for (int id = 0; id <= maxid; id++) if (cnt[id]) v[nv++] = sum[id] / cnt[id];
+                for (int i = 0; i < nv; i++) for (int j = i + 1; j < nv; j++) if (v[j] < v[i]) { double x = v[i]; v[i] = v[j]; v[j] = x; }
+                printf("one wave: %d SMs hold blocks (%d..%d blocks each); mean block lifetime per SM, sorted, every 10th: ", nv, 8, 8);
+                for (int i = 0; i < nv; i += 10) printf("%.2f ", v[i]);
+                printf("... max %.2f ms\n", v[nv - 1]);
+                printf("per SM id (mean lifetime ms):");
+                for (int id = 0; id <= maxid; id++) if (cnt[id]) printf(" %d:%.2f", id, sum[id] / cnt[id]);
+                printf("\n");
             }
         }
         // how many blocks does it take?  (1184 = one resident wave of 8 per SM)
