@@ -777,7 +777,35 @@ __global__ void __launch_bounds__(2 * SR_ABLOCK, 1) k_simrank_log(SimrankParams 
     Ring &R = *reinterpret_cast<Ring *>(smem_raw + ((sizeof(SrLogShared) + 15) & ~(size_t)15));
     const int tid = threadIdx.x, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     __shared__ uint32_t s_slot;
-    if (tid == 0) s_slot = take_slot(P);
+    // Queries are CLAIMED one at a time from a global counter (P.work[2]) by walker warp 0 and published to the other 31 warps
+    // through an 8-entry ring, ONE QUERY AHEAD of its own use (no warp ever waits for the claim): the SMs do not run at the
+    // same rate (take_slot), and a static deal ends with the slowest.  Every warp stays within two queries of every other (a
+    // walker is at most Ring::STAGES stages ahead of its accumulator, the accumulators meet at a barrier per query), so an
+    // entry is never overwritten before its last reader has taken it.
+    __shared__ int32_t s_qseq[8];
+    __shared__ uint32_t s_qpub;
+    if (tid == 0) { s_slot = take_slot(P); s_qpub = 0; }
+    auto next_query = [&](uint32_t k) -> int64_t {              // the k-th query of this CTA, -1 = none left; called by whole warps
+        int32_t q;
+        if (wrp == 0) {
+            q = 0;
+            if (lane == 0) {
+                for (uint32_t e = k == 0 ? 0u : k + 1; e <= k + 1; e++) {          // entries 0 and 1 at the start, then k + 1
+                    const uint32_t c = atomicAdd(P.work + 2, 1u);
+                    ((volatile int32_t *)s_qseq)[e & 7] = (int64_t)c < P.nq ? (int32_t)c : -1;
+                    __threadfence_block();
+                    *(volatile uint32_t *)&s_qpub = e + 1;
+                }
+                q = ((volatile int32_t *)s_qseq)[k & 7];
+            }
+            q = __shfl_sync(0xffffffffu, q, 0);
+        } else {
+            while (*(volatile uint32_t *)&s_qpub <= k) { }
+            __threadfence_block();
+            q = ((volatile int32_t *)s_qseq)[k & 7];
+        }
+        return (int64_t)q;
+    };
     uint32_t *t3keys = S.hist;
 
     if (tid < SR_PAIRS * Ring::STAGES) {
@@ -798,7 +826,9 @@ __global__ void __launch_bounds__(2 * SR_ABLOCK, 1) k_simrank_log(SimrankParams 
     if (wrp < SR_PAIRS) {
         // =============================== walkers ===============================
         unsigned long long my_steps = 0;
-        for (int64_t qi = blockIdx.x; qi < P.nq; qi += gridDim.x) {
+        for (uint32_t kq = 0;; kq++) {
+            const int64_t qi = next_query(kq);
+            if (qi < 0) break;
             const int32_t v = (int32_t)P.queries[qi];
             const uint64_t qid = P.query_id_base + (uint64_t)qi;
             const uint2 mv = __ldg(P.meta + v);
@@ -826,7 +856,9 @@ __global__ void __launch_bounds__(2 * SR_ABLOCK, 1) k_simrank_log(SimrankParams 
     const int pw = wrp - SR_PAIRS, atid = tid - SR_ABLOCK;
     const uint32_t my_slot = s_slot;                           // only the accumulator warps touch the log
     uint2 *log = P.log + (size_t)my_slot * P.log_cap;
-    for (int64_t qi = blockIdx.x; qi < P.nq; qi += gridDim.x) {
+    for (uint32_t kq = 0;; kq++) {
+        const int64_t qi = next_query(kq);
+        if (qi < 0) break;
         // ---------------- phase A: drain my walker's ring ----------------
         for (int32_t g0 = pw * 32; g0 < ngroups; g0 += SR_PAIRS * 32, stage_no++) {
             const uint32_t st = stage_no % Ring::STAGES, ph = (stage_no / Ring::STAGES) & 1;
@@ -1617,10 +1649,10 @@ static int simrank_run(gw_graph *g, const int64_t *d_queries, int64_t nq, double
     const int grid = (int)std::min<int64_t>(nq, (int64_t)sms * (hybrid ? 1 : 2));
     // log and path-tree kernels: one 1024- / 512-thread CTA is resident per SM, but the launch holds SR_WAVES CTAs per SM
     // (each with 1/SR_WAVES of the queries) -- see take_slot for the measurement behind it.  GW_SR_WAVES overrides (1 = persistent).
-    int sr_waves = 16;
-    if (const char *wv = getenv("GW_SR_WAVES")) sr_waves = std::max(1, atoi(wv));
+    int sr_waves = 16, log_waves = 1;                                               // the log kernel claims its queries one by one: persistent
+    if (const char *wv = getenv("GW_SR_WAVES")) sr_waves = log_waves = std::max(1, atoi(wv));
     const int nslots = (int)std::min<int64_t>(nq, (int64_t)sms);                    // scratch areas = CTAs that can be resident
-    const int log_grid = (int)std::min<int64_t>(nq, (int64_t)sms * sr_waves);
+    const int log_grid = (int)std::min<int64_t>(nq, (int64_t)sms * log_waves);
     const char *force = getenv("GW_SIMRANK");
     const bool use_log = !hybrid && d_out_ids && !d_out_dense && !(force && !strcmp(force, "hash"));
     // hash-kernel tier-2 table: >= 2x the distinct targets one query can produce
