@@ -94,3 +94,24 @@ def test_reference_arm_line_says_what_it_ran():
     assert "R-MAT scale-10" in line["config"]["workload"] and line["cpu_baseline"]["kind"] == "port"
     assert line["preprocess"]["entries_per_s"] > 1e4 and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["unit"] == "walk-steps/s" and line["higher_is_better"] is True
+
+
+def test_traffic_captures_cover_the_kernels_bench_reports():
+    """roofline.traffic is looked up by the exact kernel instantiation and workload key bench.py is about to report
+    (profiles/traffic.json); every headline kernel of the default run has a capture, and an unknown kernel gets None."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    walk = bench.ncu_traffic("k_walk_cn<VEC8=1,COUNT=0,MINB=5,HUB=0,RIDX=1>", "rmat22/ef16/abc=0.45,0.15,0.15/p=0.25/q=4/L=80", 330065081)
+    assert walk and 40 < walk / 330065081 < 70                                   # ~51 B of DRAM traffic per walk step
+    sr = bench.ncu_traffic("k_simrank_log<5>", "ba10000000/m8/sample=10000/step=5/k=20", 8192)
+    assert sr and 4.5e6 < sr / 8192 < 5.5e6                                      # ~5.05 MB per query
+    hy = bench.ncu_traffic("k_topsim_hybrid<5,true>", "ba10000000/m8/sample=10000/step=5/k=20", 2048)
+    assert hy and 6e6 < hy / 2048 < 7.5e6                                        # scaled to another batch size
+    sg = bench.ncu_traffic("k_sgns_pipe<4>", "rmat22/ef16/abc=0.45,0.15,0.15/p=0.25/q=4/L=80/dim=128/window=10/negative=5/sample=0.001", 10 ** 9)
+    assert sg and 6000 < sg / 10 ** 9 < 6600                                     # ~6.3 kB per trained pair
+    assert bench.ncu_traffic("k_walk_cn<VEC8=1,COUNT=0,MINB=6,HUB=0,RIDX=1>", "rmat22/ef16/abc=0.45,0.15,0.15/p=0.25/q=4/L=80") is None
+    assert bench.ncu_traffic("k_simrank_log<5>", "ba1000000/m8/sample=10000/step=5/k=20") is None
